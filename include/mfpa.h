@@ -1,0 +1,154 @@
+/*
+ * mfpa.h — C ABI of the B200-native musicFPaugment query path (libmfpa.so).
+ *
+ * The reference (deezer/musicFPaugment) is pure Python and has no FFI layer;
+ * its boundary for this path is the Python call surface listed in SURVEY.md
+ * §8(b).  Each entry point below names the reference function(s) it replaces
+ * (paths relative to the reference root).  The Python mirror in
+ * musicfpaugment_b200/ binds these with ctypes.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative MFPA_E* code otherwise;
+ *     mfpa_last_error() gives the message of the calling thread's last failure.
+ *   - "_dev" pointers are device pointers on the context's GPU, caller-owned.
+ *     "_host" pointers are ordinary host memory.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *     Device entry points are asynchronous on that stream; *_host entry points
+ *     synchronise before returning.
+ *   - a context owns scratch buffers that grow on demand; one context must not
+ *     be used from two threads at once.
+ *   - geometry is the reference's fixed analysis setting
+ *     (testing/parameters.py:17-26): n_fft 512, hop 256, 257 bins, 256 kept.
+ *
+ * "item" = one (query, shift) pair: item = query * shifts + shift.  A shifted
+ * item analyses x[off:], off = int(shift / shifts * 256)
+ * (afp/audfprint/peak_extractor.py:411-413).
+ */
+#ifndef MFPA_H
+#define MFPA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MFPA_ABI_VERSION 1
+
+#define MFPA_N_FFT 512
+#define MFPA_HOP 256
+#define MFPA_BINS 257      /* rfft bins */
+#define MFPA_ROWS 256      /* bins kept by the peak picker (Nyquist dropped) */
+#define MFPA_MAG_PITCH 264 /* elements per frame in the internal frame-major magnitude layout */
+#define MFPA_MAX_PKS 5     /* hard upper bound on pks-per-frame */
+#define MFPA_MAX_SHIFTS 8
+#define MFPA_HASHES_PER_FRAME 15 /* MFPA_MAX_PKS * fanout(3): capacity per frame of a hash list */
+
+#define MFPA_OK 0
+#define MFPA_EINVAL -1 /* bad argument */
+#define MFPA_ECUDA -2  /* CUDA runtime error */
+#define MFPA_ENOMEM -3
+#define MFPA_ECAP -4   /* an output capacity was too small */
+
+typedef struct mfpa_ctx mfpa_ctx;
+
+/* Analysis parameters of Audfprint_peaks.__init__ (peak_extractor.py:86-113)
+ * and find_peaks (:295).  mfpa_afp_defaults() fills the reference's
+ * afp_settings["audfprint"] values. */
+typedef struct mfpa_afp_params {
+  double a_dec;    /* 1 - 0.01*(density*sqrt(n_hop/352.8)/35), computed by the caller in float64 */
+  double f_sd;     /* "freq-sd": Gaussian spreading width (30) */
+  int32_t maxpks;  /* "pks-per-frame" (5), <= MFPA_MAX_PKS */
+  int32_t mindt;   /* 2  */
+  int32_t targetdt;/* 63 */
+  int32_t targetdf;/* 31 */
+  int32_t fanout;  /* maxpairsperpeak 3 */
+  int32_t reserved;
+} mfpa_afp_params;
+
+/* ---- context ---------------------------------------------------------- */
+int mfpa_abi_version(void);
+const char* mfpa_last_error(void);
+int mfpa_create(mfpa_ctx** out, int device);
+void mfpa_destroy(mfpa_ctx* ctx);
+void mfpa_afp_defaults(mfpa_afp_params* p);
+/* Upload the 513-entry spreading table exp(-0.5*((k/f_sd)^2)), k=-256..256,
+ * computed by the caller with numpy so it is bit-identical to the reference's
+ * cached __sp_vals (peak_extractor.py:159-165).  Without this call the library
+ * fills the table with the host C library's exp(). */
+int mfpa_set_spread_table(mfpa_ctx* ctx, const double* table513_host);
+
+/* ---- geometry --------------------------------------------------------- */
+int mfpa_num_frames(int n_samples);           /* afp/audfprint/stft.py:50-53 */
+int mfpa_shift_offset(int shift, int shifts); /* peak_extractor.py:412 */
+
+/* ---- S2: magnitude STFT  (afp/audfprint/stft.py:15-62 + abs, peak_extractor.py:257-261)
+ * x_dev: B rows of T float32 samples, row stride `x_stride` elements.
+ * mag_dev: [B*shifts][mfpa_num_frames(T)][MFPA_MAG_PITCH] float32, frame-major
+ *          (elements 0..256 of each frame are |rfft|; the rest is padding).
+ * qmax_dev: [B*shifts] float32, max of each item's magnitudes (the divisor of
+ *          `sgram /= np.max(sgram)`, peak_extractor.py:263). */
+int mfpa_stft_mag(mfpa_ctx* ctx, const float* x_dev, int B, int T, int64_t x_stride, int shifts,
+                  float* mag_dev, float* qmax_dev, void* stream);
+
+/* Normalised spectrogram in the reference's layout: spec[item][257][n_frames_max]
+ * float64 = mag/qmax — the `spec` returned by find_peaks (peak_extractor.py:271,311). */
+int mfpa_spec_from_mag(mfpa_ctx* ctx, const float* mag_dev, const float* qmax_dev, int B, int T,
+                       int shifts, double* spec_dev, void* stream);
+
+/* ---- S3: audfprint peak picking  (peak_extractor.py:263-311: /max, log, -mean,
+ * lfilter, _decaying_threshold_fwd_prune :173-204, _bwd_prune_peaks :206-234)
+ * Output: one 64-bit record per (item, frame): byte0 = number of peaks (<=5),
+ * bytes 1..5 = their bins in ascending order.  rec_dev: [B*shifts][n_frames_max].
+ * npeaks_dev: [B*shifts] int32 total per item (may be NULL). */
+int mfpa_audfprint_peaks(mfpa_ctx* ctx, const float* mag_dev, const float* qmax_dev, int B, int T,
+                         int shifts, const mfpa_afp_params* p, uint64_t* rec_dev,
+                         int32_t* npeaks_dev, void* stream);
+
+/* Same picker fed a float64 spectrogram in the REFERENCE layout [items][rows][n_frames]
+ * (parity entry: "bit-exact when fed the reference spectrogram").
+ * stage 0: spec is find_peaks' magnitude spectrogram, rows = 257 (normalised or not);
+ * stage 1: spec is the already filtered sgram of :286-290, rows = 256. */
+int mfpa_audfprint_peaks_from_spec(mfpa_ctx* ctx, const double* spec_dev, int items, int n_frames,
+                                   int stage, const mfpa_afp_params* p, uint64_t* rec_dev,
+                                   int32_t* npeaks_dev, void* stream);
+
+/* records -> (col, bin) int32 rows in find_peaks' pklist order (:303-309);
+ * peaks_dev: [items][cap][2]. */
+int mfpa_peaks_list(mfpa_ctx* ctx, const uint64_t* rec_dev, int items, int n_frames,
+                    int32_t* peaks_dev, int cap, int32_t* npeaks_dev, void* stream);
+/* records -> peaks_mask float32 [items][256][n_frames] (:303). */
+int mfpa_peaks_mask(mfpa_ctx* ctx, const uint64_t* rec_dev, int items, int n_frames,
+                    float* mask_dev, void* stream);
+
+/* ---- S4: landmarks + 20-bit hashes  (peaks2landmarks :313-346, landmarks2hashes :40-58)
+ * hashes_dev: [items][cap][2] int32 rows (time, hash); nh_dev: [items].
+ * sorted = 0: rows in the reference's landmark order;
+ * sorted = 1: rows ordered by (time, hash) — for shifts == 1 this is
+ *             wavfile2hashes' final unique/sorted array (:448-460).
+ * n_frames_item_dev (nullable): per-item frame counts when they differ. */
+int mfpa_landmark_hashes(mfpa_ctx* ctx, const uint64_t* rec_dev, int items, int n_frames,
+                         const mfpa_afp_params* p, int sorted, int32_t* hashes_dev, int cap,
+                         int32_t* nh_dev, void* stream);
+
+/* Concatenate the `shifts` lists of each query, unique + sort on (time, hash)
+ * (wavfile2hashes :437-460).  in: [B*shifts][cap_in][2] (each list sorted by
+ * (time,hash)); out: [B][cap_out][2]. */
+int mfpa_merge_shifts(mfpa_ctx* ctx, const int32_t* hashes_dev, const int32_t* nh_dev, int B,
+                      int shifts, int cap_in, int n_frames, int32_t* out_dev, int cap_out,
+                      int32_t* nout_dev, void* stream);
+
+/* ---- fused S2-S4: Audfprint_peaks.wavfile2hashes without the file read (:426-460)
+ * x -> unique sorted (time, hash) rows.  hashes_dev: [B][cap][2], nh_dev: [B]. */
+int mfpa_fingerprint(mfpa_ctx* ctx, const float* x_dev, int B, int T, int64_t x_stride, int shifts,
+                     const mfpa_afp_params* p, int32_t* hashes_dev, int cap, int32_t* nh_dev,
+                     void* stream);
+/* Host-buffer form: copies x in, runs mfpa_fingerprint, copies the rows back. */
+int mfpa_fingerprint_host(mfpa_ctx* ctx, const float* x_host, int B, int T, int shifts,
+                          const mfpa_afp_params* p, int32_t* hashes_host, int cap,
+                          int32_t* nh_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MFPA_H */

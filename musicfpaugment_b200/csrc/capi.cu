@@ -1,0 +1,275 @@
+// extern "C" surface of libmfpa.so (see include/mfpa.h for the contract).
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <new>
+
+#include "common.cuh"
+
+namespace mfpa {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int Scratch::reserve(size_t need) {
+  if (need <= bytes) return 0;
+  if (ptr) cudaFree(ptr);
+  ptr = nullptr;
+  bytes = 0;
+  // grow with 25 % head-room so alternating batch sizes do not thrash
+  size_t want = need + need / 4;
+  cudaError_t e = cudaMalloc(&ptr, want);
+  if (e != cudaSuccess) {
+    e = cudaMalloc(&ptr, need);
+    want = need;
+  }
+  if (e != cudaSuccess) {
+    ptr = nullptr;
+    set_error("cudaMalloc(%zu) failed: %s", need, cudaGetErrorString(e));
+    return MFPA_ENOMEM;
+  }
+  bytes = want;
+  return 0;
+}
+
+void Scratch::release() {
+  if (ptr) cudaFree(ptr);
+  ptr = nullptr;
+  bytes = 0;
+}
+
+static int check_afp(const mfpa_afp_params* p) {
+  MFPA_REQUIRE(p != nullptr, "afp params are NULL");
+  MFPA_REQUIRE(p->maxpks >= 1 && p->maxpks <= MFPA_MAX_PKS, "pks-per-frame %d not in 1..%d", p->maxpks, MFPA_MAX_PKS);
+  MFPA_REQUIRE(p->a_dec > 0.0 && p->a_dec <= 1.0, "a_dec %g not in (0,1]", p->a_dec);
+  MFPA_REQUIRE(p->mindt >= 0 && p->targetdt > p->mindt && p->targetdt <= 64, "bad mindt/targetdt %d/%d", p->mindt, p->targetdt);
+  MFPA_REQUIRE(p->targetdf >= 1 && p->targetdf <= 32, "targetdf %d not in 1..32", p->targetdf);
+  return MFPA_OK;
+}
+
+static int check_batch(int B, int T, int shifts) {
+  MFPA_REQUIRE(B >= 1, "batch %d < 1", B);
+  MFPA_REQUIRE(T >= 1, "n_samples %d < 1 (find_peaks returns an empty list for empty input; handle on the host)", T);
+  MFPA_REQUIRE(shifts >= 1 && shifts <= MFPA_MAX_SHIFTS, "shifts %d not in 1..%d", shifts, MFPA_MAX_SHIFTS);
+  MFPA_REQUIRE(T > shift_offset(shifts - 1, shifts), "n_samples %d shorter than the largest shift", T);
+  return MFPA_OK;
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+}  // namespace mfpa
+
+using namespace mfpa;
+
+extern "C" {
+
+int mfpa_abi_version(void) { return MFPA_ABI_VERSION; }
+const char* mfpa_last_error(void) { return g_err; }
+int mfpa_num_frames(int n_samples) { return num_frames(n_samples); }
+int mfpa_shift_offset(int shift, int shifts) { return shift_offset(shift, shifts); }
+
+void mfpa_afp_defaults(mfpa_afp_params* p) {
+  // testing/parameters.py:17-26 + Audfprint_peaks.__init__ (peak_extractor.py:99-108)
+  p->a_dec = 1.0 - 0.01 * (20.0 * sqrt(256.0 / 352.8) / 35.0);
+  p->f_sd = 30.0;
+  p->maxpks = 5;
+  p->mindt = 2;
+  p->targetdt = 63;
+  p->targetdf = 31;
+  p->fanout = 3;
+  p->reserved = 0;
+}
+
+int mfpa_create(mfpa_ctx** out, int device) {
+  MFPA_REQUIRE(out != nullptr, "mfpa_create: out is NULL");
+  *out = nullptr;
+  int n = 0;
+  MFPA_CUDA(cudaGetDeviceCount(&n));
+  MFPA_REQUIRE(device >= 0 && device < n, "mfpa_create: device %d not in [0,%d)", device, n);
+  DeviceGuard guard(device);
+  cudaDeviceProp prop;
+  MFPA_CUDA(cudaGetDeviceProperties(&prop, device));
+  MFPA_REQUIRE(prop.major == 10, "libmfpa is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);
+  mfpa_ctx* ctx = new (std::nothrow) mfpa_ctx();
+  if (!ctx) { set_error("out of host memory"); return MFPA_ENOMEM; }
+  ctx->device = device;
+  ctx->num_sms = prop.multiProcessorCount;
+  MFPA_CUDA(cudaMalloc(&ctx->spread_dev, sizeof(double) * kSpreadLen));
+  double tab[kSpreadLen];
+  for (int k = -kRows; k <= kRows; ++k) { const double u = (double)k / 30.0; tab[k + kRows] = exp(-0.5 * (u * u)); }
+  MFPA_CUDA(cudaMemcpy(ctx->spread_dev, tab, sizeof(tab), cudaMemcpyHostToDevice));
+  if (int e = stft_init_tables(ctx)) { mfpa_destroy(ctx); return e; }
+  *out = ctx;
+  return MFPA_OK;
+}
+
+void mfpa_destroy(mfpa_ctx* ctx) {
+  if (!ctx) return;
+  DeviceGuard guard(ctx->device);
+  cudaDeviceSynchronize();
+  Scratch* all[] = {&ctx->mag, &ctx->qmax, &ctx->rec, &ctx->fwd, &ctx->hashes, &ctx->nh, &ctx->misc, &ctx->spec64,
+                    &ctx->xin, &ctx->out_h, &ctx->out_n, &ctx->aug_a, &ctx->aug_b, &ctx->aug_c, &ctx->aug_d,
+                    &ctx->aug_small, &ctx->match_a, &ctx->match_b, &ctx->match_c};
+  for (Scratch* s : all) s->release();
+  if (ctx->spread_dev) cudaFree(ctx->spread_dev);
+  if (ctx->tw_dev) cudaFree(ctx->tw_dev);
+  if (ctx->win_dev) cudaFree(ctx->win_dev);
+  if (ctx->index_table) cudaFree(ctx->index_table);
+  if (ctx->index_counts) cudaFree(ctx->index_counts);
+  if (ctx->index_hashesperid) cudaFree(ctx->index_hashesperid);
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  delete ctx;
+}
+
+int mfpa_set_spread_table(mfpa_ctx* ctx, const double* table513_host) {
+  MFPA_REQUIRE(ctx && table513_host, "set_spread_table: NULL argument");
+  DeviceGuard guard(ctx->device);
+  MFPA_CUDA(cudaMemcpy(ctx->spread_dev, table513_host, sizeof(double) * kSpreadLen, cudaMemcpyHostToDevice));
+  return MFPA_OK;
+}
+
+int mfpa_stft_mag(mfpa_ctx* ctx, const float* x_dev, int B, int T, int64_t x_stride, int shifts,
+                  float* mag_dev, float* qmax_dev, void* stream) {
+  MFPA_REQUIRE(ctx && x_dev && mag_dev && qmax_dev, "stft_mag: NULL argument");
+  if (int e = check_batch(B, T, shifts)) return e;
+  MFPA_REQUIRE(x_stride >= T, "stft_mag: row stride %lld < n_samples %d", (long long)x_stride, T);
+  DeviceGuard guard(ctx->device);
+  return launch_stft_mag(ctx, x_dev, B, T, x_stride, shifts, mag_dev, qmax_dev, (cudaStream_t)stream);
+}
+
+int mfpa_spec_from_mag(mfpa_ctx* ctx, const float* mag_dev, const float* qmax_dev, int B, int T,
+                       int shifts, double* spec_dev, void* stream) {
+  MFPA_REQUIRE(ctx && mag_dev && qmax_dev && spec_dev, "spec_from_mag: NULL argument");
+  if (int e = check_batch(B, T, shifts)) return e;
+  DeviceGuard guard(ctx->device);
+  return launch_spec_from_mag(mag_dev, qmax_dev, B, T, shifts, spec_dev, (cudaStream_t)stream);
+}
+
+int mfpa_audfprint_peaks(mfpa_ctx* ctx, const float* mag_dev, const float* qmax_dev, int B, int T,
+                         int shifts, const mfpa_afp_params* p, uint64_t* rec_dev, int32_t* npeaks_dev,
+                         void* stream) {
+  MFPA_REQUIRE(ctx && mag_dev && rec_dev, "audfprint_peaks: NULL argument");
+  if (int e = check_batch(B, T, shifts)) return e;
+  if (int e = check_afp(p)) return e;
+  MFPA_REQUIRE(((uintptr_t)mag_dev & 15) == 0, "audfprint_peaks: mag must be 16-byte aligned");
+  DeviceGuard guard(ctx->device);
+  return launch_peaks_f32(ctx, mag_dev, qmax_dev, B, T, shifts, *p, rec_dev, npeaks_dev, (cudaStream_t)stream);
+}
+
+int mfpa_audfprint_peaks_from_spec(mfpa_ctx* ctx, const double* spec_dev, int items, int n_frames,
+                                   int stage, const mfpa_afp_params* p, uint64_t* rec_dev,
+                                   int32_t* npeaks_dev, void* stream) {
+  MFPA_REQUIRE(ctx && spec_dev && rec_dev, "peaks_from_spec: NULL argument");
+  MFPA_REQUIRE(items >= 1 && n_frames >= 1, "peaks_from_spec: items %d, n_frames %d", items, n_frames);
+  MFPA_REQUIRE(stage == 0 || stage == 1, "peaks_from_spec: stage %d not in {0,1}", stage);
+  if (int e = check_afp(p)) return e;
+  DeviceGuard guard(ctx->device);
+  return launch_peaks_from_spec(ctx, spec_dev, items, n_frames, stage, *p, rec_dev, npeaks_dev, (cudaStream_t)stream);
+}
+
+int mfpa_peaks_list(mfpa_ctx* ctx, const uint64_t* rec_dev, int items, int n_frames, int32_t* peaks_dev,
+                    int cap, int32_t* npeaks_dev, void* stream) {
+  MFPA_REQUIRE(ctx && rec_dev && peaks_dev, "peaks_list: NULL argument");
+  MFPA_REQUIRE(items >= 1 && n_frames >= 1 && cap >= 1, "peaks_list: bad sizes");
+  DeviceGuard guard(ctx->device);
+  return launch_peaks_list(rec_dev, items, n_frames, peaks_dev, cap, npeaks_dev, (cudaStream_t)stream);
+}
+
+int mfpa_peaks_mask(mfpa_ctx* ctx, const uint64_t* rec_dev, int items, int n_frames, float* mask_dev,
+                    void* stream) {
+  MFPA_REQUIRE(ctx && rec_dev && mask_dev, "peaks_mask: NULL argument");
+  MFPA_REQUIRE(items >= 1 && n_frames >= 1, "peaks_mask: bad sizes");
+  DeviceGuard guard(ctx->device);
+  return launch_peaks_mask(rec_dev, items, n_frames, mask_dev, (cudaStream_t)stream);
+}
+
+int mfpa_landmark_hashes(mfpa_ctx* ctx, const uint64_t* rec_dev, int items, int n_frames,
+                         const mfpa_afp_params* p, int sorted, int32_t* hashes_dev, int cap,
+                         int32_t* nh_dev, void* stream) {
+  MFPA_REQUIRE(ctx && rec_dev && hashes_dev && nh_dev, "landmark_hashes: NULL argument");
+  MFPA_REQUIRE(items >= 1 && n_frames >= 1 && cap >= 1, "landmark_hashes: bad sizes");
+  if (int e = check_afp(p)) return e;
+  DeviceGuard guard(ctx->device);
+  return launch_landmark_hashes(rec_dev, items, n_frames, *p, sorted, hashes_dev, cap, nh_dev, (cudaStream_t)stream);
+}
+
+int mfpa_merge_shifts(mfpa_ctx* ctx, const int32_t* hashes_dev, const int32_t* nh_dev, int B, int shifts,
+                      int cap_in, int n_frames, int32_t* out_dev, int cap_out, int32_t* nout_dev,
+                      void* stream) {
+  MFPA_REQUIRE(ctx && hashes_dev && nh_dev && out_dev && nout_dev, "merge_shifts: NULL argument");
+  MFPA_REQUIRE(B >= 1 && cap_in >= 1 && cap_out >= 1 && n_frames >= 1, "merge_shifts: bad sizes");
+  DeviceGuard guard(ctx->device);
+  return launch_merge_shifts(hashes_dev, nh_dev, B, shifts, cap_in, n_frames, out_dev, cap_out, nout_dev,
+                             (cudaStream_t)stream);
+}
+
+int mfpa_fingerprint(mfpa_ctx* ctx, const float* x_dev, int B, int T, int64_t x_stride, int shifts,
+                     const mfpa_afp_params* p, int32_t* hashes_dev, int cap, int32_t* nh_dev, void* stream) {
+  MFPA_REQUIRE(ctx && x_dev && hashes_dev && nh_dev, "fingerprint: NULL argument");
+  if (int e = check_batch(B, T, shifts)) return e;
+  if (int e = check_afp(p)) return e;
+  MFPA_REQUIRE(x_stride >= T, "fingerprint: row stride %lld < n_samples %d", (long long)x_stride, T);
+  MFPA_REQUIRE(cap >= 1, "fingerprint: cap %d < 1", cap);
+  DeviceGuard guard(ctx->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int items = B * shifts;
+  const int n_max = num_frames(T);
+  if (ctx->mag.reserve(sizeof(float) * (size_t)items * n_max * kPitch)) return MFPA_ENOMEM;
+  if (ctx->qmax.reserve(sizeof(float) * items)) return MFPA_ENOMEM;
+  if (ctx->rec.reserve(sizeof(uint64_t) * (size_t)items * n_max)) return MFPA_ENOMEM;
+  float* mag = (float*)ctx->mag.ptr;
+  float* qmax = (float*)ctx->qmax.ptr;
+  uint64_t* rec = (uint64_t*)ctx->rec.ptr;
+  if (int e = launch_stft_mag(ctx, x_dev, B, T, x_stride, shifts, mag, qmax, st)) return e;
+  if (int e = launch_peaks_f32(ctx, mag, qmax, B, T, shifts, *p, rec, nullptr, st)) return e;
+  if (shifts == 1) return launch_landmark_hashes(rec, items, n_max, *p, 1, hashes_dev, cap, nh_dev, st);
+  const int cap_in = MFPA_HASHES_PER_FRAME * n_max;
+  if (ctx->hashes.reserve(sizeof(int32_t) * 2 * (size_t)items * cap_in)) return MFPA_ENOMEM;
+  if (ctx->nh.reserve(sizeof(int32_t) * items)) return MFPA_ENOMEM;
+  if (int e = launch_landmark_hashes(rec, items, n_max, *p, 1, (int32_t*)ctx->hashes.ptr, cap_in,
+                                     (int32_t*)ctx->nh.ptr, st)) return e;
+  return launch_merge_shifts((int32_t*)ctx->hashes.ptr, (int32_t*)ctx->nh.ptr, B, shifts, cap_in, n_max,
+                             hashes_dev, cap, nh_dev, st);
+}
+
+int mfpa_fingerprint_host(mfpa_ctx* ctx, const float* x_host, int B, int T, int shifts,
+                          const mfpa_afp_params* p, int32_t* hashes_host, int cap, int32_t* nh_host) {
+  MFPA_REQUIRE(ctx && x_host && hashes_host && nh_host, "fingerprint_host: NULL argument");
+  if (int e = check_batch(B, T, shifts)) return e;
+  MFPA_REQUIRE(cap >= 1, "fingerprint_host: cap %d < 1", cap);
+  DeviceGuard guard(ctx->device);
+  if (ctx->xin.reserve(sizeof(float) * (size_t)B * T)) return MFPA_ENOMEM;
+  if (ctx->out_h.reserve(sizeof(int32_t) * 2 * (size_t)B * cap)) return MFPA_ENOMEM;
+  if (ctx->out_n.reserve(sizeof(int32_t) * B)) return MFPA_ENOMEM;
+  MFPA_CUDA(cudaMemcpyAsync(ctx->xin.ptr, x_host, sizeof(float) * (size_t)B * T, cudaMemcpyHostToDevice, 0));
+  if (int e = mfpa_fingerprint(ctx, (const float*)ctx->xin.ptr, B, T, T, shifts, p, (int32_t*)ctx->out_h.ptr, cap,
+                               (int32_t*)ctx->out_n.ptr, nullptr)) return e;
+  MFPA_CUDA(cudaMemcpyAsync(nh_host, ctx->out_n.ptr, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, 0));
+  MFPA_CUDA(cudaMemcpyAsync(hashes_host, ctx->out_h.ptr, sizeof(int32_t) * 2 * (size_t)B * cap, cudaMemcpyDeviceToHost, 0));
+  MFPA_CUDA(cudaStreamSynchronize(0));
+  for (int i = 0; i < B; ++i)
+    if (nh_host[i] > cap) {
+      set_error("fingerprint_host: query %d produced %d hashes, capacity %d", i, nh_host[i], cap);
+      return MFPA_ECAP;
+    }
+  return MFPA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,99 @@
+// Shared declarations for libmfpa (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/mfpa.h"
+
+#ifndef __CUDA_ARCH__
+#define MFPA_HOST_ONLY
+#endif
+
+namespace mfpa {
+
+constexpr int kNfft = MFPA_N_FFT;
+constexpr int kHop = MFPA_HOP;
+constexpr int kBins = MFPA_BINS;
+constexpr int kRows = MFPA_ROWS;
+constexpr int kPitch = MFPA_MAG_PITCH;
+constexpr int kMaxPks = MFPA_MAX_PKS;
+constexpr int kSpreadLen = 2 * MFPA_ROWS + 1;  // 513
+constexpr int kNumSMs = 148;                   // B200
+
+void set_error(const char* fmt, ...);
+
+#define MFPA_CUDA(call)                                                              \
+  do {                                                                               \
+    cudaError_t _e = (call);                                                         \
+    if (_e != cudaSuccess) {                                                         \
+      mfpa::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+      return MFPA_ECUDA;                                                             \
+    }                                                                                \
+  } while (0)
+
+#define MFPA_REQUIRE(cond, ...)        \
+  do {                                 \
+    if (!(cond)) {                     \
+      mfpa::set_error(__VA_ARGS__);    \
+      return MFPA_EINVAL;              \
+    }                                  \
+  } while (0)
+
+// A grow-only device buffer owned by the context.
+struct Scratch {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+  int reserve(size_t need);
+  void release();
+};
+
+inline int num_frames(int n_samples) { return 1 + n_samples / kHop; }
+inline int shift_offset(int shift, int shifts) {
+  // int(shift / shifts * n_hop) in Python float arithmetic (peak_extractor.py:412)
+  if (shifts < 2) return 0;
+  return (int)((double)shift / (double)shifts * (double)kHop);
+}
+
+}  // namespace mfpa
+
+struct mfpa_ctx {
+  int device = 0;
+  int num_sms = mfpa::kNumSMs;
+  double* spread_dev = nullptr;     // [513] Gaussian table
+  float2* tw_dev = nullptr;         // FFT twiddles (stft.cu layout)
+  float* win_dev = nullptr;         // [512] analysis window
+  mfpa::Scratch mag, qmax, rec, fwd, hashes, nh, misc, spec64, xin, out_h, out_n;
+  // augmentation / matching state is appended by their translation units
+  mfpa::Scratch aug_a, aug_b, aug_c, aug_d, aug_small;
+  // index shard (match.cu)
+  uint32_t* index_table = nullptr;
+  int32_t* index_counts = nullptr;
+  uint32_t* index_hashesperid = nullptr;
+  int index_hash_lo = 0, index_hash_hi = 0, index_depth = 0, index_ntracks = 0, index_maxtimebits = 14;
+  mfpa::Scratch match_a, match_b, match_c;
+  void* pinned = nullptr;
+  size_t pinned_bytes = 0;
+};
+
+// ---- kernel launchers implemented in the stage translation units ----------
+namespace mfpa {
+
+int launch_stft_mag(mfpa_ctx* ctx, const float* x, int B, int T, int64_t stride, int shifts,
+                    float* mag, float* qmax, cudaStream_t st);
+int launch_spec_from_mag(const float* mag, const float* qmax, int B, int T, int shifts,
+                         double* spec, cudaStream_t st);
+int launch_peaks_f32(mfpa_ctx* ctx, const float* mag, const float* qmax, int B, int T, int shifts,
+                     const mfpa_afp_params& p, uint64_t* rec, int32_t* npeaks, cudaStream_t st);
+int launch_peaks_from_spec(mfpa_ctx* ctx, const double* spec, int items, int n_frames, int stage,
+                           const mfpa_afp_params& p, uint64_t* rec, int32_t* npeaks, cudaStream_t st);
+int launch_peaks_list(const uint64_t* rec, int items, int n_frames, int32_t* peaks, int cap,
+                      int32_t* npeaks, cudaStream_t st);
+int launch_peaks_mask(const uint64_t* rec, int items, int n_frames, float* mask, cudaStream_t st);
+int launch_landmark_hashes(const uint64_t* rec, int items, int n_frames, const mfpa_afp_params& p,
+                           int sorted, int32_t* hashes, int cap, int32_t* nh, cudaStream_t st);
+int launch_merge_shifts(const int32_t* hashes, const int32_t* nh, int B, int shifts, int cap_in,
+                        int n_frames, int32_t* out, int cap_out, int32_t* nout, cudaStream_t st);
+int stft_init_tables(mfpa_ctx* ctx);
+
+}  // namespace mfpa

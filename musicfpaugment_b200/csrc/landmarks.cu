@@ -1,0 +1,237 @@
+// S4 — target-zone landmark pairing, 20-bit hash packing, shift merging, and
+// the record -> list / mask conversions.
+// Replaces Audfprint_peaks.peaks2landmarks (afp/audfprint/peak_extractor.py:313-346),
+// landmarks2hashes (:40-58) and the concatenate/unique/sort tail of wavfile2hashes (:437-460).
+//
+// Input is the packed per-frame record array produced by peaks.cu
+// (byte 0 = count, bytes 1..5 = bins ascending).  One warp handles one item,
+// one lane one start frame; the pairing window (frames c+2 .. c+62) is read as
+// consecutive 8-byte records so every step of the window is one coalesced load.
+#include "common.cuh"
+
+namespace mfpa {
+
+namespace {
+
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kWarpsPerBlock = 4;
+constexpr int kFanMax = 3;
+
+__device__ __forceinline__ int rec_bin(uint64_t r, int i) { return (int)((r >> (8 * (i + 1))) & 0xff); }
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+landmark_kernel(const uint64_t* __restrict__ rec_all, int items, int n_max, int mindt, int targetdt,
+                int targetdf, int fanout, int sorted, int32_t* __restrict__ hashes, int cap,
+                int32_t* __restrict__ nh) {
+  const int lane = threadIdx.x & 31;
+  const int item = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (item >= items) return;
+  const uint64_t* rec = rec_all + (int64_t)item * n_max;
+  int2* out = reinterpret_cast<int2*>(hashes) + (int64_t)item * cap;
+
+  // scols = column of the final peak + 1 (:325)
+  int scols = 0;
+  for (int base = 0; base < n_max; base += 32) {
+    const int c = base + lane;
+    const unsigned bal = __ballot_sync(kFull, c < n_max && (rec[c] & 0xff) != 0);
+    if (bal) scols = base + 32 - __clz(bal);
+  }
+  int written = 0;
+  for (int base = 0; base < scols; base += 32) {
+    const int c = base + lane;
+    const uint64_t r = c < scols ? rec[c] : 0;
+    const int n = (int)(r & 0xff);
+    uint32_t hb[kMaxPks * kFanMax];
+    int cnt[kMaxPks];
+#pragma unroll
+    for (int i = 0; i < kMaxPks; ++i) cnt[i] = 0;
+    if (n) {
+      const int c_end = min(scols, c + targetdt);
+      int open = n;  // peaks that can still take pairs
+      for (int c2 = c + mindt; c2 < c_end && open; ++c2) {
+        const uint64_t r2 = rec[c2];
+        const int n2 = (int)(r2 & 0xff);
+        if (!n2) continue;
+#pragma unroll
+        for (int i = 0; i < kMaxPks; ++i) {
+          if (i < n && cnt[i] < fanout) {
+            const int b = rec_bin(r, i);
+            for (int k = 0; k < n2; ++k) {
+              const int b2 = rec_bin(r2, k);
+              if (abs(b2 - b) < targetdf && cnt[i] < fanout) {
+                hb[i * kFanMax + cnt[i]] = ((uint32_t)(b & 255) << 12) | ((uint32_t)((b2 - b) & 63) << 6) |
+                                           (uint32_t)((c2 - c) & 63);
+                if (++cnt[i] == fanout) --open;
+              }
+            }
+          }
+        }
+      }
+    }
+    int mine = 0;
+#pragma unroll
+    for (int i = 0; i < kMaxPks; ++i) {
+      if (sorted && cnt[i] > 1) {  // per-peak hashes ascending; peaks are already in bin order
+        uint32_t* h = hb + i * kFanMax;
+        if (h[0] > h[1]) { const uint32_t t = h[0]; h[0] = h[1]; h[1] = t; }
+        if (cnt[i] > 2) {
+          if (h[1] > h[2]) { const uint32_t t = h[1]; h[1] = h[2]; h[2] = t; }
+          if (h[0] > h[1]) { const uint32_t t = h[0]; h[0] = h[1]; h[1] = t; }
+        }
+      }
+      mine += cnt[i];
+    }
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(kFull, incl, o);
+      if (lane >= o) incl += t;
+    }
+    int pos = written + incl - mine;
+#pragma unroll
+    for (int i = 0; i < kMaxPks; ++i)
+      for (int k = 0; k < cnt[i]; ++k) {
+        if (pos < cap) out[pos] = make_int2(c, (int)hb[i * kFanMax + k]);
+        ++pos;
+      }
+    written += __shfl_sync(kFull, incl, 31);
+  }
+  if (lane == 0) nh[item] = written;  // may exceed cap: caller checks
+}
+
+// One block per query: merge `shifts` (time,hash)-sorted lists, drop duplicates.
+// Thread t owns time value t: gathers the <= 15 rows per list with that time,
+// insertion-merges them, then a block scan places each time's run.
+__global__ void __launch_bounds__(256)
+merge_shifts_kernel(const int32_t* __restrict__ hashes, const int32_t* __restrict__ nh, int shifts,
+                    int cap_in, int n_frames, int32_t* __restrict__ out_all, int cap_out,
+                    int32_t* __restrict__ nout) {
+  __shared__ int scan[256];
+  __shared__ int carry;
+  const int q = blockIdx.x, tid = threadIdx.x;
+  int2* out = reinterpret_cast<int2*>(out_all) + (int64_t)q * cap_out;
+  if (tid == 0) carry = 0;
+  __syncthreads();
+  for (int t0 = 0; t0 < n_frames; t0 += 256) {
+    const int t = t0 + tid;
+    uint32_t buf[MFPA_HASHES_PER_FRAME * MFPA_MAX_SHIFTS];
+    int n = 0;
+    if (t < n_frames) {
+      for (int s = 0; s < shifts; ++s) {
+        const int item = q * shifts + s;
+        const int2* lst = reinterpret_cast<const int2*>(hashes) + (int64_t)item * cap_in;
+        const int len = min(nh[item], cap_in);
+        int lo = 0, hi = len;  // first row with time >= t
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (lst[mid].x < t) lo = mid + 1; else hi = mid;
+        }
+        for (; lo < len; ++lo) {
+          const int2 row = lst[lo];
+          if (row.x != t) break;
+          const uint32_t h = (uint32_t)row.y;
+          int k = n;
+          while (k > 0 && buf[k - 1] > h) --k;
+          if (k > 0 && buf[k - 1] == h) continue;  // duplicate (time, hash)
+          if (n < MFPA_HASHES_PER_FRAME * MFPA_MAX_SHIFTS) {
+            for (int m = n; m > k; --m) buf[m] = buf[m - 1];
+            buf[k] = h;
+            ++n;
+          }
+        }
+      }
+    }
+    scan[tid] = n;
+    __syncthreads();
+    for (int o = 1; o < 256; o <<= 1) {
+      const int v = tid >= o ? scan[tid - o] : 0;
+      __syncthreads();
+      scan[tid] += v;
+      __syncthreads();
+    }
+    int pos = carry + scan[tid] - n;
+    for (int k = 0; k < n; ++k, ++pos)
+      if (pos < cap_out) out[pos] = make_int2(t, (int)buf[k]);
+    __syncthreads();
+    if (tid == 255) carry += scan[255];
+    __syncthreads();
+  }
+  if (tid == 0) nout[q] = carry;
+}
+
+// records -> (col, bin) rows, pklist order (:303-309)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+peaks_list_kernel(const uint64_t* __restrict__ rec_all, int items, int n_max, int32_t* __restrict__ peaks,
+                  int cap, int32_t* __restrict__ npeaks) {
+  const int lane = threadIdx.x & 31;
+  const int item = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (item >= items) return;
+  const uint64_t* rec = rec_all + (int64_t)item * n_max;
+  int2* out = reinterpret_cast<int2*>(peaks) + (int64_t)item * cap;
+  int written = 0;
+  for (int base = 0; base < n_max; base += 32) {
+    const int c = base + lane;
+    const uint64_t r = c < n_max ? rec[c] : 0;
+    const int n = (int)(r & 0xff);
+    int incl = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(kFull, incl, o);
+      if (lane >= o) incl += t;
+    }
+    int pos = written + incl - n;
+    for (int i = 0; i < n; ++i, ++pos)
+      if (pos < cap) out[pos] = make_int2(c, rec_bin(r, i));
+    written += __shfl_sync(kFull, incl, 31);
+  }
+  if (lane == 0 && npeaks) npeaks[item] = written;
+}
+
+// records -> float mask [items][256][n_max] (already zeroed)
+__global__ void peaks_mask_kernel(const uint64_t* __restrict__ rec, int64_t total, int n_max, float* __restrict__ mask) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const uint64_t r = rec[i];
+  const int n = (int)(r & 0xff);
+  const int64_t item = i / n_max;
+  const int c = (int)(i - item * n_max);
+  for (int k = 0; k < n; ++k) mask[(item * kRows + rec_bin(r, k)) * n_max + c] = 1.0f;
+}
+
+}  // namespace
+
+int launch_landmark_hashes(const uint64_t* rec, int items, int n_frames, const mfpa_afp_params& p,
+                           int sorted, int32_t* hashes, int cap, int32_t* nh, cudaStream_t st) {
+  MFPA_REQUIRE(p.fanout >= 1 && p.fanout <= kFanMax, "landmarks: fanout %d not in 1..%d", p.fanout, kFanMax);
+  const int blocks = (items + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  landmark_kernel<<<blocks, kWarpsPerBlock * 32, 0, st>>>(rec, items, n_frames, p.mindt, p.targetdt, p.targetdf,
+                                                          p.fanout, sorted, hashes, cap, nh);
+  MFPA_CUDA(cudaGetLastError());
+  return MFPA_OK;
+}
+
+int launch_merge_shifts(const int32_t* hashes, const int32_t* nh, int B, int shifts, int cap_in,
+                        int n_frames, int32_t* out, int cap_out, int32_t* nout, cudaStream_t st) {
+  MFPA_REQUIRE(shifts >= 1 && shifts <= MFPA_MAX_SHIFTS, "merge: shifts %d not in 1..%d", shifts, MFPA_MAX_SHIFTS);
+  merge_shifts_kernel<<<B, 256, 0, st>>>(hashes, nh, shifts, cap_in, n_frames, out, cap_out, nout);
+  MFPA_CUDA(cudaGetLastError());
+  return MFPA_OK;
+}
+
+int launch_peaks_list(const uint64_t* rec, int items, int n_frames, int32_t* peaks, int cap,
+                      int32_t* npeaks, cudaStream_t st) {
+  const int blocks = (items + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  peaks_list_kernel<<<blocks, kWarpsPerBlock * 32, 0, st>>>(rec, items, n_frames, peaks, cap, npeaks);
+  MFPA_CUDA(cudaGetLastError());
+  return MFPA_OK;
+}
+
+int launch_peaks_mask(const uint64_t* rec, int items, int n_frames, float* mask, cudaStream_t st) {
+  const int64_t total = (int64_t)items * n_frames;
+  MFPA_CUDA(cudaMemsetAsync(mask, 0, sizeof(float) * total * kRows, st));
+  peaks_mask_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(rec, total, n_frames, mask);
+  MFPA_CUDA(cudaGetLastError());
+  return MFPA_OK;
+}
+
+}  // namespace mfpa

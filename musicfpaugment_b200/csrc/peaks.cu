@@ -1,0 +1,383 @@
+// S3 — audfprint peak picking: one warp per (query, shift) item, 8 frequency
+// bins per lane, time frames scanned sequentially.
+// Replaces Audfprint_peaks.find_peaks after the STFT (afp/audfprint/peak_extractor.py:263-311):
+//   sgram /= max; log(max(., max/1e6)); -= mean            :263-276
+//   lfilter([1,-1],[1,-0.98]) per bin, Nyquist row dropped   :286-290
+//   _decaying_threshold_fwd_prune                            :173-204
+//   _decaying_threshold_bwd_prune_peaks                      :206-234
+// All arithmetic is float64 with explicitly un-fused mul/add so every comparison
+// sees the value numpy/scipy would have produced; the only inexact pieces are
+// the device log() (<= 1 ulp) and the summation order of the mean.
+//
+// Data flow per item:
+//   phase 0 (only when no qmax is supplied) max over the spectrogram
+//   phase 1 mean of log: product of clamped values with exponent bookkeeping,
+//           one log per lane (more accurate than summing 64 k rounded logs)
+//   phase 2 forward scan: IIR state, threshold and current frame live in
+//           registers; kept peaks (<= 5/frame, sorted by (value, bin) desc) go
+//           to a small per-item scratch list
+//   phase 3 backward scan over the scratch list only,
+//           writing one packed 64-bit record per frame.
+#include "common.cuh"
+
+namespace mfpa {
+
+namespace {
+
+constexpr int kWarpsPerBlock = 4;
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kGPad = kSpreadLen + (kSpreadLen >> 3) + 1;  // padded Gaussian table in smem
+
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(kFull, v, src); }
+
+template <typename T> struct Loader;
+template <> struct Loader<float> {
+  static __device__ __forceinline__ void load8(const float* p, double (&v)[8]) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+};
+template <> struct Loader<double> {
+  static __device__ __forceinline__ void load8(const double* p, double (&v)[8]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const double2 a = __ldg(reinterpret_cast<const double2*>(p) + i);
+      v[2 * i] = a.x; v[2 * i + 1] = a.y;
+    }
+  }
+};
+
+struct PeakArgs {
+  const void* mag;        // [items][n_max][264]
+  const float* qmax;      // nullable
+  int items, T, shifts, n_max, n_fixed;  // n_fixed > 0: every item has n_fixed frames
+  double a_dec;
+  int maxpks;
+  const double* spread;   // [513]
+  uint64_t* rec;          // [items][n_max]
+  int32_t* npeaks;        // nullable
+  uint64_t* fwd_pack;     // [items][n_max]   bins (bytes 0..4) + count (byte 7)
+  double* fwd_val;        // [items][n_max][5]
+};
+
+// sth[j] = max(sth[j], val * G[256 + bin - pos])      (peak_extractor.py:168-170, :198-201)
+__device__ __forceinline__ void spread_one(double (&sth)[8], const double* g_s, int lane, int pos, double val) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int i = kRows + 8 * lane + j - pos;
+    sth[j] = fmax(sth[j], __dmul_rn(val, g_s[i + (i >> 3)]));
+  }
+}
+
+// locmax (peak_extractor.py:61-73) on a 256-vector held 8 bins per lane; returns an 8-bit mask.
+__device__ __forceinline__ unsigned locmax8(const double (&y)[8], int lane) {
+  const double left = __shfl_up_sync(kFull, y[7], 1);
+  const double right = __shfl_down_sync(kFull, y[0], 1);
+  unsigned m = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const bool ge = (j == 0) ? (lane == 0 ? true : (y[0] >= left)) : (y[j] >= y[j - 1]);
+    const bool ge_next = (j == 7) ? (lane == 31 ? false : (right >= y[7])) : (y[j + 1] >= y[j]);
+    if (ge && !ge_next) m |= 1u << j;
+  }
+  return m;
+}
+
+// spreadpeaksinvector (peak_extractor.py:115-125): threshold = max over local maxima of val*G, from zeros.
+__device__ __forceinline__ void spread_locmax(const double (&v)[8], double (&sth)[8], const double* g_s, int lane) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sth[j] = 0.0;
+  const unsigned lm = locmax8(v, lane);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    unsigned bal = __ballot_sync(kFull, (lm >> j) & 1u);
+    while (bal) {
+      const int src = __ffs(bal) - 1;
+      bal &= bal - 1;
+      spread_one(sth, g_s, lane, 8 * src + j, shfl_d(v[j], src));
+    }
+  }
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(kFull, v, o));
+  return v;
+}
+
+// ascending sort of up to 5 bins packed one per byte (dead entries = 0xFF), returns packed record.
+__device__ __forceinline__ uint64_t finalize_record(uint64_t pack, int n, unsigned alive) {
+  int b[5];
+  int cnt = 0;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    const bool ok = i < n && ((alive >> i) & 1u);
+    b[i] = ok ? (int)((pack >> (8 * i)) & 0xff) : 0x100;
+    cnt += ok;
+  }
+#define MFPA_CSWAP(i, j) { const int lo = min(b[i], b[j]), hi = max(b[i], b[j]); b[i] = lo; b[j] = hi; }
+  MFPA_CSWAP(0, 1) MFPA_CSWAP(3, 4) MFPA_CSWAP(2, 4) MFPA_CSWAP(2, 3) MFPA_CSWAP(0, 3)
+  MFPA_CSWAP(0, 2) MFPA_CSWAP(1, 4) MFPA_CSWAP(1, 3) MFPA_CSWAP(1, 2)
+#undef MFPA_CSWAP
+  uint64_t r = (uint64_t)cnt;
+#pragma unroll
+  for (int i = 0; i < 5; ++i)
+    if (i < cnt) r |= (uint64_t)(b[i] & 0xff) << (8 * (i + 1));
+  return r;
+}
+
+template <typename MagT, bool kPreFiltered>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) peaks_kernel(const PeakArgs a) {
+  __shared__ double g_s[kGPad];
+  for (int i = threadIdx.x; i < kSpreadLen; i += blockDim.x) g_s[i + (i >> 3)] = a.spread[i];
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31;
+  const int item = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (item >= a.items) return;
+
+  int n_frames = a.n_fixed;
+  if (n_frames <= 0) {
+    const int sh = item % a.shifts;
+    const int off = a.shifts < 2 ? 0 : (int)((double)sh / (double)a.shifts * (double)kHop);
+    n_frames = 1 + (a.T - off) / kHop;
+  }
+  const MagT* base = reinterpret_cast<const MagT*>(a.mag) + (int64_t)item * a.n_max * kPitch;
+  const MagT* col0 = base + 8 * lane;
+  uint64_t* rec = a.rec + (int64_t)item * a.n_max;
+  uint64_t* fwd_pack = a.fwd_pack + (int64_t)item * a.n_max;
+  double* fwd_val = a.fwd_val + (int64_t)item * a.n_max * kMaxPks;
+
+  double M = 1.0, mean = 0.0;
+  bool silent = false;
+  if (!kPreFiltered) {
+    // ---- phase 0: divisor of `sgram /= np.max(sgram)` (:263) ----
+    if (a.qmax) {
+      M = (double)a.qmax[item];
+    } else {
+      double m = 0.0;
+      for (int c = 0; c < n_frames; ++c) {
+        double v[8];
+        Loader<MagT>::load8(col0 + (int64_t)c * kPitch, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m = fmax(m, v[j]);
+        if (lane == 0) m = fmax(m, (double)base[(int64_t)c * kPitch + kRows]);
+      }
+      M = warp_max(m);
+    }
+    // All-zero (or NaN) input: the reference divides 0/0, skips the log and ends with no peaks (:272-280).
+    silent = !(M > 0.0);
+    if (!silent) {
+      // ---- phase 1: mean over all 257 x N of log(max(v/M, 1e-6)) (:275-276) ----
+      const double rM = 1.0 / M;
+      double P = 1.0;
+      int esum = 0;
+      for (int c = 0; c < n_frames; ++c) {
+        double v[8];
+        Loader<MagT>::load8(col0 + (int64_t)c * kPitch, v);
+        double pr = 1.0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) pr *= fmax(v[j] * rM, 1e-6);
+        if (lane == 0) pr *= fmax((double)base[(int64_t)c * kPitch + kRows] * rM, 1e-6);
+        P *= pr;  // P in [1,2) * [1e-54, 1]: no underflow
+        const int hi = __double2hiint(P);
+        esum += ((hi >> 20) & 0x7ff) - 1023;
+        P = __hiloint2double((hi & 0x800fffff) | 0x3ff00000, __double2loint(P));
+      }
+      const double total = warp_sum((double)esum * 0.69314718055994530942 + log(P));
+      mean = total / ((double)kBins * (double)n_frames);
+    }
+  }
+
+  int total_peaks = 0;
+  if (!silent) {
+    double y[8], z[8], sth[8];
+    // x -> y for one frame
+    auto advance = [&](const double (&v)[8]) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (kPreFiltered) {
+          y[j] = v[j];
+        } else {
+          const double d = fmax(v[j] / M, 1e-6);             // :263, :275
+          const double x = __dsub_rn(log(d), mean);          // :276
+          y[j] = __dadd_rn(x, z[j]);                         // lfilter DF-II transposed (:286-288)
+          z[j] = __dadd_rn(-x, __dmul_rn(0.98, y[j]));
+        }
+      }
+    };
+    // ---- initial threshold from the first min(10, N) frames (:180-182) ----
+    {
+      double m[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) z[j] = 0.0;
+      const int n0 = n_frames < 10 ? n_frames : 10;
+      for (int c = 0; c < n0; ++c) {
+        double v[8];
+        Loader<MagT>::load8(col0 + (int64_t)c * kPitch, v);
+        advance(v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m[j] = c == 0 ? y[j] : fmax(m[j], y[j]);
+      }
+      spread_locmax(m, sth, g_s, lane);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) z[j] = 0.0;
+    }
+    // ---- phase 2: forward prune (:190-203) ----
+    double vn[8];
+    Loader<MagT>::load8(col0, vn);
+    for (int c = 0; c < n_frames; ++c) {
+      double v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = vn[j];
+      if (c + 1 < n_frames) Loader<MagT>::load8(col0 + (int64_t)(c + 1) * kPitch, vn);
+      advance(v);
+      unsigned cand = locmax8(y, lane);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (!(y[j] > sth[j])) cand &= ~(1u << j);
+      uint64_t pack = 0;
+      int nk = 0;
+      if (__ballot_sync(kFull, cand != 0)) {
+        // take candidates in (value, bin) descending order, at most maxpks (:196-197)
+        while (nk < a.maxpks) {
+          double bv = 0.0;
+          int bb = -1;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (((cand >> j) & 1u) && (bb < 0 || y[j] >= bv)) { bv = y[j]; bb = 8 * lane + j; }
+#pragma unroll
+          for (int o = 16; o; o >>= 1) {
+            const double ov = __shfl_xor_sync(kFull, bv, o);
+            const int ob = __shfl_xor_sync(kFull, bb, o);
+            if (ob >= 0 && (bb < 0 || ov > bv || (ov == bv && ob > bb))) { bv = ov; bb = ob; }
+          }
+          if (bb < 0) break;
+          if ((bb >> 3) == lane) cand &= ~(1u << (bb & 7));
+          spread_one(sth, g_s, lane, bb, bv);
+          if (lane == 0) fwd_val[(int64_t)c * kMaxPks + nk] = bv;
+          pack |= (uint64_t)bb << (8 * nk);
+          ++nk;
+        }
+      }
+      if (lane == 0) fwd_pack[c] = pack | ((uint64_t)nk << 56);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sth[j] = __dmul_rn(sth[j], a.a_dec);  // :203
+    }
+    __syncwarp();
+    // ---- phase 3: backward prune (:217-233); y[] still holds the last frame ----
+    spread_locmax(y, sth, g_s, lane);
+    uint64_t prev_pack = 0;
+    int prev_n = 0;
+    unsigned prev_alive = 0;
+    for (int c = n_frames - 1; c >= 0; --c) {
+      const uint64_t fp = __ldcg(fwd_pack + c);
+      const int n = (int)(fp >> 56);
+      uint64_t cur_pack = 0;
+      int cur_n = 0;
+      for (int i = 0; i < n; ++i) {
+        const int b = (int)((fp >> (8 * i)) & 0xff);
+        const double val = __ldcg(fwd_val + (int64_t)c * kMaxPks + i);
+        double mine = sth[0];
+#pragma unroll
+        for (int j = 1; j < 8; ++j) mine = ((b & 7) == j) ? sth[j] : mine;
+        const double t = shfl_d(mine, b >> 3);
+        if (val >= t) {
+          spread_one(sth, g_s, lane, b, val);
+          cur_pack |= (uint64_t)b << (8 * cur_n);
+          ++cur_n;
+#pragma unroll
+          for (int k = 0; k < 5; ++k)  // delete a following peak in the same bin (:228-229)
+            if (k < prev_n && (int)((prev_pack >> (8 * k)) & 0xff) == b) prev_alive &= ~(1u << k);
+        }
+      }
+      if (c + 1 < n_frames) {
+        const uint64_t r = finalize_record(prev_pack, prev_n, prev_alive);
+        total_peaks += (int)(r & 0xff);
+        if (lane == 0) rec[c + 1] = r;
+      }
+      prev_pack = cur_pack; prev_n = cur_n; prev_alive = 0x1f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sth[j] = __dmul_rn(a.a_dec, sth[j]);  // :233
+    }
+    const uint64_t r = finalize_record(prev_pack, prev_n, prev_alive);
+    total_peaks += (int)(r & 0xff);
+    if (lane == 0) rec[0] = r;
+  }
+  for (int c = (silent ? 0 : n_frames) + lane; c < a.n_max; c += 32) rec[c] = 0;
+  if (lane == 0 && a.npeaks) a.npeaks[item] = total_peaks;
+}
+
+// [items][rows][n] float64 (reference layout) -> [items][n][264] float64 (frame-major)
+__global__ void spec_to_frames_kernel(const double* __restrict__ spec, int rows, int n, double* __restrict__ out) {
+  __shared__ double tile[32][33];
+  const int item = blockIdx.z;
+  const int c0 = blockIdx.x * 32, b0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  for (int i = ty; i < 32; i += 8) {
+    const int b = b0 + i, c = c0 + tx;
+    tile[i][tx] = (b < rows && c < n) ? spec[((int64_t)item * rows + b) * n + c] : 0.0;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, b = b0 + tx;
+    if (c < n && b < kPitch) out[((int64_t)item * n + c) * kPitch + b] = (b < rows) ? tile[tx][i] : 0.0;
+  }
+}
+
+}  // namespace
+
+static int fwd_scratch(mfpa_ctx* ctx, int items, int n_max, PeakArgs& a) {
+  const size_t per_item = (size_t)n_max * (8 + 8 * kMaxPks);
+  if (ctx->fwd.reserve(per_item * items)) return MFPA_ENOMEM;
+  a.fwd_pack = reinterpret_cast<uint64_t*>(ctx->fwd.ptr);
+  a.fwd_val = reinterpret_cast<double*>(a.fwd_pack + (size_t)items * n_max);
+  return MFPA_OK;
+}
+
+int launch_peaks_f32(mfpa_ctx* ctx, const float* mag, const float* qmax, int B, int T, int shifts,
+                     const mfpa_afp_params& p, uint64_t* rec, int32_t* npeaks, cudaStream_t st) {
+  PeakArgs a{};
+  a.mag = mag; a.qmax = qmax; a.items = B * shifts; a.T = T; a.shifts = shifts;
+  a.n_max = num_frames(T); a.n_fixed = 0; a.a_dec = p.a_dec; a.maxpks = p.maxpks;
+  a.spread = ctx->spread_dev; a.rec = rec; a.npeaks = npeaks;
+  if (int e = fwd_scratch(ctx, a.items, a.n_max, a)) return e;
+  const int blocks = (a.items + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  peaks_kernel<float, false><<<blocks, kWarpsPerBlock * 32, 0, st>>>(a);
+  MFPA_CUDA(cudaGetLastError());
+  return MFPA_OK;
+}
+
+int launch_peaks_from_spec(mfpa_ctx* ctx, const double* spec, int items, int n_frames, int stage,
+                           const mfpa_afp_params& p, uint64_t* rec, int32_t* npeaks, cudaStream_t st) {
+  const int rows = stage == 0 ? kBins : kRows;
+  if (ctx->spec64.reserve(sizeof(double) * (size_t)items * n_frames * kPitch)) return MFPA_ENOMEM;
+  double* frames = reinterpret_cast<double*>(ctx->spec64.ptr);
+  for (int i0 = 0; i0 < items; i0 += 32768) {
+    const int n = items - i0 < 32768 ? items - i0 : 32768;
+    dim3 grid((n_frames + 31) / 32, (kPitch + 31) / 32, n);
+    spec_to_frames_kernel<<<grid, dim3(32, 8), 0, st>>>(spec + (int64_t)i0 * rows * n_frames, rows, n_frames,
+                                                       frames + (int64_t)i0 * n_frames * kPitch);
+    MFPA_CUDA(cudaGetLastError());
+  }
+  PeakArgs a{};
+  a.mag = frames; a.qmax = nullptr; a.items = items; a.T = 0; a.shifts = 1;
+  a.n_max = n_frames; a.n_fixed = n_frames; a.a_dec = p.a_dec; a.maxpks = p.maxpks;
+  a.spread = ctx->spread_dev; a.rec = rec; a.npeaks = npeaks;
+  if (int e = fwd_scratch(ctx, items, n_frames, a)) return e;
+  const int blocks = (items + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  if (stage == 0)
+    peaks_kernel<double, false><<<blocks, kWarpsPerBlock * 32, 0, st>>>(a);
+  else
+    peaks_kernel<double, true><<<blocks, kWarpsPerBlock * 32, 0, st>>>(a);
+  MFPA_CUDA(cudaGetLastError());
+  return MFPA_OK;
+}
+
+}  // namespace mfpa

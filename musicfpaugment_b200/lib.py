@@ -1,0 +1,278 @@
+"""ctypes binding of libmfpa.so (include/mfpa.h).
+
+There is no CPU fallback: importing this module raises ``ImportError`` when the
+shared library has not been built (``python -m musicfpaugment_b200.build``),
+and ``Context()`` raises when no sm_100 GPU is visible.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.environ.get("MFPA_LIB", os.path.join(_HERE, "libmfpa.so"))
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing - build it with `python -m musicfpaugment_b200.build`; "
+        "musicfpaugment_b200 has no CPU fallback"
+    )
+
+_lib = C.CDLL(LIB_PATH)
+
+
+class AfpParams(C.Structure):
+    """mfpa_afp_params (include/mfpa.h)."""
+
+    _fields_ = [
+        ("a_dec", C.c_double), ("f_sd", C.c_double), ("maxpks", C.c_int32), ("mindt", C.c_int32),
+        ("targetdt", C.c_int32), ("targetdf", C.c_int32), ("fanout", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+class MfpaError(RuntimeError):
+    pass
+
+
+_vp, _i, _i64 = C.c_void_p, C.c_int, C.c_int64
+_P = C.POINTER(AfpParams)
+
+# name -> (restype, argtypes); every symbol declared in include/mfpa.h
+SIGNATURES = {
+    "mfpa_abi_version": (_i, []),
+    "mfpa_last_error": (C.c_char_p, []),
+    "mfpa_create": (_i, [C.POINTER(_vp), _i]),
+    "mfpa_destroy": (None, [_vp]),
+    "mfpa_afp_defaults": (None, [_P]),
+    "mfpa_set_spread_table": (_i, [_vp, _vp]),
+    "mfpa_num_frames": (_i, [_i]),
+    "mfpa_shift_offset": (_i, [_i, _i]),
+    "mfpa_stft_mag": (_i, [_vp, _vp, _i, _i, _i64, _i, _vp, _vp, _vp]),
+    "mfpa_spec_from_mag": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "mfpa_audfprint_peaks": (_i, [_vp, _vp, _vp, _i, _i, _i, _P, _vp, _vp, _vp]),
+    "mfpa_audfprint_peaks_from_spec": (_i, [_vp, _vp, _i, _i, _i, _P, _vp, _vp, _vp]),
+    "mfpa_peaks_list": (_i, [_vp, _vp, _i, _i, _vp, _i, _vp, _vp]),
+    "mfpa_peaks_mask": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
+    "mfpa_landmark_hashes": (_i, [_vp, _vp, _i, _i, _P, _i, _vp, _i, _vp, _vp]),
+    "mfpa_merge_shifts": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _vp]),
+    "mfpa_fingerprint": (_i, [_vp, _vp, _i, _i, _i64, _i, _P, _vp, _i, _vp, _vp]),
+    "mfpa_fingerprint_host": (_i, [_vp, _vp, _i, _i, _i, _P, _vp, _i, _vp]),
+}
+
+
+def _bind(sigs):
+    for name, (res, args) in sigs.items():
+        fn = getattr(_lib, name)
+        fn.restype = res
+        fn.argtypes = args
+
+
+_bind(SIGNATURES)
+ALL_SIGNATURES = dict(SIGNATURES)
+
+N_FFT, HOP, BINS, ROWS, MAG_PITCH, MAX_PKS, MAX_SHIFTS, HASHES_PER_FRAME = 512, 256, 257, 256, 264, 5, 8, 15
+
+
+def last_error() -> str:
+    return _lib.mfpa_last_error().decode()
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise MfpaError(f"libmfpa error {rc}: {last_error()}")
+
+
+def raw():
+    """The ctypes CDLL handle (for code that needs an entry point directly)."""
+    return _lib
+
+
+def num_frames(n_samples: int) -> int:
+    return _lib.mfpa_num_frames(n_samples)
+
+
+def shift_offset(shift: int, shifts: int) -> int:
+    return _lib.mfpa_shift_offset(shift, shifts)
+
+
+def afp_defaults() -> AfpParams:
+    p = AfpParams()
+    _lib.mfpa_afp_defaults(C.byref(p))
+    return p
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    import torch
+
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Context:
+    """Owns one ``mfpa_ctx`` on one GPU.  Methods take/return torch CUDA tensors;
+    torch is used for device memory and streams only."""
+
+    def __init__(self, device: int | None = None, spread_table=None):
+        import torch
+
+        if not torch.cuda.is_available():
+            raise MfpaError("no CUDA device visible: musicfpaugment_b200 has no CPU fallback")
+        if device is None:
+            device = torch.cuda.current_device()
+        self.device = int(device)
+        self._h = C.c_void_p()
+        check(_lib.mfpa_create(C.byref(self._h), self.device))
+        if spread_table is not None:
+            self.set_spread_table(spread_table)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            _lib.mfpa_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    # ---- helpers -------------------------------------------------------
+    def _dev(self):
+        import torch
+
+        return torch.device("cuda", self.device)
+
+    def set_spread_table(self, table):
+        import numpy as np
+
+        t = np.ascontiguousarray(table, dtype=np.float64)
+        assert t.shape == (2 * ROWS + 1,)
+        check(_lib.mfpa_set_spread_table(self._h, t.ctypes.data_as(C.c_void_p)))
+
+    # ---- S2 --------------------------------------------------------------
+    def stft_mag(self, x, shifts: int = 1):
+        """x: [B,T] float32 cuda -> (mag [B*shifts, N, 264] f32, qmax [B*shifts] f32)."""
+        import torch
+
+        assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
+        B, T = x.shape
+        n = num_frames(T)
+        mag = torch.empty(B * shifts, n, MAG_PITCH, dtype=torch.float32, device=x.device)
+        qmax = torch.empty(B * shifts, dtype=torch.float32, device=x.device)
+        check(_lib.mfpa_stft_mag(self._h, _ptr(x), B, T, x.stride(0), shifts, _ptr(mag), _ptr(qmax), _stream()))
+        return mag, qmax
+
+    def spec_from_mag(self, mag, qmax, T: int, shifts: int = 1):
+        import torch
+
+        items, n = mag.shape[0], mag.shape[1]
+        spec = torch.empty(items, BINS, n, dtype=torch.float64, device=mag.device)
+        check(_lib.mfpa_spec_from_mag(self._h, _ptr(mag), _ptr(qmax), items // shifts, T, shifts, _ptr(spec), _stream()))
+        return spec
+
+    # ---- S3 --------------------------------------------------------------
+    def audfprint_peaks(self, mag, qmax, T: int, shifts: int, params: AfpParams):
+        """-> (rec uint64-as-int64 [items, N], npeaks int32 [items])."""
+        import torch
+
+        items, n = mag.shape[0], mag.shape[1]
+        rec = torch.empty(items, n, dtype=torch.int64, device=mag.device)
+        npk = torch.empty(items, dtype=torch.int32, device=mag.device)
+        check(_lib.mfpa_audfprint_peaks(self._h, _ptr(mag), _ptr(qmax), items // shifts, T, shifts,
+                                        C.byref(params), _ptr(rec), _ptr(npk), _stream()))
+        return rec, npk
+
+    def audfprint_peaks_from_spec(self, spec, stage: int, params: AfpParams):
+        """spec: [items, 257|256, N] float64 cuda in the reference layout."""
+        import torch
+
+        assert spec.is_cuda and spec.dtype == torch.float64 and spec.dim() == 3
+        spec = spec.contiguous()
+        items, rows, n = spec.shape
+        assert rows == (BINS if stage == 0 else ROWS)
+        rec = torch.empty(items, n, dtype=torch.int64, device=spec.device)
+        npk = torch.empty(items, dtype=torch.int32, device=spec.device)
+        check(_lib.mfpa_audfprint_peaks_from_spec(self._h, _ptr(spec), items, n, stage, C.byref(params),
+                                                  _ptr(rec), _ptr(npk), _stream()))
+        return rec, npk
+
+    def peaks_list(self, rec):
+        import torch
+
+        items, n = rec.shape
+        cap = MAX_PKS * n
+        peaks = torch.empty(items, cap, 2, dtype=torch.int32, device=rec.device)
+        npk = torch.empty(items, dtype=torch.int32, device=rec.device)
+        check(_lib.mfpa_peaks_list(self._h, _ptr(rec), items, n, _ptr(peaks), cap, _ptr(npk), _stream()))
+        return peaks, npk
+
+    def peaks_mask(self, rec):
+        import torch
+
+        items, n = rec.shape
+        mask = torch.empty(items, ROWS, n, dtype=torch.float32, device=rec.device)
+        check(_lib.mfpa_peaks_mask(self._h, _ptr(rec), items, n, _ptr(mask), _stream()))
+        return mask
+
+    # ---- S4 --------------------------------------------------------------
+    def landmark_hashes(self, rec, params: AfpParams, sorted_rows: bool = False):
+        import torch
+
+        items, n = rec.shape
+        cap = HASHES_PER_FRAME * n
+        hashes = torch.empty(items, cap, 2, dtype=torch.int32, device=rec.device)
+        nh = torch.empty(items, dtype=torch.int32, device=rec.device)
+        check(_lib.mfpa_landmark_hashes(self._h, _ptr(rec), items, n, C.byref(params), int(sorted_rows),
+                                        _ptr(hashes), cap, _ptr(nh), _stream()))
+        return hashes, nh
+
+    def merge_shifts(self, hashes, nh, shifts: int, n_frames: int):
+        import torch
+
+        items, cap_in, _ = hashes.shape
+        B = items // shifts
+        cap_out = cap_in * shifts
+        out = torch.empty(B, cap_out, 2, dtype=torch.int32, device=hashes.device)
+        nout = torch.empty(B, dtype=torch.int32, device=hashes.device)
+        check(_lib.mfpa_merge_shifts(self._h, _ptr(hashes), _ptr(nh), B, shifts, cap_in, n_frames, _ptr(out),
+                                     cap_out, _ptr(nout), _stream()))
+        return out, nout
+
+    # ---- fused -----------------------------------------------------------
+    def fingerprint(self, x, shifts: int, params: AfpParams, out=None, nh=None, cap: int | None = None):
+        """x [B,T] f32 cuda -> (hashes [B,cap,2] int32, nh [B] int32), rows unique and
+        sorted by (time, hash) like wavfile2hashes."""
+        import torch
+
+        assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
+        B, T = x.shape
+        if cap is None:
+            cap = HASHES_PER_FRAME * num_frames(T) * shifts
+        if out is None:
+            out = torch.empty(B, cap, 2, dtype=torch.int32, device=x.device)
+        if nh is None:
+            nh = torch.empty(B, dtype=torch.int32, device=x.device)
+        check(_lib.mfpa_fingerprint(self._h, _ptr(x), B, T, x.stride(0), shifts, C.byref(params), _ptr(out),
+                                    out.shape[1], _ptr(nh), _stream()))
+        return out, nh
+
+    def fingerprint_host(self, x_np, shifts: int, params: AfpParams, cap: int | None = None):
+        """numpy [B,T] float32 (host) -> (hashes int32 [B,cap,2], nh int32 [B]) numpy."""
+        import numpy as np
+
+        x_np = np.ascontiguousarray(x_np, dtype=np.float32)
+        B, T = x_np.shape
+        if cap is None:
+            cap = HASHES_PER_FRAME * num_frames(T) * shifts
+        out = np.empty((B, cap, 2), dtype=np.int32)
+        nh = np.empty(B, dtype=np.int32)
+        check(_lib.mfpa_fingerprint_host(self._h, x_np.ctypes.data_as(C.c_void_p), B, T, shifts, C.byref(params),
+                                         out.ctypes.data_as(C.c_void_p), cap, nh.ctypes.data_as(C.c_void_p)))
+        return out, nh

@@ -1,0 +1,26 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
+
+
+@pytest.fixture(scope="session")
+def mfpa_ctx():
+    """One libmfpa context on cuda:0 with the numpy-computed spreading table."""
+    import torch
+
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    from musicfpaugment_b200 import lib
+    from oracle import audfprint_np as O
+
+    ctx = lib.Context(0, spread_table=O.gaussian_table(256, 30.0))
+    yield ctx
+    ctx.close()

@@ -1,0 +1,188 @@
+"""GPU parity: CUDA audfprint path (through the C ABI) vs the numpy oracle.
+
+Tolerances (BASELINE.json north_star): spectrograms within 1e-4 relative;
+peak / landmark / hash sets bit-exact when fed the reference spectrogram;
+>= 99.9 % hash agreement end to end.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import audfprint_np as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _lib():
+    from musicfpaugment_b200 import lib
+
+    return lib
+
+
+def _queries(n_music=6, n_noise=2):
+    from musicfpaugment_b200 import synth
+
+    return np.concatenate([synth.music_like(n_music).numpy(), synth.white_noise(n_noise).numpy()])
+
+
+def _rec_to_pklist(rec_row):
+    out = []
+    for c, r in enumerate(rec_row.tolist()):
+        r &= (1 << 64) - 1
+        for i in range(r & 0xFF):
+            out.append((c, (r >> (8 * (i + 1))) & 0xFF))
+    return out
+
+
+def _params(lib):
+    p = lib.afp_defaults()
+    assert p.a_dec == O.a_dec()
+    return p
+
+
+def test_stft_mag_matches_oracle(mfpa_ctx):
+    lib = _lib()
+    X = _queries()
+    mag, qmax = mfpa_ctx.stft_mag(torch.from_numpy(X).cuda(), shifts=1)
+    mag = mag.cpu().numpy()
+    for i, x in enumerate(X):
+        ref = O.stft_mag(x)  # [257, N] float64
+        got = mag[i, :, :257].T.astype(np.float64)
+        assert got.shape == ref.shape
+        err = np.abs(got - ref).max() / ref.max()
+        assert err < 1e-4, err  # north_star tolerance
+        assert err < 2e-6, err  # what the fp32 FFT actually delivers
+        assert abs(float(qmax[i]) - ref.max()) / ref.max() < 2e-6
+
+
+def test_stft_shifts_and_odd_lengths(mfpa_ctx):
+    X = _queries(2, 0)[:, :12345]
+    mag, qmax = mfpa_ctx.stft_mag(torch.from_numpy(X).cuda().contiguous(), shifts=4)
+    mag = mag.cpu().numpy()
+    for q in range(2):
+        for s, off in enumerate(O.shift_offsets(4)):
+            ref = O.stft_mag(X[q][off:])
+            got = mag[q * 4 + s, : ref.shape[1], :257].T
+            assert np.abs(got - ref).max() / ref.max() < 2e-6
+
+
+def test_spec_from_mag_layout(mfpa_ctx):
+    X = _queries(2, 0)
+    mag, qmax = mfpa_ctx.stft_mag(torch.from_numpy(X).cuda(), shifts=1)
+    spec = mfpa_ctx.spec_from_mag(mag, qmax, X.shape[1]).cpu().numpy()
+    for i, x in enumerate(X):
+        ref = O.normalise(O.stft_mag(x))
+        assert spec[i].shape == ref.shape
+        assert np.abs(spec[i] - ref).max() < 1e-5
+
+
+@pytest.mark.parametrize("stage", [1, 0])
+def test_peaks_bit_exact_from_reference_spectrogram(mfpa_ctx, stage):
+    """stage 1: fed the filtered sgram (deterministic float64 ops only);
+    stage 0: fed find_peaks' normalised magnitude spectrogram."""
+    lib = _lib()
+    X = list(_queries()) + [_queries(1, 0)[0][:2000], _queries(1, 0)[0][:12345]]
+    p = _params(lib)
+    for x in X:
+        spec = O.normalise(O.stft_mag(x))
+        sg = O.onset_filter(spec)
+        want, _ = O.peaks_from_sgram(sg)
+        feed = sg if stage == 1 else spec
+        rec, npk = mfpa_ctx.audfprint_peaks_from_spec(torch.from_numpy(feed[None].copy()).cuda(), stage, p)
+        got = _rec_to_pklist(rec[0].cpu().numpy())
+        assert got == want
+        assert int(npk[0]) == len(want)
+
+
+def test_peaks_unnormalised_spectrogram(mfpa_ctx):
+    lib = _lib()
+    x = _queries(1, 0)[0]
+    mag = O.stft_mag(x)
+    want = O.peaks_from_mag(mag)[0]
+    rec, _ = mfpa_ctx.audfprint_peaks_from_spec(torch.from_numpy(mag[None].copy()).cuda(), 0, _params(lib))
+    assert _rec_to_pklist(rec[0].cpu().numpy()) == want
+
+
+def test_peaks_list_and_mask(mfpa_ctx):
+    lib = _lib()
+    X = _queries(2, 1)
+    specs = np.stack([O.normalise(O.stft_mag(x)) for x in X])
+    rec, npk = mfpa_ctx.audfprint_peaks_from_spec(torch.from_numpy(specs).cuda(), 0, _params(lib))
+    peaks, n2 = mfpa_ctx.peaks_list(rec)
+    mask = mfpa_ctx.peaks_mask(rec).cpu().numpy()
+    for i, x in enumerate(X):
+        pk, m, _ = O.find_peaks(x)
+        assert int(n2[i]) == len(pk) == int(npk[i])
+        assert [tuple(r) for r in peaks[i, : len(pk)].cpu().numpy().tolist()] == pk
+        assert np.array_equal(mask[i], m)
+
+
+def test_landmark_hashes_bit_exact(mfpa_ctx):
+    lib = _lib()
+    X = _queries(3, 2)
+    specs = np.stack([O.normalise(O.stft_mag(x)) for x in X])
+    p = _params(lib)
+    rec, _ = mfpa_ctx.audfprint_peaks_from_spec(torch.from_numpy(specs).cuda(), 0, p)
+    h_ref_order, nh = mfpa_ctx.landmark_hashes(rec, p, sorted_rows=False)
+    h_sorted, nh2 = mfpa_ctx.landmark_hashes(rec, p, sorted_rows=True)
+    for i, x in enumerate(X):
+        pk = O.find_peaks(x)[0]
+        want = O.landmarks2hashes(O.peaks2landmarks(pk))
+        assert int(nh[i]) == len(want) == int(nh2[i])
+        assert np.array_equal(h_ref_order[i, : len(want)].cpu().numpy(), want)
+        assert np.array_equal(h_sorted[i, : len(want)].cpu().numpy(), O.unique_sorted_hashes(want))
+
+
+@pytest.mark.parametrize("shifts", [1, 4])
+def test_fingerprint_end_to_end(mfpa_ctx, shifts):
+    lib = _lib()
+    X = _queries(6, 2)
+    out, nh = mfpa_ctx.fingerprint(torch.from_numpy(X).cuda(), shifts, _params(lib))
+    out, nh = out.cpu().numpy(), nh.cpu().numpy()
+    agree = total = 0
+    for i, x in enumerate(X):
+        want = {tuple(r) for r in O.wave2hashes(x, shifts).tolist()}
+        rows = out[i, : nh[i]]
+        key = rows[:, 0].astype(np.int64) << 32 | rows[:, 1]
+        assert np.all(np.diff(key) > 0), "rows must be unique and sorted by (time, hash)"
+        got = {tuple(r) for r in rows.tolist()}
+        agree += len(want & got)
+        total += len(want | got)
+    assert agree / total >= 0.999, (agree, total)
+
+
+def test_fingerprint_host_matches_device(mfpa_ctx):
+    lib = _lib()
+    X = _queries(3, 1)
+    p = _params(lib)
+    d_out, d_nh = mfpa_ctx.fingerprint(torch.from_numpy(X).cuda(), 1, p)
+    h_out, h_nh = mfpa_ctx.fingerprint_host(X, 1, p)
+    assert np.array_equal(d_nh.cpu().numpy(), h_nh)
+    for i in range(len(X)):
+        assert np.array_equal(d_out[i, : h_nh[i]].cpu().numpy(), h_out[i, : h_nh[i]])
+
+
+def test_silent_and_tiny_inputs(mfpa_ctx):
+    lib = _lib()
+    p = _params(lib)
+    x = np.zeros((2, 4000), np.float32)
+    x[1] = _queries(1, 0)[0][:4000]
+    out, nh = mfpa_ctx.fingerprint(torch.from_numpy(x).cuda(), 1, p)
+    assert int(nh[0]) == 0  # all-zero input -> no peaks (peak_extractor.py:272-280)
+    assert int(nh[1]) == len(O.wave2hashes(x[1]))
+    for T in (1, 2, 255, 256, 257, 700):
+        xs = _queries(1, 0)[:, :T].copy()
+        o, n = mfpa_ctx.fingerprint(torch.from_numpy(xs).cuda(), 1, p)
+        want = O.wave2hashes(xs[0])
+        assert int(n[0]) == len(want)
+        assert np.array_equal(o[0, : len(want)].cpu().numpy(), want)
+
+
+def test_bad_arguments_raise(mfpa_ctx):
+    lib = _lib()
+    p = _params(lib)
+    p.maxpks = 9
+    with pytest.raises(lib.MfpaError):
+        mfpa_ctx.fingerprint(torch.zeros(1, 1000, device="cuda"), 1, p)
+    with pytest.raises(lib.MfpaError):
+        mfpa_ctx.fingerprint(torch.zeros(1, 1000, device="cuda"), 9, _params(lib))
