@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""Benchmark of the query-side hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload fingerprint] [--queries 10000]
+
+One "step" = one pass of the hot path over one batch of synthetic 8 s / 8 kHz
+queries.  At N = 1 the workload is BASELINE.json configs[1]: 10 k queries
+through batched STFT (n_fft 512, hop 256) + audfprint peak picking + 20-bit
+landmark hashes.  N > 1 (torchrun, one rank per GPU) shards queries with no
+data-path collective: every rank runs its own 10 k batch (weak scaling).
+
+* value    device-timed queries/s, inputs resident in HBM (CUDA events, max over ranks)
+* e2e      the same batch through the C-ABI host entry point mfpa_fingerprint_host:
+           pinned host waveforms in, CSR hash rows out, copies inside the timed region
+* roofline dominant kernel: algorithmic bytes / CUDA-event time vs MEASURED_PEAKS.json
+* cpu_baseline  the numpy oracle (port of the reference CPU path) on the host cores,
+           bounded sample, rank 0 / N = 1 only
+--impl reference times that CPU path alone (rank 0; other ranks exit).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "8s_query_fingerprints_per_sec"
+UNIT = "queries/s"
+T_QUERY = 64000
+N_FRAMES = 251
+# SURVEY.md §8(d) algorithmic bytes per query (each stage reads its input once, writes its output once)
+BYTES_STFT = 256_000 + 257 * N_FRAMES * 4          # S2: waveform in, magnitudes out
+BYTES_PEAKS = 257 * N_FRAMES * 4 + 256 * N_FRAMES  # S3: magnitudes in, peak mask (u8-equivalent) out
+BYTES_FUSED = 256_000                              # S2-S4 fused: waveform in (+ 8 B per hash out)
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self._halt = gpu_index, [], threading.Event()
+
+    def run(self):
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.gpu)], capture_output=True, text=True, timeout=5).stdout
+                for line in out.strip().splitlines():
+                    self.rows.append([c.strip() for c in line.split(",")])
+            except Exception:
+                pass
+            self._halt.wait(0.1)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=5)
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = max(mx, float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------ CPU arm
+def _cpu_worker(args):
+    seed, n, shifts = args
+    os.environ["OMP_NUM_THREADS"] = "1"
+    import torch
+
+    torch.set_num_threads(1)
+    from musicfpaugment_b200 import synth
+    from oracle import audfprint_np as O
+
+    X = synth.music_like(min(n, 8), seed=seed).numpy()  # 8 distinct queries per worker, cycled
+    t0 = time.perf_counter()
+    nh = 0
+    for i in range(n):
+        nh += len(O.wave2hashes(X[i % len(X)], shifts))
+    return time.perf_counter() - t0, n, nh
+
+
+def cpu_fingerprint_rate(per_core: int, shifts: int = 1, cores: int | None = None):
+    """queries/s of the oracle (port of afp/audfprint wavfile2hashes) using all host cores."""
+    import multiprocessing as mp
+
+    cores = cores or os.cpu_count() or 1
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        pool.map(_cpu_worker, [(1, 1, shifts)] * cores)  # warm the workers (imports)
+        t0 = time.perf_counter()
+        res = pool.map(_cpu_worker, [(1000 + i, per_core, shifts) for i in range(cores)])
+        wall = time.perf_counter() - t0
+    n = sum(r[1] for r in res)
+    busy = max(r[0] for r in res)
+    return n / busy, cores, n, wall
+
+
+def run_reference(args, rank: int, world: int):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    per_core = max(4, args.cpu_queries_per_core)
+    rates = []
+    for i in range(args.warmup + args.steps):
+        rate, cores, n, wall = cpu_fingerprint_rate(per_core, args.shifts, cores)
+        if i >= args.warmup:
+            rates.append((rate, n, wall))
+    value = sum(r[0] for r in rates) / len(rates)
+    n = rates[0][1]
+    sample = f"{n} synthetic 8 s queries per step ({per_core} per core), oracle port of wavfile2hashes, shifts={args.shifts}"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * n / value, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args), "queries_per_step": n, "n_samples": T_QUERY, "shifts": args.shifts},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(args):
+    return (f"{args.queries} synthetic 8 s 8 kHz mono queries per GPU: batched STFT (n_fft 512, hop 256) + audfprint "
+            f"peak picking + 20-bit landmark hashes, shifts={args.shifts} (BASELINE.json configs[1])")
+
+
+# ------------------------------------------------------------------ GPU arm
+def run_ours(args, rank: int, world: int, local_rank: int):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from musicfpaugment_b200 import lib, synth
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = lib.Context(local_rank, spread_table=np.exp(-0.5 * ((np.arange(-256, 257) / 30.0) ** 2)))
+    p = lib.afp_defaults()
+    B, S = args.queries, args.shifts
+    items = B * S
+
+    x = synth.music_like(B, seed=1234 + rank, device=dev, chunk=32)
+    n = lib.num_frames(T_QUERY)
+    mag = torch.empty(items, n, lib.MAG_PITCH, dtype=torch.float32, device=dev)
+    qmax = torch.empty(items, dtype=torch.float32, device=dev)
+    rec = torch.empty(items, n, dtype=torch.int64, device=dev)
+    cap = lib.HASHES_PER_FRAME * n
+    hashes = torch.empty(items, cap, 2, dtype=torch.int32, device=dev)
+    nh = torch.empty(items, dtype=torch.int32, device=dev)
+    out = torch.empty(B, cap * S, 2, dtype=torch.int32, device=dev) if S > 1 else hashes
+    nout = torch.empty(B, dtype=torch.int32, device=dev) if S > 1 else nh
+    L = lib.raw()
+    C = lib.C if hasattr(lib, "C") else __import__("ctypes")
+    h = ctx.handle
+    ptr = lambda t: C.c_void_p(t.data_ptr())
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    launches_per_step = 3 + (1 if S > 1 else 0)
+
+    def step(ev=None):
+        if ev:
+            ev[0].record()
+        lib.check(L.mfpa_stft_mag(h, ptr(x), B, T_QUERY, x.stride(0), S, ptr(mag), ptr(qmax), stream))
+        if ev:
+            ev[1].record()
+        lib.check(L.mfpa_audfprint_peaks(h, ptr(mag), ptr(qmax), B, T_QUERY, S, C.byref(p), ptr(rec), None, stream))
+        if ev:
+            ev[2].record()
+        lib.check(L.mfpa_landmark_hashes(h, ptr(rec), items, n, C.byref(p), 1, ptr(hashes), cap, ptr(nh), stream))
+        if S > 1:
+            lib.check(L.mfpa_merge_shifts(h, ptr(hashes), ptr(nh), B, S, cap, n, ptr(out), cap * S, ptr(nout), stream))
+        if ev:
+            ev[3].record()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for k in range(args.steps):
+        step(evs[k])
+    t_end.record()
+    barrier()
+    clocks = sampler.stop()
+    ms_total = t_start.elapsed_time(t_end)
+    t_stft = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps
+    t_peaks = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps
+    t_lm = sum(e[2].elapsed_time(e[3]) for e in evs) / args.steps
+    tot_hashes = int(nout.sum().item())
+
+    # ---- end to end through the host C-ABI entry point (pinned host memory in, CSR rows out)
+    x_host = torch.empty(B, T_QUERY, dtype=torch.float32).pin_memory()
+    x_host.copy_(x)
+    rows_host = torch.empty(max(tot_hashes * 2, 1024), 2, dtype=torch.int32).pin_memory()
+    offs_host = torch.empty(B + 1, dtype=torch.int64).pin_memory()
+    e2e_steps = max(1, min(args.steps, 5))
+
+    def e2e_step():
+        lib.check(L.mfpa_fingerprint_host(h, ptr(x_host), B, T_QUERY, S, C.byref(p), ptr(rows_host), rows_host.shape[0],
+                                          ptr(offs_host)))
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    assert int(offs_host[-1]) == tot_hashes, (int(offs_host[-1]), tot_hashes)
+
+    times = torch.tensor([ms_total, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms = times.tolist()
+    if rank == 0:
+        hbm, how = _peaks()
+        ms_step = ms_total / args.steps
+        value = world * B / (ms_step * 1e-3)
+        stage_ms = {"stft_mag": t_stft, "audfprint_peaks": t_peaks, "landmark_hashes(+merge)": t_lm}
+        dom = max(stage_ms, key=stage_ms.get)
+        dom_bytes = {"stft_mag": BYTES_STFT, "audfprint_peaks": BYTES_PEAKS, "landmark_hashes(+merge)": 8000}[dom] * items
+        achieved = dom_bytes / (stage_ms[dom] * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args), "queries_per_gpu": B, "n_samples": T_QUERY, "shifts": S,
+                       "l2_policy": "inputs larger than L2 (2.56 GB waveforms + 2.65 GB magnitudes per step)",
+                       "hashes_per_query": tot_hashes / B, "parallelism": f"query-sharded x{world}, no collective"},
+            "stage_ms": stage_ms,
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm, "unit": "GB/s",
+                         "frac": achieved / hbm, "traffic": None, "peak_source": how,
+                         "algorithmic_bytes_per_launch": dom_bytes,
+                         "whole_path_frac": (BYTES_FUSED * B + 8 * tot_hashes) / (ms_step * 1e-3) / 1e9 / hbm},
+            "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": B * T_QUERY * 4, "d2h_bytes_per_step": tot_hashes * 8 + (B + 1) * 8,
+                    "api": "mfpa_fingerprint_host (pinned host buffers, chunked copy/compute overlap)"},
+            "gpu_launches": launches_per_step * args.steps,
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            rate, cores, nq, wall = cpu_fingerprint_rate(args.cpu_queries_per_core, S)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{nq} of the same synthetic queries ({args.cpu_queries_per_core} per core), "
+                                              f"numpy oracle of wavfile2hashes, {wall:.1f} s wall"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    ctx.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--queries", type=int, default=10000)
+    ap.add_argument("--shifts", type=int, default=1)
+    ap.add_argument("--cpu-queries-per-core", type=int, default=200)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -143,10 +143,21 @@ int mfpa_merge_shifts(mfpa_ctx* ctx, const int32_t* hashes_dev, const int32_t* n
 int mfpa_fingerprint(mfpa_ctx* ctx, const float* x_dev, int B, int T, int64_t x_stride, int shifts,
                      const mfpa_afp_params* p, int32_t* hashes_dev, int cap, int32_t* nh_dev,
                      void* stream);
-/* Host-buffer form: copies x in, runs mfpa_fingerprint, copies the rows back. */
+/* Host-buffer form of mfpa_fingerprint (the call a reference user makes once per batch
+ * instead of looping wavfile2hashes over files).  x_host: [B][T] float32 (pinned memory
+ * lets the copies overlap the kernels; pageable memory works, slower).  The batch is
+ * processed in chunks: host->device copy of chunk i+1 overlaps the kernels of chunk i.
+ * Output is CSR: rows of query q are rows_host[offsets_host[q] .. offsets_host[q+1]) as
+ * (time, hash) int32 pairs; offsets_host has B+1 entries.  Returns MFPA_ECAP (offsets
+ * still filled in) when more than rows_cap rows were produced. */
 int mfpa_fingerprint_host(mfpa_ctx* ctx, const float* x_host, int B, int T, int shifts,
-                          const mfpa_afp_params* p, int32_t* hashes_host, int cap,
-                          int32_t* nh_host);
+                          const mfpa_afp_params* p, int32_t* rows_host, int64_t rows_cap,
+                          int64_t* offsets_host);
+
+/* Ragged [items][cap][2] rows + counts -> CSR on the device: offsets_dev [items+1] int64
+ * (exclusive scan of min(n, cap)), rows_dev [>= total][2]. */
+int mfpa_compact_rows(mfpa_ctx* ctx, const int32_t* rows_in_dev, const int32_t* n_dev, int items, int cap,
+                      int64_t* offsets_dev, int32_t* rows_dev, int64_t rows_cap, void* stream);
 
 #ifdef __cplusplus
 }

@@ -116,6 +116,14 @@ int mfpa_create(mfpa_ctx** out, int device) {
   for (int k = -kRows; k <= kRows; ++k) { const double u = (double)k / 30.0; tab[k + kRows] = exp(-0.5 * (u * u)); }
   MFPA_CUDA(cudaMemcpy(ctx->spread_dev, tab, sizeof(tab), cudaMemcpyHostToDevice));
   if (int e = stft_init_tables(ctx)) { mfpa_destroy(ctx); return e; }
+  MFPA_CUDA(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+  MFPA_CUDA(cudaStreamCreateWithFlags(&ctx->s_run, cudaStreamNonBlocking));
+  MFPA_CUDA(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+  for (int b = 0; b < 2; ++b) {
+    MFPA_CUDA(cudaEventCreateWithFlags(&ctx->ev_in[b], cudaEventDisableTiming));
+    MFPA_CUDA(cudaEventCreateWithFlags(&ctx->ev_run[b], cudaEventDisableTiming));
+    MFPA_CUDA(cudaEventCreateWithFlags(&ctx->ev_out[b], cudaEventDisableTiming));
+  }
   *out = ctx;
   return MFPA_OK;
 }
@@ -128,6 +136,15 @@ void mfpa_destroy(mfpa_ctx* ctx) {
                     &ctx->xin, &ctx->out_h, &ctx->out_n, &ctx->aug_a, &ctx->aug_b, &ctx->aug_c, &ctx->aug_d,
                     &ctx->aug_small, &ctx->match_a, &ctx->match_b, &ctx->match_c};
   for (Scratch* s : all) s->release();
+  for (int b = 0; b < 2; ++b) {
+    ctx->h_x[b].release(); ctx->h_rows[b].release(); ctx->h_csr[b].release(); ctx->h_n[b].release(); ctx->h_off[b].release();
+    if (ctx->ev_in[b]) cudaEventDestroy(ctx->ev_in[b]);
+    if (ctx->ev_run[b]) cudaEventDestroy(ctx->ev_run[b]);
+    if (ctx->ev_out[b]) cudaEventDestroy(ctx->ev_out[b]);
+  }
+  if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
+  if (ctx->s_run) cudaStreamDestroy(ctx->s_run);
+  if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
   if (ctx->spread_dev) cudaFree(ctx->spread_dev);
   if (ctx->tw_dev) cudaFree(ctx->tw_dev);
   if (ctx->win_dev) cudaFree(ctx->win_dev);
@@ -249,26 +266,92 @@ int mfpa_fingerprint(mfpa_ctx* ctx, const float* x_dev, int B, int T, int64_t x_
                              hashes_dev, cap, nh_dev, st);
 }
 
-int mfpa_fingerprint_host(mfpa_ctx* ctx, const float* x_host, int B, int T, int shifts,
-                          const mfpa_afp_params* p, int32_t* hashes_host, int cap, int32_t* nh_host) {
-  MFPA_REQUIRE(ctx && x_host && hashes_host && nh_host, "fingerprint_host: NULL argument");
-  if (int e = check_batch(B, T, shifts)) return e;
-  MFPA_REQUIRE(cap >= 1, "fingerprint_host: cap %d < 1", cap);
+int mfpa_compact_rows(mfpa_ctx* ctx, const int32_t* rows_in_dev, const int32_t* n_dev, int items, int cap,
+                      int64_t* offsets_dev, int32_t* rows_dev, int64_t rows_cap, void* stream) {
+  MFPA_REQUIRE(ctx && rows_in_dev && n_dev && offsets_dev && rows_dev, "compact_rows: NULL argument");
+  MFPA_REQUIRE(items >= 1 && cap >= 1 && rows_cap >= 0, "compact_rows: bad sizes");
   DeviceGuard guard(ctx->device);
-  if (ctx->xin.reserve(sizeof(float) * (size_t)B * T)) return MFPA_ENOMEM;
-  if (ctx->out_h.reserve(sizeof(int32_t) * 2 * (size_t)B * cap)) return MFPA_ENOMEM;
-  if (ctx->out_n.reserve(sizeof(int32_t) * B)) return MFPA_ENOMEM;
-  MFPA_CUDA(cudaMemcpyAsync(ctx->xin.ptr, x_host, sizeof(float) * (size_t)B * T, cudaMemcpyHostToDevice, 0));
-  if (int e = mfpa_fingerprint(ctx, (const float*)ctx->xin.ptr, B, T, T, shifts, p, (int32_t*)ctx->out_h.ptr, cap,
-                               (int32_t*)ctx->out_n.ptr, nullptr)) return e;
-  MFPA_CUDA(cudaMemcpyAsync(nh_host, ctx->out_n.ptr, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, 0));
-  MFPA_CUDA(cudaMemcpyAsync(hashes_host, ctx->out_h.ptr, sizeof(int32_t) * 2 * (size_t)B * cap, cudaMemcpyDeviceToHost, 0));
-  MFPA_CUDA(cudaStreamSynchronize(0));
-  for (int i = 0; i < B; ++i)
-    if (nh_host[i] > cap) {
-      set_error("fingerprint_host: query %d produced %d hashes, capacity %d", i, nh_host[i], cap);
-      return MFPA_ECAP;
+  return launch_compact_rows(rows_in_dev, n_dev, items, cap, offsets_dev, rows_dev, rows_cap, (cudaStream_t)stream);
+}
+
+// Chunked, double-buffered host path: H2D of chunk i+1 (s_in) overlaps the kernels of
+// chunk i (s_run); compacted rows leave on s_out.  Scratch used by the kernels is only
+// touched from s_run, so chunks never race on it.
+int mfpa_fingerprint_host(mfpa_ctx* ctx, const float* x_host, int B, int T, int shifts,
+                          const mfpa_afp_params* p, int32_t* rows_host, int64_t rows_cap,
+                          int64_t* offsets_host) {
+  MFPA_REQUIRE(ctx && x_host && rows_host && offsets_host, "fingerprint_host: NULL argument");
+  if (int e = check_batch(B, T, shifts)) return e;
+  if (int e = check_afp(p)) return e;
+  MFPA_REQUIRE(rows_cap >= 0, "fingerprint_host: rows_cap < 0");
+  DeviceGuard guard(ctx->device);
+  const int n_max = num_frames(T);
+  const int cap = MFPA_HASHES_PER_FRAME * n_max * shifts;
+  int chunk = (int)((int64_t)(256 << 20) / ((int64_t)T * (int64_t)sizeof(float)));  // ~256 MiB of samples
+  if (chunk < 1) chunk = 1;
+  if (chunk > B) chunk = B;
+  for (int b = 0; b < 2; ++b) {
+    if (ctx->h_x[b].reserve(sizeof(float) * (size_t)chunk * T)) return MFPA_ENOMEM;
+    if (ctx->h_rows[b].reserve(sizeof(int32_t) * 2 * (size_t)chunk * cap)) return MFPA_ENOMEM;
+    if (ctx->h_csr[b].reserve(sizeof(int32_t) * 2 * (size_t)chunk * cap)) return MFPA_ENOMEM;
+    if (ctx->h_n[b].reserve(sizeof(int32_t) * chunk)) return MFPA_ENOMEM;
+    if (ctx->h_off[b].reserve(sizeof(int64_t) * ((size_t)chunk + 1))) return MFPA_ENOMEM;
+  }
+  if (ctx->pinned_bytes < 2 * sizeof(int64_t) * ((size_t)chunk + 1)) {
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    ctx->pinned = nullptr;
+    ctx->pinned_bytes = 2 * sizeof(int64_t) * ((size_t)chunk + 1);
+    MFPA_CUDA(cudaMallocHost(&ctx->pinned, ctx->pinned_bytes));
+  }
+  int64_t* off_pinned[2] = {(int64_t*)ctx->pinned, (int64_t*)ctx->pinned + chunk + 1};
+  const int n_chunks = (B + chunk - 1) / chunk;
+  int64_t total = 0;
+  bool overflow = false;
+  offsets_host[0] = 0;
+  auto issue = [&](int ci) -> int {
+    const int b = ci & 1, q0 = ci * chunk, nq = (B - q0 < chunk) ? (B - q0) : chunk;
+    // chunk ci-2 used these buffers: its kernels and its copy-out must be done
+    if (ci >= 2) {
+      MFPA_CUDA(cudaStreamWaitEvent(ctx->s_in, ctx->ev_run[b], 0));
     }
+    MFPA_CUDA(cudaMemcpyAsync(ctx->h_x[b].ptr, x_host + (size_t)q0 * T, sizeof(float) * (size_t)nq * T,
+                              cudaMemcpyHostToDevice, ctx->s_in));
+    MFPA_CUDA(cudaEventRecord(ctx->ev_in[b], ctx->s_in));
+    MFPA_CUDA(cudaStreamWaitEvent(ctx->s_run, ctx->ev_in[b], 0));
+    if (ci >= 2) MFPA_CUDA(cudaStreamWaitEvent(ctx->s_run, ctx->ev_out[b], 0));
+    if (int e = mfpa_fingerprint(ctx, (const float*)ctx->h_x[b].ptr, nq, T, T, shifts, p, (int32_t*)ctx->h_rows[b].ptr,
+                                 cap, (int32_t*)ctx->h_n[b].ptr, ctx->s_run)) return e;
+    if (int e = launch_compact_rows((int32_t*)ctx->h_rows[b].ptr, (int32_t*)ctx->h_n[b].ptr, nq, cap,
+                                    (int64_t*)ctx->h_off[b].ptr, (int32_t*)ctx->h_csr[b].ptr, (int64_t)nq * cap,
+                                    ctx->s_run)) return e;
+    MFPA_CUDA(cudaMemcpyAsync(off_pinned[b], ctx->h_off[b].ptr, sizeof(int64_t) * (nq + 1), cudaMemcpyDeviceToHost,
+                              ctx->s_run));
+    MFPA_CUDA(cudaEventRecord(ctx->ev_run[b], ctx->s_run));
+    return MFPA_OK;
+  };
+  if (int e = issue(0)) return e;
+  for (int ci = 0; ci < n_chunks; ++ci) {
+    const int b = ci & 1, q0 = ci * chunk, nq = (B - q0 < chunk) ? (B - q0) : chunk;
+    if (ci + 1 < n_chunks)
+      if (int e = issue(ci + 1)) return e;
+    MFPA_CUDA(cudaEventSynchronize(ctx->ev_run[b]));
+    const int64_t n_rows = off_pinned[b][nq];
+    for (int i = 1; i <= nq; ++i) offsets_host[q0 + i] = total + off_pinned[b][i];
+    if (total + n_rows > rows_cap) overflow = true;
+    if (!overflow && n_rows > 0) {
+      MFPA_CUDA(cudaStreamWaitEvent(ctx->s_out, ctx->ev_run[b], 0));
+      MFPA_CUDA(cudaMemcpyAsync(rows_host + 2 * total, ctx->h_csr[b].ptr, sizeof(int32_t) * 2 * (size_t)n_rows,
+                                cudaMemcpyDeviceToHost, ctx->s_out));
+    }
+    MFPA_CUDA(cudaEventRecord(ctx->ev_out[b], ctx->s_out));
+    total += n_rows;
+  }
+  MFPA_CUDA(cudaStreamSynchronize(ctx->s_out));
+  MFPA_CUDA(cudaStreamSynchronize(ctx->s_run));
+  if (overflow) {
+    set_error("fingerprint_host: %lld rows produced, capacity %lld", (long long)total, (long long)rows_cap);
+    return MFPA_ECAP;
+  }
   return MFPA_OK;
 }
 

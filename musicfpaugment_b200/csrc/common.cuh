@@ -74,6 +74,10 @@ struct mfpa_ctx {
   mfpa::Scratch match_a, match_b, match_c;
   void* pinned = nullptr;
   size_t pinned_bytes = 0;
+  // host-path pipeline (capi.cu): copy-in, compute and copy-out streams, double-buffered chunks
+  cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_run[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+  mfpa::Scratch h_x[2], h_rows[2], h_csr[2], h_n[2], h_off[2];
 };
 
 // ---- kernel launchers implemented in the stage translation units ----------
@@ -94,6 +98,8 @@ int launch_landmark_hashes(const uint64_t* rec, int items, int n_frames, const m
                            int sorted, int32_t* hashes, int cap, int32_t* nh, cudaStream_t st);
 int launch_merge_shifts(const int32_t* hashes, const int32_t* nh, int B, int shifts, int cap_in,
                         int n_frames, int32_t* out, int cap_out, int32_t* nout, cudaStream_t st);
+int launch_compact_rows(const int32_t* rows_in, const int32_t* n, int items, int cap, int64_t* offsets,
+                        int32_t* rows, int64_t rows_cap, cudaStream_t st);
 int stft_init_tables(mfpa_ctx* ctx);
 
 }  // namespace mfpa

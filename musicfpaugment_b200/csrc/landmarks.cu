@@ -198,7 +198,66 @@ __global__ void peaks_mask_kernel(const uint64_t* __restrict__ rec, int64_t tota
   for (int k = 0; k < n; ++k) mask[(item * kRows + rec_bin(r, k)) * n_max + c] = 1.0f;
 }
 
+// exclusive scan of min(n[i], cap) -> offsets[items+1] (one block; items is O(10^4))
+__global__ void __launch_bounds__(1024) offsets_scan_kernel(const int32_t* __restrict__ n, int items, int cap,
+                                                            int64_t* __restrict__ offsets) {
+  __shared__ int64_t warp_tot[32];
+  __shared__ int64_t carry;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < items; base += 1024) {
+    const int i = base + tid;
+    const int64_t v = i < items ? (int64_t)min(n[i], cap) : 0;
+    int64_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int64_t t = __shfl_up_sync(kFull, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int64_t w = warp_tot[lane], wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int64_t t = __shfl_up_sync(kFull, wi, o);
+        if (lane >= o) wi += t;
+      }
+      warp_tot[lane] = wi - w;  // exclusive
+    }
+    __syncthreads();
+    const int64_t excl = carry + warp_tot[warp] + incl - v;
+    if (i < items) offsets[i] = excl;
+    __syncthreads();
+    if (tid == 1023) carry = excl + v;
+    __syncthreads();
+  }
+  if (tid == 0) offsets[items] = carry;
+}
+
+__global__ void __launch_bounds__(128) compact_rows_kernel(const int32_t* __restrict__ rows_in, const int32_t* __restrict__ n,
+                                                           int cap, const int64_t* __restrict__ offsets,
+                                                           int32_t* __restrict__ rows, int64_t rows_cap) {
+  const int item = blockIdx.x;
+  const int cnt = min(n[item], cap);
+  const int64_t off = offsets[item];
+  const int2* src = reinterpret_cast<const int2*>(rows_in) + (int64_t)item * cap;
+  int2* dst = reinterpret_cast<int2*>(rows);
+  for (int k = threadIdx.x; k < cnt; k += blockDim.x)
+    if (off + k < rows_cap) dst[off + k] = src[k];
+}
+
 }  // namespace
+
+int launch_compact_rows(const int32_t* rows_in, const int32_t* n, int items, int cap, int64_t* offsets,
+                        int32_t* rows, int64_t rows_cap, cudaStream_t st) {
+  offsets_scan_kernel<<<1, 1024, 0, st>>>(n, items, cap, offsets);
+  MFPA_CUDA(cudaGetLastError());
+  compact_rows_kernel<<<items, 128, 0, st>>>(rows_in, n, cap, offsets, rows, rows_cap);
+  MFPA_CUDA(cudaGetLastError());
+  return MFPA_OK;
+}
 
 int launch_landmark_hashes(const uint64_t* rec, int items, int n_frames, const mfpa_afp_params& p,
                            int sorted, int32_t* hashes, int cap, int32_t* nh, cudaStream_t st) {

@@ -32,12 +32,33 @@ __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync
 
 template <typename T> struct Loader;
 template <> struct Loader<float> {
-  static __device__ __forceinline__ void load8(const float* p, double (&v)[8]) {
+  static __device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
     const float4 a = __ldg(reinterpret_cast<const float4*>(p));
     const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
   }
 };
+
+// log() of a positive normal float as float64, accurate to ~1e-15 absolute:
+// 128-entry table on the top mantissa bits (1/c, log c), log1p polynomial on the
+// remainder, exponent * ln2 from a second table.  Used on the fused float32-STFT
+// path only; the float64 parity path calls the CUDA math library log().
+struct LogTables {
+  double2 c[128];   // {1/c_i, log(c_i)}, c_i = 1 + (i + 0.5)/128
+  double e[256];    // (biased exponent - 127) * ln2
+};
+__device__ __forceinline__ double log_fast(float v, const LogTables& t) {
+  const unsigned u = __float_as_uint(v);
+  const unsigned mant = u & 0x7fffffu;
+  const double m = __hiloint2double((int)(0x3ff00000u | (mant >> 3)), (int)(mant << 29));
+  const double2 ci = t.c[mant >> 16];
+  const double r = fma(m, ci.x, -1.0);  // |r| <= 2^-8
+  double q = fma(r, 0.2, -0.25);
+  q = fma(q, r, 1.0 / 3.0);
+  q = fma(q, r, -0.5);
+  q = fma(q, r, 1.0);
+  return t.e[u >> 23] + fma(r, q, ci.y);
+}
 template <> struct Loader<double> {
   static __device__ __forceinline__ void load8(const double* p, double (&v)[8]) {
 #pragma unroll
@@ -134,8 +155,17 @@ __device__ __forceinline__ uint64_t finalize_record(uint64_t pack, int n, unsign
 
 template <typename MagT, bool kPreFiltered>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) peaks_kernel(const PeakArgs a) {
+  constexpr bool kFast = sizeof(MagT) == 4 && !kPreFiltered;
   __shared__ double g_s[kGPad];
+  __shared__ LogTables lt;
   for (int i = threadIdx.x; i < kSpreadLen; i += blockDim.x) g_s[i + (i >> 3)] = a.spread[i];
+  if (kFast) {
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) {
+      const double c = 1.0 + ((double)i + 0.5) / 128.0;
+      lt.c[i] = make_double2(1.0 / c, log(c));
+    }
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) lt.e[i] = (double)(i - 127) * 0.69314718055994530942;
+  }
   __syncthreads();
 
   const int lane = threadIdx.x & 31;
@@ -155,7 +185,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) peaks_kernel(const PeakAr
   double* fwd_val = a.fwd_val + (int64_t)item * a.n_max * kMaxPks;
 
   double M = 1.0, mean = 0.0;
-  bool silent = false;
+  float floor_f = 0.f;   // kFast: clamp level 1e-6 * M in float32
+  double c0 = 0.0;       // kFast: log(M) + mean
+  bool silent = false, fast = false;
   if (!kPreFiltered) {
     // ---- phase 0: divisor of `sgram /= np.max(sgram)` (:263) ----
     if (a.qmax) {
@@ -163,35 +195,64 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) peaks_kernel(const PeakAr
     } else {
       double m = 0.0;
       for (int c = 0; c < n_frames; ++c) {
-        double v[8];
+        MagT v[8];
         Loader<MagT>::load8(col0 + (int64_t)c * kPitch, v);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) m = fmax(m, v[j]);
+        for (int j = 0; j < 8; ++j) m = fmax(m, (double)v[j]);
         if (lane == 0) m = fmax(m, (double)base[(int64_t)c * kPitch + kRows]);
       }
       M = warp_max(m);
     }
     // All-zero (or NaN) input: the reference divides 0/0, skips the log and ends with no peaks (:272-280).
     silent = !(M > 0.0);
+    fast = kFast && M > 1e-30 && M < 1e30;  // else (absurd scale) take the exact float64 route
     if (!silent) {
       // ---- phase 1: mean over all 257 x N of log(max(v/M, 1e-6)) (:275-276) ----
-      const double rM = 1.0 / M;
-      double P = 1.0;
+      // Sum of logs = log of product: multiply the clamped values, peel the exponent off
+      // after every few factors, take one log per lane at the end.
       int esum = 0;
-      for (int c = 0; c < n_frames; ++c) {
-        double v[8];
-        Loader<MagT>::load8(col0 + (int64_t)c * kPitch, v);
-        double pr = 1.0;
+      double lane_log;
+      if (kFast && fast) {
+        const float rMf = 1.0f / (float)M;
+        float P = 1.0f;
+        for (int c = 0; c < n_frames; ++c) {
+          float v[8];
+          Loader<float>::load8(reinterpret_cast<const float*>(col0) + (int64_t)c * kPitch, v);
+          const float ny = lane == 0 ? (float)base[(int64_t)c * kPitch + kRows] * rMf : 1.0f;
+          const float p0 = fmaxf(v[0] * rMf, 1e-6f) * fmaxf(v[1] * rMf, 1e-6f) * fmaxf(v[2] * rMf, 1e-6f) * fmaxf(v[3] * rMf, 1e-6f);
+          const float p1 = fmaxf(v[4] * rMf, 1e-6f) * fmaxf(v[5] * rMf, 1e-6f) * fmaxf(v[6] * rMf, 1e-6f) * fmaxf(v[7] * rMf, 1e-6f);
+          P *= p0;  // [1,2) * [1e-24, ~1]
+          unsigned u = __float_as_uint(P);
+          esum += (int)(u >> 23) - 127;
+          P = __uint_as_float((u & 0x007fffffu) | 0x3f800000u) * (p1 * fmaxf(ny, 1e-6f));  // >= 1e-30
+          u = __float_as_uint(P);
+          esum += (int)(u >> 23) - 127;
+          P = __uint_as_float((u & 0x007fffffu) | 0x3f800000u);
+        }
+        lane_log = log((double)P);
+      } else {
+        const double rM = 1.0 / M;
+        double P = 1.0;
+        for (int c = 0; c < n_frames; ++c) {
+          MagT v[8];
+          Loader<MagT>::load8(col0 + (int64_t)c * kPitch, v);
+          double pr = 1.0;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) pr *= fmax(v[j] * rM, 1e-6);
-        if (lane == 0) pr *= fmax((double)base[(int64_t)c * kPitch + kRows] * rM, 1e-6);
-        P *= pr;  // P in [1,2) * [1e-54, 1]: no underflow
-        const int hi = __double2hiint(P);
-        esum += ((hi >> 20) & 0x7ff) - 1023;
-        P = __hiloint2double((hi & 0x800fffff) | 0x3ff00000, __double2loint(P));
+          for (int j = 0; j < 8; ++j) pr *= fmax((double)v[j] * rM, 1e-6);
+          if (lane == 0) pr *= fmax((double)base[(int64_t)c * kPitch + kRows] * rM, 1e-6);
+          P *= pr;  // P in [1,2) * [1e-54, 1]: no underflow
+          const int hi = __double2hiint(P);
+          esum += ((hi >> 20) & 0x7ff) - 1023;
+          P = __hiloint2double((hi & 0x800fffff) | 0x3ff00000, __double2loint(P));
+        }
+        lane_log = log(P);
       }
-      const double total = warp_sum((double)esum * 0.69314718055994530942 + log(P));
+      const double total = warp_sum((double)esum * 0.69314718055994530942 + lane_log);
       mean = total / ((double)kBins * (double)n_frames);
+      if (kFast && fast) {
+        floor_f = 1e-6f * (float)M;
+        c0 = log(M) + mean;
+      }
     }
   }
 
@@ -199,14 +260,20 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) peaks_kernel(const PeakAr
   if (!silent) {
     double y[8], z[8], sth[8];
     // x -> y for one frame
-    auto advance = [&](const double (&v)[8]) {
+    auto advance = [&](const MagT (&v)[8]) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         if (kPreFiltered) {
-          y[j] = v[j];
+          y[j] = (double)v[j];
         } else {
-          const double d = fmax(v[j] / M, 1e-6);             // :263, :275
-          const double x = __dsub_rn(log(d), mean);          // :276
+          double x;
+          if (kFast && fast) {
+            // log(max(v/M, 1e-6)) - mean = log(max(v, 1e-6 M)) - (log M + mean)
+            x = __dsub_rn(log_fast(fmaxf((float)v[j], floor_f), lt), c0);
+          } else {
+            const double d = fmax((double)v[j] / M, 1e-6);   // :263, :275
+            x = __dsub_rn(log(d), mean);                     // :276
+          }
           y[j] = __dadd_rn(x, z[j]);                         // lfilter DF-II transposed (:286-288)
           z[j] = __dadd_rn(-x, __dmul_rn(0.98, y[j]));
         }
@@ -219,7 +286,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) peaks_kernel(const PeakAr
       for (int j = 0; j < 8; ++j) z[j] = 0.0;
       const int n0 = n_frames < 10 ? n_frames : 10;
       for (int c = 0; c < n0; ++c) {
-        double v[8];
+        MagT v[8];
         Loader<MagT>::load8(col0 + (int64_t)c * kPitch, v);
         advance(v);
 #pragma unroll
@@ -230,10 +297,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) peaks_kernel(const PeakAr
       for (int j = 0; j < 8; ++j) z[j] = 0.0;
     }
     // ---- phase 2: forward prune (:190-203) ----
-    double vn[8];
+    MagT vn[8];
     Loader<MagT>::load8(col0, vn);
     for (int c = 0; c < n_frames; ++c) {
-      double v[8];
+      MagT v[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = vn[j];
       if (c + 1 < n_frames) Loader<MagT>::load8(col0 + (int64_t)(c + 1) * kPitch, vn);

@@ -23,6 +23,7 @@ constexpr int kFramesPerWarp = 2;
 constexpr int kTile = kWarps * kFramesPerWarp;  // 16 frames per block
 constexpr int kExStride = 36;                   // padded row stride of the exchange tile
 constexpr int kExSize = 8 * kExStride;          // 288 floats per component
+constexpr size_t kStftSmem = sizeof(float) * (2 * (kTile + 1) * kHop + kNfft + 2 * kWarps * kExSize);
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
@@ -54,37 +55,69 @@ __device__ __forceinline__ int reflect_index(int s, int len) {
   return s < len ? s : period - s;
 }
 
-__global__ void __launch_bounds__(kWarps * 32)
-stft_mag_kernel(const float* __restrict__ x, int T, int64_t x_stride, int shifts, int n_max,
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));  // MUFU.SQRT, <= 1 ulp-ish; tolerance is 1e-4
+  return r;
+}
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
+struct TileInfo {
+  const float* xq;  // first sample of the item (after its shift offset)
+  int len, n_frames, f0, item;
+};
+
+__device__ __forceinline__ TileInfo tile_info(int64_t tile, int tiles, const float* x, int T, int64_t x_stride, int shifts) {
+  TileInfo t;
+  t.item = (int)(tile / tiles);
+  const int q = t.item / shifts, sh = t.item - q * shifts;
+  const int off = shifts < 2 ? 0 : (int)((double)sh / (double)shifts * (double)kHop);
+  t.len = T - off;
+  t.n_frames = 1 + t.len / kHop;
+  t.f0 = (int)(tile - (int64_t)t.item * tiles) * kTile;
+  t.xq = x + (int64_t)q * x_stride + off;
+  return t;
+}
+
+// Stage samples [256*(f0-1), 256*(f0+kTile)) of one item into xs.  Interior tiles whose
+// source is 16-byte aligned go through cp.async (overlapping the previous tile's FFTs);
+// tiles touching either end of the signal apply numpy's reflect padding with plain loads.
+__device__ __forceinline__ void stage_tile(const TileInfo& t, float* xs, int tid) {
+  if (t.f0 >= t.n_frames) return;
+  const int s0 = kHop * (t.f0 - 1);
+  const bool interior = s0 >= 0 && s0 + (kTile + 1) * kHop <= t.len && ((((uintptr_t)(t.xq + s0)) & 15) == 0);
+  if (interior) {
+    for (int i = tid * 4; i < (kTile + 1) * kHop; i += kWarps * 32 * 4) cp_async16(xs + i, t.xq + s0 + i);
+  } else {
+    for (int i = tid; i < (kTile + 1) * kHop; i += kWarps * 32) {
+      int s = s0 + i;
+      if (s < 0 || s >= t.len) s = reflect_index(s, t.len);
+      xs[i] = __ldg(t.xq + s);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kWarps * 32, 3)
+stft_mag_kernel(const float* __restrict__ x, int T, int64_t x_stride, int shifts, int n_max, int64_t total_tiles,
                 const float2* __restrict__ tw, const float* __restrict__ win,
                 float* __restrict__ mag, float* __restrict__ qmax) {
-  __shared__ __align__(16) float xs[(kTile + 1) * kHop];
-  __shared__ __align__(16) float win_s[kNfft];
-  __shared__ float ex_re[kWarps][kExSize];
-  __shared__ float ex_im[kWarps][kExSize];
-  __shared__ float blk_max[kWarps];
+  extern __shared__ __align__(16) float smem[];
+  float (*xs)[(kTile + 1) * kHop] = reinterpret_cast<float (*)[(kTile + 1) * kHop]>(smem);
+  float* win_s = smem + 2 * (kTile + 1) * kHop;
+  float (*ex_re)[kExSize] = reinterpret_cast<float (*)[kExSize]>(win_s + kNfft);
+  float (*ex_im)[kExSize] = reinterpret_cast<float (*)[kExSize]>(win_s + kNfft + kWarps * kExSize);
 
   const int tiles = (n_max + kTile - 1) / kTile;
-  const int item = blockIdx.x / tiles;
-  const int q = item / shifts, sh = item - q * shifts;
-  const int off = shifts < 2 ? 0 : (int)((double)sh / (double)shifts * (double)kHop);
-  const int len = T - off;
-  const int n_frames = 1 + len / kHop;
-  const int f0 = (blockIdx.x - item * tiles) * kTile;
-  if (f0 >= n_frames) return;
-  const float* xq = x + (int64_t)q * x_stride + off;
-
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // stage samples [256*(f0-1), 256*(f0+kTile)) with reflect padding
-  const int s0 = kHop * (f0 - 1);
-  for (int i = tid; i < (kTile + 1) * kHop; i += kWarps * 32) {
-    int s = s0 + i;
-    if (s < 0 || s >= len) s = reflect_index(s, len);
-    xs[i] = __ldg(xq + s);
-  }
   for (int i = tid; i < kNfft; i += kWarps * 32) win_s[i] = win[i];
 
-  // per-lane twiddles
+  // per-lane twiddles, loaded once per (persistent) block
   float2 tw1[8], tw2[8], tw3[8];
   const int g = lane >> 2, p = lane & 3;
 #pragma unroll
@@ -94,88 +127,94 @@ stft_mag_kernel(const float* __restrict__ x, int T, int64_t x_stride, int shifts
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) tw3[j] = __ldg(tw + 256 + lane + 32 * j);  // W512^k
-  __syncthreads();
 
   float* er = ex_re[warp];
   float* ei = ex_im[warp];
-  float vmax = 0.f;
 
-  for (int fi = 0; fi < kFramesPerWarp; ++fi) {
-    const int fl = warp + kWarps * fi;
-    const int f = f0 + fl;
-    if (f >= n_frames) break;  // warp-uniform
-    const float* xf = xs + fl * kHop;
-    float2 v[8];
+  int64_t tile = blockIdx.x;
+  int buf = 0;
+  if (tile < total_tiles) stage_tile(tile_info(tile, tiles, x, T, x_stride, shifts), xs[0], tid);
+  cp_async_commit();
+  for (; tile < total_tiles; tile += gridDim.x, buf ^= 1) {
+    const TileInfo ti = tile_info(tile, tiles, x, T, x_stride, shifts);
+    const int64_t next = tile + gridDim.x;
+    if (next < total_tiles) stage_tile(tile_info(next, tiles, x, T, x_stride, shifts), xs[buf ^ 1], tid);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    float vmax = 0.f;
+    for (int fi = 0; fi < kFramesPerWarp; ++fi) {
+      const int fl = warp + kWarps * fi;
+      const int f = ti.f0 + fl;
+      if (f >= ti.n_frames) break;  // warp-uniform
+      const float* xf = xs[buf] + fl * kHop;
+      float2 v[8];
 #pragma unroll
-    for (int n1 = 0; n1 < 8; ++n1) {
-      const int n = 2 * (32 * n1 + lane);
-      const float2 s = *reinterpret_cast<const float2*>(xf + n);
-      const float2 w = *reinterpret_cast<const float2*>(win_s + n);
-      v[n1] = make_float2(s.x * w.x, s.y * w.y);
+      for (int n1 = 0; n1 < 8; ++n1) {
+        const int n = 2 * (32 * n1 + lane);
+        const float2 s = *reinterpret_cast<const float2*>(xf + n);
+        const float2 w = *reinterpret_cast<const float2*>(win_s + n);
+        v[n1] = make_float2(s.x * w.x, s.y * w.y);
+      }
+      fft8(v);  // over n1 -> k1
+#pragma unroll
+      for (int k = 1; k < 8; ++k) v[k] = cmul(v[k], tw1[k]);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { er[k * kExStride + lane] = v[k].x; ei[k * kExStride + lane] = v[k].y; }
+      __syncwarp();
+#pragma unroll
+      for (int m = 0; m < 8; ++m) {
+        const int idx = g * kExStride + 4 * m + p;
+        v[m] = make_float2(er[idx], ei[idx]);
+      }
+      __syncwarp();
+      fft8(v);  // over m -> q
+#pragma unroll
+      for (int k = 1; k < 8; ++k) v[k] = cmul(v[k], tw2[k]);
+      // radix-4 across the lane quad (p); lane p ends with output r = bitrev2(p)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float2 t = make_float2(__shfl_xor_sync(0xffffffffu, v[k].x, 2), __shfl_xor_sync(0xffffffffu, v[k].y, 2));
+        float2 c = (p & 2) ? csub(t, v[k]) : cadd(v[k], t);
+        if (p == 3) c = mul_mi(c);
+        t = make_float2(__shfl_xor_sync(0xffffffffu, c.x, 1), __shfl_xor_sync(0xffffffffu, c.y, 1));
+        v[k] = (p & 1) ? csub(t, c) : cadd(c, t);
+      }
+      const int r = ((p & 1) << 1) | (p >> 1);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int kk = g + 8 * k + 72 * r;  // natural index g + 8q + 64r, padded by 8 per 64
+        er[kk] = v[k].x; ei[kk] = v[k].y;
+      }
+      __syncwarp();
+      float* out = mag + ((int64_t)ti.item * n_max + f) * kPitch;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int k = lane + 32 * j;
+        const int kc = (256 - k) & 255;
+        const int ka = k + 8 * (k >> 6), kb = kc + 8 * (kc >> 6);
+        const float ar = er[ka], ai = ei[ka], cr = er[kb], ci = ei[kb];
+        const float e_r = 0.5f * (ar + cr), e_i = 0.5f * (ai - ci);
+        const float o_r = 0.5f * (ai + ci), o_i = -0.5f * (ar - cr);
+        const float xr = e_r + tw3[j].x * o_r - tw3[j].y * o_i;
+        const float xi = e_i + tw3[j].x * o_i + tw3[j].y * o_r;
+        const float m = sqrt_approx(xr * xr + xi * xi);
+        out[k] = m;
+        vmax = fmaxf(vmax, m);
+      }
+      if (lane == 0) {  // Nyquist bin: Re(Z0) - Im(Z0)
+        const float m = fabsf(er[0] - ei[0]);
+        out[256] = m;
+        vmax = fmaxf(vmax, m);
+      }
+      __syncwarp();
     }
-    fft8(v);  // over n1 -> k1
 #pragma unroll
-    for (int k = 1; k < 8; ++k) v[k] = cmul(v[k], tw1[k]);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { er[k * kExStride + lane] = v[k].x; ei[k * kExStride + lane] = v[k].y; }
-    __syncwarp();
-#pragma unroll
-    for (int m = 0; m < 8; ++m) {
-      const int idx = g * kExStride + 4 * m + p;
-      v[m] = make_float2(er[idx], ei[idx]);
-    }
-    __syncwarp();
-    fft8(v);  // over m -> q
-#pragma unroll
-    for (int k = 1; k < 8; ++k) v[k] = cmul(v[k], tw2[k]);
-    // radix-4 across the lane quad (p); lane p ends with output r = bitrev2(p)
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      float2 t = make_float2(__shfl_xor_sync(0xffffffffu, v[k].x, 2), __shfl_xor_sync(0xffffffffu, v[k].y, 2));
-      float2 c = (p & 2) ? csub(t, v[k]) : cadd(v[k], t);
-      if (p == 3) c = mul_mi(c);
-      t = make_float2(__shfl_xor_sync(0xffffffffu, c.x, 1), __shfl_xor_sync(0xffffffffu, c.y, 1));
-      v[k] = (p & 1) ? csub(t, c) : cadd(c, t);
-    }
-    const int r = ((p & 1) << 1) | (p >> 1);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int kk = g + 8 * k + 72 * r;  // natural index g + 8q + 64r, padded by 8 per 64
-      er[kk] = v[k].x; ei[kk] = v[k].y;
-    }
-    __syncwarp();
-    float* out = mag + ((int64_t)item * n_max + f) * kPitch;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int k = lane + 32 * j;
-      const int kc = (256 - k) & 255;
-      const int ka = k + 8 * (k >> 6), kb = kc + 8 * (kc >> 6);
-      const float ar = er[ka], ai = ei[ka], cr = er[kb], ci = ei[kb];
-      const float e_r = 0.5f * (ar + cr), e_i = 0.5f * (ai - ci);
-      const float o_r = 0.5f * (ai + ci), o_i = -0.5f * (ar - cr);
-      const float xr = e_r + tw3[j].x * o_r - tw3[j].y * o_i;
-      const float xi = e_i + tw3[j].x * o_i + tw3[j].y * o_r;
-      const float m = sqrtf(xr * xr + xi * xi);
-      out[k] = m;
-      vmax = fmaxf(vmax, m);
-    }
-    if (lane == 0) {  // Nyquist bin: Re(Z0) - Im(Z0)
-      const float m = fabsf(er[0] - ei[0]);
-      out[256] = m;
-      vmax = fmaxf(vmax, m);
-    }
-    __syncwarp();
+    for (int o = 16; o; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    if (lane == 0 && ti.f0 + warp < ti.n_frames) atomicMax(reinterpret_cast<int*>(qmax + ti.item), __float_as_int(vmax));
+    __syncthreads();  // everyone is done with xs[buf] before it is refilled two iterations later
   }
-#pragma unroll
-  for (int o = 16; o; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-  if (lane == 0) blk_max[warp] = vmax;
-  __syncthreads();
-  if (tid == 0) {
-    float m = blk_max[0];
-#pragma unroll
-    for (int w = 1; w < kWarps; ++w) m = fmaxf(m, blk_max[w]);
-    atomicMax(reinterpret_cast<int*>(qmax + item), __float_as_int(m));  // m >= 0
-  }
+  cp_async_wait<0>();
 }
 
 // mag [item][frame][264] f32 -> spec [item][257][n_max] f64, divided by qmax.
@@ -224,9 +263,12 @@ int launch_stft_mag(mfpa_ctx* ctx, const float* x, int B, int T, int64_t stride,
   const int items = B * shifts;
   const int n_max = num_frames(T);
   MFPA_CUDA(cudaMemsetAsync(qmax, 0, sizeof(float) * items, st));
-  const int64_t blocks = (int64_t)items * ((n_max + kTile - 1) / kTile);
-  MFPA_REQUIRE(blocks < (1ll << 31), "stft: batch too large (%lld blocks)", (long long)blocks);
-  stft_mag_kernel<<<(unsigned)blocks, kWarps * 32, 0, st>>>(x, T, stride, shifts, n_max, ctx->tw_dev, ctx->win_dev, mag, qmax);
+  const int64_t total_tiles = (int64_t)items * ((n_max + kTile - 1) / kTile);
+  const int64_t resident = (int64_t)ctx->num_sms * 3;  // persistent blocks, 3 per SM (__launch_bounds__)
+  const unsigned blocks = (unsigned)(total_tiles < resident ? total_tiles : resident);
+  MFPA_CUDA(cudaFuncSetAttribute(stft_mag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStftSmem));
+  stft_mag_kernel<<<blocks, kWarps * 32, kStftSmem, st>>>(x, T, stride, shifts, n_max, total_tiles, ctx->tw_dev, ctx->win_dev,
+                                                  mag, qmax);
   MFPA_CUDA(cudaGetLastError());
   return MFPA_OK;
 }

@@ -56,7 +56,8 @@ SIGNATURES = {
     "mfpa_landmark_hashes": (_i, [_vp, _vp, _i, _i, _P, _i, _vp, _i, _vp, _vp]),
     "mfpa_merge_shifts": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _vp]),
     "mfpa_fingerprint": (_i, [_vp, _vp, _i, _i, _i64, _i, _P, _vp, _i, _vp, _vp]),
-    "mfpa_fingerprint_host": (_i, [_vp, _vp, _i, _i, _i, _P, _vp, _i, _vp]),
+    "mfpa_fingerprint_host": (_i, [_vp, _vp, _i, _i, _i, _P, _vp, _i64, _vp]),
+    "mfpa_compact_rows": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _i64, _vp]),
 }
 
 
@@ -263,16 +264,26 @@ class Context:
                                     out.shape[1], _ptr(nh), _stream()))
         return out, nh
 
-    def fingerprint_host(self, x_np, shifts: int, params: AfpParams, cap: int | None = None):
-        """numpy [B,T] float32 (host) -> (hashes int32 [B,cap,2], nh int32 [B]) numpy."""
+    def fingerprint_host(self, x, shifts: int, params: AfpParams, rows=None, offsets=None):
+        """Host buffers in, host buffers out (CSR).  x: [B,T] float32 numpy array or CPU torch
+        tensor (pinned memory makes the chunked copies overlap the kernels).
+        -> (rows int32 [total,2], offsets int64 [B+1]) as numpy views."""
         import numpy as np
+        import torch
 
-        x_np = np.ascontiguousarray(x_np, dtype=np.float32)
-        B, T = x_np.shape
-        if cap is None:
-            cap = HASHES_PER_FRAME * num_frames(T) * shifts
-        out = np.empty((B, cap, 2), dtype=np.int32)
-        nh = np.empty(B, dtype=np.int32)
-        check(_lib.mfpa_fingerprint_host(self._h, x_np.ctypes.data_as(C.c_void_p), B, T, shifts, C.byref(params),
-                                         out.ctypes.data_as(C.c_void_p), cap, nh.ctypes.data_as(C.c_void_p)))
-        return out, nh
+        if isinstance(x, np.ndarray):
+            x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+        assert not x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.is_contiguous()
+        B, T = x.shape
+        if rows is None:
+            rows = torch.empty(B * 1024 * shifts, 2, dtype=torch.int32)
+        if offsets is None:
+            offsets = torch.empty(B + 1, dtype=torch.int64)
+        rc = _lib.mfpa_fingerprint_host(self._h, _ptr(x), B, T, shifts, C.byref(params), _ptr(rows), rows.shape[0],
+                                        _ptr(offsets))
+        if rc == -4:  # MFPA_ECAP: offsets are valid, retry with the exact size
+            rows = torch.empty(int(offsets[-1]), 2, dtype=torch.int32)
+            rc = _lib.mfpa_fingerprint_host(self._h, _ptr(x), B, T, shifts, C.byref(params), _ptr(rows),
+                                            rows.shape[0], _ptr(offsets))
+        check(rc)
+        return rows[: int(offsets[-1])].numpy(), offsets.numpy()

@@ -153,13 +153,18 @@ def test_fingerprint_end_to_end(mfpa_ctx, shifts):
 
 def test_fingerprint_host_matches_device(mfpa_ctx):
     lib = _lib()
-    X = _queries(3, 1)
+    X = _queries(5, 2)
     p = _params(lib)
-    d_out, d_nh = mfpa_ctx.fingerprint(torch.from_numpy(X).cuda(), 1, p)
-    h_out, h_nh = mfpa_ctx.fingerprint_host(X, 1, p)
-    assert np.array_equal(d_nh.cpu().numpy(), h_nh)
-    for i in range(len(X)):
-        assert np.array_equal(d_out[i, : h_nh[i]].cpu().numpy(), h_out[i, : h_nh[i]])
+    for shifts in (1, 4):
+        d_out, d_nh = mfpa_ctx.fingerprint(torch.from_numpy(X).cuda(), shifts, p)
+        rows, offs = mfpa_ctx.fingerprint_host(X, shifts, p)
+        assert np.array_equal(np.diff(offs), d_nh.cpu().numpy())
+        for i in range(len(X)):
+            assert np.array_equal(d_out[i, : int(d_nh[i])].cpu().numpy(), rows[offs[i]: offs[i + 1]])
+    # tiny capacity -> retried with the exact size
+    rows2, offs2 = mfpa_ctx.fingerprint_host(torch.from_numpy(X).pin_memory(), 1, p, rows=torch.empty(8, 2, dtype=torch.int32))
+    r1, o1 = mfpa_ctx.fingerprint_host(X, 1, p)
+    assert np.array_equal(rows2, r1) and np.array_equal(offs2, o1)
 
 
 def test_silent_and_tiny_inputs(mfpa_ctx):
@@ -186,3 +191,35 @@ def test_bad_arguments_raise(mfpa_ctx):
         mfpa_ctx.fingerprint(torch.zeros(1, 1000, device="cuda"), 1, p)
     with pytest.raises(lib.MfpaError):
         mfpa_ctx.fingerprint(torch.zeros(1, 1000, device="cuda"), 9, _params(lib))
+
+
+def test_fingerprint_agreement_many_queries(mfpa_ctx):
+    """>= 99.9 % of hashes agree with the oracle over a larger seeded sample (fast float path)."""
+    from musicfpaugment_b200 import synth
+
+    lib = _lib()
+    X = np.concatenate([synth.music_like(40, seed=4321).numpy(), synth.white_noise(8, seed=99).numpy()])
+    out, nh = mfpa_ctx.fingerprint(torch.from_numpy(X).cuda(), 1, _params(lib))
+    out, nh = out.cpu().numpy(), nh.cpu().numpy()
+    agree = total = exact = 0
+    for i, x in enumerate(X):
+        want = O.wave2hashes(x, 1)
+        got = out[i, : nh[i]]
+        exact += int(np.array_equal(want, got))
+        a, b = {tuple(r) for r in want.tolist()}, {tuple(r) for r in got.tolist()}
+        agree += len(a & b)
+        total += len(a | b)
+    assert agree / total >= 0.999, (agree, total, exact)
+
+
+def test_scale_invariance(mfpa_ctx):
+    """The path is scale invariant (sgram /= max) over 24 orders of magnitude of input level."""
+    lib = _lib()
+    x = _queries(1, 0)[:, :16000]
+    for scale in (1e-12, 1e-4, 1.0, 1e12):
+        xs = (x.astype(np.float64) * scale).astype(np.float32)
+        out, nh = mfpa_ctx.fingerprint(torch.from_numpy(xs).cuda(), 1, _params(lib))
+        want = O.wave2hashes(xs[0], 1)
+        got = out[0, : int(nh[0])].cpu().numpy()
+        a, b = {tuple(r) for r in want.tolist()}, {tuple(r) for r in got.tolist()}
+        assert len(a & b) >= 0.98 * len(a | b), (scale, len(a), len(b))

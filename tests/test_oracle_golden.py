@@ -87,3 +87,34 @@ def test_dejavu_peaks_golden():
         pk, mask = D.get_2d_peaks(g[f"arr{i}"], amp_min=float(g[f"amp_min{i}"]))
         assert np.array_equal(np.asarray(pk, np.int32).reshape(-1, 2), g[f"peaks{i}"]), i
         assert np.array_equal(mask.astype(np.uint8), g[f"mask{i}"]), i
+
+
+def test_augment_chain_golden():
+    """AugmentFP arithmetic vs the reference's transform classes (dumped parameters);
+    1e-4 relative is the north-star tolerance, the oracle is ~1e-6."""
+    from oracle import augment_np as A
+
+    g = np.load(os.path.join(GOLD, "augment.npz"))
+    keys = ("fc1", "ir", "noise", "snr_db", "gain_factor", "clip_p", "fc2", "fc3")
+    for i in range(int(g["n_cases"])):
+        prm = {k: (g[f"p{i}_{k}"] if g[f"p{i}_{k}"].ndim else float(g[f"p{i}_{k}"])) for k in keys if f"p{i}_{k}" in g}
+        y, stages = A.augment_chain(g[f"x{i}"], prm, return_stages=True)
+        ref = g[f"out{i}"]
+        assert y.dtype == np.float32 and y.shape == ref.shape
+        assert np.abs(y - ref).max() / np.abs(ref).max() < 5e-6, i
+        if i == 0:
+            for k in A.STAGES:
+                r = g[f"stage0_{k}"]
+                assert np.abs(stages[k] - r).max() / np.abs(r).max() < 5e-6, k
+
+
+def test_fir_taps_properties():
+    from oracle import augment_np as A
+
+    for fc, half in ((150.0, 213), (30.0, 1066), (3999.0, 8), (3000.0, 10)):
+        h = A.lowpass_taps(A.cutoff_fraction(fc, 8000))
+        assert len(h) == 2 * half + 1 and abs(float(h.sum()) - 1) < 1e-5
+        assert np.allclose(h, h[::-1], atol=1e-7)
+    for bad in (-0.1, 0.6, 0.0):
+        with pytest.raises(ValueError):
+            A.lowpass_taps(bad)
