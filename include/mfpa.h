@@ -159,6 +159,105 @@ int mfpa_fingerprint_host(mfpa_ctx* ctx, const float* x_host, int B, int T, int 
 int mfpa_compact_rows(mfpa_ctx* ctx, const int32_t* rows_in_dev, const int32_t* n_dev, int items, int cap,
                       int64_t* offsets_dev, int32_t* rows_dev, int64_t rows_cap, void* stream);
 
+/* ---- S1: AugmentFP degradation chain  (augmentation/__init__.py:46-97) -------------
+ * One record per query with the parameters the reference samples in
+ * randomize_parameters() (SURVEY.md App. C dump schema).  `apply` bit i set = the i-th
+ * transform's Bernoulli gate (transform.py:101-105) fired for this query. */
+#define MFPA_AUG_HPF1 1u  /* HighPassFilter  "cutoff_freq1" (loudspeaker)  pass_filters.py:144-155 */
+#define MFPA_AUG_IR 2u    /* ApplyImpulseResponse                           impulse_response.py:73-116 */
+#define MFPA_AUG_NOISE 4u /* AddBackgroundNoise                             background_noise.py:183-213 */
+#define MFPA_AUG_GAIN 8u  /* Gain                                           gain.py:62-70 */
+#define MFPA_AUG_CLIP 16u /* Clipping                                       clipping.py:67-101 */
+#define MFPA_AUG_LPF 32u  /* LowPassFilter   "cutoff_freq2"                 pass_filters.py:84-115 */
+#define MFPA_AUG_HPF3 64u /* HighPassFilter  "cutoff_freq3" (microphone) */
+#define MFPA_AUG_NORM 128u /* final PeakNormalization (p = 1 in AugmentFP)  peak_normalization.py:38-67 */
+
+typedef struct mfpa_aug_params {
+  uint32_t apply;     /* MFPA_AUG_* bits */
+  float fc1_hz;       /* transform_parameters["cutoff_freq"] of the three pass filters, in Hz */
+  float fc2_hz;
+  float fc3_hz;
+  float snr_db;       /* transform_parameters["snr_in_db"] */
+  float gain_factor;  /* transform_parameters["gain_factors"] = 10^(dB/20) */
+  float clip_p;       /* transform_parameters["percentile_threshold"] */
+  int32_t ir_len;     /* valid samples of this query's impulse response (<= ir_stride) */
+} mfpa_aug_params;
+
+/* Longest FIR the CUDA path accepts (taps = 2*int(4*sr/fc)+1 <= this). */
+#define MFPA_AUG_MAX_TAPS 8193
+/* Longest impulse response, in samples. */
+#define MFPA_AUG_MAX_IR 8192
+
+/* AugmentFP.__call__ / batch_augment on dumped parameters, per-query semantics (the
+ * reference drivers call it with B = 1; Clipping's quantiles are per query).
+ * x_dev [B][T] (row stride x_stride), ir_dev [B][ir_stride] (may be NULL when no query has
+ * MFPA_AUG_IR), noise_dev [B][T] contiguous, RMS-normalised like random_background()
+ * leaves it (may be NULL when no query has MFPA_AUG_NOISE), params_host [B],
+ * out_dev [B][T] contiguous.  Cut-offs that the reference rejects (<= 0 or > sr/2,
+ * pass_filters.py:103-110) and filters longer than MFPA_AUG_MAX_TAPS return MFPA_EINVAL. */
+int mfpa_augment(mfpa_ctx* ctx, const float* x_dev, int B, int T, int64_t x_stride, int sample_rate,
+                 const mfpa_aug_params* params_host, const float* ir_dev, int ir_stride,
+                 const float* noise_dev, float* out_dev, void* stream);
+
+/* Fused S1-S4 (BASELINE.json config 3): augment, then fingerprint the degraded queries
+ * without leaving the device.  The final peak normalisation is skipped on this path
+ * (the spectrogram is divided by its own maximum, peak_extractor.py:263). */
+int mfpa_augment_fingerprint(mfpa_ctx* ctx, const float* x_dev, int B, int T, int64_t x_stride, int sample_rate,
+                             const mfpa_aug_params* params_host, const float* ir_dev, int ir_stride,
+                             const float* noise_dev, int shifts, const mfpa_afp_params* p,
+                             int32_t* hashes_dev, int cap, int32_t* nh_dev, void* stream);
+
+/* ---- S5: landmark-hash matching  (HashTable.get_hits hash_table.py:220-246,
+ * Matcher._best_count_ids / _approx_match_counts / match_hashes audfprint_match.py:102-129,235-349)
+ *
+ * mfpa_index_load uploads one hash-range shard of a reference HashTable: the rows
+ * [hash_lo, hash_lo + n_buckets) of `table` (uint32 [n_buckets][depth], entry =
+ * ((id+1) << maxtimebits) + time, hash_table.py:53-68,100) and of `counts`, plus the full
+ * `hashesperid` [n_tracks].  hashbits is the table's (20).  A single-GPU user passes
+ * hash_lo = 0, n_buckets = 1 << hashbits. */
+int mfpa_index_load(mfpa_ctx* ctx, const uint32_t* table_host, const int32_t* counts_host, int hash_lo,
+                    int n_buckets, int depth, int hashbits, int maxtimebits,
+                    const uint32_t* hashesperid_host, int n_tracks);
+
+typedef struct mfpa_match_params {  /* Matcher.__init__ defaults, audfprint_match.py:76-100 */
+  int32_t window;        /* 2   */
+  int32_t threshcount;   /* 5   */
+  int32_t search_depth;  /* 100 (<= 128) */
+  int32_t max_alignments_per_id; /* 100 */
+} mfpa_match_params;
+void mfpa_match_defaults(mfpa_match_params* p);
+
+/* get_hits for ONE query: hashes_dev [n][2] (time, hash) -> hits_dev [<= hits_cap][4] int32 rows
+ * [id, t_ref - t_q, hash, t_q] in the reference's order; *nhits_dev (int64, device) = rows produced
+ * by this shard (may exceed hits_cap; only hits_cap rows are written). */
+int mfpa_get_hits(mfpa_ctx* ctx, const int32_t* hashes_dev, int n, int32_t* hits_dev, int64_t hits_cap,
+                  int64_t* nhits_dev, void* stream);
+
+/* The four steps of match_hashes for a batch of B queries (hashes_dev [B][cap][2], nh_dev [B]).
+ * Multi-GPU (index sharded by hash range): all-reduce(sum) counts_dev between steps 1 and 2,
+ * all-gather list_dev/nlist_dev between steps 3 and 4; single GPU: call mfpa_match.
+ *  1 counts : counts_dev [B][n_tracks] int32 raw hit counts from this shard's buckets
+ *  2 select : cand_dev [B][search_depth][2] (id, raw) in _best_count_ids order, ncand_dev [B]
+ *  3 collect: list_dev [B][list_cap] uint32 = (candidate index << 16) | (t_ref - t_q + 16384),
+ *             nlist_dev [B] (may exceed list_cap -> step 4 reports -1 for that query)
+ *  4 align  : results_dev [B][max_rows][7] int32 rows [id, filtered count, time skew, raw count,
+ *             candidate rank, 0, 0] ordered by filtered count descending; nrows_dev [B]
+ *             (-1 / -2 = a capacity was exceeded for that query). */
+int mfpa_match_counts(mfpa_ctx* ctx, const int32_t* hashes_dev, const int32_t* nh_dev, int B, int cap,
+                      int32_t* counts_dev, void* stream);
+int mfpa_match_select(mfpa_ctx* ctx, const int32_t* counts_dev, int B, const mfpa_match_params* p,
+                      int32_t* cand_dev, int32_t* ncand_dev, void* stream);
+int mfpa_match_collect(mfpa_ctx* ctx, const int32_t* hashes_dev, const int32_t* nh_dev, int B, int cap,
+                       const int32_t* cand_dev, const int32_t* ncand_dev, const mfpa_match_params* p,
+                       uint32_t* list_dev, int list_cap, int32_t* nlist_dev, void* stream);
+int mfpa_match_align(mfpa_ctx* ctx, const uint32_t* lists_dev, const int32_t* nlists_dev, int n_lists, int B,
+                     int list_cap, const int32_t* cand_dev, const int32_t* ncand_dev,
+                     const mfpa_match_params* p, int32_t* results_dev, int32_t* nrows_dev, int max_rows,
+                     void* stream);
+/* Single-shard convenience: steps 1-4 with internal scratch, queries processed in sub-batches. */
+int mfpa_match(mfpa_ctx* ctx, const int32_t* hashes_dev, const int32_t* nh_dev, int B, int cap,
+               const mfpa_match_params* p, int32_t* results_dev, int32_t* nrows_dev, int max_rows, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

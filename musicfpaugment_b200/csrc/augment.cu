@@ -1,0 +1,639 @@
+// S1 — AugmentFP degradation chain on dumped parameters (augmentation/__init__.py:46-97).
+//
+//   stage 1  HighPassFilter(fc1)        x - lowpass(x)                     pass_filters.py:144-155
+//   stage 2  ApplyImpulseResponse       full conv, / peak of FULL result   impulse_response.py:73-116
+//   stage 3  AddBackgroundNoise         + rms/10^(snr/20) * noise, / peak  background_noise.py:183-213
+//   stage 4  Gain, Clipping             * g, clamp to p/2, 1-p/2 quantiles gain.py:62-70, clipping.py:67-101
+//   stage 5  LowPassFilter(fc2)         windowed-sinc FIR (julius)         pass_filters.py:84-115
+//   stage 6  HighPassFilter(fc3)
+//   stage 7  PeakNormalization          / peak if > 0                      peak_normalization.py:38-67
+//
+// Long convolutions (stages 1, 2, 6) are overlap-save blocks of one 16384-point complex
+// FFT held entirely in shared memory: the signal block goes into the real part, the
+// filter (FIR taps generated on the fly, or the impulse response) into the imaginary
+// part, one forward transform yields both spectra (split by conjugate symmetry), their
+// product is inverse-transformed in place.  Forward is decimation-in-frequency and the
+// inverse undoes it pass by pass, so no bit-reversal pass is ever needed.  The per-query
+// reductions that gate the next stage (peak of the full convolution, RMS, peak after the
+// mix, clip quantiles, final peak) are produced by the kernel that writes the data.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace mfpa {
+
+namespace {
+
+constexpr int FN = 16384;          // FFT length
+constexpr int FT = 512;            // threads per FFT block
+constexpr int FPAD = FN + FN / 16; // padded smem array (conflict-free radix-16 / radix-4 passes)
+constexpr size_t kConvSmem = sizeof(float2) * (FPAD + 1024) + 64 * sizeof(float);
+constexpr float kPi = 3.14159265358979323846f;
+
+struct AugQ {            // per-query derived parameters (device copy)
+  uint32_t apply;
+  int half1, half2, half3, ir_len;
+  float c1x2, c2x2, c3x2;         // float(2*cutoff)
+  float arg1, arg2, arg3;         // float(2*cutoff*pi)
+  float snr_div;                  // 10^(snr_db/20)
+  float gain, q_lo;
+};
+
+struct AugS {            // per-query running statistics (zeroed per call)
+  double ss_a, ss_b;     // sum of squares of the stage-1 / stage-2 output (first T samples)
+  float max_a, max_b;    // peak of stage-1 output / of the FULL stage-2 convolution
+  float max_z, max_v;    // peak after the noise mix / after stage 6
+  float lo, hi;          // clip thresholds in the gained domain
+  float pad[2];
+};
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ int pidx(int i) { return i + (i >> 4); }
+
+// 4-point DFT with kernel e^{S i 2 pi nk/4}; S = -1 forward, +1 inverse (unscaled).
+template <int S> __device__ __forceinline__ void dft4(float2& a, float2& b, float2& c, float2& d) {
+  const float2 s0 = cadd(a, c), s1 = csub(a, c), s2 = cadd(b, d), s3 = csub(b, d);
+  const float2 t = S < 0 ? make_float2(s3.y, -s3.x) : make_float2(-s3.y, s3.x);
+  a = cadd(s0, s2); c = csub(s0, s2); b = cadd(s1, t); d = csub(s1, t);
+}
+
+// 16-point DFT, natural order in; output X[k] lands in v[4*(k&3) + (k>>2)].
+template <int S> __device__ __forceinline__ void dft16(float2 (&v)[16]) {
+  constexpr float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f, h = 0.70710678118654752440f;
+#pragma unroll
+  for (int n2 = 0; n2 < 4; ++n2) dft4<S>(v[n2], v[4 + n2], v[8 + n2], v[12 + n2]);
+  // v[4*k1 + n2] *= W16^(n2*k1)
+  const float sg = S < 0 ? -1.f : 1.f;
+  v[5] = cmul(v[5], make_float2(c1, sg * s1));
+  v[6] = cmul(v[6], make_float2(h, sg * h));
+  v[7] = cmul(v[7], make_float2(s1, sg * c1));
+  v[9] = cmul(v[9], make_float2(h, sg * h));
+  v[10] = S < 0 ? make_float2(v[10].y, -v[10].x) : make_float2(-v[10].y, v[10].x);
+  v[11] = cmul(v[11], make_float2(-h, sg * h));
+  v[13] = cmul(v[13], make_float2(s1, sg * c1));
+  v[14] = cmul(v[14], make_float2(-h, sg * h));
+  v[15] = cmul(v[15], make_float2(-c1, sg * -s1));
+#pragma unroll
+  for (int k1 = 0; k1 < 4; ++k1) dft4<S>(v[4 * k1], v[4 * k1 + 1], v[4 * k1 + 2], v[4 * k1 + 3]);
+}
+
+// One radix-16 pass over sub-transforms of length 16*s.  tw[e] = exp(-2 pi i e / FN), e < 1024;
+// the twiddle of element k in a group is tw[j * tw_mul]^k.
+template <bool INV> __device__ __forceinline__ void pass16(float2* buf, const float2* tw, int log2s, int tw_mul, int tid) {
+  const int s = 1 << log2s;
+#pragma unroll 1
+  for (int g = 0; g < FN / 16 / FT; ++g) {
+    const int gid = tid + FT * g;
+    const int j = gid & (s - 1);
+    const int base = ((gid >> log2s) << (log2s + 4)) + j;
+    float2 v[16];
+#pragma unroll
+    for (int t = 0; t < 16; ++t) v[t] = buf[pidx(base + (t << log2s))];
+    float2 w1 = tw[j * tw_mul];
+    if (INV) w1.y = -w1.y;
+    // powers w^2 .. w^15 with multiplication depth <= 4
+    float2 w[16];
+    w[1] = w1; w[2] = cmul(w1, w1); w[3] = cmul(w[2], w1); w[4] = cmul(w[2], w[2]);
+    w[5] = cmul(w[4], w1); w[6] = cmul(w[3], w[3]); w[7] = cmul(w[4], w[3]); w[8] = cmul(w[4], w[4]);
+    w[9] = cmul(w[8], w1); w[10] = cmul(w[5], w[5]); w[11] = cmul(w[8], w[3]); w[12] = cmul(w[6], w[6]);
+    w[13] = cmul(w[8], w[5]); w[14] = cmul(w[7], w[7]); w[15] = cmul(w[8], w[7]);
+    if (INV) {
+#pragma unroll
+      for (int t = 1; t < 16; ++t) v[t] = cmul(v[t], w[t]);
+      dft16<1>(v);
+#pragma unroll
+      for (int k = 0; k < 16; ++k) buf[pidx(base + (k << log2s))] = v[4 * (k & 3) + (k >> 2)];
+    } else {
+      dft16<-1>(v);
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const float2 x = v[4 * (k & 3) + (k >> 2)];
+        buf[pidx(base + (k << log2s))] = k ? cmul(x, w[k]) : x;
+      }
+    }
+  }
+}
+
+template <int S> __device__ __forceinline__ void pass4(float2* buf, int tid) {
+#pragma unroll 2
+  for (int g = 0; g < FN / 4 / FT; ++g) {
+    const int base = 4 * (tid + FT * g);
+    float2 a = buf[pidx(base)], b = buf[pidx(base + 1)], c = buf[pidx(base + 2)], d = buf[pidx(base + 3)];
+    dft4<S>(a, b, c, d);
+    buf[pidx(base)] = a; buf[pidx(base + 1)] = b; buf[pidx(base + 2)] = c; buf[pidx(base + 3)] = d;
+  }
+}
+
+// forward: natural order in, digit-reversed out.  inverse: digit-reversed in, natural out (x FN).
+__device__ __forceinline__ void fft_forward(float2* buf, const float2* tw, int tid) {
+  pass16<false>(buf, tw, 10, 1, tid);   __syncthreads();
+  pass16<false>(buf, tw, 6, 16, tid);   __syncthreads();
+  pass16<false>(buf, tw, 2, 256, tid);  __syncthreads();
+  pass4<-1>(buf, tid);                  __syncthreads();
+}
+__device__ __forceinline__ void fft_inverse(float2* buf, const float2* tw, int tid) {
+  pass4<1>(buf, tid);                   __syncthreads();
+  pass16<true>(buf, tw, 2, 256, tid);   __syncthreads();
+  pass16<true>(buf, tw, 6, 16, tid);    __syncthreads();
+  pass16<true>(buf, tw, 10, 1, tid);    __syncthreads();
+}
+// position of frequency k after fft_forward
+__device__ __forceinline__ int rev_pos(int k) {
+  return ((k & 15) << 10) | (((k >> 4) & 15) << 6) | (((k >> 8) & 15) << 2) | (k >> 12);
+}
+
+__device__ __forceinline__ float block_sum(float v, float* red, int tid) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((tid & 31) == 0) red[tid >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int w = 0; w < FT / 32; ++w) t += red[w];
+  __syncthreads();
+  return t;
+}
+__device__ __forceinline__ float block_max(float v, float* red, int tid) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if ((tid & 31) == 0) red[tid >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int w = 0; w < FT / 32; ++w) t = fmaxf(t, red[w]);
+  __syncthreads();
+  return t;
+}
+__device__ __forceinline__ void atomic_max_pos(float* addr, float v) { atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v)); }
+
+// julius low-pass tap i of a filter with half-width `half` (unnormalised): 2c * hann * sinc
+__device__ __forceinline__ float fir_tap(int i, int half, float c2, float argscale) {
+  if (half == 0) return c2;
+  const float win = 0.5f - 0.5f * cosf(2.0f * kPi * (float)i / (float)(2 * half));
+  const float arg = (float)(i - half) * argscale;
+  const float sinc = arg == 0.f ? 1.f : sinf(arg) / arg;
+  return c2 * win * sinc;
+}
+
+enum { kModeHP = 0, kModeIR = 1, kModeLP = 2 };
+
+struct ConvArgs {
+  const float* in; int64_t in_stride;   // [B][T]
+  float* out;                            // [B][T] contiguous
+  const float* ir; int ir_stride;        // kModeIR
+  const AugQ* q; AugS* st;
+  int T; uint32_t bit; int which;        // which FIR (1 or 3) / which stats slot (0 = a, 1 = b, 2 = v)
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(FT, 1) fftconv_kernel(const ConvArgs a, const float2* __restrict__ tw_g) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* buf = reinterpret_cast<float2*>(smem_raw);
+  float2* tw = buf + FPAD;
+  float* red = reinterpret_cast<float*>(tw + 1024);
+  const int tid = threadIdx.x, qi = blockIdx.y, blk = blockIdx.x;
+  const AugQ q = a.q[qi];
+  const float* in = a.in + (int64_t)qi * a.in_stride;
+  float* out = a.out + (int64_t)qi * a.T;
+  const int T = a.T;
+  float vmax = 0.f, vss = 0.f;
+
+  if (!(q.apply & a.bit)) {
+    // transform not applied to this query: pass the samples through, still report statistics
+    for (int n = blk * FN + tid; n < min(T, (blk + 1) * FN); n += FT) {
+      const float v = in[n];
+      out[n] = v;
+      vmax = fmaxf(vmax, fabsf(v));
+      vss += v * v;
+    }
+  } else {
+    int K, lead, half = 0;
+    float c2 = 0.f, argscale = 0.f;
+    if (MODE == kModeIR) {
+      K = q.ir_len; lead = K - 1;
+    } else {
+      half = a.which == 1 ? q.half1 : (a.which == 2 ? q.half2 : q.half3);
+      c2 = a.which == 1 ? q.c1x2 : (a.which == 2 ? q.c2x2 : q.c3x2);
+      argscale = a.which == 1 ? q.arg1 : (a.which == 2 ? q.arg2 : q.arg3);
+      K = 2 * half + 1; lead = half;
+    }
+    const int V = FN - K + 1;
+    const int n_total = MODE == kModeIR ? T + K - 1 : T;
+    const int n0 = blk * V;
+    if (n0 >= n_total) return;  // block-uniform
+    for (int i = tid; i < 1024; i += FT) tw[i] = tw_g[i];
+    const float* ir = MODE == kModeIR ? a.ir + (int64_t)qi * a.ir_stride : nullptr;
+    float hs = 0.f;
+    for (int i = tid; i < FN; i += FT) {
+      const int n = n0 - lead + i;
+      float x, h = 0.f;
+      if (MODE == kModeIR) {
+        x = (n >= 0 && n < T) ? in[n] : 0.f;                      // zero extension
+        if (i < K) h = ir[i];
+      } else {
+        x = in[min(max(n, 0), T - 1)];                            // replicate padding (julius)
+        if (i < K) { h = fir_tap(i, half, c2, argscale); hs += h; }
+      }
+      buf[pidx(i)] = make_float2(x, h);
+    }
+    float scale = 1.0f / (float)FN;
+    if (MODE != kModeIR) scale /= block_sum(hs, red, tid);         // taps are normalised to sum 1
+    __syncthreads();
+    fft_forward(buf, tw, tid);
+    // Z = X + iH  ->  Y = X.H = (Z1^2 - conj(Z2)^2) / (4i), Z1 = Z[k], Z2 = Z[N-k]
+    for (int k = tid; k <= FN / 2; k += FT) {
+      const int p1 = pidx(rev_pos(k)), p2 = pidx(rev_pos((FN - k) & (FN - 1)));
+      const float2 z1 = buf[p1], z2 = buf[p2];
+      const float2 c = make_float2(z2.x, -z2.y);
+      const float2 d = csub(cmul(z1, z1), cmul(c, c));
+      const float2 y = make_float2(0.25f * d.y, -0.25f * d.x);    // d / (4i)
+      buf[p1] = y;
+      if (p2 != p1) buf[p2] = make_float2(y.x, -y.y);
+    }
+    __syncthreads();
+    fft_inverse(buf, tw, tid);
+    const int n_end = min(n_total, n0 + V);
+    for (int n = n0 + tid; n < n_end; n += FT) {
+      const float c = buf[pidx(n - n0 + K - 1)].x * scale;
+      float v;
+      if (MODE == kModeHP) v = in[n] - c; else v = c;
+      vmax = fmaxf(vmax, fabsf(v));
+      if (n < T) { out[n] = v; vss += v * v; }
+    }
+  }
+  vmax = block_max(vmax, red, tid);
+  vss = block_sum(vss, red, tid);
+  if (tid == 0) {
+    AugS* s = a.st + qi;
+    if (MODE == kModeHP && a.which == 1) { atomic_max_pos(&s->max_a, vmax); atomicAdd(&s->ss_a, (double)vss); }
+    else if (MODE == kModeIR) { atomic_max_pos(&s->max_b, vmax); atomicAdd(&s->ss_b, (double)vss); }
+    else if (MODE == kModeHP && a.which == 3) atomic_max_pos(&s->max_v, vmax);
+  }
+}
+
+// stage 3: z = in/peak_b + (rms/10^(snr/20)) * noise ; statistics: peak of z
+__global__ void __launch_bounds__(256) mix_kernel(const float* __restrict__ in, const float* __restrict__ noise,
+                                                  float* __restrict__ z, const AugQ* __restrict__ qs, AugS* st, int T) {
+  __shared__ float red[8];
+  const int qi = blockIdx.y, tid = threadIdx.x;
+  const AugQ q = qs[qi];
+  AugS* s = st + qi;
+  const bool ir_on = q.apply & MFPA_AUG_IR, nz_on = q.apply & MFPA_AUG_NOISE;
+  const float peak = ir_on ? s->max_b : 1.f;
+  // calculate_rms of the (already peak-normalised) stage-2 output: sqrt(mean(x^2)) (utils.py:23-29)
+  const float rms = sqrtf((float)(s->ss_b / (double)T)) / peak;
+  const float ns = nz_on ? rms / q.snr_div : 0.f;
+  float vmax = 0.f;
+  const int64_t row = (int64_t)qi * T;
+  for (int n = blockIdx.x * blockDim.x * 4 + tid * 4; n < T; n += gridDim.x * blockDim.x * 4) {
+    if (n + 3 < T && ((row + n) & 3) == 0) {
+      float4 v = *reinterpret_cast<const float4*>(in + row + n);
+      if (ir_on) { v.x /= peak; v.y /= peak; v.z /= peak; v.w /= peak; }
+      if (nz_on) {
+        const float4 b = *reinterpret_cast<const float4*>(noise + row + n);
+        v.x += ns * b.x; v.y += ns * b.y; v.z += ns * b.z; v.w += ns * b.w;
+      }
+      *reinterpret_cast<float4*>(z + row + n) = v;
+      vmax = fmaxf(fmaxf(vmax, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+    } else {
+      for (int m = n; m < min(n + 4, T); ++m) {
+        float v = in[row + m];
+        if (ir_on) v /= peak;
+        if (nz_on) v += ns * noise[row + m];
+        z[row + m] = v;
+        vmax = fmaxf(vmax, fabsf(v));
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+  if ((tid & 31) == 0) red[tid >> 5] = vmax;
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < 8; ++w) vmax = fmaxf(vmax, red[w]);
+    atomic_max_pos(&s->max_z, vmax);
+  }
+}
+
+// ---- stage 4: clip thresholds by exact radix select (torch.quantile, linear interpolation) ----
+__device__ __forceinline__ unsigned order_key(float v) {
+  const unsigned u = __float_as_uint(v);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_value(unsigned k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+constexpr int kSelThreads = 1024;
+
+// One block per query.  Finds sorted[r] for two ranks at once, 8 bits per pass, then one more pass
+// for the successors sorted[r+1].
+__global__ void __launch_bounds__(kSelThreads) clip_select_kernel(const float* __restrict__ z_all, const AugQ* __restrict__ qs,
+                                                                  AugS* st, int T) {
+  __shared__ unsigned hist[2][256];
+  __shared__ unsigned sel_prefix[2], sel_rank[2];
+  __shared__ unsigned cnt_le[2], min_gt[2];
+  const int qi = blockIdx.x, tid = threadIdx.x;
+  const AugQ q = qs[qi];
+  AugS* s = st + qi;
+  if (!(q.apply & MFPA_AUG_CLIP)) {
+    if (tid == 0) { s->lo = -INFINITY; s->hi = INFINITY; }
+    return;
+  }
+  const float* z = z_all + (int64_t)qi * T;
+  // torch.quantile: rank = q * (n - 1) in float32, lo = floor(rank)
+  const float q_hi = 1.0f - q.q_lo;
+  const float pos[2] = {q.q_lo * (float)(T - 1), q_hi * (float)(T - 1)};
+  const int r0[2] = {min((int)floorf(pos[0]), T - 1), min((int)floorf(pos[1]), T - 1)};
+  if (tid < 2) { sel_prefix[tid] = 0; sel_rank[tid] = (unsigned)r0[tid]; }
+  __syncthreads();
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    for (int i = tid; i < 512; i += kSelThreads) hist[i >> 8][i & 255] = 0;
+    __syncthreads();
+    const unsigned pre0 = sel_prefix[0], pre1 = sel_prefix[1];
+    const unsigned himask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+    for (int n = tid; n < T; n += kSelThreads) {
+      const unsigned k = order_key(z[n]);
+      const unsigned d = (k >> shift) & 255u;
+      const bool m0 = (k & himask) == pre0, m1 = (k & himask) == pre1;
+      // warp-aggregated shared-memory atomics: audio samples share their leading bits
+      const unsigned active = __activemask();
+      const unsigned code = (m0 ? 0x100u : 0u) | (m1 ? 0x200u : 0u) | d;
+      const unsigned peers = __match_any_sync(active, code);
+      if ((int)(__ffs(peers) - 1) == (tid & 31)) {
+        const unsigned c = __popc(peers);
+        if (m0) atomicAdd(&hist[0][d], c);
+        if (m1) atomicAdd(&hist[1][d], c);
+      }
+    }
+    __syncthreads();
+    if (tid < 2) {
+      unsigned r = sel_rank[tid], acc = 0;
+      int d = 0;
+      for (; d < 256; ++d) {
+        const unsigned c = hist[tid][d];
+        if (acc + c > r) break;
+        acc += c;
+      }
+      sel_rank[tid] = r - acc;
+      sel_prefix[tid] |= (unsigned)d << shift;
+    }
+    __syncthreads();
+  }
+  const unsigned k0 = sel_prefix[0], k1 = sel_prefix[1];
+  if (tid < 2) { cnt_le[tid] = 0; min_gt[tid] = 0xffffffffu; }
+  __syncthreads();
+  unsigned c0 = 0, c1 = 0, g0 = 0xffffffffu, g1 = 0xffffffffu;
+  for (int n = tid; n < T; n += kSelThreads) {
+    const unsigned k = order_key(z[n]);
+    if (k <= k0) ++c0; else g0 = min(g0, k);
+    if (k <= k1) ++c1; else g1 = min(g1, k);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    c0 += __shfl_xor_sync(0xffffffffu, c0, o); c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+    g0 = min(g0, __shfl_xor_sync(0xffffffffu, g0, o)); g1 = min(g1, __shfl_xor_sync(0xffffffffu, g1, o));
+  }
+  if ((tid & 31) == 0) {
+    atomicAdd(&cnt_le[0], c0); atomicAdd(&cnt_le[1], c1);
+    atomicMin(&min_gt[0], g0); atomicMin(&min_gt[1], g1);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    // elementwise map into the gained domain, monotone so the order statistics carry over
+    const bool nz_on = q.apply & MFPA_AUG_NOISE;
+    const float peak = nz_on ? s->max_z : 1.f;
+    const float g = (q.apply & MFPA_AUG_GAIN) ? q.gain : 1.f;
+    float thr[2];
+    for (int i = 0; i < 2; ++i) {
+      const unsigned ka = i ? k1 : k0;
+      const float va = key_value(ka);
+      const bool same = cnt_le[i] >= (unsigned)r0[i] + 2u || r0[i] + 1 > T - 1;
+      const float vb = same ? va : key_value(min_gt[i]);
+      const float fa = (nz_on ? va / peak : va) * g, fb = (nz_on ? vb / peak : vb) * g;
+      const float w = pos[i] - (float)r0[i];
+      thr[i] = fa + (fb - fa) * w;
+    }
+    s->lo = thr[0];
+    s->hi = thr[1];
+  }
+}
+
+// stage 3b-5: w = clamp((z/peak_z)*gain, lo, hi); u = lowpass(w) with a short FIR (direct form)
+constexpr int kLpMaxHalf = 64;
+__global__ void __launch_bounds__(256) clip_lpf_kernel(const float* __restrict__ z_all, float* __restrict__ u_all,
+                                                       const AugQ* __restrict__ qs, const AugS* __restrict__ st, int T,
+                                                       int materialise_only) {
+  __shared__ float taps[2 * kLpMaxHalf + 1];
+  __shared__ float tile[1024 + 2 * kLpMaxHalf];
+  __shared__ float red[8];
+  const int qi = blockIdx.y, tid = threadIdx.x;
+  const AugQ q = qs[qi];
+  const AugS s = st[qi];
+  const bool nz_on = q.apply & MFPA_AUG_NOISE;
+  const float peak = nz_on ? s.max_z : 1.f;
+  const float g = (q.apply & MFPA_AUG_GAIN) ? q.gain : 1.f;
+  const bool lp_on = (q.apply & MFPA_AUG_LPF) && !materialise_only;
+  const int half = lp_on ? q.half2 : 0;
+  const float* z = z_all + (int64_t)qi * T;
+  float* u = u_all + (int64_t)qi * T;
+  float hsum = 1.f;
+  if (lp_on) {
+    float hs = 0.f;
+    for (int i = tid; i < 2 * half + 1; i += 256) { const float h = fir_tap(i, half, q.c2x2, q.arg2); taps[i] = h; hs += h; }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) hs += __shfl_xor_sync(0xffffffffu, hs, o);
+    if ((tid & 31) == 0) red[tid >> 5] = hs;
+    __syncthreads();
+    hsum = 0.f;
+    for (int w = 0; w < 8; ++w) hsum += red[w];
+  }
+  const float inv = 1.0f / hsum;
+  for (int n0 = blockIdx.x * 1024; n0 < T; n0 += gridDim.x * 1024) {
+    __syncthreads();
+    for (int i = tid; i < 1024 + 2 * half; i += 256) {
+      const int n = min(max(n0 - half + i, 0), T - 1);
+      float v = z[n];
+      if (nz_on) v /= peak;
+      v *= g;
+      tile[i] = fminf(fmaxf(v, s.lo), s.hi);
+    }
+    __syncthreads();
+    for (int i = tid; i < 1024 && n0 + i < T; i += 256) {
+      float acc;
+      if (lp_on) {
+        acc = 0.f;
+        for (int k = 0; k <= 2 * half; ++k) acc += taps[k] * tile[i + k];
+        acc *= inv;
+      } else {
+        acc = tile[i];
+      }
+      u[n0 + i] = acc;
+    }
+  }
+}
+
+// stage 7 (or a plain copy when final_norm is off / the peak is 0)
+__global__ void __launch_bounds__(256) norm_kernel(const float* __restrict__ v, float* __restrict__ out,
+                                                   const AugS* __restrict__ st, int T, int normalise) {
+  const int qi = blockIdx.y;
+  const float peak = st[qi].max_v;
+  const bool on = normalise && peak > 0.f;
+  const int64_t row = (int64_t)qi * T;
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < T; n += gridDim.x * blockDim.x) {
+    const float x = v[row + n];
+    out[row + n] = on ? x / peak : x;
+  }
+}
+
+}  // namespace
+
+static int aug_init_tables(mfpa_ctx* ctx) {
+  if (ctx->aug_tw_dev) return MFPA_OK;
+  static float2 tw[1024];
+  const double pi = 3.14159265358979323846;
+  for (int e = 0; e < 1024; ++e) tw[e] = make_float2((float)cos(2 * pi * e / FN), (float)-sin(2 * pi * e / FN));
+  MFPA_CUDA(cudaMalloc(&ctx->aug_tw_dev, sizeof(tw)));
+  MFPA_CUDA(cudaMemcpy(ctx->aug_tw_dev, tw, sizeof(tw), cudaMemcpyHostToDevice));
+  MFPA_CUDA(cudaFuncSetAttribute(fftconv_kernel<kModeHP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmem));
+  MFPA_CUDA(cudaFuncSetAttribute(fftconv_kernel<kModeIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmem));
+  MFPA_CUDA(cudaFuncSetAttribute(fftconv_kernel<kModeLP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmem));
+  return MFPA_OK;
+}
+
+// julius: half = int(zeros / cutoff / 2) with zeros = 8, cutoff = float32(fc) / float32(sr) as a Python float
+static int fir_half(float fc_hz, int sample_rate, const char* name, int qi, double* cutoff_out) {
+  const double c = (double)(fc_hz / (float)sample_rate);
+  if (!(c > 0.0) || c > 0.5) {
+    set_error("augment: query %d: %s cut-off %g Hz is outside (0, sr/2] - the reference raises ValueError "
+              "(pass_filters.py:103-110)", qi, name, (double)fc_hz);
+    return -1;
+  }
+  *cutoff_out = c;
+  const double h = 8.0 / c / 2.0;
+  if (h > 1e9) return 1 << 30;
+  return (int)h;
+}
+
+int launch_augment(mfpa_ctx* ctx, const float* x, int B, int T, int64_t x_stride, int sample_rate,
+                   const mfpa_aug_params* pp, const float* ir, int ir_stride, const float* noise, float* out,
+                   bool final_norm, cudaStream_t st) {
+  if (int e = aug_init_tables(ctx)) return e;
+  // ---- derive per-query parameters on the host
+  const size_t need = sizeof(AugQ) * (size_t)B;
+  if (ctx->aug_pinned_bytes < need) {
+    if (ctx->aug_pinned) cudaFreeHost(ctx->aug_pinned);
+    ctx->aug_pinned = nullptr;
+    ctx->aug_pinned_bytes = need + need / 4;
+    MFPA_CUDA(cudaMallocHost(&ctx->aug_pinned, ctx->aug_pinned_bytes));
+  }
+  AugQ* hq = (AugQ*)ctx->aug_pinned;
+  int min_v1 = FN, min_v3 = FN, min_vir = FN, max_half2 = 0;
+  bool any_long_lp = false;
+  for (int i = 0; i < B; ++i) {
+    const mfpa_aug_params& p = pp[i];
+    AugQ q{};
+    q.apply = p.apply;
+    double c;
+    if (p.apply & MFPA_AUG_HPF1) {
+      q.half1 = fir_half(p.fc1_hz, sample_rate, "loudspeaker high-pass", i, &c);
+      if (q.half1 < 0) return MFPA_EINVAL;
+      MFPA_REQUIRE(2 * (int64_t)q.half1 + 1 <= MFPA_AUG_MAX_TAPS, "augment: query %d: high-pass cut-off %g Hz needs %lld taps "
+                   "(limit %d)", i, (double)p.fc1_hz, 2ll * q.half1 + 1, MFPA_AUG_MAX_TAPS);
+      q.c1x2 = (float)(2.0 * c); q.arg1 = (float)(2.0 * c * 3.14159265358979323846);
+      min_v1 = FN - 2 * q.half1 < min_v1 ? FN - 2 * q.half1 : min_v1;
+    }
+    if (p.apply & MFPA_AUG_LPF) {
+      q.half2 = fir_half(p.fc2_hz, sample_rate, "low-pass", i, &c);
+      if (q.half2 < 0) return MFPA_EINVAL;
+      MFPA_REQUIRE(2 * (int64_t)q.half2 + 1 <= MFPA_AUG_MAX_TAPS, "augment: query %d: low-pass cut-off %g Hz needs %lld taps "
+                   "(limit %d)", i, (double)p.fc2_hz, 2ll * q.half2 + 1, MFPA_AUG_MAX_TAPS);
+      q.c2x2 = (float)(2.0 * c); q.arg2 = (float)(2.0 * c * 3.14159265358979323846);
+      if (q.half2 > kLpMaxHalf) any_long_lp = true;
+      max_half2 = q.half2 > max_half2 ? q.half2 : max_half2;
+    }
+    if (p.apply & MFPA_AUG_HPF3) {
+      q.half3 = fir_half(p.fc3_hz, sample_rate, "microphone high-pass", i, &c);
+      if (q.half3 < 0) return MFPA_EINVAL;
+      MFPA_REQUIRE(2 * (int64_t)q.half3 + 1 <= MFPA_AUG_MAX_TAPS, "augment: query %d: high-pass cut-off %g Hz needs %lld taps "
+                   "(limit %d)", i, (double)p.fc3_hz, 2ll * q.half3 + 1, MFPA_AUG_MAX_TAPS);
+      q.c3x2 = (float)(2.0 * c); q.arg3 = (float)(2.0 * c * 3.14159265358979323846);
+      min_v3 = FN - 2 * q.half3 < min_v3 ? FN - 2 * q.half3 : min_v3;
+    }
+    if (p.apply & MFPA_AUG_IR) {
+      MFPA_REQUIRE(ir != nullptr, "augment: query %d applies an impulse response but ir_dev is NULL", i);
+      MFPA_REQUIRE(p.ir_len >= 1 && p.ir_len <= ir_stride && p.ir_len <= MFPA_AUG_MAX_IR,
+                   "augment: query %d: ir_len %d not in [1, min(ir_stride %d, %d)]", i, p.ir_len, ir_stride, MFPA_AUG_MAX_IR);
+      q.ir_len = p.ir_len;
+      min_vir = FN - p.ir_len + 1 < min_vir ? FN - p.ir_len + 1 : min_vir;
+    }
+    if (p.apply & MFPA_AUG_NOISE) MFPA_REQUIRE(noise != nullptr, "augment: query %d mixes noise but noise_dev is NULL", i);
+    q.snr_div = powf(10.0f, p.snr_db / 20.0f);
+    q.gain = p.gain_factor;
+    q.q_lo = p.clip_p / 2.0f;
+    hq[i] = q;
+  }
+  MFPA_REQUIRE(noise == nullptr || ((uintptr_t)noise & 15) == 0, "augment: noise_dev must be 16-byte aligned");
+  const size_t rows = sizeof(float) * (size_t)B * T;
+  if (ctx->aug_a.reserve(rows) || ctx->aug_b.reserve(rows)) return MFPA_ENOMEM;
+  if (ctx->aug_small.reserve((sizeof(AugQ) + sizeof(AugS)) * (size_t)B)) return MFPA_ENOMEM;
+  float* bufA = (float*)ctx->aug_a.ptr;
+  float* bufB = (float*)ctx->aug_b.ptr;
+  AugQ* dq = (AugQ*)ctx->aug_small.ptr;
+  AugS* ds = (AugS*)(dq + B);
+  MFPA_CUDA(cudaMemcpyAsync(dq, hq, sizeof(AugQ) * (size_t)B, cudaMemcpyHostToDevice, st));
+  MFPA_CUDA(cudaMemsetAsync(ds, 0, sizeof(AugS) * (size_t)B, st));
+
+  auto blocks_for = [&](int n_total, int min_v) { return (unsigned)((n_total + min_v - 1) / min_v); };
+  // stage 1: x -> A
+  {
+    ConvArgs a{x, x_stride, bufA, nullptr, 0, dq, ds, T, MFPA_AUG_HPF1, 1};
+    fftconv_kernel<kModeHP><<<dim3(blocks_for(T, min_v1), B), FT, kConvSmem, st>>>(a, ctx->aug_tw_dev);
+    MFPA_CUDA(cudaGetLastError());
+  }
+  // stage 2: A -> B
+  {
+    ConvArgs a{bufA, T, bufB, ir, ir_stride, dq, ds, T, MFPA_AUG_IR, 0};
+    fftconv_kernel<kModeIR><<<dim3(blocks_for(T + FN - min_vir, min_vir), B), FT, kConvSmem, st>>>(a, ctx->aug_tw_dev);
+    MFPA_CUDA(cudaGetLastError());
+  }
+  // stage 3: B -> A (z)
+  {
+    const unsigned gx = (unsigned)((T + 4095) / 4096);
+    mix_kernel<<<dim3(gx, B), 256, 0, st>>>(bufB, noise, bufA, dq, ds, T);
+    MFPA_CUDA(cudaGetLastError());
+  }
+  // stage 4: clip thresholds from z
+  clip_select_kernel<<<B, kSelThreads, 0, st>>>(bufA, dq, ds, T);
+  MFPA_CUDA(cudaGetLastError());
+  // stage 5: A -> B (u)
+  {
+    const unsigned gx = (unsigned)((T + 4095) / 4096);
+    if (!any_long_lp) {
+      clip_lpf_kernel<<<dim3(gx, B), 256, 0, st>>>(bufA, bufB, dq, ds, T, 0);
+      MFPA_CUDA(cudaGetLastError());
+    } else {
+      // a low cut-off makes the "low-pass" FIR long: materialise the clipped signal, then FFT-convolve
+      if (ctx->aug_c.reserve(rows)) return MFPA_ENOMEM;
+      float* bufC = (float*)ctx->aug_c.ptr;
+      clip_lpf_kernel<<<dim3(gx, B), 256, 0, st>>>(bufA, bufC, dq, ds, T, 1);
+      MFPA_CUDA(cudaGetLastError());
+      ConvArgs a{bufC, T, bufB, nullptr, 0, dq, ds, T, MFPA_AUG_LPF, 2};
+      fftconv_kernel<kModeLP><<<dim3(blocks_for(T, FN - 2 * max_half2), B), FT, kConvSmem, st>>>(a, ctx->aug_tw_dev);
+      MFPA_CUDA(cudaGetLastError());
+    }
+  }
+  // stage 6: B -> A (v) ; stage 7: A -> out
+  {
+    ConvArgs a{bufB, T, bufA, nullptr, 0, dq, ds, T, MFPA_AUG_HPF3, 3};
+    fftconv_kernel<kModeHP><<<dim3(blocks_for(T, min_v3), B), FT, kConvSmem, st>>>(a, ctx->aug_tw_dev);
+    MFPA_CUDA(cudaGetLastError());
+    const unsigned gx = (unsigned)((T + 4095) / 4096);
+    norm_kernel<<<dim3(gx, B), 256, 0, st>>>(bufA, out, ds, T, final_norm ? 1 : 0);
+    MFPA_CUDA(cudaGetLastError());
+  }
+  return MFPA_OK;
+}
+
+}  // namespace mfpa

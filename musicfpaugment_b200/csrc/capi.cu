@@ -152,6 +152,8 @@ void mfpa_destroy(mfpa_ctx* ctx) {
   if (ctx->index_counts) cudaFree(ctx->index_counts);
   if (ctx->index_hashesperid) cudaFree(ctx->index_hashesperid);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->aug_pinned) cudaFreeHost(ctx->aug_pinned);
+  if (ctx->aug_tw_dev) cudaFree(ctx->aug_tw_dev);
   delete ctx;
 }
 
@@ -351,6 +353,154 @@ int mfpa_fingerprint_host(mfpa_ctx* ctx, const float* x_host, int B, int T, int 
   if (overflow) {
     set_error("fingerprint_host: %lld rows produced, capacity %lld", (long long)total, (long long)rows_cap);
     return MFPA_ECAP;
+  }
+  return MFPA_OK;
+}
+
+static int check_augment(mfpa_ctx* ctx, const float* x_dev, int B, int T, int64_t x_stride, int sample_rate,
+                         const mfpa_aug_params* params_host) {
+  MFPA_REQUIRE(ctx && x_dev && params_host, "augment: NULL argument");
+  MFPA_REQUIRE(B >= 1 && T >= 2, "augment: batch %d, n_samples %d", B, T);
+  MFPA_REQUIRE(x_stride >= T, "augment: row stride %lld < n_samples %d", (long long)x_stride, T);
+  MFPA_REQUIRE(sample_rate > 0, "augment: sample_rate %d", sample_rate);
+  return MFPA_OK;
+}
+
+int mfpa_augment(mfpa_ctx* ctx, const float* x_dev, int B, int T, int64_t x_stride, int sample_rate,
+                 const mfpa_aug_params* params_host, const float* ir_dev, int ir_stride,
+                 const float* noise_dev, float* out_dev, void* stream) {
+  if (int e = check_augment(ctx, x_dev, B, T, x_stride, sample_rate, params_host)) return e;
+  MFPA_REQUIRE(out_dev != nullptr, "augment: out_dev is NULL");
+  DeviceGuard guard(ctx->device);
+  return launch_augment(ctx, x_dev, B, T, x_stride, sample_rate, params_host, ir_dev, ir_stride, noise_dev, out_dev,
+                        true, (cudaStream_t)stream);
+}
+
+int mfpa_augment_fingerprint(mfpa_ctx* ctx, const float* x_dev, int B, int T, int64_t x_stride, int sample_rate,
+                             const mfpa_aug_params* params_host, const float* ir_dev, int ir_stride,
+                             const float* noise_dev, int shifts, const mfpa_afp_params* p,
+                             int32_t* hashes_dev, int cap, int32_t* nh_dev, void* stream) {
+  if (int e = check_augment(ctx, x_dev, B, T, x_stride, sample_rate, params_host)) return e;
+  DeviceGuard guard(ctx->device);
+  if (ctx->aug_d.reserve(sizeof(float) * (size_t)B * T)) return MFPA_ENOMEM;
+  float* y = (float*)ctx->aug_d.ptr;
+  if (int e = launch_augment(ctx, x_dev, B, T, x_stride, sample_rate, params_host, ir_dev, ir_stride, noise_dev, y,
+                             false, (cudaStream_t)stream)) return e;
+  return mfpa_fingerprint(ctx, y, B, T, T, shifts, p, hashes_dev, cap, nh_dev, stream);
+}
+
+void mfpa_match_defaults(mfpa_match_params* p) {
+  p->window = 2; p->threshcount = 5; p->search_depth = 100; p->max_alignments_per_id = 100;
+}
+
+static int check_match(mfpa_ctx* ctx, const mfpa_match_params* p) {
+  MFPA_REQUIRE(ctx != nullptr, "match: ctx is NULL");
+  MFPA_REQUIRE(ctx->index_table != nullptr, "match: no index loaded (mfpa_index_load)");
+  if (p) {
+    MFPA_REQUIRE(p->search_depth >= 1 && p->search_depth <= 128, "match: search_depth %d not in 1..128", p->search_depth);
+    MFPA_REQUIRE(p->window >= 0 && p->threshcount >= 0 && p->max_alignments_per_id >= 0, "match: negative parameter");
+  }
+  return MFPA_OK;
+}
+
+int mfpa_index_load(mfpa_ctx* ctx, const uint32_t* table_host, const int32_t* counts_host, int hash_lo, int n_buckets,
+                    int depth, int hashbits, int maxtimebits, const uint32_t* hashesperid_host, int n_tracks) {
+  MFPA_REQUIRE(ctx && table_host && counts_host && hashesperid_host, "index_load: NULL argument");
+  MFPA_REQUIRE(hashbits >= 1 && hashbits <= 30 && maxtimebits >= 1 && maxtimebits <= 15, "index_load: hashbits %d / maxtimebits %d", hashbits, maxtimebits);
+  MFPA_REQUIRE(hash_lo >= 0 && n_buckets >= 1 && hash_lo + (int64_t)n_buckets <= (1ll << hashbits), "index_load: bad hash range");
+  MFPA_REQUIRE(depth >= 1 && n_tracks >= 1 && (int64_t)n_tracks + 1 < (1ll << (32 - maxtimebits)), "index_load: depth %d / n_tracks %d", depth, n_tracks);
+  DeviceGuard guard(ctx->device);
+  if (ctx->index_table) cudaFree(ctx->index_table);
+  if (ctx->index_counts) cudaFree(ctx->index_counts);
+  if (ctx->index_hashesperid) cudaFree(ctx->index_hashesperid);
+  ctx->index_table = nullptr; ctx->index_counts = nullptr; ctx->index_hashesperid = nullptr;
+  const size_t tb = sizeof(uint32_t) * (size_t)n_buckets * depth;
+  MFPA_CUDA(cudaMalloc(&ctx->index_table, tb));
+  MFPA_CUDA(cudaMalloc(&ctx->index_counts, sizeof(int32_t) * (size_t)n_buckets));
+  MFPA_CUDA(cudaMalloc(&ctx->index_hashesperid, sizeof(uint32_t) * (size_t)n_tracks));
+  MFPA_CUDA(cudaMemcpy(ctx->index_table, table_host, tb, cudaMemcpyHostToDevice));
+  MFPA_CUDA(cudaMemcpy(ctx->index_counts, counts_host, sizeof(int32_t) * (size_t)n_buckets, cudaMemcpyHostToDevice));
+  MFPA_CUDA(cudaMemcpy(ctx->index_hashesperid, hashesperid_host, sizeof(uint32_t) * (size_t)n_tracks, cudaMemcpyHostToDevice));
+  ctx->index_hash_lo = hash_lo; ctx->index_hash_hi = hash_lo + n_buckets; ctx->index_depth = depth;
+  ctx->index_ntracks = n_tracks; ctx->index_maxtimebits = maxtimebits; ctx->index_hashmask = (1 << hashbits) - 1;
+  return MFPA_OK;
+}
+
+int mfpa_get_hits(mfpa_ctx* ctx, const int32_t* hashes_dev, int n, int32_t* hits_dev, int64_t hits_cap,
+                  int64_t* nhits_dev, void* stream) {
+  if (int e = check_match(ctx, nullptr)) return e;
+  MFPA_REQUIRE(hashes_dev && hits_dev && nhits_dev && n >= 0 && hits_cap >= 0, "get_hits: bad argument");
+  MFPA_REQUIRE(((uintptr_t)hits_dev & 15) == 0, "get_hits: hits_dev must be 16-byte aligned");
+  DeviceGuard guard(ctx->device);
+  return launch_get_hits(ctx, hashes_dev, n, hits_dev, hits_cap, nhits_dev, (cudaStream_t)stream);
+}
+
+int mfpa_match_counts(mfpa_ctx* ctx, const int32_t* hashes_dev, const int32_t* nh_dev, int B, int cap,
+                      int32_t* counts_dev, void* stream) {
+  if (int e = check_match(ctx, nullptr)) return e;
+  MFPA_REQUIRE(hashes_dev && nh_dev && counts_dev && B >= 1 && cap >= 1, "match_counts: bad argument");
+  DeviceGuard guard(ctx->device);
+  return launch_match_counts(ctx, hashes_dev, nh_dev, B, cap, counts_dev, (cudaStream_t)stream);
+}
+
+int mfpa_match_select(mfpa_ctx* ctx, const int32_t* counts_dev, int B, const mfpa_match_params* p,
+                      int32_t* cand_dev, int32_t* ncand_dev, void* stream) {
+  if (int e = check_match(ctx, p)) return e;
+  MFPA_REQUIRE(p && counts_dev && cand_dev && ncand_dev && B >= 1, "match_select: bad argument");
+  DeviceGuard guard(ctx->device);
+  return launch_match_select(ctx, counts_dev, B, p->threshcount, p->search_depth, cand_dev, ncand_dev, (cudaStream_t)stream);
+}
+
+int mfpa_match_collect(mfpa_ctx* ctx, const int32_t* hashes_dev, const int32_t* nh_dev, int B, int cap,
+                       const int32_t* cand_dev, const int32_t* ncand_dev, const mfpa_match_params* p,
+                       uint32_t* list_dev, int list_cap, int32_t* nlist_dev, void* stream) {
+  if (int e = check_match(ctx, p)) return e;
+  MFPA_REQUIRE(p && hashes_dev && nh_dev && cand_dev && ncand_dev && list_dev && nlist_dev && B >= 1 && cap >= 1 && list_cap >= 1,
+               "match_collect: bad argument");
+  DeviceGuard guard(ctx->device);
+  return launch_match_collect(ctx, hashes_dev, nh_dev, B, cap, cand_dev, ncand_dev, p->search_depth, list_dev, list_cap,
+                              nlist_dev, (cudaStream_t)stream);
+}
+
+int mfpa_match_align(mfpa_ctx* ctx, const uint32_t* lists_dev, const int32_t* nlists_dev, int n_lists, int B,
+                     int list_cap, const int32_t* cand_dev, const int32_t* ncand_dev, const mfpa_match_params* p,
+                     int32_t* results_dev, int32_t* nrows_dev, int max_rows, void* stream) {
+  MFPA_REQUIRE(ctx && p && lists_dev && nlists_dev && cand_dev && ncand_dev && results_dev && nrows_dev, "match_align: NULL argument");
+  MFPA_REQUIRE(n_lists >= 1 && B >= 1 && list_cap >= 1 && max_rows >= 1, "match_align: bad sizes");
+  MFPA_REQUIRE(p->search_depth >= 1 && p->search_depth <= 128, "match_align: search_depth %d", p->search_depth);
+  DeviceGuard guard(ctx->device);
+  return launch_match_align(lists_dev, nlists_dev, n_lists, B, list_cap, cand_dev, ncand_dev, p->search_depth, p->window,
+                            p->threshcount, p->max_alignments_per_id, results_dev, nrows_dev, max_rows, (cudaStream_t)stream);
+}
+
+int mfpa_match(mfpa_ctx* ctx, const int32_t* hashes_dev, const int32_t* nh_dev, int B, int cap,
+               const mfpa_match_params* p, int32_t* results_dev, int32_t* nrows_dev, int max_rows, void* stream) {
+  if (int e = check_match(ctx, p)) return e;
+  MFPA_REQUIRE(p && hashes_dev && nh_dev && results_dev && nrows_dev && B >= 1 && cap >= 1 && max_rows >= 1, "match: bad argument");
+  DeviceGuard guard(ctx->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nt = ctx->index_ntracks;
+  int sub = (int)((int64_t)(256 << 20) / ((int64_t)nt * 4));  // ~256 MiB of dense counts per sub-batch
+  if (sub < 1) sub = 1;
+  if (sub > B) sub = B;
+  const int list_cap = 8192;
+  if (ctx->match_a.reserve(sizeof(int32_t) * (size_t)sub * nt)) return MFPA_ENOMEM;
+  if (ctx->match_b.reserve(sizeof(int32_t) * (size_t)sub * (2 * p->search_depth + 2))) return MFPA_ENOMEM;
+  if (ctx->match_c.reserve(sizeof(uint32_t) * (size_t)sub * list_cap)) return MFPA_ENOMEM;
+  int32_t* counts = (int32_t*)ctx->match_a.ptr;
+  int32_t* cand = (int32_t*)ctx->match_b.ptr;
+  int32_t* ncand = cand + (size_t)sub * 2 * p->search_depth;
+  int32_t* nlist = ncand + sub;
+  uint32_t* list = (uint32_t*)ctx->match_c.ptr;
+  for (int q0 = 0; q0 < B; q0 += sub) {
+    const int nq = B - q0 < sub ? B - q0 : sub;
+    const int32_t* hq = hashes_dev + (size_t)q0 * cap * 2;
+    if (int e = launch_match_counts(ctx, hq, nh_dev + q0, nq, cap, counts, st)) return e;
+    if (int e = launch_match_select(ctx, counts, nq, p->threshcount, p->search_depth, cand, ncand, st)) return e;
+    if (int e = launch_match_collect(ctx, hq, nh_dev + q0, nq, cap, cand, ncand, p->search_depth, list, list_cap, nlist, st)) return e;
+    if (int e = launch_match_align(list, nlist, 1, nq, list_cap, cand, ncand, p->search_depth, p->window, p->threshcount,
+                                   p->max_alignments_per_id, results_dev + (size_t)q0 * max_rows * 7, nrows_dev + q0,
+                                   max_rows, st)) return e;
   }
   return MFPA_OK;
 }

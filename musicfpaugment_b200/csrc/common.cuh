@@ -66,11 +66,15 @@ struct mfpa_ctx {
   mfpa::Scratch mag, qmax, rec, fwd, hashes, nh, misc, spec64, xin, out_h, out_n;
   // augmentation / matching state is appended by their translation units
   mfpa::Scratch aug_a, aug_b, aug_c, aug_d, aug_small;
+  float2* aug_tw_dev = nullptr;     // two-level twiddle tables of the 16384-point FFT (augment.cu)
+  void* aug_pinned = nullptr;
+  size_t aug_pinned_bytes = 0;
   // index shard (match.cu)
   uint32_t* index_table = nullptr;
   int32_t* index_counts = nullptr;
   uint32_t* index_hashesperid = nullptr;
   int index_hash_lo = 0, index_hash_hi = 0, index_depth = 0, index_ntracks = 0, index_maxtimebits = 14;
+  int index_hashmask = (1 << 20) - 1;
   mfpa::Scratch match_a, match_b, match_c;
   void* pinned = nullptr;
   size_t pinned_bytes = 0;
@@ -100,6 +104,21 @@ int launch_merge_shifts(const int32_t* hashes, const int32_t* nh, int B, int shi
                         int n_frames, int32_t* out, int cap_out, int32_t* nout, cudaStream_t st);
 int launch_compact_rows(const int32_t* rows_in, const int32_t* n, int items, int cap, int64_t* offsets,
                         int32_t* rows, int64_t rows_cap, cudaStream_t st);
+int launch_augment(mfpa_ctx* ctx, const float* x, int B, int T, int64_t x_stride, int sample_rate,
+                   const mfpa_aug_params* params_host, const float* ir, int ir_stride, const float* noise,
+                   float* out, bool final_norm, cudaStream_t st);
+int launch_match_counts(mfpa_ctx* ctx, const int32_t* hashes, const int32_t* nh, int B, int cap, int32_t* counts,
+                        cudaStream_t st);
+int launch_match_select(mfpa_ctx* ctx, const int32_t* counts, int B, int threshcount, int search_depth, int32_t* cand,
+                        int32_t* ncand, cudaStream_t st);
+int launch_match_collect(mfpa_ctx* ctx, const int32_t* hashes, const int32_t* nh, int B, int cap, const int32_t* cand,
+                         const int32_t* ncand, int search_depth, uint32_t* list, int list_cap, int32_t* nlist,
+                         cudaStream_t st);
+int launch_match_align(const uint32_t* lists, const int32_t* nlists, int n_lists, int B, int list_cap, const int32_t* cand,
+                       const int32_t* ncand, int search_depth, int window, int threshcount, int max_align,
+                       int32_t* results, int32_t* nrows, int max_rows, cudaStream_t st);
+int launch_get_hits(mfpa_ctx* ctx, const int32_t* hashes, int n, int32_t* hits, int64_t hits_cap, int64_t* nhits,
+                    cudaStream_t st);
 int stft_init_tables(mfpa_ctx* ctx);
 
 }  // namespace mfpa

@@ -1,0 +1,413 @@
+// S5 — landmark-hash matching against a hash-range shard of the reference index.
+// Replaces HashTable.get_hits (afp/audfprint/hash_table.py:220-246) and
+// Matcher.match_hashes (afp/audfprint/audfprint_match.py:102-129, 235-349).
+//
+// Index layout is the reference's own (hash_table.py:53-68): table[bucket][depth] uint32,
+// entry = ((id + 1) << maxtimebits) + time, counts[bucket] int32 (may exceed depth).
+// A context holds the buckets [hash_lo, hash_lo + n_buckets) only; queries are matched in
+// four steps so that the two reductions the algorithm needs can cross GPUs with plain
+// NCCL collectives between them:
+//   counts   per-(query, track) raw hit counts from the local buckets (shared-memory histogram,
+//            dense int32 row out)                        -> all-reduce(sum) across shards
+//   select   candidates: top min(#{raw > 5}, 100) by raw / hashesperid (:110-129)
+//   collect  (candidate, delta-t) of every local hit of a candidate -> all-gather across shards
+//   align    per candidate delta-t histogram, local-max modes > 5, +-window sum (:266-316), rows
+//            ordered by filtered count descending (:341)
+#include "common.cuh"
+
+namespace mfpa {
+
+namespace {
+
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kCountThreads = 512;
+constexpr int kMaxTracksSmem = 110000;  // packed 16-bit counters: 220 KB of shared memory
+constexpr int kAlignCap = 8192;         // hits of all candidates of one query that align_kernel can sort
+constexpr int kDtOff = 16384;
+
+struct IndexView {
+  const uint32_t* table;
+  const int32_t* counts;
+  const uint32_t* hashesperid;
+  int hash_lo, n_buckets, depth, maxtimebits, n_tracks, hashmask;
+};
+
+// ---- counts ------------------------------------------------------------------------------
+// One block per query.  Every query hash that falls in this shard contributes the first
+// min(depth, counts[h]) entries of its bucket (hash_table.py:235-236).  One warp per hash,
+// lanes stride the 400-byte bucket row.
+__global__ void __launch_bounds__(kCountThreads) match_counts_kernel(const IndexView ix, const int32_t* __restrict__ hashes,
+                                                                    const int32_t* __restrict__ nh, int cap,
+                                                                    int32_t* __restrict__ out) {
+  extern __shared__ unsigned hist[];  // two 16-bit counters per word
+  const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int words = (ix.n_tracks + 1) >> 1;
+  for (int i = tid; i < words; i += kCountThreads) hist[i] = 0;
+  __syncthreads();
+  const int2* rows = reinterpret_cast<const int2*>(hashes) + (int64_t)q * cap;
+  const int n = min(nh[q], cap);
+  for (int r = warp; r < n; r += kCountThreads / 32) {
+    const int h = (rows[r].y & ix.hashmask) - ix.hash_lo;
+    if (h < 0 || h >= ix.n_buckets) continue;  // warp-uniform
+    const int cnt = min(ix.depth, ix.counts[h]);
+    const uint32_t* bucket = ix.table + (int64_t)h * ix.depth;
+    for (int s = lane; s < cnt; s += 32) {
+      const int id = (int)(bucket[s] >> ix.maxtimebits) - 1;
+      if (id >= 0 && id < ix.n_tracks) atomicAdd(&hist[id >> 1], (id & 1) ? 0x10000u : 1u);
+    }
+  }
+  __syncthreads();
+  int32_t* o = out + (int64_t)q * ix.n_tracks;
+  for (int i = tid; i < ix.n_tracks; i += kCountThreads) o[i] = (int)((hist[i >> 1] >> ((i & 1) * 16)) & 0xffffu);
+}
+
+// Fallback for indexes with more tracks than the shared-memory histogram holds: atomics on the dense row.
+__global__ void __launch_bounds__(kCountThreads) match_counts_global_kernel(const IndexView ix, const int32_t* __restrict__ hashes,
+                                                                           const int32_t* __restrict__ nh, int cap,
+                                                                           int32_t* __restrict__ out) {
+  const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int32_t* o = out + (int64_t)q * ix.n_tracks;
+  const int2* rows = reinterpret_cast<const int2*>(hashes) + (int64_t)q * cap;
+  const int n = min(nh[q], cap);
+  for (int r = warp; r < n; r += kCountThreads / 32) {
+    const int h = (rows[r].y & ix.hashmask) - ix.hash_lo;
+    if (h < 0 || h >= ix.n_buckets) continue;
+    const int cnt = min(ix.depth, ix.counts[h]);
+    const uint32_t* bucket = ix.table + (int64_t)h * ix.depth;
+    for (int s = lane; s < cnt; s += 32) {
+      const int id = (int)(bucket[s] >> ix.maxtimebits) - 1;
+      if (id >= 0 && id < ix.n_tracks) atomicAdd(&o[id], 1);
+    }
+  }
+}
+
+// ---- select ------------------------------------------------------------------------------
+// Order of _best_count_ids: weighted count raw/hashesperid descending; ties -> higher id first
+// (what argsort(...)[::-1] gives for a stable sort; numpy's is unstable, ties are arbitrary there).
+struct Cand { long long raw; long long hp; int id; };
+__device__ __forceinline__ bool before(const Cand& a, const Cand& b) {  // a ranks ahead of b
+  const long long l = a.raw * b.hp, r = b.raw * a.hp;
+  return l > r || (l == r && a.id > b.id);
+}
+
+__global__ void __launch_bounds__(512) match_select_kernel(const int32_t* __restrict__ counts, const uint32_t* __restrict__ hpid,
+                                                           int n_tracks, int threshcount, int search_depth,
+                                                           int32_t* __restrict__ cand, int32_t* __restrict__ ncand) {
+  __shared__ int s_int[16];
+  __shared__ Cand s_best[16];
+  __shared__ Cand s_prev;
+  const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int32_t* c = counts + (int64_t)q * n_tracks;
+  int gt = 0;
+  for (int i = tid; i < n_tracks; i += 512) gt += c[i] > threshcount;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) gt += __shfl_xor_sync(kFull, gt, o);
+  if (lane == 0) s_int[warp] = gt;
+  __syncthreads();
+  gt = 0;
+  for (int w = 0; w < 16; ++w) gt += s_int[w];
+  const int depth = min(gt, search_depth);
+  if (tid == 0) { ncand[q] = depth; s_prev = Cand{1, 0, 0x7fffffff}; }  // +infinity sentinel (hp = 0)
+  __syncthreads();
+  for (int k = 0; k < depth; ++k) {
+    const Cand prev = s_prev;
+    Cand best{-1, 1, -1};
+    for (int i = tid; i < n_tracks; i += 512) {
+      const int raw = c[i];
+      if (raw <= 0) continue;
+      const Cand x{raw, (long long)hpid[i], i};
+      const bool after_prev = prev.hp == 0 || before(prev, x);
+      if (after_prev && (best.id < 0 || before(x, best))) best = x;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      Cand y;
+      y.raw = __shfl_xor_sync(kFull, best.raw, o); y.hp = __shfl_xor_sync(kFull, best.hp, o); y.id = __shfl_xor_sync(kFull, best.id, o);
+      if (y.id >= 0 && (best.id < 0 || before(y, best))) best = y;
+    }
+    if (lane == 0) s_best[warp] = best;
+    __syncthreads();
+    if (tid == 0) {
+      Cand b = s_best[0];
+      for (int w = 1; w < 16; ++w) if (s_best[w].id >= 0 && (b.id < 0 || before(s_best[w], b))) b = s_best[w];
+      s_prev = b;
+      cand[((int64_t)q * search_depth + k) * 2] = b.id;
+      cand[((int64_t)q * search_depth + k) * 2 + 1] = (int)b.raw;
+    }
+    __syncthreads();
+  }
+}
+
+// ---- collect -----------------------------------------------------------------------------
+// (candidate index << 16) | (t_ref - t_q + 16384) for every local hit of a candidate track.
+__global__ void __launch_bounds__(256) match_collect_kernel(const IndexView ix, const int32_t* __restrict__ hashes,
+                                                            const int32_t* __restrict__ nh, int cap,
+                                                            const int32_t* __restrict__ cand, const int32_t* __restrict__ ncand,
+                                                            int search_depth, uint32_t* __restrict__ list, int list_cap,
+                                                            int32_t* __restrict__ nlist) {
+  __shared__ int s_ids[128];
+  __shared__ int s_n;
+  const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nc = min(ncand[q], min(search_depth, 128));
+  for (int i = tid; i < nc; i += 256) s_ids[i] = cand[((int64_t)q * search_depth + i) * 2];
+  if (tid == 0) s_n = 0;
+  __syncthreads();
+  if (nc > 0) {
+    const int2* rows = reinterpret_cast<const int2*>(hashes) + (int64_t)q * cap;
+    uint32_t* out = list + (int64_t)q * list_cap;
+    const int n = min(nh[q], cap);
+    const uint32_t tmask = (1u << ix.maxtimebits) - 1u;
+    for (int r = warp; r < n; r += 8) {
+      const int2 row = rows[r];
+      const int h = (row.y & ix.hashmask) - ix.hash_lo;
+      if (h < 0 || h >= ix.n_buckets) continue;
+      const int cnt = min(ix.depth, ix.counts[h]);
+      const uint32_t* bucket = ix.table + (int64_t)h * ix.depth;
+      for (int s = lane; s < cnt; s += 32) {
+        const uint32_t v = bucket[s];
+        const int id = (int)(v >> ix.maxtimebits) - 1;
+        for (int k = 0; k < nc; ++k)
+          if (s_ids[k] == id) {
+            const int dt = (int)(v & tmask) - row.x;
+            const int pos = atomicAdd(&s_n, 1);
+            if (pos < list_cap) out[pos] = ((uint32_t)k << 16) | (uint32_t)(dt + kDtOff);
+            break;
+          }
+      }
+    }
+  }
+  __syncthreads();
+  if (tid == 0) nlist[q] = s_n;
+}
+
+// ---- align -------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) match_align_kernel(const uint32_t* __restrict__ lists, const int32_t* __restrict__ nlists,
+                                                          int n_lists, int B, int list_cap, const int32_t* __restrict__ cand,
+                                                          const int32_t* __restrict__ ncand, int search_depth, int window,
+                                                          int threshcount, int max_align, int32_t* __restrict__ results,
+                                                          int32_t* __restrict__ nrows, int max_rows) {
+  extern __shared__ uint32_t sm[];
+  uint32_t* keys = sm;                    // [kAlignCap] sorted hits
+  uint32_t* bin_key = sm + kAlignCap;     // [kAlignCap] run starts: key of each distinct (cand, dt)
+  int* bin_cnt = reinterpret_cast<int*>(sm + 2 * kAlignCap);  // [kAlignCap]
+  __shared__ int s_total, s_nbins, s_rows, s_seg[130];
+  const int q = blockIdx.x, tid = threadIdx.x;
+  const int nc = min(ncand[q], min(search_depth, 128));
+  if (tid == 0) { s_total = 0; s_rows = 0; }
+  __syncthreads();
+  // gather the per-shard lists
+  bool overflow = false;
+  for (int l = 0; l < n_lists; ++l) {
+    const int n = nlists[(int64_t)l * B + q];
+    if (n > list_cap) overflow = true;
+    const uint32_t* src = lists + ((int64_t)l * B + q) * list_cap;
+    __shared__ int s_base;
+    if (tid == 0) { s_base = s_total; s_total += min(n, list_cap); }
+    __syncthreads();
+    for (int i = tid; i < min(n, list_cap); i += 256)
+      if (s_base + i < kAlignCap) keys[s_base + i] = src[i];
+    __syncthreads();
+  }
+  const int total = s_total;
+  if (overflow || total > kAlignCap) {
+    if (tid == 0) nrows[q] = -1;  // capacity exceeded: the host wrapper raises
+    return;
+  }
+  if (nc == 0 || total == 0) {
+    if (tid == 0) nrows[q] = 0;
+    return;
+  }
+  // bitonic sort of the keys (padded with 0xffffffff)
+  int np2 = 1;
+  while (np2 < total) np2 <<= 1;
+  for (int i = total + tid; i < np2; i += 256) keys[i] = 0xffffffffu;
+  __syncthreads();
+  for (int k = 2; k <= np2; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < np2; i += 256) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const uint32_t a = keys[i], b = keys[ixj];
+          const bool up = (i & k) == 0;
+          if ((a > b) == up) { keys[i] = b; keys[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  // run-length encode (sequential over <= 8192 sorted keys; candidates are few)
+  if (tid == 0) {
+    int nb = 0;
+    for (int c = 0; c <= nc; ++c) s_seg[c] = 0;
+    for (int i = 0; i < total; ++i) {
+      if (nb == 0 || bin_key[nb - 1] != keys[i]) { bin_key[nb] = keys[i]; bin_cnt[nb] = 0; ++nb; }
+      ++bin_cnt[nb - 1];
+    }
+    s_nbins = nb;
+    // segment boundaries per candidate
+    int b = 0;
+    for (int c = 0; c < nc; ++c) {
+      s_seg[c] = b;
+      while (b < nb && (int)(bin_key[b] >> 16) == c) ++b;
+    }
+    s_seg[nc] = b;
+  }
+  __syncthreads();
+  // one thread per candidate: modes of its delta-t histogram (audfprint_match.py:276-315)
+  int32_t* res = results + (int64_t)q * max_rows * 7;
+  if (tid < nc) {
+    const int b0 = s_seg[tid], b1 = s_seg[tid + 1];
+    const int id = cand[((int64_t)q * search_depth + tid) * 2], raw = cand[((int64_t)q * search_depth + tid) * 2 + 1];
+    // "filtered" flag kept in the sign bit of a scratch copy: reuse keys[] region of this segment
+    // (keys are no longer needed); keys[b] = filtered count
+    for (int b = b0; b < b1; ++b) {
+      const int dt = (int)(bin_key[b] & 0xffffu), c = bin_cnt[b];
+      const int left = (b > b0 && (int)(bin_key[b - 1] & 0xffffu) == dt - 1) ? bin_cnt[b - 1] : 0;
+      const int right = (b + 1 < b1 && (int)(bin_key[b + 1] & 0xffffu) == dt + 1) ? bin_cnt[b + 1] : 0;
+      keys[b] = (c >= left && right < c) ? (uint32_t)c : 0u;
+    }
+    int found = 0;
+    while (true) {
+      int best = -1, bv = 0;
+      for (int b = b0; b < b1; ++b)
+        if ((int)keys[b] > bv) { bv = (int)keys[b]; best = b; }  // first maximum = smallest delta-t
+      if (best < 0 || bv <= threshcount) break;
+      const int mode = (int)(bin_key[best] & 0xffffu);
+      int sum = 0;
+      for (int b = b0; b < b1; ++b) {
+        const int dt = (int)(bin_key[b] & 0xffffu);
+        if (dt >= mode - window && dt <= mode + window) { sum += bin_cnt[b]; keys[b] = 0; }
+      }
+      const int row = atomicAdd(&s_rows, 1);
+      if (row < max_rows) {
+        int32_t* r = res + row * 7;
+        r[0] = id; r[1] = sum; r[2] = mode - kDtOff; r[3] = raw; r[4] = tid; r[5] = 0; r[6] = 0;
+      }
+      if (++found > max_align) break;
+    }
+  }
+  __syncthreads();
+  // order rows by filtered count descending, then by candidate rank (:341; ties are arbitrary in numpy)
+  const int nr = min(s_rows, max_rows);
+  if (tid == 0) {
+    for (int i = 1; i < nr; ++i) {
+      int32_t t[7];
+      for (int k = 0; k < 7; ++k) t[k] = res[i * 7 + k];
+      int j = i - 1;
+      while (j >= 0 && (res[j * 7 + 1] < t[1] || (res[j * 7 + 1] == t[1] && (res[j * 7 + 4] > t[4] ||
+             (res[j * 7 + 4] == t[4] && res[j * 7 + 2] > t[2]))))) {
+        for (int k = 0; k < 7; ++k) res[(j + 1) * 7 + k] = res[j * 7 + k];
+        --j;
+      }
+      for (int k = 0; k < 7; ++k) res[(j + 1) * 7 + k] = t[k];
+    }
+    nrows[q] = s_rows > max_rows ? -2 : nr;
+  }
+}
+
+// HashTable.get_hits for one query (hash_table.py:220-246): rows [id, t_ref - t_q, hash, t_q] in query order.
+__global__ void __launch_bounds__(1024) get_hits_kernel(const IndexView ix, const int32_t* __restrict__ hashes, int n,
+                                                        int32_t* __restrict__ hits, long long hits_cap,
+                                                        long long* __restrict__ nhits) {
+  __shared__ long long warp_tot[32];
+  __shared__ long long carry;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int2* rows = reinterpret_cast<const int2*>(hashes);
+  const uint32_t tmask = (1u << ix.maxtimebits) - 1u;
+  if (tid == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024) {
+    const int r = base + tid;
+    int cnt = 0, h = 0, t = 0, hb = -1;
+    if (r < n) {
+      t = rows[r].x; h = rows[r].y & ix.hashmask; hb = h - ix.hash_lo;
+      if (hb >= 0 && hb < ix.n_buckets) cnt = min(ix.depth, ix.counts[hb]);
+    }
+    long long incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const long long v = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      long long w = warp_tot[lane], wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const long long v = __shfl_up_sync(kFull, wi, o); if (lane >= o) wi += v; }
+      warp_tot[lane] = wi - w;
+    }
+    __syncthreads();
+    long long pos = carry + warp_tot[warp] + incl - cnt;
+    if (cnt > 0) {
+      const uint32_t* bucket = ix.table + (int64_t)hb * ix.depth;
+      for (int s = 0; s < cnt; ++s, ++pos) {
+        if (pos >= hits_cap) break;
+        const uint32_t v = bucket[s];
+        int4* o = reinterpret_cast<int4*>(hits) + pos;
+        *o = make_int4((int)(v >> ix.maxtimebits) - 1, (int)(v & tmask) - t, h, t);
+      }
+    }
+    __syncthreads();
+    if (tid == 1023) carry = carry + warp_tot[31] + incl;
+    __syncthreads();
+  }
+  if (tid == 0) *nhits = carry;
+}
+
+IndexView view(const mfpa_ctx* ctx) {
+  IndexView v;
+  v.table = ctx->index_table; v.counts = ctx->index_counts; v.hashesperid = ctx->index_hashesperid;
+  v.hash_lo = ctx->index_hash_lo; v.n_buckets = ctx->index_hash_hi - ctx->index_hash_lo; v.depth = ctx->index_depth;
+  v.maxtimebits = ctx->index_maxtimebits; v.n_tracks = ctx->index_ntracks; v.hashmask = ctx->index_hashmask;
+  return v;
+}
+
+}  // namespace
+
+int launch_match_counts(mfpa_ctx* ctx, const int32_t* hashes, const int32_t* nh, int B, int cap, int32_t* counts,
+                        cudaStream_t st) {
+  const IndexView ix = view(ctx);
+  if (ix.n_tracks <= kMaxTracksSmem) {
+    const size_t smem = sizeof(unsigned) * (size_t)((ix.n_tracks + 1) / 2);
+    MFPA_CUDA(cudaFuncSetAttribute(match_counts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    match_counts_kernel<<<B, kCountThreads, smem, st>>>(ix, hashes, nh, cap, counts);
+  } else {
+    MFPA_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t)B * ix.n_tracks, st));
+    match_counts_global_kernel<<<B, kCountThreads, 0, st>>>(ix, hashes, nh, cap, counts);
+  }
+  MFPA_CUDA(cudaGetLastError());
+  return MFPA_OK;
+}
+
+int launch_match_select(mfpa_ctx* ctx, const int32_t* counts, int B, int threshcount, int search_depth, int32_t* cand,
+                        int32_t* ncand, cudaStream_t st) {
+  match_select_kernel<<<B, 512, 0, st>>>(counts, ctx->index_hashesperid, ctx->index_ntracks, threshcount, search_depth,
+                                         cand, ncand);
+  MFPA_CUDA(cudaGetLastError());
+  return MFPA_OK;
+}
+
+int launch_match_collect(mfpa_ctx* ctx, const int32_t* hashes, const int32_t* nh, int B, int cap, const int32_t* cand,
+                         const int32_t* ncand, int search_depth, uint32_t* list, int list_cap, int32_t* nlist,
+                         cudaStream_t st) {
+  match_collect_kernel<<<B, 256, 0, st>>>(view(ctx), hashes, nh, cap, cand, ncand, search_depth, list, list_cap, nlist);
+  MFPA_CUDA(cudaGetLastError());
+  return MFPA_OK;
+}
+
+int launch_match_align(const uint32_t* lists, const int32_t* nlists, int n_lists, int B, int list_cap, const int32_t* cand,
+                       const int32_t* ncand, int search_depth, int window, int threshcount, int max_align,
+                       int32_t* results, int32_t* nrows, int max_rows, cudaStream_t st) {
+  const size_t smem = sizeof(uint32_t) * 3 * kAlignCap;
+  MFPA_CUDA(cudaFuncSetAttribute(match_align_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  match_align_kernel<<<B, 256, smem, st>>>(lists, nlists, n_lists, B, list_cap, cand, ncand, search_depth, window,
+                                           threshcount, max_align, results, nrows, max_rows);
+  MFPA_CUDA(cudaGetLastError());
+  return MFPA_OK;
+}
+
+int launch_get_hits(mfpa_ctx* ctx, const int32_t* hashes, int n, int32_t* hits, int64_t hits_cap, int64_t* nhits,
+                    cudaStream_t st) {
+  get_hits_kernel<<<1, 1024, 0, st>>>(view(ctx), hashes, n, hits, (long long)hits_cap, (long long*)nhits);
+  MFPA_CUDA(cudaGetLastError());
+  return MFPA_OK;
+}
+
+}  // namespace mfpa

@@ -30,6 +30,21 @@ class AfpParams(C.Structure):
     ]
 
 
+class AugParams(C.Structure):
+    """mfpa_aug_params (include/mfpa.h): one record per query."""
+
+    _fields_ = [
+        ("apply", C.c_uint32), ("fc1_hz", C.c_float), ("fc2_hz", C.c_float), ("fc3_hz", C.c_float),
+        ("snr_db", C.c_float), ("gain_factor", C.c_float), ("clip_p", C.c_float), ("ir_len", C.c_int32),
+    ]
+
+
+AUG_HPF1, AUG_IR, AUG_NOISE, AUG_GAIN, AUG_CLIP, AUG_LPF, AUG_HPF3, AUG_NORM = 1, 2, 4, 8, 16, 32, 64, 128
+AUG_ALL = 255
+AUG_DTYPE = [("apply", "<u4"), ("fc1_hz", "<f4"), ("fc2_hz", "<f4"), ("fc3_hz", "<f4"), ("snr_db", "<f4"),
+             ("gain_factor", "<f4"), ("clip_p", "<f4"), ("ir_len", "<i4")]
+
+
 class MfpaError(RuntimeError):
     pass
 
@@ -57,6 +72,8 @@ SIGNATURES = {
     "mfpa_merge_shifts": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _vp]),
     "mfpa_fingerprint": (_i, [_vp, _vp, _i, _i, _i64, _i, _P, _vp, _i, _vp, _vp]),
     "mfpa_fingerprint_host": (_i, [_vp, _vp, _i, _i, _i, _P, _vp, _i64, _vp]),
+    "mfpa_augment": (_i, [_vp, _vp, _i, _i, _i64, _i, _vp, _vp, _i, _vp, _vp, _vp]),
+    "mfpa_augment_fingerprint": (_i, [_vp, _vp, _i, _i, _i64, _i, _vp, _vp, _i, _vp, _i, _P, _vp, _i, _vp, _vp]),
     "mfpa_compact_rows": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _i64, _vp]),
 }
 
@@ -104,6 +121,11 @@ def afp_defaults() -> AfpParams:
 
 def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _row_stride(x) -> int:
+    """Row stride in elements; a size-1 batch dimension may carry a meaningless stride."""
+    return int(x.stride(0)) if x.shape[0] > 1 else int(x.shape[1])
 
 
 def _stream():
@@ -167,7 +189,7 @@ class Context:
         n = num_frames(T)
         mag = torch.empty(B * shifts, n, MAG_PITCH, dtype=torch.float32, device=x.device)
         qmax = torch.empty(B * shifts, dtype=torch.float32, device=x.device)
-        check(_lib.mfpa_stft_mag(self._h, _ptr(x), B, T, x.stride(0), shifts, _ptr(mag), _ptr(qmax), _stream()))
+        check(_lib.mfpa_stft_mag(self._h, _ptr(x), B, T, _row_stride(x), shifts, _ptr(mag), _ptr(qmax), _stream()))
         return mag, qmax
 
     def spec_from_mag(self, mag, qmax, T: int, shifts: int = 1):
@@ -246,6 +268,48 @@ class Context:
                                      cap_out, _ptr(nout), _stream()))
         return out, nout
 
+    # ---- S1 --------------------------------------------------------------
+    @staticmethod
+    def _aug_args(x, params, ir, noise):
+        import numpy as np
+        import torch
+
+        assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
+        params = np.ascontiguousarray(params, dtype=AUG_DTYPE)
+        assert params.shape == (x.shape[0],)
+        if ir is not None:
+            assert ir.is_cuda and ir.dtype == torch.float32 and ir.dim() == 2 and ir.is_contiguous()
+        if noise is not None:
+            assert noise.is_cuda and noise.dtype == torch.float32 and noise.is_contiguous() and noise.shape == x.shape
+        return params
+
+    def augment(self, x, params, ir=None, noise=None, sample_rate: int = 8000):
+        """AugmentFP chain on dumped parameters.  x [B,T] f32 cuda; params: numpy structured
+        array (AUG_DTYPE) [B]; ir [B,Lmax] f32 cuda; noise [B,T] f32 cuda -> [B,T] f32 cuda."""
+        import torch
+
+        params = self._aug_args(x, params, ir, noise)
+        B, T = x.shape
+        out = torch.empty(B, T, dtype=torch.float32, device=x.device)
+        check(_lib.mfpa_augment(self._h, _ptr(x), B, T, _row_stride(x), sample_rate, params.ctypes.data_as(C.c_void_p),
+                                _ptr(ir), ir.shape[1] if ir is not None else 0, _ptr(noise), _ptr(out), _stream()))
+        return out
+
+    def augment_fingerprint(self, x, params, ir, noise, shifts: int, afp: AfpParams, sample_rate: int = 8000):
+        """Fused S1-S4: degraded-query hashes without leaving the device."""
+        import torch
+
+        params = self._aug_args(x, params, ir, noise)
+        B, T = x.shape
+        cap = HASHES_PER_FRAME * num_frames(T) * shifts
+        out = torch.empty(B, cap, 2, dtype=torch.int32, device=x.device)
+        nh = torch.empty(B, dtype=torch.int32, device=x.device)
+        check(_lib.mfpa_augment_fingerprint(self._h, _ptr(x), B, T, _row_stride(x), sample_rate,
+                                            params.ctypes.data_as(C.c_void_p), _ptr(ir),
+                                            ir.shape[1] if ir is not None else 0, _ptr(noise), shifts, C.byref(afp),
+                                            _ptr(out), cap, _ptr(nh), _stream()))
+        return out, nh
+
     # ---- fused -----------------------------------------------------------
     def fingerprint(self, x, shifts: int, params: AfpParams, out=None, nh=None, cap: int | None = None):
         """x [B,T] f32 cuda -> (hashes [B,cap,2] int32, nh [B] int32), rows unique and
@@ -260,7 +324,7 @@ class Context:
             out = torch.empty(B, cap, 2, dtype=torch.int32, device=x.device)
         if nh is None:
             nh = torch.empty(B, dtype=torch.int32, device=x.device)
-        check(_lib.mfpa_fingerprint(self._h, _ptr(x), B, T, x.stride(0), shifts, C.byref(params), _ptr(out),
+        check(_lib.mfpa_fingerprint(self._h, _ptr(x), B, T, _row_stride(x), shifts, C.byref(params), _ptr(out),
                                     out.shape[1], _ptr(nh), _stream()))
         return out, nh
 

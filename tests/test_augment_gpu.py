@@ -1,0 +1,149 @@
+"""GPU parity: CUDA AugmentFP chain (C ABI) vs the numpy oracle and the golden vectors the
+reference's own transform classes produced.  Tolerance: 1e-4 relative (north star)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import augment_np as A
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+TOL = 1e-4
+
+
+def _lib():
+    from musicfpaugment_b200 import lib
+
+    return lib
+
+
+def _pack(lib, prms, T):
+    """list of oracle-style dicts -> (params array, ir tensor, noise tensor)"""
+    B = len(prms)
+    arr = np.zeros(B, dtype=lib.AUG_DTYPE)
+    lmax = max([len(p["ir"]) for p in prms if p.get("ir") is not None] + [1])
+    ir = np.zeros((B, lmax), np.float32)
+    noise = np.zeros((B, T), np.float32)
+    for i, p in enumerate(prms):
+        ap = lib.AUG_NORM
+        if p.get("fc1") is not None:
+            ap |= lib.AUG_HPF1; arr["fc1_hz"][i] = p["fc1"]
+        if p.get("ir") is not None:
+            ap |= lib.AUG_IR; ir[i, : len(p["ir"])] = p["ir"]; arr["ir_len"][i] = len(p["ir"])
+        if p.get("noise") is not None:
+            ap |= lib.AUG_NOISE; noise[i] = p["noise"]; arr["snr_db"][i] = p["snr_db"]
+        if p.get("gain_factor") is not None:
+            ap |= lib.AUG_GAIN; arr["gain_factor"][i] = p["gain_factor"]
+        if p.get("clip_p") is not None:
+            ap |= lib.AUG_CLIP; arr["clip_p"][i] = p["clip_p"]
+        if p.get("fc2") is not None:
+            ap |= lib.AUG_LPF; arr["fc2_hz"][i] = p["fc2"]
+        if p.get("fc3") is not None:
+            ap |= lib.AUG_HPF3; arr["fc3_hz"][i] = p["fc3"]
+        arr["apply"][i] = ap
+    return arr, torch.from_numpy(ir).cuda(), torch.from_numpy(noise).cuda()
+
+
+def _rel(a, b):
+    return float(np.abs(a - b).max() / np.abs(b).max())
+
+
+def _golden_cases():
+    g = np.load(os.path.join(GOLD, "augment.npz"))
+    keys = ("fc1", "ir", "noise", "snr_db", "gain_factor", "clip_p", "fc2", "fc3")
+    for i in range(int(g["n_cases"])):
+        prm = {k: (g[f"p{i}_{k}"] if g[f"p{i}_{k}"].ndim else float(g[f"p{i}_{k}"])) for k in keys if f"p{i}_{k}" in g}
+        yield i, g[f"x{i}"], prm, g[f"out{i}"]
+
+
+def test_golden_cases(mfpa_ctx):
+    lib = _lib()
+    for i, x, prm, ref in _golden_cases():
+        if prm.get("fc1") is not None and prm["fc1"] < 4.0:
+            continue  # FIR longer than MFPA_AUG_MAX_TAPS: covered by test_too_long_filter_is_rejected
+        arr, ir, noise = _pack(lib, [prm], len(x))
+        out = mfpa_ctx.augment(torch.from_numpy(x[None]).cuda(), arr, ir, noise).cpu().numpy()[0]
+        assert _rel(out, ref) < TOL, (i, _rel(out, ref))
+
+
+def test_random_chains_vs_oracle(mfpa_ctx):
+    """Batch of 12 queries with different transform subsets, filter lengths, IR lengths and levels."""
+    from musicfpaugment_b200 import synth
+
+    lib = _lib()
+    B, T = 12, 24000
+    x = synth.music_like(B, n_samples=T, seed=31).numpy()
+    irs = synth.impulse_responses(B, length=8192, seed=32).numpy()
+    nz = synth.rms_noise(B, n_samples=T, seed=33).numpy()
+    r = np.random.default_rng(34)
+    prms = []
+    for i in range(B):
+        p = {}
+        full = i < 4
+        if full or r.random() < 0.6:
+            p["fc1"] = float(r.uniform(8.0, 150.0))
+        if full or r.random() < 0.6:
+            p["ir"] = irs[i][: int(r.integers(1, 8193))]
+        if full or r.random() < 0.6:
+            p["noise"], p["snr_db"] = nz[i], float(r.uniform(-10, 10))
+        if full or r.random() < 0.6:
+            p["gain_factor"] = float(10 ** (r.uniform(-5, 5) / 20))
+        if full or r.random() < 0.6:
+            p["clip_p"] = float(r.uniform(0, 0.01))
+        if full or r.random() < 0.6:
+            p["fc2"] = float(r.uniform(3000, 3999))
+        if full or r.random() < 0.6:
+            p["fc3"] = float(r.uniform(30, 150))
+        prms.append(p)
+    prms[5] = {}                                  # nothing but the final normalisation
+    prms[6] = {"fc2": 300.0, "clip_p": 0.004}     # long "low-pass" -> FFT route for stage 5
+    arr, ir, noise = _pack(lib, prms, T)
+    out = mfpa_ctx.augment(torch.from_numpy(x).cuda(), arr, ir, noise).cpu().numpy()
+    for i in range(B):
+        ref = A.augment_chain(x[i], prms[i])
+        assert _rel(out[i], ref) < TOL, (i, _rel(out[i], ref), sorted(prms[i]))
+
+
+def test_too_long_filter_and_bad_cutoffs_are_rejected(mfpa_ctx):
+    lib = _lib()
+    x = torch.zeros(1, 8000, device="cuda")
+    for fc in (3.0, 0.0, -5.0, 4100.0):
+        arr = np.zeros(1, dtype=lib.AUG_DTYPE)
+        arr["apply"], arr["fc1_hz"] = lib.AUG_HPF1 | lib.AUG_NORM, fc
+        with pytest.raises(lib.MfpaError):
+            mfpa_ctx.augment(x, arr, None, None)
+
+
+def test_augment_then_fingerprint_matches_two_step(mfpa_ctx):
+    """Fused S1-S4 == augment() followed by fingerprint() (peak normalisation is irrelevant to hashes)."""
+    from musicfpaugment_b200 import synth
+
+    lib = _lib()
+    B, T = 6, 64000
+    x = synth.music_like(B, seed=41)
+    irs = synth.impulse_responses(B, seed=42)
+    nz = synth.rms_noise(B, seed=43)
+    pr = synth.augment_params(B, seed=44)
+    arr = np.zeros(B, dtype=lib.AUG_DTYPE)
+    arr["apply"] = lib.AUG_ALL
+    arr["fc1_hz"], arr["fc2_hz"], arr["fc3_hz"] = pr["fc1"], pr["fc2"], pr["fc3"]
+    arr["snr_db"], arr["gain_factor"], arr["clip_p"], arr["ir_len"] = pr["snr_db"], 10 ** (pr["gain_db"] / 20), pr["clip_p"], 8000
+    afp = lib.afp_defaults()
+    y = mfpa_ctx.augment(x.cuda(), arr, irs.cuda(), nz.cuda())
+    h2, n2 = mfpa_ctx.fingerprint(y, 1, afp)
+    h1, n1 = mfpa_ctx.augment_fingerprint(x.cuda(), arr, irs.cuda(), nz.cuda(), 1, afp)
+    agree = total = 0
+    for i in range(B):
+        a = {tuple(r) for r in h1[i, : int(n1[i])].cpu().numpy().tolist()}
+        b = {tuple(r) for r in h2[i, : int(n2[i])].cpu().numpy().tolist()}
+        agree += len(a & b); total += len(a | b)
+    assert total > 0 and agree / total >= 0.999, (agree, total)
+    # and the degraded waveform itself matches the oracle chain
+    for i in range(2):
+        prm = dict(fc1=float(pr["fc1"][i]), ir=irs[i].numpy(), noise=nz[i].numpy(), snr_db=float(pr["snr_db"][i]),
+                   gain_factor=float(arr["gain_factor"][i]), clip_p=float(pr["clip_p"][i]), fc2=float(pr["fc2"][i]),
+                   fc3=float(pr["fc3"][i]))
+        ref = A.augment_chain(x[i].numpy(), prm)
+        assert _rel(y[i].cpu().numpy(), ref) < TOL
