@@ -258,6 +258,15 @@ int mfpa_match_align(mfpa_ctx* ctx, const uint32_t* lists_dev, const int32_t* nl
 int mfpa_match(mfpa_ctx* ctx, const int32_t* hashes_dev, const int32_t* nh_dev, int B, int cap,
                const mfpa_match_params* p, int32_t* results_dev, int32_t* nrows_dev, int max_rows, void* stream);
 
+/* ---- Dejavu 2-D peak finder  (afp/dejavu/fingerprint.py:94-171; PEAK_NEIGHBORHOOD_SIZE 10,
+ * amp_min 50: afp/dejavu/variables.py:19, testing/parameters.py:27-34)
+ * arr_dev: [B][F][N] float64 (is_f64 = 1, the reference's dtype) or float32, the log spectrogram
+ * that fingerprint() passes to get_2D_peaks.  mask_dev: [B][F][N] uint8 peak mask.
+ * peaks_dev (nullable): [B][cap][2] int32 (freq, time) rows in np.where order; npeaks_dev [B]. */
+int mfpa_dejavu_peaks(mfpa_ctx* ctx, const void* arr_dev, int is_f64, int B, int F, int N, int neighborhood,
+                      double amp_min, uint8_t* mask_dev, int32_t* peaks_dev, int cap, int32_t* npeaks_dev,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

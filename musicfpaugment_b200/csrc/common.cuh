@@ -119,6 +119,8 @@ int launch_match_align(const uint32_t* lists, const int32_t* nlists, int n_lists
                        int32_t* results, int32_t* nrows, int max_rows, cudaStream_t st);
 int launch_get_hits(mfpa_ctx* ctx, const int32_t* hashes, int n, int32_t* hits, int64_t hits_cap, int64_t* nhits,
                     cudaStream_t st);
+int launch_dejavu_peaks(const void* arr, int is_f64, int B, int F, int N, int r, double amp_min, uint8_t* mask,
+                        int32_t* peaks, int cap, int32_t* npeaks, cudaStream_t st);
 int stft_init_tables(mfpa_ctx* ctx);
 
 }  // namespace mfpa

@@ -45,6 +45,13 @@ AUG_DTYPE = [("apply", "<u4"), ("fc1_hz", "<f4"), ("fc2_hz", "<f4"), ("fc3_hz", 
              ("gain_factor", "<f4"), ("clip_p", "<f4"), ("ir_len", "<i4")]
 
 
+class MatchParams(C.Structure):
+    """mfpa_match_params (include/mfpa.h) = Matcher.__init__ defaults."""
+
+    _fields_ = [("window", C.c_int32), ("threshcount", C.c_int32), ("search_depth", C.c_int32),
+                ("max_alignments_per_id", C.c_int32)]
+
+
 class MfpaError(RuntimeError):
     pass
 
@@ -74,6 +81,15 @@ SIGNATURES = {
     "mfpa_fingerprint_host": (_i, [_vp, _vp, _i, _i, _i, _P, _vp, _i64, _vp]),
     "mfpa_augment": (_i, [_vp, _vp, _i, _i, _i64, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     "mfpa_augment_fingerprint": (_i, [_vp, _vp, _i, _i, _i64, _i, _vp, _vp, _i, _vp, _i, _P, _vp, _i, _vp, _vp]),
+    "mfpa_index_load": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i]),
+    "mfpa_match_defaults": (None, [C.POINTER(MatchParams)]),
+    "mfpa_get_hits": (_i, [_vp, _vp, _i, _vp, _i64, _vp, _vp]),
+    "mfpa_match_counts": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
+    "mfpa_match_select": (_i, [_vp, _vp, _i, C.POINTER(MatchParams), _vp, _vp, _vp]),
+    "mfpa_match_collect": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, C.POINTER(MatchParams), _vp, _i, _vp, _vp]),
+    "mfpa_match_align": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, C.POINTER(MatchParams), _vp, _vp, _i, _vp]),
+    "mfpa_match": (_i, [_vp, _vp, _vp, _i, _i, C.POINTER(MatchParams), _vp, _vp, _i, _vp]),
+    "mfpa_dejavu_peaks": (_i, [_vp, _vp, _i, _i, _i, _i, _i, C.c_double, _vp, _vp, _i, _vp, _vp]),
     "mfpa_compact_rows": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _i64, _vp]),
 }
 
@@ -116,6 +132,12 @@ def shift_offset(shift: int, shifts: int) -> int:
 def afp_defaults() -> AfpParams:
     p = AfpParams()
     _lib.mfpa_afp_defaults(C.byref(p))
+    return p
+
+
+def match_defaults() -> MatchParams:
+    p = MatchParams()
+    _lib.mfpa_match_defaults(C.byref(p))
     return p
 
 
@@ -309,6 +331,103 @@ class Context:
                                             ir.shape[1] if ir is not None else 0, _ptr(noise), shifts, C.byref(afp),
                                             _ptr(out), cap, _ptr(nh), _stream()))
         return out, nh
+
+    # ---- S5 --------------------------------------------------------------
+    def index_load(self, table, counts, hashesperid, hash_lo: int = 0, hashbits: int = 20, maxtimebits: int = 14):
+        """Upload (a hash-range shard of) a reference HashTable.  table: uint32 [n_buckets, depth] numpy
+        (rows hash_lo .. hash_lo+n_buckets of the full table), counts int32 [n_buckets], hashesperid uint32."""
+        import numpy as np
+
+        table = np.ascontiguousarray(table, dtype=np.uint32)
+        counts = np.ascontiguousarray(counts, dtype=np.int32)
+        hpid = np.ascontiguousarray(hashesperid, dtype=np.uint32)
+        assert table.ndim == 2 and counts.shape == (table.shape[0],)
+        check(_lib.mfpa_index_load(self._h, table.ctypes.data_as(C.c_void_p), counts.ctypes.data_as(C.c_void_p),
+                                   hash_lo, table.shape[0], table.shape[1], hashbits, maxtimebits,
+                                   hpid.ctypes.data_as(C.c_void_p), len(hpid)))
+        self.n_tracks = len(hpid)
+
+    def get_hits(self, hashes):
+        """hashes: int32 [n,2] cuda -> int32 [nhits,4] cuda (HashTable.get_hits order)."""
+        import torch
+
+        hashes = hashes.contiguous()
+        n = hashes.shape[0]
+        cap = max(1, n * 128)
+        hits = torch.empty(cap, 4, dtype=torch.int32, device=hashes.device)
+        nh = torch.zeros(1, dtype=torch.int64, device=hashes.device)
+        check(_lib.mfpa_get_hits(self._h, _ptr(hashes), n, _ptr(hits), cap, _ptr(nh), _stream()))
+        k = int(nh.item())
+        if k > cap:
+            hits = torch.empty(k, 4, dtype=torch.int32, device=hashes.device)
+            check(_lib.mfpa_get_hits(self._h, _ptr(hashes), n, _ptr(hits), k, _ptr(nh), _stream()))
+        return hits[:k]
+
+    def match(self, hashes, nh, params: MatchParams | None = None, max_rows: int = 16):
+        """Single-shard match_hashes for a batch: hashes int32 [B,cap,2] cuda, nh int32 [B] cuda ->
+        (results int32 [B,max_rows,7], nrows int32 [B])."""
+        import torch
+
+        params = params or match_defaults()
+        B, cap, _ = hashes.shape
+        res = torch.zeros(B, max_rows, 7, dtype=torch.int32, device=hashes.device)
+        nrows = torch.empty(B, dtype=torch.int32, device=hashes.device)
+        check(_lib.mfpa_match(self._h, _ptr(hashes), _ptr(nh), B, cap, C.byref(params), _ptr(res), _ptr(nrows),
+                              max_rows, _stream()))
+        return res, nrows
+
+    def match_counts(self, hashes, nh):
+        import torch
+
+        B, cap, _ = hashes.shape
+        counts = torch.empty(B, self.n_tracks, dtype=torch.int32, device=hashes.device)
+        check(_lib.mfpa_match_counts(self._h, _ptr(hashes), _ptr(nh), B, cap, _ptr(counts), _stream()))
+        return counts
+
+    def match_select(self, counts, params: MatchParams):
+        import torch
+
+        B = counts.shape[0]
+        cand = torch.zeros(B, params.search_depth, 2, dtype=torch.int32, device=counts.device)
+        ncand = torch.empty(B, dtype=torch.int32, device=counts.device)
+        check(_lib.mfpa_match_select(self._h, _ptr(counts), B, C.byref(params), _ptr(cand), _ptr(ncand), _stream()))
+        return cand, ncand
+
+    def match_collect(self, hashes, nh, cand, ncand, params: MatchParams, list_cap: int = 2048):
+        import torch
+
+        B, cap, _ = hashes.shape
+        lst = torch.empty(B, list_cap, dtype=torch.int32, device=hashes.device)
+        nlist = torch.empty(B, dtype=torch.int32, device=hashes.device)
+        check(_lib.mfpa_match_collect(self._h, _ptr(hashes), _ptr(nh), B, cap, _ptr(cand), _ptr(ncand), C.byref(params),
+                                      _ptr(lst), list_cap, _ptr(nlist), _stream()))
+        return lst, nlist
+
+    def match_align(self, lists, nlists, cand, ncand, params: MatchParams, max_rows: int = 16):
+        """lists int32 [n_lists,B,list_cap], nlists int32 [n_lists,B]."""
+        import torch
+
+        n_lists, B, list_cap = lists.shape
+        res = torch.zeros(B, max_rows, 7, dtype=torch.int32, device=lists.device)
+        nrows = torch.empty(B, dtype=torch.int32, device=lists.device)
+        check(_lib.mfpa_match_align(self._h, _ptr(lists), _ptr(nlists), n_lists, B, list_cap, _ptr(cand), _ptr(ncand),
+                                    C.byref(params), _ptr(res), _ptr(nrows), max_rows, _stream()))
+        return res, nrows
+
+    # ---- Dejavu ----------------------------------------------------------
+    def dejavu_peaks(self, arr, amp_min: float = 50.0, neighborhood: int = 10, cap: int = 4096):
+        """arr [B,F,N] float64|float32 cuda -> (mask uint8 [B,F,N], peaks int32 [B,cap,2] (freq,time), npeaks [B])."""
+        import torch
+
+        assert arr.is_cuda and arr.dim() == 3 and arr.dtype in (torch.float64, torch.float32)
+        arr = arr.contiguous()
+        B, F, N = arr.shape
+        mask = torch.empty(B, F, N, dtype=torch.uint8, device=arr.device)
+        peaks = torch.empty(B, cap, 2, dtype=torch.int32, device=arr.device)
+        npk = torch.empty(B, dtype=torch.int32, device=arr.device)
+        check(_lib.mfpa_dejavu_peaks(self._h, _ptr(arr), int(arr.dtype == torch.float64), B, F, N, neighborhood,
+                                     float(amp_min), _ptr(mask), _ptr(peaks), cap, _ptr(npk), _stream()))
+        return mask, peaks, npk
 
     # ---- fused -----------------------------------------------------------
     def fingerprint(self, x, shifts: int, params: AfpParams, out=None, nh=None, cap: int | None = None):
