@@ -1,0 +1,122 @@
+"""GPU: the drop-in modules (reference import paths) end to end against the oracle."""
+import os
+import pickle
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import audfprint_np as O
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DROPIN = os.path.join(ROOT, "musicfpaugment_b200", "dropin")
+PRM = {"density": 20, "pks-per-frame": 5, "freq-sd": 30, "shifts": 1, "samplerate": 8000, "n_fft": 512, "n_hop": 256}
+
+
+@pytest.fixture(scope="module")
+def mods():
+    for k in [k for k in sys.modules if k.split(".")[0] in ("afp", "augmentation", "dejavu")]:
+        del sys.modules[k]
+    sys.path.insert(0, DROPIN)
+    import afp.audfprint.audfprint_match as m
+    import afp.audfprint.hash_table as ht
+    import afp.audfprint.peak_extractor as pe
+    import afp.dejavu.fingerprint as fp
+    import augmentation as aug
+
+    yield {"pe": pe, "ht": ht, "match": m, "fp": fp, "aug": aug}
+    sys.path.remove(DROPIN)
+    for k in [k for k in sys.modules if k.split(".")[0] in ("afp", "augmentation", "dejavu")]:
+        del sys.modules[k]
+
+
+def _queries(n):
+    from musicfpaugment_b200 import synth
+
+    return synth.music_like(n, seed=808).numpy()
+
+
+def test_find_peaks_and_landmarks(mods):
+    a = mods["pe"].Audfprint_peaks(PRM)
+    x = _queries(2)[1]
+    pk, mask, spec = a.find_peaks(x)
+    pk_o, mask_o, spec_o = O.find_peaks(x)
+    assert mask.shape == mask_o.shape and mask.dtype == np.float32 and spec.shape == spec_o.shape and spec.dtype == np.float64
+    assert np.abs(spec - spec_o).max() < 1e-4
+    both = len(set(pk) & set(pk_o)) / len(set(pk) | set(pk_o))
+    assert both >= 0.98
+    assert a.peaks2landmarks(pk_o) == O.peaks2landmarks(pk_o)  # bit-exact given the same peaks
+
+
+def test_wavfile2hashes_and_match_file(mods, tmp_path):
+    pe, ht_mod, m_mod = mods["pe"], mods["ht"], mods["match"]
+    X = _queries(6)
+    index = pe.Audfprint_peaks(PRM)
+    ht = ht_mod.HashTable()
+    for i, x in enumerate(X):  # "index" the clean tracks through ingest()
+        p = str(tmp_path / f"track{i}.pkl")
+        with open(p, "wb") as f:
+            pickle.dump(x, f)
+        dur, n = index.ingest(ht, p)
+        assert abs(dur - 8.0) < 1e-6 and n == len(O.wave2hashes(x))
+    qa = pe.Audfprint_peaks(PRM)
+    qa.shifts = 4  # audfprint_exps.py:167
+    matcher = m_mod.Matcher()
+    hits = 0
+    for i, x in enumerate(X):
+        seg = x[8000:40000] + 0.01 * np.random.default_rng(i).standard_normal(32000).astype(np.float32)
+        p = str(tmp_path / f"query{i}.pkl")
+        with open(p, "wb") as f:
+            pickle.dump(seg.astype(np.float32), f)
+        h = qa.wavfile2hashes(p)
+        want = O.wave2hashes(seg.astype(np.float32), 4)
+        a, b = {tuple(r) for r in h.tolist()}, {tuple(r) for r in want.tolist()}
+        assert len(a & b) >= 0.99 * len(a | b)
+        status, name, n = matcher.file_match_to_msgs(qa, ht, p)
+        hits += int(status == "MATCH" and name.endswith(f"track{i}.pkl"))
+    assert hits == len(X)
+    # get_hits parity on the shim table
+    oracle_ht = O.HashTable()
+    oracle_ht.table, oracle_ht.counts, oracle_ht.hashesperid = ht.table, ht.counts, ht.hashesperid
+    assert np.array_equal(ht.get_hits(want), oracle_ht.get_hits(want))
+    res, _ = matcher.match_hashes(ht, want)
+    ref = O.match_hashes(oracle_ht, want)
+    assert res.shape == ref.shape and np.array_equal(res[:, :4], ref[:, :4])
+
+
+def test_get_2d_peaks(mods):
+    from oracle import dejavu_np as D
+
+    g = np.load(os.path.join(ROOT, "tests", "golden", "dejavu.npz"))
+    pk, mask = mods["fp"].get_2D_peaks(g["arr0"], plot=False, amp_min=50)
+    assert [tuple(map(int, p)) for p in pk] == [tuple(r) for r in g["peaks0"].tolist()]
+    assert mask.dtype == np.float64 and np.array_equal(mask.astype(np.uint8), g["mask0"])
+
+
+def test_augmentfp_call_matches_oracle_on_dumped_parameters(mods):
+    from oracle import augment_np as A
+
+    aug = mods["aug"]
+    g = torch.Generator().manual_seed(3)
+    irs = [{"samples": torch.randn(1, n, generator=g) * torch.exp(-torch.arange(n) / 200.0), "sample_rate": 8000} for n in (500, 800)]
+    bg = {"street": [{"samples": torch.randn(1, 90000, generator=g), "sample_rate": 8000}]}
+    params = dict(aug.DEFAULT_PARAMETERS)
+    params.update({k: 1.0 for k in params if k.startswith("proba_")})
+    params["min_cutoff_freq1"] = 20.0
+    a = aug.AugmentFP(bg, 8000, parameters=params, impulse_response_dir=irs)
+    a.augmentation_pipeline.freeze_parameters(42)
+    x = torch.from_numpy(_queries(1)[0][:32000])
+    y = a(x.unsqueeze(0))
+    assert y.shape == (1, 32000) and not y.is_cuda
+    t = a.augmentation_pipeline.transforms
+    prm = dict(fc1=float(t[0].transform_parameters["cutoff_freq"][0]), ir=t[1].transform_parameters["ir"][0, 0].numpy(),
+               noise=t[2].transform_parameters["background"][0, 0].numpy(), snr_db=float(t[2].transform_parameters["snr_in_db"][0]),
+               gain_factor=float(t[3].transform_parameters["gain_factors"].reshape(-1)[0]),
+               clip_p=float(t[4].transform_parameters["percentile_threshold"].reshape(-1)[0]),
+               fc2=float(t[5].transform_parameters["cutoff_freq"][0]), fc3=float(t[6].transform_parameters["cutoff_freq"][0]))
+    ref = A.augment_chain(x.numpy(), prm)
+    assert np.abs(y[0].numpy() - ref).max() / np.abs(ref).max() < 1e-4
+    yb = a.batch_augment(torch.from_numpy(_queries(3)[:, None, :16000]))
+    assert yb.shape == (3, 1, 16000) and torch.isfinite(yb).all()

@@ -1,0 +1,181 @@
+"""CPU: host-side logic of the drop-in modules (no kernels are launched here)."""
+import os
+import pickle
+import random
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DROPIN = os.path.join(ROOT, "musicfpaugment_b200", "dropin")
+
+
+@pytest.fixture()
+def dropin_modules():
+    """Import the drop-ins under their reference module names, then restore sys.modules."""
+    from musicfpaugment_b200 import build
+
+    build.build()
+    from oracle import ref_loader
+
+    if ref_loader.available():
+        ref_loader.load()  # import the real reference first; its modules are parked while the drop-ins own the names
+    saved = {k: v for k, v in sys.modules.items() if k.split(".")[0] in ("afp", "augmentation", "dejavu")}
+    for k in saved:
+        del sys.modules[k]
+    sys.path.insert(0, DROPIN)
+    try:
+        import afp.audfprint.audfprint_match as m
+        import afp.audfprint.hash_table as ht
+        import afp.audfprint.peak_extractor as pe
+        import afp.dejavu.fingerprint as fp
+        import augmentation as aug
+
+        yield {"pe": pe, "ht": ht, "match": m, "fp": fp, "aug": aug}
+    finally:
+        sys.path.remove(DROPIN)
+        for k in [k for k in sys.modules if k.split(".")[0] in ("afp", "augmentation", "dejavu")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+
+
+def test_landmark_hash_round_trip(dropin_modules):
+    from oracle import audfprint_np as O
+
+    pe = dropin_modules["pe"]
+    lms = [(3, 10, 40, 2), (3, 250, 220, 62), (9, 0, 30, 5), (9, 255, 225, 33)]
+    h = pe.landmarks2hashes(lms)
+    assert np.array_equal(h, O.landmarks2hashes(lms)) and h.dtype == np.int32
+    assert pe.hashes2landmarks(h) == lms
+    assert pe.landmarks2hashes([]).shape == (0, 2)
+    v = np.array([1.0, 3.0, 3.0, 2.0, 5.0])
+    assert np.array_equal(pe.locmax(v), O.locmax(v))
+
+
+def test_analyzer_surface_and_errors(dropin_modules):
+    pe = dropin_modules["pe"]
+    prm = {"density": 20, "pks-per-frame": 5, "freq-sd": 30, "shifts": 1, "samplerate": 8000, "n_fft": 512, "n_hop": 256}
+    a = pe.Audfprint_peaks(prm)
+    assert (a.maxpairsperpeak, a.mindt, a.targetdt, a.targetdf) == (3, 2, 63, 31)
+    p = a._afp()
+    from oracle import audfprint_np as O
+
+    assert p.a_dec == O.a_dec() and p.maxpks == 5
+    assert a.find_peaks(np.zeros(0, np.float32))[0] == []
+    with pytest.raises(NotImplementedError):
+        pe.Audfprint_peaks(prm, denoising=True, denoising_model="unet")
+    with pytest.raises(ValueError):
+        pe.Audfprint_peaks(dict(prm, n_fft=1024))
+
+
+def test_hash_table_store_and_pickle_format(dropin_modules, tmp_path):
+    from oracle import audfprint_np as O
+
+    ht_mod = dropin_modules["ht"]
+    r = np.random.default_rng(5)
+    ht, ref = ht_mod.HashTable(), O.HashTable()
+    for t in range(6):
+        rows = np.stack([np.sort(r.integers(0, 900, 300)), r.integers(0, 8, 300) * 977], axis=1).astype(np.int32)
+        random.seed(t)
+        ht.store(f"t{t}", rows)
+        random.seed(t)
+        ref.store(f"t{t}", rows)
+    assert ht.counts.max() > ht.depth  # overflowing buckets exercised the random overwrite
+    assert np.array_equal(ht.table, ref.table) and np.array_equal(ht.counts, ref.counts)
+    assert np.array_equal(ht.hashesperid, ref.hashesperid) and ht.names == ref.names
+    path = str(tmp_path / "db.pklz")
+    ht.save(path)
+    back = ht_mod.HashTable(path)
+    assert np.array_equal(back.table, ht.table) and back.names == ht.names and back.depth == 100 and back.hashbits == 20
+    import gzip
+
+    with gzip.open(path, "rb") as f:
+        raw = pickle.load(f)
+    assert type(raw).__module__ == "afp.audfprint.hash_table" and not any(k.startswith("_dev") for k in raw.__dict__)
+
+
+def test_matcher_defaults(dropin_modules):
+    m = dropin_modules["match"].Matcher()
+    assert (m.window, m.threshcount, m.max_returns, m.search_depth, m.exact_count, m.max_alignments_per_id) == (2, 5, 1, 100, False, 100)
+    p = m._params()
+    assert (p.window, p.threshcount, p.search_depth, p.max_alignments_per_id) == (2, 5, 100, 100)
+
+
+def test_dejavu_generate_hashes(dropin_modules):
+    import hashlib
+
+    fp = dropin_modules["fp"]
+    peaks = [(10, 5), (20, 3), (30, 3), (40, 9)]
+    hs = fp.generate_hashes(list(peaks), fan_value=3)
+    assert hs[0] == (hashlib.sha1(b"20|30|0").hexdigest()[:20], 3)
+    assert len(hs) == 5
+
+
+def _in_memory_sources():
+    g = torch.Generator().manual_seed(3)
+    irs = [{"samples": torch.randn(1, n, generator=g), "sample_rate": 8000} for n in (500, 800, 300)]
+    bg = {"street": [{"samples": torch.randn(1, 30000, generator=g), "sample_rate": 8000}],
+          "cafe": [{"samples": torch.randn(1, 5000, generator=g), "sample_rate": 8000},
+                   {"samples": torch.randn(1, 9000, generator=g), "sample_rate": 8000}]}
+    return irs, bg
+
+
+def test_augmentfp_parameter_draws(dropin_modules):
+    aug = dropin_modules["aug"]
+    irs, bg = _in_memory_sources()
+    a = aug.AugmentFP(bg, 8000, impulse_response_dir=irs)
+    pipe = a.augmentation_pipeline
+    assert len(pipe.transforms) == 8
+    pipe.freeze_parameters(42)
+    arr, ir, noise = pipe.pack(64, 16000)
+    on = lambda bit: (arr["apply"] & bit) != 0
+    from musicfpaugment_b200 import lib
+
+    assert on(lib.AUG_NORM).all() and 0.5 < on(lib.AUG_HPF1).mean() < 1.0
+    assert ((arr["fc1_hz"][on(lib.AUG_HPF1)] >= 0) & (arr["fc1_hz"][on(lib.AUG_HPF1)] <= 150)).all()
+    assert ((arr["fc2_hz"][on(lib.AUG_LPF)] >= 3000) & (arr["fc2_hz"][on(lib.AUG_LPF)] <= 3999)).all()
+    assert ((arr["fc3_hz"][on(lib.AUG_HPF3)] >= 30) & (arr["fc3_hz"][on(lib.AUG_HPF3)] <= 150)).all()
+    assert (np.abs(arr["snr_db"][on(lib.AUG_NOISE)]) <= 10).all()
+    g = arr["gain_factor"][on(lib.AUG_GAIN)]
+    assert ((g >= 10 ** (-5 / 20) - 1e-6) & (g <= 10 ** (5 / 20) + 1e-6)).all()
+    assert ((arr["clip_p"][on(lib.AUG_CLIP)] >= 0) & (arr["clip_p"][on(lib.AUG_CLIP)] <= 0.01)).all()
+    assert noise.shape == (64, 16000) and ir.shape[0] == 64
+    rms = noise[torch.from_numpy(on(lib.AUG_NOISE))].square().mean(dim=1).sqrt()
+    assert torch.allclose(rms, torch.ones_like(rms), atol=1e-4)  # double RMS normalisation (background_noise.py:139-141)
+    # same seed -> same draws
+    pipe.freeze_parameters(42)
+    arr2, _, _ = pipe.pack(64, 16000)
+    assert np.array_equal(arr, arr2)
+    # per-transform dumps follow the App. C schema
+    t = pipe.transforms
+    assert t[0].transform_parameters["should_apply"].shape == (64,)
+    assert t[3].transform_parameters["gain_factors"].dim() == 3 and t[4].transform_parameters["percentile_threshold"].dim() == 2
+    with pytest.raises(RuntimeError):
+        pipe(torch.zeros(4, 16000))
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/augmentation"), reason="reference mount absent")
+def test_parameter_draws_match_reference_rng_order(dropin_modules):
+    """With the same seeds the drop-in draws exactly the reference's parameters for the
+    pass filters, gain and clipping (transform.py:101-114 + each randomize_parameters)."""
+    aug = dropin_modules["aug"]
+    from oracle import ref_loader
+
+    ns = ref_loader.load()
+    x = torch.zeros(16, 1, 8000)
+    pairs = [
+        (aug.HighPassFilter(0.0, 150.0, p=0.8, sample_rate=8000), ns.pass_filters.HighPassFilter(0.0, 150.0, p=0.8, sample_rate=8000), "cutoff_freq"),
+        (aug.LowPassFilter(3000.0, 3999.0, p=0.8, sample_rate=8000), ns.pass_filters.LowPassFilter(3000.0, 3999.0, p=0.8, sample_rate=8000), "cutoff_freq"),
+        (aug.Gain(-5.0, 5.0, p=0.8), ns.gain.Gain(-5.0, 5.0, p=0.8), "gain_factors"),
+        (aug.Clipping(0, 0.01, p=0.8), ns.clipping.Clipping(0, 0.01, p=0.8), "percentile_threshold"),
+    ]
+    for mine, ref, key in pairs:
+        torch.manual_seed(7)
+        mine.draw(16, 8000)
+        torch.manual_seed(7)
+        ref.transform_parameters = {"should_apply": ref.bernoulli_distribution.sample((16,)).to(torch.bool)}
+        ref.randomize_parameters(x[ref.transform_parameters["should_apply"]])
+        assert torch.equal(mine.transform_parameters["should_apply"], ref.transform_parameters["should_apply"])
+        assert torch.equal(mine.transform_parameters[key], ref.transform_parameters[key]), key
