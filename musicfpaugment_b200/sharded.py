@@ -49,10 +49,12 @@ def match_sharded(ctx, hashes, nh, params=None, max_rows: int = 16, list_cap: in
         cand, ncand = ctx.match_select(counts, params)
         lst, nlist = ctx.match_collect(hq, nq, cand, ncand, params, list_cap)
         if world > 1:
-            lists = torch.empty(world, *lst.shape, dtype=lst.dtype, device=lst.device)
-            nlists = torch.empty(world, *nlist.shape, dtype=nlist.dtype, device=nlist.device)
+            # outputs are the inputs concatenated along dim 0 (the only shape every backend accepts)
+            lists = torch.empty(world * lst.shape[0], lst.shape[1], dtype=lst.dtype, device=lst.device)
+            nlists = torch.empty(world * nlist.shape[0], dtype=nlist.dtype, device=nlist.device)
             dist.all_gather_into_tensor(lists, lst, group=group)            # candidates' (track, delta-t) hits
             dist.all_gather_into_tensor(nlists, nlist, group=group)
+            lists, nlists = lists.view(world, *lst.shape), nlists.view(world, *nlist.shape)
         else:
             lists, nlists = lst[None], nlist[None]
         r, n = ctx.match_align(lists, nlists, cand, ncand, params, max_rows)

@@ -1,0 +1,168 @@
+"""CPU tests of the multi-GPU plumbing (musicfpaugment_b200/sharded.py) under gloo, world size 2.
+
+The four matching kernels are replaced by a numpy stand-in built from the oracle (test
+infrastructure only), so what is exercised here is the host logic a real run depends on:
+the hash-range partition of the index, the all-reduce of per-track raw counts, the
+all-gather of the candidates' (track, delta-t) lists and the contiguous query partition.
+The same `match_sharded` drives the CUDA kernels over NCCL on the GPU box.
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from musicfpaugment_b200 import sharded, synth
+from oracle import audfprint_np as O
+
+
+class _P:  # mfpa_match_params stand-in
+    window, threshcount, search_depth, max_alignments_per_id = 2, 5, 100, 100
+
+
+class NumpyShardCtx:
+    """The step-wise matching interface of lib.Context over one hash-range shard, in numpy."""
+
+    def __init__(self, table, counts, hpid, lo, hi):
+        self.ht = O.HashTable()
+        self.ht.table = np.zeros_like(table)
+        self.ht.counts = np.zeros_like(counts)
+        self.ht.table[lo:hi] = table[lo:hi]
+        self.ht.counts[lo:hi] = counts[lo:hi]
+        self.ht.hashesperid = hpid
+        self.n_tracks = len(hpid)
+
+    def _hits(self, hq, n):
+        return self.ht.get_hits(hq[:n].numpy())
+
+    def match_counts(self, hashes, nh):
+        out = torch.zeros(hashes.shape[0], self.n_tracks, dtype=torch.int32)
+        for i in range(hashes.shape[0]):
+            ids = self._hits(hashes[i], int(nh[i]))[:, 0]
+            out[i] = torch.from_numpy(np.bincount(ids, minlength=self.n_tracks).astype(np.int32))
+        return out
+
+    def match_select(self, counts, p):
+        B = counts.shape[0]
+        cand = torch.zeros(B, p.search_depth, 2, dtype=torch.int32)
+        ncand = torch.zeros(B, dtype=torch.int32)
+        for i in range(B):
+            c = counts[i].numpy()
+            ids = np.nonzero(c)[0]
+            raw = c[ids]
+            wtd = raw / self.ht.hashesperid[ids].astype(float)
+            order = np.argsort(wtd)[::-1][: min(int(np.count_nonzero(raw > p.threshcount)), p.search_depth)]
+            ncand[i] = len(order)
+            cand[i, : len(order), 0] = torch.from_numpy(ids[order].astype(np.int32))
+            cand[i, : len(order), 1] = torch.from_numpy(raw[order].astype(np.int32))
+        return cand, ncand
+
+    def match_collect(self, hashes, nh, cand, ncand, p, list_cap):
+        B = hashes.shape[0]
+        lst = torch.zeros(B, list_cap, dtype=torch.int32)
+        nlist = torch.zeros(B, dtype=torch.int32)
+        for i in range(B):
+            hits = self._hits(hashes[i], int(nh[i]))
+            ids = cand[i, : int(ncand[i]), 0].numpy()
+            rank = {int(t): k for k, t in enumerate(ids)}
+            rows = [(rank[int(h[0])] << 16) | (int(h[1]) + 16384) for h in hits if int(h[0]) in rank]
+            nlist[i] = len(rows)
+            lst[i, : len(rows)] = torch.tensor(rows[:list_cap], dtype=torch.int32)
+        return lst, nlist
+
+    def match_align(self, lists, nlists, cand, ncand, p, max_rows):
+        n_lists, B, _ = lists.shape
+        res = torch.zeros(B, max_rows, 7, dtype=torch.int32)
+        nrows = torch.zeros(B, dtype=torch.int32)
+        for i in range(B):
+            ent = np.concatenate([lists[s, i, : int(nlists[s, i])].numpy() for s in range(n_lists)]).astype(np.int64)
+            rows = []
+            mint = int((ent & 0xFFFF).min()) - 16384 if len(ent) else 0
+            for rank in range(int(ncand[i])):
+                dt = (ent[(ent >> 16) == rank] & 0xFFFF) - 16384 - mint
+                bc = np.bincount(dt)
+                f = np.zeros(bc.shape, np.float32)
+                lm = np.nonzero(O.locmax(bc))[0]
+                f[lm] = bc[lm]
+                found = 0
+                while True:
+                    mode = int(np.argmax(f))
+                    if f[mode] <= p.threshcount:
+                        break
+                    lo, hi = max(0, mode - p.window), mode + p.window + 1
+                    rows.append([int(cand[i, rank, 0]), int(bc[lo:hi].sum()), mode + mint, int(cand[i, rank, 1]), rank, 0, 0])
+                    f[lo:hi] = 0
+                    found += 1
+                    if found > p.max_alignments_per_id:
+                        break
+            rows = np.asarray(rows, np.int32).reshape(-1, 7)
+            rows = rows[(-rows[:, 1]).argsort(kind="stable")][:max_rows]
+            nrows[i] = len(rows)
+            res[i, : len(rows)] = torch.from_numpy(rows)
+        return res, nrows
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        table, counts, hpid, th = synth.hash_index(300, 400, seed=21, depth=20)
+        q, nq, truth = synth.planted_queries(th, 6, n_hashes=200, frac=0.4, seed=22)
+        lo, hi = sharded.hash_range(rank, world)
+        ctx = NumpyShardCtx(table, counts, hpid, lo, hi)
+        res, nrows = sharded.match_sharded(ctx, torch.from_numpy(q), torch.from_numpy(nq), params=_P, max_rows=8,
+                                           list_cap=4096, sub_batch=4)
+        # every rank must hold identical results
+        gathered = [torch.zeros_like(res) for _ in range(world)]
+        dist.all_gather(gathered, res)
+        assert all(torch.equal(gathered[0], g) for g in gathered)
+        # query-sharded fingerprint slices cover the batch exactly once
+        mine = torch.zeros(11, dtype=torch.int32)
+        a, b = sharded.query_slice(11, rank, world)
+        mine[a:b] = 1
+        dist.all_reduce(mine)
+        assert torch.equal(mine, torch.ones(11, dtype=torch.int32))
+        if rank == 0:
+            np.savez(os.path.join(out_dir, "out.npz"), res=res.numpy(), nrows=nrows.numpy(), q=q, nq=nq, truth=truth)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_match_sharded_world2_equals_single_table(tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    g = np.load(tmp_path / "out.npz")
+    table, counts, hpid, _ = synth.hash_index(300, 400, seed=21, depth=20)
+    ht = O.HashTable(depth=20)
+    ht.table, ht.counts, ht.hashesperid = table, counts, hpid
+    top1 = 0
+    for i in range(len(g["q"])):
+        want = O.match_hashes(ht, g["q"][i, : g["nq"][i]])[:8]
+        n = int(g["nrows"][i])
+        assert n == len(want), i
+        got = g["res"][i, :n]
+        assert np.array_equal(got[:, 1], want[:, 1])
+        assert sorted(map(tuple, got[:, :4].tolist())) == sorted(map(tuple, want[:, :4].tolist()))
+        top1 += int(n > 0 and got[0, 0] == g["truth"][i])
+    assert top1 >= len(g["q"]) - 1
+
+
+def test_partitions():
+    for world in (1, 2, 3, 4, 8):
+        edges = [sharded.hash_range(r, world) for r in range(world)]
+        assert edges[0][0] == 0 and edges[-1][1] == 1 << 20
+        assert all(edges[r][1] == edges[r + 1][0] for r in range(world - 1))
+        for n in (0, 1, 7, 10000):
+            sl = [sharded.query_slice(n, r, world) for r in range(world)]
+            assert sl[0][0] == 0 and sl[-1][1] == n
+            assert all(sl[r][1] == sl[r + 1][0] for r in range(world - 1))
