@@ -261,7 +261,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
+            "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args), "queries_per_gpu": B, "n_samples": T_QUERY, "shifts": S,
                        "l2_policy": "inputs larger than L2 (2.56 GB waveforms + 2.65 GB magnitudes per step)",
                        "hashes_per_query": tot_hashes / B, "parallelism": f"query-sharded x{world}, no collective"},

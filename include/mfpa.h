@@ -78,6 +78,12 @@ void mfpa_afp_defaults(mfpa_afp_params* p);
  * fills the table with the host C library's exp(). */
 int mfpa_set_spread_table(mfpa_ctx* ctx, const double* table513_host);
 
+/* Options.  MFPA_OPT_PEAKS_F64 (default 0): 1 makes mfpa_audfprint_peaks / mfpa_fingerprint* run the
+ * float64 picker (the one behind mfpa_audfprint_peaks_from_spec) on the float32 magnitudes instead of
+ * the float32 picker; slower, same hashes on every input tested. */
+#define MFPA_OPT_PEAKS_F64 1
+int mfpa_set_option(mfpa_ctx* ctx, int option, int value);
+
 /* ---- geometry --------------------------------------------------------- */
 int mfpa_num_frames(int n_samples);           /* afp/audfprint/stft.py:50-53 */
 int mfpa_shift_offset(int shift, int shifts); /* peak_extractor.py:412 */

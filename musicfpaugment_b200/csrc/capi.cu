@@ -164,6 +164,16 @@ int mfpa_set_spread_table(mfpa_ctx* ctx, const double* table513_host) {
   return MFPA_OK;
 }
 
+int mfpa_set_option(mfpa_ctx* ctx, int option, int value) {
+  MFPA_REQUIRE(ctx != nullptr, "set_option: ctx is NULL");
+  switch (option) {
+    case MFPA_OPT_PEAKS_F64: ctx->opt_peaks_f64 = value != 0; return MFPA_OK;
+    default: break;
+  }
+  set_error("set_option: unknown option %d", option);
+  return MFPA_EINVAL;
+}
+
 int mfpa_stft_mag(mfpa_ctx* ctx, const float* x_dev, int B, int T, int64_t x_stride, int shifts,
                   float* mag_dev, float* qmax_dev, void* stream) {
   MFPA_REQUIRE(ctx && x_dev && mag_dev && qmax_dev, "stft_mag: NULL argument");

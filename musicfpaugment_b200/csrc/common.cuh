@@ -60,6 +60,7 @@ inline int shift_offset(int shift, int shifts) {
 struct mfpa_ctx {
   int device = 0;
   int num_sms = mfpa::kNumSMs;
+  int opt_peaks_f64 = 0;            // MFPA_OPT_PEAKS_F64
   double* spread_dev = nullptr;     // [513] Gaussian table
   float2* tw_dev = nullptr;         // FFT twiddles (stft.cu layout)
   float* win_dev = nullptr;         // [512] analysis window

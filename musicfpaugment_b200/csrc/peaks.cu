@@ -381,6 +381,299 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) peaks_kernel(const PeakAr
   if (lane == 0 && a.npeaks) a.npeaks[item] = total_peaks;
 }
 
+// ---------------------------------------------------------------------------------------
+// Fast float32 picker for the fused path (mag produced by stft_mag_kernel, itself float32).
+// The float64 kernel above stays the parity entry ("bit-exact when fed the reference
+// spectrogram"); end to end the float32 STFT already differs from the reference's float64
+// one by ~1e-7 relative, and a float32 picker changes no hash over 516 seeded queries
+// ("precision of the fused path"), so the hot path does not pay for float64.
+//
+// One warp per item.  Lane l owns bins l, l+32, ..., l+224 (interleaved: the Gaussian
+// table reads of a spread are conflict-free with immediate offsets, loads are 128-byte
+// coalesced).  Everything is in log2 units (the picker is invariant to the log base).
+//   pass 1   mean of log2(max(v, 1e-6 M))
+//   pass 2   forward scan; kept peaks of frame c (<= 5, sorted by (value, bin) desc by a
+//            lane-parallel rank) go to a per-warp shared-memory list
+//   pass 3   backward scan over that list only; peaks that pass are appended to P[c]
+//   pass 4   lane-parallel finalise: record[f] = sorted(P[f] \ P[f-1])   (:227-229)
+constexpr int kFW = 4;          // warps (items) per block
+constexpr int kRawCap = 128;    // local maxima per frame <= 128
+constexpr int kGF = 516;        // float Gaussian table, padded to a multiple of 4
+
+struct FastArgs {
+  const float* mag;     // [items][n_max][264]
+  const float* qmax;    // [items]
+  int items, T, shifts, n_max;
+  float a_dec;
+  int maxpks;
+  const double* spread;  // [513]
+  uint64_t* rec;         // [items][n_max]
+  int32_t* npeaks;       // nullable
+};
+
+__device__ __forceinline__ float lg2_ftz(float x) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+__device__ __forceinline__ void load_frame(const float* p, float (&v)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = __ldg(p + 32 * j);
+}
+
+// sth[j] = max(sth[j], val * G[256 + bin - pos]) for this lane's bins (bin = lane + 32 j)
+__device__ __forceinline__ void spread_f(float (&sth)[8], const float* g_s, int lane, int pos, float val) {
+  const float* gp = g_s + (kRows + lane - pos);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sth[j] = fmaxf(sth[j], val * gp[32 * j]);
+}
+
+// locmax (:61-73) over the interleaved layout; bit j of the result = bin lane + 32 j.
+__device__ __forceinline__ unsigned locmax_f(const float (&y)[8], int lane) {
+  unsigned ge = 0;
+  float prev_rot = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float rot = __shfl_sync(kFull, y[j], (lane + 31) & 31);  // bin - 1 for lanes > 0
+    const float left = lane == 0 ? prev_rot : rot;                 // lane 0: bin 32 j - 1 = lane 31 of j - 1
+    const bool g = (j == 0 && lane == 0) ? true : (y[j] >= left);
+    ge |= (g ? 1u : 0u) << j;
+    prev_rot = rot;
+  }
+  const unsigned nb = __shfl_sync(kFull, ge, (lane + 1) & 31);     // ge of bin + 1
+  const unsigned ge_next = lane == 31 ? (nb >> 1) : nb;            // bin 255 has no right neighbour
+  return ge & ~ge_next & 0xffu;
+}
+
+__device__ __forceinline__ void spread_locmax_f(const float (&v)[8], float (&sth)[8], const float* g_s, int lane) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sth[j] = 0.f;
+  const unsigned lm = locmax_f(v, lane);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    unsigned bal = __ballot_sync(kFull, ((lm >> j) & 1u) && v[j] > 0.f);  // <= 0 cannot raise a zero base
+    while (bal) {
+      const int src = __ffs(bal) - 1;
+      bal &= bal - 1;
+      spread_f(sth, g_s, lane, src + 32 * j, __shfl_sync(kFull, v[j], src));
+    }
+  }
+}
+
+template <bool kPre>
+__device__ __forceinline__ void fast_item(const FastArgs& a, int item, int lane, int n_frames, float M,
+                                          const float* g_s, float* ybuf, float* pv, uint8_t* pb, uint8_t* pc,
+                                          uint8_t* raw) {
+  const float* base = a.mag + (int64_t)item * a.n_max * kPitch;
+  const float* col = base + lane;
+  // kPre: absurdly small scale; bring the data into the normal range first (exact power of two)
+  const float pre = kPre ? 1.8446744e19f : 1.0f;  // 2^64
+  const float floor_v = 1e-6f * (M * pre);
+  // ---- pass 1: mean over 257 x N of log2(max(v, floor)) (:275-276) ----
+  double acc = 0.0;
+  for (int c = 0; c < n_frames; ++c) {
+    float v[8];
+    load_frame(col + (int64_t)c * kPitch, v);
+    float l[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) l[j] = lg2_ftz(fmaxf(kPre ? v[j] * pre : v[j], floor_v));
+    float s = ((l[0] + l[1]) + (l[2] + l[3])) + ((l[4] + l[5]) + (l[6] + l[7]));
+    if (lane == 0) {
+      const float ny = __ldg(base + (int64_t)c * kPitch + kRows);
+      s += lg2_ftz(fmaxf(kPre ? ny * pre : ny, floor_v));
+    }
+    acc += (double)s;
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(kFull, acc, o);
+  const float c0 = (float)(acc / ((double)kBins * (double)n_frames));
+
+  float y[8], z[8], sth[8];
+  auto advance = [&](const float (&v)[8]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float x = lg2_ftz(fmaxf(kPre ? v[j] * pre : v[j], floor_v)) - c0;
+      y[j] = x + z[j];                 // lfilter([1,-1],[1,-0.98]) DF-II transposed (:286-288)
+      z[j] = fmaf(0.98f, y[j], -x);
+    }
+  };
+  // ---- initial threshold from the first min(10, N) frames (:180-182) ----
+  {
+    float m[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) z[j] = 0.f;
+    const int n0 = n_frames < 10 ? n_frames : 10;
+    for (int c = 0; c < n0; ++c) {
+      float v[8];
+      load_frame(col + (int64_t)c * kPitch, v);
+      advance(v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) m[j] = c == 0 ? y[j] : fmaxf(m[j], y[j]);
+    }
+    spread_locmax_f(m, sth, g_s, lane);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) z[j] = 0.f;
+  }
+  // ---- pass 2: forward prune (:190-203) ----
+  const unsigned lt_mask = (1u << lane) - 1u;
+  float v1[8], v2[8];
+  load_frame(col, v1);
+  load_frame(col + (int64_t)(n_frames > 1 ? 1 : 0) * kPitch, v2);
+  for (int c = 0; c < n_frames; ++c) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { v[j] = v1[j]; v1[j] = v2[j]; }
+    if (c + 2 < n_frames) load_frame(col + (int64_t)(c + 2) * kPitch, v2);
+    advance(v);
+    unsigned cand = locmax_f(y, lane);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (!(y[j] > sth[j])) cand &= ~(1u << j);
+    const int cnt = __popc(cand);
+    const unsigned has = __ballot_sync(kFull, cnt != 0);
+    int nk = 0;
+    if (has) {
+      int excl, total;
+      if (!__any_sync(kFull, cnt > 1)) {
+        excl = __popc(has & lt_mask);
+        total = __popc(has);
+      } else {
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(kFull, incl, o);
+          if (lane >= o) incl += t;
+        }
+        excl = incl - cnt;
+        total = __shfl_sync(kFull, incl, 31);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ybuf[lane + 32 * j] = y[j];
+      for (unsigned m = cand; m; m &= m - 1) raw[excl++] = (uint8_t)(lane + 32 * (__ffs(m) - 1));
+      __syncwarp();
+      // rank by (value, bin) descending; the first maxpks ranks are kept, already in order (:196-197)
+      for (int e = lane; e < total; e += 32) {
+        const int b = raw[e];
+        const float val = ybuf[b];
+        int rank = 0;
+        for (int k = 0; k < total; ++k) {
+          const int bk = raw[k];
+          const float vk = ybuf[bk];
+          rank += (vk > val || (vk == val && bk > b)) ? 1 : 0;
+        }
+        if (rank < a.maxpks) { pv[c * kMaxPks + rank] = val; pb[c * kMaxPks + rank] = (uint8_t)b; }
+      }
+      nk = total < a.maxpks ? total : a.maxpks;
+      __syncwarp();
+      for (int i = 0; i < nk; ++i) spread_f(sth, g_s, lane, pb[c * kMaxPks + i], pv[c * kMaxPks + i]);
+    }
+    if (lane == 0) pc[c] = (uint8_t)nk;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sth[j] *= a.a_dec;  // :203
+  }
+  __syncwarp();
+  // ---- pass 3: backward prune (:217-233); y[] still holds the last frame ----
+  spread_locmax_f(y, sth, g_s, lane);
+  for (int c = n_frames - 1; c >= 0; --c) {
+    const int n = pc[c];
+    int kept = 0;
+    for (int i = 0; i < n; ++i) {
+      const int b = pb[c * kMaxPks + i];
+      const float val = pv[c * kMaxPks + i];
+      const int jj = b >> 5;
+      float mine = sth[0];
+#pragma unroll
+      for (int j = 1; j < 8; ++j) mine = (jj == j) ? sth[j] : mine;
+      const float t = __shfl_sync(kFull, mine, b & 31);
+      if (val >= t) {
+        spread_f(sth, g_s, lane, b, val);
+        if (lane == 0) pb[c * kMaxPks + kept] = (uint8_t)b;  // P[c], compacted in place (kept <= i)
+        ++kept;
+      }
+    }
+    if (lane == 0) pc[c] = (uint8_t)kept;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sth[j] *= a.a_dec;  // :233
+  }
+  __syncwarp();
+  // ---- pass 4: record[f] = sorted(P[f] \ P[f-1]), one frame per lane ----
+  uint64_t* rec = a.rec + (int64_t)item * a.n_max;
+  int total_peaks = 0;
+  for (int f0 = 0; f0 < a.n_max; f0 += 32) {
+    const int f = f0 + lane;
+    uint64_t r = 0;
+    if (f < n_frames) {
+      const int n = pc[f];
+      const int np = f > 0 ? pc[f - 1] : 0;
+      int b[5];
+      int cntb = 0;
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        int bi = 0x100;
+        if (i < n) {
+          bi = pb[f * kMaxPks + i];
+          for (int k = 0; k < np; ++k)
+            if (pb[(f - 1) * kMaxPks + k] == bi) bi = 0x100;  // cleared by the same bin one frame earlier
+        }
+        b[i] = bi;
+        cntb += bi < 0x100;
+      }
+#define MFPA_CSWAP(i, j) { const int lo = min(b[i], b[j]), hi = max(b[i], b[j]); b[i] = lo; b[j] = hi; }
+      MFPA_CSWAP(0, 1) MFPA_CSWAP(3, 4) MFPA_CSWAP(2, 4) MFPA_CSWAP(2, 3) MFPA_CSWAP(0, 3)
+      MFPA_CSWAP(0, 2) MFPA_CSWAP(1, 4) MFPA_CSWAP(1, 3) MFPA_CSWAP(1, 2)
+#undef MFPA_CSWAP
+      r = (uint64_t)cntb;
+#pragma unroll
+      for (int i = 0; i < 5; ++i)
+        if (i < cntb) r |= (uint64_t)(b[i] & 0xff) << (8 * (i + 1));
+      total_peaks += cntb;
+    }
+    if (f < a.n_max) rec[f] = r;
+  }
+  if (a.npeaks) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) total_peaks += __shfl_xor_sync(kFull, total_peaks, o);
+    if (lane == 0) a.npeaks[item] = total_peaks;
+  }
+}
+
+__global__ void __launch_bounds__(kFW * 32) peaks_fast_kernel(const FastArgs a) {
+  extern __shared__ __align__(16) unsigned char fast_smem[];
+  float* g_s = reinterpret_cast<float*>(fast_smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nm = a.n_max;
+  float* ybuf = g_s + kGF + warp * kRows;
+  float* pv = g_s + kGF + kFW * kRows + (size_t)warp * nm * kMaxPks;
+  uint8_t* bytes = reinterpret_cast<uint8_t*>(g_s + kGF + kFW * kRows + (size_t)kFW * nm * kMaxPks);
+  uint8_t* pb = bytes + (size_t)warp * nm * kMaxPks;
+  uint8_t* pc = bytes + (size_t)kFW * nm * kMaxPks + (size_t)warp * nm;
+  uint8_t* raw = bytes + (size_t)kFW * nm * (kMaxPks + 1) + warp * kRawCap;
+  for (int i = threadIdx.x; i < kSpreadLen; i += blockDim.x) g_s[i] = (float)a.spread[i];
+  __syncthreads();
+  const int item = blockIdx.x * kFW + warp;
+  if (item >= a.items) return;
+  const int sh = item % a.shifts;
+  const int off = a.shifts < 2 ? 0 : (int)((double)sh / (double)a.shifts * (double)kHop);
+  const int n_frames = 1 + (a.T - off) / kHop;
+  const float M = a.qmax[item];
+  if (!(M > 0.f)) {  // all-zero (or NaN) input: no peaks (:272-280)
+    uint64_t* rec = a.rec + (int64_t)item * a.n_max;
+    for (int c = lane; c < a.n_max; c += 32) rec[c] = 0;
+    if (lane == 0 && a.npeaks) a.npeaks[item] = 0;
+    return;
+  }
+  if (M >= 1e-30f)
+    fast_item<false>(a, item, lane, n_frames, M, g_s, ybuf, pv, pb, pc, raw);
+  else
+    fast_item<true>(a, item, lane, n_frames, M, g_s, ybuf, pv, pb, pc, raw);
+}
+
+static size_t fast_smem_bytes(int n_max) {
+  return sizeof(float) * (kGF + kFW * kRows + (size_t)kFW * n_max * kMaxPks) +
+         (size_t)kFW * n_max * (kMaxPks + 1) + kFW * kRawCap;
+}
+
 // [items][rows][n] float64 (reference layout) -> [items][n][264] float64 (frame-major)
 __global__ void spec_to_frames_kernel(const double* __restrict__ spec, int rows, int n, double* __restrict__ out) {
   __shared__ double tile[32][33];
@@ -410,6 +703,18 @@ static int fwd_scratch(mfpa_ctx* ctx, int items, int n_max, PeakArgs& a) {
 
 int launch_peaks_f32(mfpa_ctx* ctx, const float* mag, const float* qmax, int B, int T, int shifts,
                      const mfpa_afp_params& p, uint64_t* rec, int32_t* npeaks, cudaStream_t st) {
+  const int n_max_f = num_frames(T);
+  const size_t fast_bytes = fast_smem_bytes(n_max_f);
+  if (!ctx->opt_peaks_f64 && qmax != nullptr && fast_bytes <= 100 * 1024) {
+    // float32 picker: pick lists live in shared memory, no global scratch
+    FastArgs f{};
+    f.mag = mag; f.qmax = qmax; f.items = B * shifts; f.T = T; f.shifts = shifts; f.n_max = n_max_f;
+    f.a_dec = (float)p.a_dec; f.maxpks = p.maxpks; f.spread = ctx->spread_dev; f.rec = rec; f.npeaks = npeaks;
+    MFPA_CUDA(cudaFuncSetAttribute(peaks_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_bytes));
+    peaks_fast_kernel<<<(f.items + kFW - 1) / kFW, kFW * 32, fast_bytes, st>>>(f);
+    MFPA_CUDA(cudaGetLastError());
+    return MFPA_OK;
+  }
   PeakArgs a{};
   a.mag = mag; a.qmax = qmax; a.items = B * shifts; a.T = T; a.shifts = shifts;
   a.n_max = num_frames(T); a.n_fixed = 0; a.a_dec = p.a_dec; a.maxpks = p.maxpks;

@@ -67,6 +67,7 @@ SIGNATURES = {
     "mfpa_destroy": (None, [_vp]),
     "mfpa_afp_defaults": (None, [_P]),
     "mfpa_set_spread_table": (_i, [_vp, _vp]),
+    "mfpa_set_option": (_i, [_vp, _i, _i]),
     "mfpa_num_frames": (_i, [_i]),
     "mfpa_shift_offset": (_i, [_i, _i]),
     "mfpa_stft_mag": (_i, [_vp, _vp, _i, _i, _i64, _i, _vp, _vp, _vp]),
@@ -104,6 +105,7 @@ def _bind(sigs):
 _bind(SIGNATURES)
 ALL_SIGNATURES = dict(SIGNATURES)
 
+OPT_PEAKS_F64 = 1
 N_FFT, HOP, BINS, ROWS, MAG_PITCH, MAX_PKS, MAX_SHIFTS, HASHES_PER_FRAME = 512, 256, 257, 256, 264, 5, 8, 15
 
 
@@ -200,6 +202,9 @@ class Context:
         t = np.ascontiguousarray(table, dtype=np.float64)
         assert t.shape == (2 * ROWS + 1,)
         check(_lib.mfpa_set_spread_table(self._h, t.ctypes.data_as(C.c_void_p)))
+
+    def set_option(self, option: int, value: int):
+        check(_lib.mfpa_set_option(self._h, option, value))
 
     # ---- S2 --------------------------------------------------------------
     def stft_mag(self, x, shifts: int = 1):

@@ -223,3 +223,28 @@ def test_scale_invariance(mfpa_ctx):
         got = out[0, : int(nh[0])].cpu().numpy()
         a, b = {tuple(r) for r in want.tolist()}, {tuple(r) for r in got.tolist()}
         assert len(a & b) >= 0.98 * len(a | b), (scale, len(a), len(b))
+
+
+def test_float32_picker_equals_float64_picker(mfpa_ctx):
+    """The hot path's float32 picker and the float64 picker (MFPA_OPT_PEAKS_F64) fed the same float32
+    magnitudes produce the same records on music-like and white-noise queries, all shift offsets."""
+    from musicfpaugment_b200 import synth
+
+    lib = _lib()
+    p = _params(lib)
+    X = torch.cat([synth.music_like(48, seed=31), synth.white_noise(16, seed=32), 1e-9 * synth.music_like(4, seed=33)]).cuda()
+    X[5, 20000:] = 0.0  # digital silence: exercises the 1e-6 floor and the plateau tie-breaks
+    T = X.shape[1]
+    same = total = 0
+    for shifts in (1, 4):
+        mag, qmax = mfpa_ctx.stft_mag(X, shifts)
+        rec32, n32 = mfpa_ctx.audfprint_peaks(mag, qmax, T, shifts, p)
+        mfpa_ctx.set_option(lib.OPT_PEAKS_F64, 1)
+        try:
+            rec64, n64 = mfpa_ctx.audfprint_peaks(mag, qmax, T, shifts, p)
+        finally:
+            mfpa_ctx.set_option(lib.OPT_PEAKS_F64, 0)
+        same += int((rec32 == rec64).sum())
+        total += rec32.numel()
+        assert int((n32 - n64).abs().sum()) <= 2
+    assert same / total >= 0.9995, (same, total)
