@@ -1,13 +1,15 @@
 // S2 — batched magnitude STFT (n_fft 512, hop 256, reflect padding, Hann(514)[1:-1]).
 // Replaces afp/audfprint/stft.py:15-62 + np.abs (peak_extractor.py:257-261).
 //
-// One warp transforms one frame: the 512 real samples are packed into a
-// 256-point complex FFT (z[n] = x[2n] + i x[2n+1]) computed as radix 8 x 8 x 4 —
-// two in-register radix-8 passes exchanged through a conflict-free padded
-// shared-memory tile, one radix-4 pass across lane quads with shuffles — and
-// un-packed to the 257 real-FFT bins.  A block stages 16 consecutive frames
-// (17 * 256 samples, read once, coalesced) so the 50 % frame overlap never
-// re-reads HBM.  Twiddles come from a float64-computed table.
+// A half-warp transforms one frame: the 512 windowed real samples are packed into a
+// 256-point complex FFT (z[n] = x[2n] + i x[2n+1]) computed as 16 x 16 — a radix-16
+// butterfly entirely in registers (two layers of radix-4 with constant twiddles), one
+// transpose through a conflict-free padded shared-memory tile, a second radix-16 — and
+// un-packed to the 257 real-FFT bins pair-wise (bins k and 256-k share their loads and
+// even/odd parts).  A block stages 16 consecutive frames (17 * 256 samples, read once,
+// coalesced, cp.async double-buffered) so the 50 % frame overlap never re-reads HBM.
+// Twiddles come from float64-computed tables; the window is stored pre-multiplied by 1/2
+// (the real-FFT un-packing's factor).
 // Output is frame-major [item][frame][264] so both this kernel's stores and the
 // peak picker's per-frame loads are fully coalesced.
 #include <math.h>
@@ -19,31 +21,45 @@ namespace mfpa {
 namespace {
 
 constexpr int kWarps = 8;
-constexpr int kFramesPerWarp = 2;
+constexpr int kFramesPerWarp = 2;               // one per half-warp
 constexpr int kTile = kWarps * kFramesPerWarp;  // 16 frames per block
-constexpr int kExStride = 36;                   // padded row stride of the exchange tile
-constexpr int kExSize = 8 * kExStride;          // 288 floats per component
-constexpr size_t kStftSmem = sizeof(float) * (2 * (kTile + 1) * kHop + kNfft + 2 * kWarps * kExSize);
+constexpr int kExF2 = 272;                      // float2 per frame exchange tile (16 rows x 17)
+constexpr size_t kStftSmem =
+    sizeof(float) * (2 * (kTile + 1) * kHop + kNfft) + sizeof(float2) * (256 + kWarps * 2 * kExF2);
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }  // a * (-i)
 
-// In-place forward 8-point DFT, natural order in and out.
-__device__ __forceinline__ void fft8(float2 (&v)[8]) {
-  const float h = 0.70710678118654752440f;
-  float2 a0 = cadd(v[0], v[4]), a1 = cadd(v[1], v[5]), a2 = cadd(v[2], v[6]), a3 = cadd(v[3], v[7]);
-  float2 b0 = csub(v[0], v[4]), b1 = csub(v[1], v[5]), b2 = csub(v[2], v[6]), b3 = csub(v[3], v[7]);
-  b1 = make_float2(h * (b1.x + b1.y), h * (b1.y - b1.x));   // * (1 - i)/sqrt2
-  b2 = mul_mi(b2);                                          // * (-i)
-  b3 = make_float2(h * (b3.y - b3.x), -h * (b3.x + b3.y));  // * (-1 - i)/sqrt2
-  float2 c0 = cadd(a0, a2), c1 = cadd(a1, a3), d0 = csub(a0, a2), d1 = mul_mi(csub(a1, a3));
-  v[0] = cadd(c0, c1); v[4] = csub(c0, c1); v[2] = cadd(d0, d1); v[6] = csub(d0, d1);
-  c0 = cadd(b0, b2); c1 = cadd(b1, b3); d0 = csub(b0, b2); d1 = mul_mi(csub(b1, b3));
-  v[1] = cadd(c0, c1); v[5] = csub(c0, c1); v[3] = cadd(d0, d1); v[7] = csub(d0, d1);
+// forward 4-point DFT in place: (a, b, c, d) = inputs n = 0..3 -> outputs k = 0..3
+__device__ __forceinline__ void dft4(float2& a, float2& b, float2& c, float2& d) {
+  const float2 s0 = cadd(a, c), s1 = csub(a, c), s2 = cadd(b, d), s3 = csub(b, d);
+  a = cadd(s0, s2);
+  c = csub(s0, s2);
+  b = make_float2(s1.x + s3.y, s1.y - s3.x);  // s1 - i s3
+  d = make_float2(s1.x - s3.y, s1.y + s3.x);  // s1 + i s3
+}
+
+// forward 16-point DFT in registers.  Input v[n]; output X[k] is left at v[4 (k & 3) + (k >> 2)].
+#define FFT16_OUT(v, k) v[4 * ((k) & 3) + ((k) >> 2)]
+__device__ __forceinline__ void fft16(float2 (&v)[16]) {
+  const float h = 0.70710678118654752440f, c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f;
+#pragma unroll
+  for (int n2 = 0; n2 < 4; ++n2) dft4(v[n2], v[4 + n2], v[8 + n2], v[12 + n2]);  // v[4 k1 + n2] = a[k1][n2]
+  // a[k1][n2] *= W16^(n2 k1),  W16^m = cos(pi m / 8) - i sin(pi m / 8)
+  v[5] = make_float2(v[5].x * c1 + v[5].y * s1, v[5].y * c1 - v[5].x * s1);        // m = 1
+  v[6] = make_float2(h * (v[6].x + v[6].y), h * (v[6].y - v[6].x));                // m = 2
+  v[7] = make_float2(v[7].x * s1 + v[7].y * c1, v[7].y * s1 - v[7].x * c1);        // m = 3
+  v[9] = make_float2(h * (v[9].x + v[9].y), h * (v[9].y - v[9].x));                // m = 2
+  v[10] = make_float2(v[10].y, -v[10].x);                                          // m = 4: * (-i)
+  v[11] = make_float2(h * (v[11].y - v[11].x), -h * (v[11].x + v[11].y));          // m = 6
+  v[13] = make_float2(v[13].x * s1 + v[13].y * c1, v[13].y * s1 - v[13].x * c1);   // m = 3
+  v[14] = make_float2(h * (v[14].y - v[14].x), -h * (v[14].x + v[14].y));          // m = 6
+  v[15] = make_float2(-v[15].x * c1 - v[15].y * s1, v[15].x * s1 - v[15].y * c1);  // m = 9: (-c1, +s1)
+#pragma unroll
+  for (int k1 = 0; k1 < 4; ++k1) dft4(v[4 * k1], v[4 * k1 + 1], v[4 * k1 + 2], v[4 * k1 + 3]);  // -> X[k1 + 4 k2]
 }
 
 __device__ __forceinline__ int reflect_index(int s, int len) {
@@ -110,26 +126,22 @@ stft_mag_kernel(const float* __restrict__ x, int T, int64_t x_stride, int shifts
   extern __shared__ __align__(16) float smem[];
   float (*xs)[(kTile + 1) * kHop] = reinterpret_cast<float (*)[(kTile + 1) * kHop]>(smem);
   float* win_s = smem + 2 * (kTile + 1) * kHop;
-  float (*ex_re)[kExSize] = reinterpret_cast<float (*)[kExSize]>(win_s + kNfft);
-  float (*ex_im)[kExSize] = reinterpret_cast<float (*)[kExSize]>(win_s + kNfft + kWarps * kExSize);
+  float2* tw_s = reinterpret_cast<float2*>(win_s + kNfft);  // [k1][n2] = W256^(n2 k1)
+  float2* ex_all = tw_s + 256;
 
   const int tiles = (n_max + kTile - 1) / kTile;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int half = lane >> 4, l16 = lane & 15;
   for (int i = tid; i < kNfft; i += kWarps * 32) win_s[i] = win[i];
+  for (int i = tid; i < 256; i += kWarps * 32) tw_s[i] = __ldg(tw + (((i >> 4) * (i & 15)) & 255));
 
-  // per-lane twiddles, loaded once per (persistent) block
-  float2 tw1[8], tw2[8], tw3[8];
-  const int g = lane >> 2, p = lane & 3;
+  // un-packing twiddles W512^k for this lane's pairs k = lane + 32 j
+  float2 tw3[4];
 #pragma unroll
-  for (int k = 1; k < 8; ++k) {
-    tw1[k] = __ldg(tw + lane * k);   // W256^(n2*k1)
-    tw2[k] = __ldg(tw + 8 * p * k);  // W32^(p*q)
-  }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) tw3[j] = __ldg(tw + 256 + lane + 32 * j);  // W512^k
+  for (int j = 0; j < 4; ++j) tw3[j] = __ldg(tw + 256 + lane + 32 * j);
 
-  float* er = ex_re[warp];
-  float* ei = ex_im[warp];
+  float2* exw = ex_all + warp * 2 * kExF2;  // this warp's two tiles
+  float2* ex = exw + half * kExF2;          // this half-warp's tile
 
   int64_t tile = blockIdx.x;
   int buf = 0;
@@ -143,75 +155,60 @@ stft_mag_kernel(const float* __restrict__ x, int T, int64_t x_stride, int shifts
     cp_async_wait<1>();
     __syncthreads();
     float vmax = 0.f;
-    for (int fi = 0; fi < kFramesPerWarp; ++fi) {
-      const int fl = warp + kWarps * fi;
-      const int f = ti.f0 + fl;
-      if (f >= ti.n_frames) break;  // warp-uniform
-      const float* xf = xs[buf] + fl * kHop;
-      float2 v[8];
+    if (ti.f0 + 2 * warp < ti.n_frames) {  // warp-uniform: at least this warp's first frame exists
+      const float* xf = xs[buf] + (2 * warp + half) * kHop + 2 * l16;
+      const float* wf = win_s + 2 * l16;
+      float2 v[16];
 #pragma unroll
-      for (int n1 = 0; n1 < 8; ++n1) {
-        const int n = 2 * (32 * n1 + lane);
-        const float2 s = *reinterpret_cast<const float2*>(xf + n);
-        const float2 w = *reinterpret_cast<const float2*>(win_s + n);
+      for (int n1 = 0; n1 < 16; ++n1) {  // z[16 n1 + l16]
+        const float2 s = *reinterpret_cast<const float2*>(xf + 32 * n1);
+        const float2 w = *reinterpret_cast<const float2*>(wf + 32 * n1);
         v[n1] = make_float2(s.x * w.x, s.y * w.y);
       }
-      fft8(v);  // over n1 -> k1
+      fft16(v);  // over n1 -> k1
+      ex[l16] = FFT16_OUT(v, 0);
 #pragma unroll
-      for (int k = 1; k < 8; ++k) v[k] = cmul(v[k], tw1[k]);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) { er[k * kExStride + lane] = v[k].x; ei[k * kExStride + lane] = v[k].y; }
+      for (int k1 = 1; k1 < 16; ++k1) ex[k1 * 17 + l16] = cmul(FFT16_OUT(v, k1), tw_s[k1 * 16 + l16]);
       __syncwarp();
 #pragma unroll
-      for (int m = 0; m < 8; ++m) {
-        const int idx = g * kExStride + 4 * m + p;
-        v[m] = make_float2(er[idx], ei[idx]);
-      }
+      for (int n2 = 0; n2 < 16; ++n2) v[n2] = ex[l16 * 17 + n2];  // lane = k1 now
       __syncwarp();
-      fft8(v);  // over m -> q
+      fft16(v);  // over n2 -> k2: Z[l16 + 16 k2]
 #pragma unroll
-      for (int k = 1; k < 8; ++k) v[k] = cmul(v[k], tw2[k]);
-      // radix-4 across the lane quad (p); lane p ends with output r = bitrev2(p)
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        float2 t = make_float2(__shfl_xor_sync(0xffffffffu, v[k].x, 2), __shfl_xor_sync(0xffffffffu, v[k].y, 2));
-        float2 c = (p & 2) ? csub(t, v[k]) : cadd(v[k], t);
-        if (p == 3) c = mul_mi(c);
-        t = make_float2(__shfl_xor_sync(0xffffffffu, c.x, 1), __shfl_xor_sync(0xffffffffu, c.y, 1));
-        v[k] = (p & 1) ? csub(t, c) : cadd(c, t);
-      }
-      const int r = ((p & 1) << 1) | (p >> 1);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int kk = g + 8 * k + 72 * r;  // natural index g + 8q + 64r, padded by 8 per 64
-        er[kk] = v[k].x; ei[kk] = v[k].y;
-      }
+      for (int k2 = 0; k2 < 16; ++k2) ex[l16 + 16 * k2] = FFT16_OUT(v, k2);
       __syncwarp();
-      float* out = mag + ((int64_t)ti.item * n_max + f) * kPitch;
+      // real-FFT un-packing, whole warp per frame: X[k] = E + W^k O, X[256-k] = conj(E - W^k O)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int k = lane + 32 * j;
-        const int kc = (256 - k) & 255;
-        const int ka = k + 8 * (k >> 6), kb = kc + 8 * (kc >> 6);
-        const float ar = er[ka], ai = ei[ka], cr = er[kb], ci = ei[kb];
-        const float e_r = 0.5f * (ar + cr), e_i = 0.5f * (ai - ci);
-        const float o_r = 0.5f * (ai + ci), o_i = -0.5f * (ar - cr);
-        const float xr = e_r + tw3[j].x * o_r - tw3[j].y * o_i;
-        const float xi = e_i + tw3[j].x * o_i + tw3[j].y * o_r;
-        const float m = sqrt_approx(xr * xr + xi * xi);
-        out[k] = m;
-        vmax = fmaxf(vmax, m);
-      }
-      if (lane == 0) {  // Nyquist bin: Re(Z0) - Im(Z0)
-        const float m = fabsf(er[0] - ei[0]);
-        out[256] = m;
-        vmax = fmaxf(vmax, m);
+      for (int hh = 0; hh < 2; ++hh) {
+        const int f = ti.f0 + 2 * warp + hh;
+        if (f < ti.n_frames) {  // warp-uniform
+          const float2* zs = exw + hh * kExF2;
+          float* out = mag + ((int64_t)ti.item * n_max + f) * kPitch;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int k = lane + 32 * j;
+            const float2 a = zs[k], c = zs[(256 - k) & 255];
+            const float er = a.x + c.x, ei = a.y - c.y, o_r = a.y + c.y, o_i = c.x - a.x;
+            const float tr = tw3[j].x * o_r - tw3[j].y * o_i, ti_ = tw3[j].x * o_i + tw3[j].y * o_r;
+            const float x1r = er + tr, x1i = ei + ti_, x2r = er - tr, x2i = ei - ti_;
+            const float m1 = sqrt_approx(x1r * x1r + x1i * x1i), m2 = sqrt_approx(x2r * x2r + x2i * x2i);
+            out[k] = m1;
+            out[256 - k] = m2;
+            vmax = fmaxf(vmax, fmaxf(m1, m2));
+          }
+          if (lane == 0) {  // bin 128 pairs with itself: |X[128]| = |Z[128]| (Z was halved by the window)
+            const float2 a = zs[128];
+            const float m = 2.0f * sqrt_approx(a.x * a.x + a.y * a.y);
+            out[128] = m;
+            vmax = fmaxf(vmax, m);
+          }
+        }
       }
       __syncwarp();
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-    if (lane == 0 && ti.f0 + warp < ti.n_frames) atomicMax(reinterpret_cast<int*>(qmax + ti.item), __float_as_int(vmax));
+    if (lane == 0 && ti.f0 + 2 * warp < ti.n_frames) atomicMax(reinterpret_cast<int*>(qmax + ti.item), __float_as_int(vmax));
     __syncthreads();  // everyone is done with xs[buf] before it is refilled two iterations later
   }
   cp_async_wait<0>();
@@ -250,7 +247,7 @@ int stft_init_tables(mfpa_ctx* ctx) {
   for (int k = 0; k < 256; ++k) tw[k] = make_float2((float)cos(2 * pi * k / 256), (float)-sin(2 * pi * k / 256));
   for (int k = 0; k <= 256; ++k) tw[256 + k] = make_float2((float)cos(2 * pi * k / 512), (float)-sin(2 * pi * k / 512));
   // np.hanning(514)[1:-1]: 0.5 - 0.5*cos(2*pi*n/513), n = 1..512
-  for (int n = 0; n < kNfft; ++n) win[n] = (float)(0.5 - 0.5 * cos(2 * pi * (n + 1) / (kNfft + 1)));
+  for (int n = 0; n < kNfft; ++n) win[n] = (float)(0.5 * (0.5 - 0.5 * cos(2 * pi * (n + 1) / (kNfft + 1))));  // x 1/2: real-FFT un-packing factor
   MFPA_CUDA(cudaMalloc(&ctx->tw_dev, sizeof(tw)));
   MFPA_CUDA(cudaMalloc(&ctx->win_dev, sizeof(win)));
   MFPA_CUDA(cudaMemcpy(ctx->tw_dev, tw, sizeof(tw), cudaMemcpyHostToDevice));
