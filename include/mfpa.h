@@ -90,8 +90,11 @@ int mfpa_shift_offset(int shift, int shifts); /* peak_extractor.py:412 */
 
 /* ---- S2: magnitude STFT  (afp/audfprint/stft.py:15-62 + abs, peak_extractor.py:257-261)
  * x_dev: B rows of T float32 samples, row stride `x_stride` elements.
- * mag_dev: [B*shifts][mfpa_num_frames(T)][MFPA_MAG_PITCH] float32, frame-major
- *          (elements 0..256 of each frame are |rfft|; the rest is padding).
+ * mag_dev: [B*shifts][mfpa_num_frames(T)][MFPA_MAG_PITCH] float32, frame-major.
+ *          Elements 0..256 of each frame row are |rfft|.  Elements 258/259 of every EVEN frame row
+ *          carry picker statistics of the frame pair (2k, 2k+1): the sum of log2 and the minimum
+ *          of their magnitudes (mfpa_audfprint_peaks uses them to skip a pass over the data);
+ *          the remaining elements are padding.
  * qmax_dev: [B*shifts] float32, max of each item's magnitudes (the divisor of
  *          `sgram /= np.max(sgram)`, peak_extractor.py:263). */
 int mfpa_stft_mag(mfpa_ctx* ctx, const float* x_dev, int B, int T, int64_t x_stride, int shifts,
@@ -106,7 +109,9 @@ int mfpa_spec_from_mag(mfpa_ctx* ctx, const float* mag_dev, const float* qmax_de
  * lfilter, _decaying_threshold_fwd_prune :173-204, _bwd_prune_peaks :206-234)
  * Output: one 64-bit record per (item, frame): byte0 = number of peaks (<=5),
  * bytes 1..5 = their bins in ascending order.  rec_dev: [B*shifts][n_frames_max].
- * npeaks_dev: [B*shifts] int32 total per item (may be NULL). */
+ * npeaks_dev: [B*shifts] int32 total per item (may be NULL).
+ * With qmax_dev != NULL, mag_dev must have been written by mfpa_stft_mag (statistics in the row
+ * padding, see above); with qmax_dev == NULL the float64 picker runs on elements 0..256 only. */
 int mfpa_audfprint_peaks(mfpa_ctx* ctx, const float* mag_dev, const float* qmax_dev, int B, int T,
                          int shifts, const mfpa_afp_params* p, uint64_t* rec_dev,
                          int32_t* npeaks_dev, void* stream);

@@ -471,22 +471,43 @@ __device__ __forceinline__ void fast_item(const FastArgs& a, int item, int lane,
   const float pre = kPre ? 1.8446744e19f : 1.0f;  // 2^64
   const float floor_v = 1e-6f * (M * pre);
   // ---- pass 1: mean over 257 x N of log2(max(v, floor)) (:275-276) ----
+  // stft_mag_kernel leaves, in elements 258/259 of every even frame row, the sum of log2 and the
+  // minimum of the magnitudes of that frame pair.  When nothing lies below the floor the clamp is
+  // the identity and the mean follows from those ~N/2 partial sums; otherwise scan the data.
   double acc = 0.0;
-  for (int c = 0; c < n_frames; ++c) {
-    float v[8];
-    load_frame(col + (int64_t)c * kPitch, v);
-    float l[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) l[j] = lg2_ftz(fmaxf(kPre ? v[j] * pre : v[j], floor_v));
-    float s = ((l[0] + l[1]) + (l[2] + l[3])) + ((l[4] + l[5]) + (l[6] + l[7]));
-    if (lane == 0) {
-      const float ny = __ldg(base + (int64_t)c * kPitch + kRows);
-      s += lg2_ftz(fmaxf(kPre ? ny * pre : ny, floor_v));
+  bool scan = kPre;
+  if (!kPre) {
+    float mn = 3.4e38f;
+    for (int c = 2 * lane; c < n_frames; c += 64) {
+      const float2 st = __ldg(reinterpret_cast<const float2*>(base + (int64_t)c * kPitch + kBins + 1));
+      acc += (double)st.x;
+      mn = fminf(mn, st.y);
     }
-    acc += (double)s;
-  }
 #pragma unroll
-  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(kFull, acc, o);
+    for (int o = 16; o; o >>= 1) {
+      acc += __shfl_xor_sync(kFull, acc, o);
+      mn = fminf(mn, __shfl_xor_sync(kFull, mn, o));
+    }
+    scan = !(mn >= floor_v) || !(fabs(acc) < 1e30);  // something is clamped (or -inf / NaN): exact pass
+  }
+  if (scan) {
+    acc = 0.0;
+    for (int c = 0; c < n_frames; ++c) {
+      float v[8];
+      load_frame(col + (int64_t)c * kPitch, v);
+      float l[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) l[j] = lg2_ftz(fmaxf(kPre ? v[j] * pre : v[j], floor_v));
+      float s = ((l[0] + l[1]) + (l[2] + l[3])) + ((l[4] + l[5]) + (l[6] + l[7]));
+      if (lane == 0) {
+        const float ny = __ldg(base + (int64_t)c * kPitch + kRows);
+        s += lg2_ftz(fmaxf(kPre ? ny * pre : ny, floor_v));
+      }
+      acc += (double)s;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(kFull, acc, o);
+  }
   const float c0 = (float)(acc / ((double)kBins * (double)n_frames));
 
   float y[8], z[8], sth[8];

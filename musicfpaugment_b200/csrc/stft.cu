@@ -77,6 +77,12 @@ __device__ __forceinline__ float sqrt_approx(float x) {
   return r;
 }
 
+__device__ __forceinline__ float lg2_ftz(float x) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem));
@@ -89,14 +95,18 @@ struct TileInfo {
   int len, n_frames, f0, item;
 };
 
-__device__ __forceinline__ TileInfo tile_info(int64_t tile, int tiles, const float* x, int T, int64_t x_stride, int shifts) {
+struct ShiftOffsets { int off[MFPA_MAX_SHIFTS]; };  // int(shift / shifts * 256), computed on the host
+
+__device__ __forceinline__ TileInfo tile_info(unsigned tile, unsigned tiles, const float* x, int T, int64_t x_stride,
+                                              unsigned shifts, const ShiftOffsets& so) {
   TileInfo t;
-  t.item = (int)(tile / tiles);
-  const int q = t.item / shifts, sh = t.item - q * shifts;
-  const int off = shifts < 2 ? 0 : (int)((double)sh / (double)shifts * (double)kHop);
+  const unsigned item = tile / tiles;
+  const unsigned q = item / shifts, sh = item - q * shifts;
+  const int off = so.off[sh];
+  t.item = (int)item;
   t.len = T - off;
   t.n_frames = 1 + t.len / kHop;
-  t.f0 = (int)(tile - (int64_t)t.item * tiles) * kTile;
+  t.f0 = (int)(tile - item * tiles) * kTile;
   t.xq = x + (int64_t)q * x_stride + off;
   return t;
 }
@@ -120,8 +130,8 @@ __device__ __forceinline__ void stage_tile(const TileInfo& t, float* xs, int tid
 }
 
 __global__ void __launch_bounds__(kWarps * 32, 3)
-stft_mag_kernel(const float* __restrict__ x, int T, int64_t x_stride, int shifts, int n_max, int64_t total_tiles,
-                const float2* __restrict__ tw, const float* __restrict__ win,
+stft_mag_kernel(const float* __restrict__ x, int T, int64_t x_stride, int shifts, int n_max, unsigned total_tiles,
+                const __grid_constant__ ShiftOffsets so, const float2* __restrict__ tw, const float* __restrict__ win,
                 float* __restrict__ mag, float* __restrict__ qmax) {
   extern __shared__ __align__(16) float smem[];
   float (*xs)[(kTile + 1) * kHop] = reinterpret_cast<float (*)[(kTile + 1) * kHop]>(smem);
@@ -129,7 +139,7 @@ stft_mag_kernel(const float* __restrict__ x, int T, int64_t x_stride, int shifts
   float2* tw_s = reinterpret_cast<float2*>(win_s + kNfft);  // [k1][n2] = W256^(n2 k1)
   float2* ex_all = tw_s + 256;
 
-  const int tiles = (n_max + kTile - 1) / kTile;
+  const unsigned tiles = (n_max + kTile - 1) / kTile;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int half = lane >> 4, l16 = lane & 15;
   for (int i = tid; i < kNfft; i += kWarps * 32) win_s[i] = win[i];
@@ -143,14 +153,14 @@ stft_mag_kernel(const float* __restrict__ x, int T, int64_t x_stride, int shifts
   float2* exw = ex_all + warp * 2 * kExF2;  // this warp's two tiles
   float2* ex = exw + half * kExF2;          // this half-warp's tile
 
-  int64_t tile = blockIdx.x;
+  unsigned tile = blockIdx.x;
   int buf = 0;
-  if (tile < total_tiles) stage_tile(tile_info(tile, tiles, x, T, x_stride, shifts), xs[0], tid);
+  if (tile < total_tiles) stage_tile(tile_info(tile, tiles, x, T, x_stride, shifts, so), xs[0], tid);
   cp_async_commit();
   for (; tile < total_tiles; tile += gridDim.x, buf ^= 1) {
-    const TileInfo ti = tile_info(tile, tiles, x, T, x_stride, shifts);
-    const int64_t next = tile + gridDim.x;
-    if (next < total_tiles) stage_tile(tile_info(next, tiles, x, T, x_stride, shifts), xs[buf ^ 1], tid);
+    const TileInfo ti = tile_info(tile, tiles, x, T, x_stride, shifts, so);
+    const unsigned next = tile + gridDim.x;
+    if (next < total_tiles) stage_tile(tile_info(next, tiles, x, T, x_stride, shifts, so), xs[buf ^ 1], tid);
     cp_async_commit();
     cp_async_wait<1>();
     __syncthreads();
@@ -178,6 +188,7 @@ stft_mag_kernel(const float* __restrict__ x, int T, int64_t x_stride, int shifts
       for (int k2 = 0; k2 < 16; ++k2) ex[l16 + 16 * k2] = FFT16_OUT(v, k2);
       __syncwarp();
       // real-FFT un-packing, whole warp per frame: X[k] = E + W^k O, X[256-k] = conj(E - W^k O)
+      float lsum = 0.f, lmin = 3.4e38f;  // picker statistics of this warp's frame pair (see mfpa.h, mag layout)
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         const int f = ti.f0 + 2 * warp + hh;
@@ -195,16 +206,29 @@ stft_mag_kernel(const float* __restrict__ x, int T, int64_t x_stride, int shifts
             out[k] = m1;
             out[256 - k] = m2;
             vmax = fmaxf(vmax, fmaxf(m1, m2));
+            lsum += lg2_ftz(m1) + lg2_ftz(m2);
+            lmin = fminf(lmin, fminf(m1, m2));
           }
           if (lane == 0) {  // bin 128 pairs with itself: |X[128]| = |Z[128]| (Z was halved by the window)
             const float2 a = zs[128];
             const float m = 2.0f * sqrt_approx(a.x * a.x + a.y * a.y);
             out[128] = m;
             vmax = fmaxf(vmax, m);
+            lsum += lg2_ftz(m);
+            lmin = fminf(lmin, m);
           }
         }
       }
       __syncwarp();
+#pragma unroll
+      for (int o = 16; o; o >>= 1) {
+        lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+        lmin = fminf(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
+      }
+      if (lane == 0) {
+        float* row = mag + ((int64_t)ti.item * n_max + ti.f0 + 2 * warp) * kPitch;
+        *reinterpret_cast<float2*>(row + kBins + 1) = make_float2(lsum, lmin);  // elements 258, 259
+      }
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
@@ -261,11 +285,14 @@ int launch_stft_mag(mfpa_ctx* ctx, const float* x, int B, int T, int64_t stride,
   const int n_max = num_frames(T);
   MFPA_CUDA(cudaMemsetAsync(qmax, 0, sizeof(float) * items, st));
   const int64_t total_tiles = (int64_t)items * ((n_max + kTile - 1) / kTile);
+  MFPA_REQUIRE(total_tiles < (1ll << 31) - 4096, "stft_mag: batch too large (%lld tiles); split it", (long long)total_tiles);
   const int64_t resident = (int64_t)ctx->num_sms * 3;  // persistent blocks, 3 per SM (__launch_bounds__)
   const unsigned blocks = (unsigned)(total_tiles < resident ? total_tiles : resident);
+  ShiftOffsets so{};
+  for (int sft = 0; sft < shifts; ++sft) so.off[sft] = shift_offset(sft, shifts);
   MFPA_CUDA(cudaFuncSetAttribute(stft_mag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStftSmem));
-  stft_mag_kernel<<<blocks, kWarps * 32, kStftSmem, st>>>(x, T, stride, shifts, n_max, total_tiles, ctx->tw_dev, ctx->win_dev,
-                                                  mag, qmax);
+  stft_mag_kernel<<<blocks, kWarps * 32, kStftSmem, st>>>(x, T, stride, shifts, n_max, (unsigned)total_tiles, so, ctx->tw_dev,
+                                                          ctx->win_dev, mag, qmax);
   MFPA_CUDA(cudaGetLastError());
   return MFPA_OK;
 }
