@@ -39,6 +39,7 @@ N_FRAMES = 251
 BYTES_STFT = 256_000 + 257 * N_FRAMES * 4          # S2: waveform in, magnitudes out
 BYTES_PEAKS = 257 * N_FRAMES * 4 + 256 * N_FRAMES  # S3: magnitudes in, peak mask (u8-equivalent) out
 BYTES_FUSED = 256_000                              # S2-S4 fused: waveform in (+ 8 B per hash out)
+BYTES_CHAIN = 544_000                              # S1-S4 fused: x + noise + IR in (+ 8 B per hash out)
 
 
 def _peaks():
@@ -281,10 +282,160 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"{nq} of the same synthetic queries ({args.cpu_queries_per_core} per core), "
                                               f"numpy oracle of wavfile2hashes, {wall:.1f} s wall"}
+    del x, mag, rec, hashes, out, x_host, rows_host
+    torch.cuda.empty_cache()
+    # ---- the other BASELINE configs, device-timed (extra keys of the same JSON line)
+    extras = {}
+    if "chain" in args.also:
+        ms, nhash = bench_full_chain(ctx, lib, dev, rank, B, 1, max(2, args.steps // 2), 3, barrier)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        hbm, _ = _peaks()
+        extras["full_chain"] = {
+            "workload": f"{B} queries per GPU through the AugmentFP chain (HPF, 1 s IR conv, noise at random SNR, gain, "
+                        "clipping, LPF, HPF) fused with STFT + peaks + hashes, shifts=1 (BASELINE.json configs[2]); "
+                        "loudspeaker cut-off clamped to >= 20 Hz",
+            "value": world * B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "hashes_per_query": nhash / B,
+            "algorithmic_bytes_per_query": BYTES_CHAIN,
+            "hbm_frac": BYTES_CHAIN * B / (ms * 1e-3) / 1e9 / hbm}
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            rate, cores, nq = cpu_chain_rate(2, 1)
+            extras["full_chain"]["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                                                    "sample": f"{nq} queries (2 per core), numpy oracle of the chain + wavfile2hashes"}
+    if "match" in args.also:
+        ms, top1, nqh = bench_match(ctx, lib, dev, rank, world, B, args.tracks, max(2, args.steps // 2), 3, barrier)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        extras["match"] = {
+            "workload": f"{B} planted 400-hash queries (the same batch on every rank) vs a synthetic {args.tracks}-track index "
+                        f"(1000 hashes/track, depth 100) sharded by hash range over {world} GPU(s) (BASELINE.json configs[4])",
+            "value": B / (ms * 1e-3), "unit": "queries/s", "ms_per_step": ms, "scaling": "strong",
+            "top1_equals_planted_track": top1, "query_hashes": nqh,
+            "collective": "none" if world == 1 else "NCCL all-reduce of per-track counts + all-gather of candidate hit lists"}
+    if rank == 0:
+        line.update(extras)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
     ctx.close()
+
+
+
+# ------------------------------------------------------------------ other BASELINE configs (device-timed)
+def _cpu_chain_worker(args):
+    """configs[0]/[2] on the CPU: oracle AugmentFP chain + wavfile2hashes on one core."""
+    seed, n, shifts = args
+    os.environ["OMP_NUM_THREADS"] = "1"
+    import numpy as np
+    import torch
+
+    torch.set_num_threads(1)
+    from musicfpaugment_b200 import synth
+    from oracle import audfprint_np as O
+    from oracle import augment_np as A
+
+    x = synth.music_like(n, seed=seed).numpy()
+    ir = synth.impulse_responses(n, seed=seed + 1).numpy()
+    noise = synth.rms_noise(n, seed=seed + 2).numpy()
+    pr = synth.augment_params(n, seed=seed + 3)
+    t0 = time.perf_counter()
+    for i in range(n):
+        prm = {"fc1": float(pr["fc1"][i]), "ir": ir[i], "noise": noise[i], "snr_db": float(pr["snr_db"][i]),
+               "gain_factor": float(np.float32(10.0) ** (pr["gain_db"][i] / np.float32(20.0))),
+               "clip_p": float(pr["clip_p"][i]), "fc2": float(pr["fc2"][i]), "fc3": float(pr["fc3"][i])}
+        y = A.augment_chain(x[i], prm)
+        O.wave2hashes(np.asarray(y, dtype=np.float32), shifts)
+    return time.perf_counter() - t0, n
+
+
+def cpu_chain_rate(per_core: int, shifts: int, cores: int | None = None):
+    import multiprocessing as mp
+
+    cores = cores or os.cpu_count() or 1
+    with mp.get_context("spawn").Pool(cores) as pool:
+        pool.map(_cpu_chain_worker, [(1, 1, shifts)] * cores)
+        res = pool.map(_cpu_chain_worker, [(2000 + 10 * i, per_core, shifts) for i in range(cores)])
+    return sum(r[1] for r in res) / max(r[0] for r in res), cores, sum(r[1] for r in res)
+
+
+def aug_param_array(lib, n, seed, ir_len):
+    import numpy as np
+
+    from musicfpaugment_b200 import synth
+
+    pr = synth.augment_params(n, seed=seed)
+    arr = np.zeros(n, dtype=lib.AUG_DTYPE)
+    arr["apply"] = lib.AUG_ALL
+    arr["fc1_hz"], arr["fc2_hz"], arr["fc3_hz"] = pr["fc1"], pr["fc2"], pr["fc3"]
+    arr["snr_db"], arr["clip_p"] = pr["snr_db"], pr["clip_p"]
+    arr["gain_factor"] = np.float32(10.0) ** (pr["gain_db"] / np.float32(20.0))
+    arr["ir_len"] = ir_len
+    return arr
+
+
+def bench_full_chain(ctx, lib, dev, rank, B, shifts, steps, warmup, barrier):
+    """BASELINE configs[2]: AugmentFP chain (1 s IR, noise at random SNR, filters, clipping) fused with
+    STFT + peaks + hashes; x, noise and IR resident in HBM, hashes left in HBM."""
+    import torch
+
+    from musicfpaugment_b200 import synth
+
+    x = synth.music_like(B, seed=1234 + rank, device=dev, chunk=32)
+    ir = synth.impulse_responses(B, seed=2000 + rank, device=dev)
+    noise = synth.rms_noise(B, seed=3000 + rank, device=dev)
+    prm = aug_param_array(lib, B, 4000 + rank, ir.shape[1])
+    p = lib.afp_defaults()
+    hashes = nh = None
+    for _ in range(warmup):
+        hashes, nh = ctx.augment_fingerprint(x, prm, ir, noise, shifts, p)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        hashes, nh = ctx.augment_fingerprint(x, prm, ir, noise, shifts, p)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / steps
+    return ms, int(nh.sum().item())
+
+
+def bench_match(ctx, lib, dev, rank, world, B, n_tracks, steps, warmup, barrier):
+    """BASELINE configs[4]: match B planted 400-hash queries against a synthetic n_tracks-track index
+    sharded by hash range over the ranks; per-track histograms summed with an NCCL all-reduce."""
+    import torch
+
+    from musicfpaugment_b200 import sharded, synth
+
+    lo, hi = sharded.hash_range(rank, world)
+    table, counts, hpid, tt, th = synth.hash_index_device(n_tracks, 1000, seed=5000, device=dev, hash_lo=lo, hash_hi=hi)
+    ctx.index_load(table.cpu().numpy().view("uint32"), counts.cpu().numpy(), hpid.cpu().numpy().astype("uint32"), hash_lo=lo)
+    del table
+    q, nq, truth = synth.planted_queries_device(tt, th, B, n_hashes=400, frac=0.3, seed=6000)
+    del tt, th
+    torch.cuda.empty_cache()
+    mp = lib.match_defaults()
+
+    def step():
+        if world == 1:
+            return ctx.match(q, nq, mp, max_rows=4)
+        return sharded.match_sharded(ctx, q, nq, mp, max_rows=4, sub_batch=512)
+
+    for _ in range(warmup):
+        res, nrows = step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        res, nrows = step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / steps
+    top1 = float(((nrows > 0) & (res[:, 0, 0] == truth)).float().mean().item())
+    return ms, top1, int(nq.sum().item())
 
 
 def main():
@@ -297,6 +448,9 @@ def main():
     ap.add_argument("--shifts", type=int, default=1)
     ap.add_argument("--cpu-queries-per-core", type=int, default=200)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--also", default="chain,match",
+                    help="comma list of the other BASELINE configs to time after the headline: chain, match, or none")
+    ap.add_argument("--tracks", type=int, default=100000, help="tracks in the synthetic index of the match workload")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

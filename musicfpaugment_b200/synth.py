@@ -148,3 +148,71 @@ def planted_queries(track_hashes: np.ndarray, n_queries: int, n_hashes: int = 40
         out[q, :k, 1] = key & 0xFFFFFFFF
         nh[q] = k
     return out, nh, truth
+
+
+def hash_index_device(n_tracks: int, hashes_per_track: int = 1000, seed: int = 5000, depth: int = 100,
+                      hashbits: int = 20, maxtimebits: int = 14, t_max: int = 940, device="cuda",
+                      hash_lo: int = 0, hash_hi: int | None = None):
+    """`hash_index` built with torch on `device` (the 100 k-track benchmark index is 10^8 entries;
+    numpy's argsort of that takes most of a minute).  Same layout and fill rule as `hash_index`,
+    different random stream.  Only buckets [hash_lo, hash_hi) are materialised (a hash-range shard:
+    every rank draws the same stream from the same seed and keeps its own rows).
+    Returns (table uint32-as-int32 [hash_hi-hash_lo, depth], counts int32, hashesperid int32,
+    track_t int16 [n_tracks, hpt], track_h int32 [n_tracks, hpt])."""
+    dev = torch.device(device)
+    nb = 1 << hashbits
+    hash_hi = nb if hash_hi is None else hash_hi
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    n = n_tracks * hashes_per_track
+    h = torch.randint(0, nb, (n,), generator=g, device=dev, dtype=torch.int32)
+    t = torch.randint(0, t_max, (n,), generator=g, device=dev, dtype=torch.int32)
+    track_h, track_t = h.view(n_tracks, hashes_per_track), t.view(n_tracks, hashes_per_track).to(torch.int16)
+    counts_all = torch.bincount(h, minlength=nb)
+    hs, order = torch.sort(h, stable=True)  # stable: track order inside a bucket
+    start = torch.cumsum(counts_all, 0) - counts_all
+    slot = torch.arange(n, device=dev, dtype=torch.int64) - start[hs.long()]
+    keep = (slot < depth) & (hs >= hash_lo) & (hs < hash_hi)
+    ids = (order // hashes_per_track)
+    val = ((ids + 1) << maxtimebits) + (t[order].long() & ((1 << maxtimebits) - 1))
+    table = torch.zeros(hash_hi - hash_lo, depth, dtype=torch.int64, device=dev)
+    table[(hs[keep] - hash_lo).long(), slot[keep]] = val[keep]
+    table = (table & 0xFFFFFFFF).to(torch.int64)
+    table = torch.where(table >= (1 << 31), table - (1 << 32), table).to(torch.int32)  # uint32 bit pattern
+    counts = counts_all[hash_lo:hash_hi].to(torch.int32)
+    hpid = torch.full((n_tracks,), hashes_per_track, dtype=torch.int32, device=dev)
+    return table, counts, hpid, track_t, track_h
+
+
+def planted_queries_device(track_t, track_h, n_queries: int, n_hashes: int = 400, frac: float = 0.3,
+                           seed: int = 6000, hashbits: int = 20, t_q_max: int = 251):
+    """`planted_queries` with torch on the tracks' device.  Query q plants ≈frac·n_hashes hashes of track
+    q mod n_tracks at one time offset; the rest is uniform random.  Rows unique, sorted by (time, hash).
+    Returns (hashes int32 [n_queries, n_hashes, 2], nh int32 [n_queries], truth int32 [n_queries])."""
+    dev = track_h.device
+    n_tracks, hpt = track_h.shape
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    truth = torch.arange(n_queries, device=dev) % n_tracks
+    n_pl = int(frac * n_hashes)
+    off = torch.randint(0, 600, (n_queries, 1), generator=g, device=dev)
+    tt, hh = track_t[truth].long(), track_h[truth].long()
+    inwin = (tt >= off) & (tt < off + t_q_max)
+    score = torch.rand(n_queries, hpt, generator=g, device=dev) + inwin.float()  # in-window entries first
+    sel = torch.topk(score, n_pl, dim=1).indices
+    ok = torch.gather(inwin, 1, sel)
+    pt = torch.gather(tt, 1, sel) - off
+    ph = torch.gather(hh, 1, sel)
+    rt = torch.randint(0, t_q_max, (n_queries, n_hashes), generator=g, device=dev)
+    rh = torch.randint(0, 1 << hashbits, (n_queries, n_hashes), generator=g, device=dev)
+    rt[:, :n_pl] = torch.where(ok, pt, rt[:, :n_pl])
+    rh[:, :n_pl] = torch.where(ok, ph, rh[:, :n_pl])
+    key, _ = torch.sort((rt << 32) + rh, dim=1)
+    dup = torch.zeros_like(key, dtype=torch.bool)
+    dup[:, 1:] = key[:, 1:] == key[:, :-1]
+    big = torch.iinfo(torch.int64).max
+    key, _ = torch.sort(torch.where(dup, torch.full_like(key, big), key), dim=1)
+    nh = (~dup).sum(dim=1).to(torch.int32)
+    valid = key != big
+    out = torch.stack([torch.where(valid, key >> 32, 0), torch.where(valid, key & 0xFFFFFFFF, 0)], dim=2).to(torch.int32)
+    return out.contiguous(), nh, truth.to(torch.int32)
