@@ -324,27 +324,33 @@ __device__ __forceinline__ float key_value(unsigned k) {
   return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
-constexpr int kSelThreads = 1024;
+constexpr int kSelThreads = 512;
+constexpr int kSelSample = 2048;   // strided sample that places the tail thresholds
+constexpr int kSelCap = 2048;      // capacity of each tail list
 
-// One block per query.  Finds sorted[r] for two ranks at once, 8 bits per pass, then one more pass
-// for the successors sorted[r+1].
-__global__ void __launch_bounds__(kSelThreads) clip_select_kernel(const float* __restrict__ z_all, const AugQ* __restrict__ qs,
-                                                                  AugS* st, int T) {
-  __shared__ unsigned hist[2][256];
-  __shared__ unsigned sel_prefix[2], sel_rank[2];
-  __shared__ unsigned cnt_le[2], min_gt[2];
-  const int qi = blockIdx.x, tid = threadIdx.x;
-  const AugQ q = qs[qi];
-  AugS* s = st + qi;
-  if (!(q.apply & MFPA_AUG_CLIP)) {
-    if (tid == 0) { s->lo = -INFINITY; s->hi = INFINITY; }
-    return;
+// ascending bitonic sort of a[0..n), n a power of two <= 2048, by the whole block
+__device__ __forceinline__ void bitonic_sort(unsigned* a, int n, int tid) {
+  for (int k = 2; k <= n; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < (n >> 1); i += kSelThreads) {
+        const int l = ((i & ~(j - 1)) << 1) | (i & (j - 1)), r = l | j;
+        const unsigned x = a[l], y = a[r];
+        if ((x > y) == ((l & k) == 0)) { a[l] = y; a[r] = x; }
+      }
+      __syncthreads();
+    }
   }
-  const float* z = z_all + (int64_t)qi * T;
-  // torch.quantile: rank = q * (n - 1) in float32, lo = floor(rank)
-  const float q_hi = 1.0f - q.q_lo;
-  const float pos[2] = {q.q_lo * (float)(T - 1), q_hi * (float)(T - 1)};
-  const int r0[2] = {min((int)floorf(pos[0]), T - 1), min((int)floorf(pos[1]), T - 1)};
+}
+
+// General exact radix select (any rank): sorted[r] for two ranks at once, 8 bits per pass, then one
+// more pass for the successors sorted[r+1].  Fallback of clip_select_kernel.
+__device__ void clip_select_general(const float* __restrict__ z, int T, const int (&r0)[2], unsigned (&hist)[2][256],
+                                    unsigned* sh, unsigned (&kout)[2], unsigned (&ksucc)[2]) {
+  unsigned* sel_prefix = sh;      // [2]
+  unsigned* sel_rank = sh + 2;    // [2]
+  unsigned* cnt_le = sh + 4;      // [2]
+  unsigned* min_gt = sh + 6;      // [2]
+  const int tid = threadIdx.x;
   if (tid < 2) { sel_prefix[tid] = 0; sel_rank[tid] = (unsigned)r0[tid]; }
   __syncthreads();
   for (int pass = 0; pass < 4; ++pass) {
@@ -400,6 +406,104 @@ __global__ void __launch_bounds__(kSelThreads) clip_select_kernel(const float* _
     atomicMin(&min_gt[0], g0); atomicMin(&min_gt[1], g1);
   }
   __syncthreads();
+  kout[0] = k0; kout[1] = k1;
+  for (int i = 0; i < 2; ++i) {
+    const bool same = cnt_le[i] >= (unsigned)r0[i] + 2u || r0[i] + 1 > T - 1;
+    ksucc[i] = same ? kout[i] : min_gt[i];
+  }
+}
+
+// One block per query: the order statistics sorted[r], sorted[r+1] of torch.quantile's two ranks.
+// Clipping percentiles are small (p <= 0.01 in AugmentFP), so both ranks sit in the tails: a sorted
+// strided sample places two thresholds that provably (checked by counting) bracket the wanted ranks,
+// ONE pass over the query collects the few hundred samples beyond them into shared memory, and a
+// bitonic sort of those lists gives the exact order statistics.  When the count check fails (ranks
+// not in the tails, pathological data) the general radix select runs instead: always exact.
+__global__ void __launch_bounds__(kSelThreads) clip_select_kernel(const float* __restrict__ z_all, const AugQ* __restrict__ qs,
+                                                                  AugS* st, int T) {
+  __shared__ unsigned lo_list[kSelCap], hi_list[kSelCap];
+  __shared__ unsigned hist[2][256];   // sample sort reuses lo_list; hist only for the fallback
+  __shared__ unsigned sh[8];
+  __shared__ unsigned cnt[2], thr_key[2];
+  const int qi = blockIdx.x, tid = threadIdx.x;
+  const AugQ q = qs[qi];
+  AugS* s = st + qi;
+  if (!(q.apply & MFPA_AUG_CLIP)) {
+    if (tid == 0) { s->lo = -INFINITY; s->hi = INFINITY; }
+    return;
+  }
+  const float* z = z_all + (int64_t)qi * T;
+  // torch.quantile: rank = q * (n - 1) in float32, lo = floor(rank)
+  const float q_hi = 1.0f - q.q_lo;
+  const float pos[2] = {q.q_lo * (float)(T - 1), q_hi * (float)(T - 1)};
+  const int r0[2] = {min((int)floorf(pos[0]), T - 1), min((int)floorf(pos[1]), T - 1)};
+  const int need_lo = min(r0[0] + 2, T);   // smallest elements needed: sorted[0 .. r0[0]+1]
+  const int need_hi = T - r0[1];           // largest elements needed: sorted[r0[1] .. T-1]
+  unsigned kout[2], ksucc[2];
+  bool fast = T >= 4 * kSelSample;
+  int s_lo = 0, s_hi = 0;
+  if (fast) {
+    // sample order statistic whose full-data count exceeds `need` with > 4 sigma margin
+    const float f = (float)kSelSample / (float)T;
+    const float m_lo = need_lo * f, m_hi = need_hi * f;
+    s_lo = (int)ceilf(m_lo + 4.f * sqrtf(m_lo) + 6.f);
+    s_hi = (int)ceilf(m_hi + 4.f * sqrtf(m_hi) + 6.f);
+    fast = s_lo < kSelSample / 8 && s_hi < kSelSample / 8;   // expected list length stays well below kSelCap
+  }
+  if (fast) {
+    unsigned* sample = lo_list;   // kSelSample == kSelCap
+    for (int i = tid; i < kSelSample; i += kSelThreads) sample[i] = order_key(z[(int)(((int64_t)i * T) / kSelSample)]);
+    if (tid < 2) cnt[tid] = 0;
+    __syncthreads();
+    bitonic_sort(sample, kSelSample, tid);
+    if (tid == 0) { thr_key[0] = sample[s_lo]; thr_key[1] = sample[kSelSample - 1 - s_hi]; }
+    __syncthreads();
+    const unsigned t_lo = thr_key[0], t_hi = thr_key[1];
+    __syncthreads();   // sample (= lo_list) is dead from here
+    const int lane = tid & 31;
+    for (int n0 = 0; n0 < T; n0 += kSelThreads) {
+      const int n = n0 + tid;
+      const unsigned k = n < T ? order_key(z[n]) : 0u;
+      const bool is_lo = n < T && k <= t_lo, is_hi = n < T && k >= t_hi;
+      const unsigned b_lo = __ballot_sync(0xffffffffu, is_lo), b_hi = __ballot_sync(0xffffffffu, is_hi);
+      if (b_lo) {
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(&cnt[0], __popc(b_lo));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const unsigned slot = base + __popc(b_lo & ((1u << lane) - 1u));
+        if (is_lo && slot < kSelCap) lo_list[slot] = k;
+      }
+      if (b_hi) {
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(&cnt[1], __popc(b_hi));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const unsigned slot = base + __popc(b_hi & ((1u << lane) - 1u));
+        if (is_hi && slot < kSelCap) hi_list[slot] = k;
+      }
+    }
+    __syncthreads();
+    const int c_lo = (int)cnt[0], c_hi = (int)cnt[1];
+    fast = c_lo >= need_lo && c_lo <= kSelCap && c_hi >= need_hi && c_hi <= kSelCap;
+    if (fast) {
+      int p_lo = 32, p_hi = 32;
+      while (p_lo < c_lo) p_lo <<= 1;
+      while (p_hi < c_hi) p_hi <<= 1;
+      for (int i = c_lo + tid; i < p_lo; i += kSelThreads) lo_list[i] = 0xffffffffu;   // pad above
+      for (int i = c_hi + tid; i < p_hi; i += kSelThreads) hi_list[i] = 0u;            // pad below
+      __syncthreads();
+      bitonic_sort(lo_list, p_lo, tid);
+      bitonic_sort(hi_list, p_hi, tid);
+      kout[0] = lo_list[r0[0]];
+      ksucc[0] = r0[0] + 1 > T - 1 ? kout[0] : lo_list[r0[0] + 1];
+      const int j = T - 1 - r0[1];          // sorted[r0[1]] is the j-th largest (0-based)
+      kout[1] = hi_list[p_hi - 1 - j];
+      ksucc[1] = j >= 1 ? hi_list[p_hi - j] : kout[1];
+    }
+  }
+  if (!fast) {
+    __syncthreads();
+    clip_select_general(z, T, r0, hist, sh, kout, ksucc);
+  }
   if (tid == 0) {
     // elementwise map into the gained domain, monotone so the order statistics carry over
     const bool nz_on = q.apply & MFPA_AUG_NOISE;
@@ -407,10 +511,7 @@ __global__ void __launch_bounds__(kSelThreads) clip_select_kernel(const float* _
     const float g = (q.apply & MFPA_AUG_GAIN) ? q.gain : 1.f;
     float thr[2];
     for (int i = 0; i < 2; ++i) {
-      const unsigned ka = i ? k1 : k0;
-      const float va = key_value(ka);
-      const bool same = cnt_le[i] >= (unsigned)r0[i] + 2u || r0[i] + 1 > T - 1;
-      const float vb = same ? va : key_value(min_gt[i]);
+      const float va = key_value(kout[i]), vb = key_value(ksucc[i]);
       const float fa = (nz_on ? va / peak : va) * g, fb = (nz_on ? vb / peak : vb) * g;
       const float w = pos[i] - (float)r0[i];
       thr[i] = fa + (fb - fa) * w;
