@@ -40,6 +40,10 @@ BYTES_STFT = 256_000 + 257 * N_FRAMES * 4          # S2: waveform in, magnitudes
 BYTES_PEAKS = 257 * N_FRAMES * 4 + 256 * N_FRAMES  # S3: magnitudes in, peak mask (u8-equivalent) out
 BYTES_FUSED = 256_000                              # S2-S4 fused: waveform in (+ 8 B per hash out)
 BYTES_CHAIN = 544_000                              # S1-S4 fused: x + noise + IR in (+ 8 B per hash out)
+# dram__bytes_read.sum + dram__bytes_write.sum per launch at 10 000 queries, shifts=1, from the
+# `ncu --set full` capture summarised in profiles/r01f_summary.txt (scaled by items/10000 for other sizes)
+NCU_TRAFFIC_10K = {"stft_mag": 2.730195e9 + 2.606733e9, "audfprint_peaks": 2.962223e9 + 0.020727e9,
+                   "landmark_hashes(+merge)": 0.020237e9 + 0.000085e9}
 
 
 def _peaks():
@@ -268,7 +272,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                        "hashes_per_query": tot_hashes / B, "parallelism": f"query-sharded x{world}, no collective"},
             "stage_ms": stage_ms,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm, "unit": "GB/s",
-                         "frac": achieved / hbm, "traffic": None, "peak_source": how,
+                         "frac": achieved / hbm, "traffic": NCU_TRAFFIC_10K[dom] * items / 10000,
+                         "traffic_source": "profiles/r01f_summary.txt (ncu --set full, dram read+write)", "peak_source": how,
                          "algorithmic_bytes_per_launch": dom_bytes,
                          "whole_path_frac": (BYTES_FUSED * B + 8 * tot_hashes) / (ms_step * 1e-3) / 1e9 / hbm},
             "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
