@@ -321,6 +321,27 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "value": B / (ms * 1e-3), "unit": "queries/s", "ms_per_step": ms, "scaling": "strong",
             "top1_equals_planted_track": top1, "query_hashes": nqh,
             "collective": "none" if world == 1 else "NCCL all-reduce of per-track counts + all-gather of candidate hit lists"}
+    if "unet" in args.also:
+        Bu = args.unet_queries
+        ms, finite = bench_unet(ctx, lib, dev, rank, Bu, max(2, args.steps // 3), 2, barrier, args.unet_chunk)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        tf = UNET_GFLOP * Bu / ms  # GFLOP / ms = TFLOP/s
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+        sustained = float(pk.get("bf16_tflops_sustained", 1400.0))
+        extras["unet"] = {
+            "workload": f"UNet(1,1) denoiser forward on {Bu} normalised 257x251 magnitude spectrograms per GPU, random init, "
+                        f"bf16 operands / fp32 accumulate, tcgen05 implicit GEMM, chunks of {args.unet_chunk} (BASELINE.json configs[3])",
+            "value": world * Bu / (ms * 1e-3), "unit": "spectrograms/s", "ms_per_step": ms, "dtype": "bf16",
+            "gflop_per_spectrogram": UNET_GFLOP, "finite": finite,
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": sustained, "unit": "TFLOP/s", "frac": tf / sustained,
+                         "peak_source": "measured sustained bf16" if pk else "fallback", "traffic": None}}
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            rate, threads = _cpu_unet_rate(3)
+            extras["unet"]["cpu_baseline"] = {"value": rate, "unit": "spectrograms/s", "cores": threads, "kind": "port",
+                                              "sample": "3 forwards of the fp32 torch oracle UNet, 1x1x257x251"}
     if rank == 0:
         line.update(extras)
         print(json.dumps(line), flush=True)
@@ -443,6 +464,54 @@ def bench_match(ctx, lib, dev, rank, world, B, n_tracks, steps, warmup, barrier)
     return ms, top1, int(nq.sum().item())
 
 
+UNET_GFLOP = 93.40  # per 257x251 spectrogram, SURVEY.md App. A.8
+
+
+def _cpu_unet_rate(n_images: int):
+    """torch fp32 forward of the oracle UNet on all host cores (the reference's CPU path for a19)."""
+    import torch
+
+    from oracle.unet_torch import seeded_unet
+
+    net = seeded_unet(0)
+    x = torch.rand(1, 1, 257, 251)
+    with torch.no_grad():
+        net(x)
+        t0 = time.perf_counter()
+        for _ in range(n_images):
+            net(x)
+    return n_images / (time.perf_counter() - t0), torch.get_num_threads()
+
+
+def bench_unet(ctx, lib, dev, rank, B, steps, warmup, barrier, chunk):
+    """BASELINE configs[3]: UNet denoiser forward on B normalised 257x251 magnitude spectrograms
+    (random init, bf16, tcgen05 implicit GEMM), in place between the STFT and the picker."""
+    import torch
+
+    from musicfpaugment_b200 import synth
+
+    den = lib.UNetDenoiser(ctx, max_chunk=chunk)
+    den.load(synth.unet_random_params(0))
+    x = synth.music_like(B, seed=1234 + rank, device=dev, chunk=32)
+    mag, qmax = ctx.stft_mag(x, 1)
+    ref = mag.clone()
+    for _ in range(warmup):
+        mag.copy_(ref)
+        den.denoise_mag(mag, qmax)
+    barrier()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for e0, e1 in evs:
+        mag.copy_(ref)
+        e0.record()
+        den.denoise_mag(mag, qmax)
+        e1.record()
+    barrier()
+    ms = sum(e0.elapsed_time(e1) for e0, e1 in evs) / steps
+    finite = bool(torch.isfinite(mag[:, :, :257]).all().item())
+    den.close()
+    return ms, finite
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -453,8 +522,10 @@ def main():
     ap.add_argument("--shifts", type=int, default=1)
     ap.add_argument("--cpu-queries-per-core", type=int, default=200)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--also", default="chain,match",
-                    help="comma list of the other BASELINE configs to time after the headline: chain, match, or none")
+    ap.add_argument("--also", default="chain,match,unet",
+                    help="comma list of the other BASELINE configs to time after the headline: chain, match, unet, or none")
+    ap.add_argument("--unet-queries", type=int, default=128, help="spectrograms per step of the UNet leg")
+    ap.add_argument("--unet-chunk", type=int, default=32, help="images per pass through the UNet (activation arena size)")
     ap.add_argument("--tracks", type=int, default=100000, help="tracks in the synthetic index of the match workload")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

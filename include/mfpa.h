@@ -278,6 +278,33 @@ int mfpa_dejavu_peaks(mfpa_ctx* ctx, const void* arr_dev, int is_f64, int B, int
                       double amp_min, uint8_t* mask_dev, int32_t* peaks_dev, int cap, int32_t* npeaks_dev,
                       void* stream);
 
+/* ---- optional UNet magnitude-spectrogram denoiser  (training/unet.py:75-108: UNet(1, 1, bilinear=False),
+ * eval mode; inserted between `sgram /= max` and the log at afp/audfprint/peak_extractor.py:265-269 and
+ * afp/dejavu/fingerprint.py:70-75).  bf16 activations/weights, fp32 accumulation, BatchNorm folded;
+ * every 3x3 / transposed convolution is a tcgen05 implicit GEMM (csrc/unet.cu). */
+typedef struct mfpa_unet mfpa_unet;
+/* Number of float32 values mfpa_unet_load expects: the reference model's state_dict() in its own
+ * order, every floating tensor flattened and concatenated, `num_batches_tracked` entries skipped. */
+int64_t mfpa_unet_num_params(void);
+int mfpa_unet_create(mfpa_ctx* ctx, mfpa_unet** out);
+void mfpa_unet_destroy(mfpa_unet* unet);
+int mfpa_unet_load(mfpa_unet* unet, const float* params_host, int64_t n_floats);
+/* Images per pass through the network (activation arena = ~45 MB per 257x251 image); default 16. */
+int mfpa_unet_set_max_chunk(mfpa_unet* unet, int images);
+/* out[b] = unet(in[b] / div[b]) for B single-channel H x W images.  in/out are float32 device arrays
+ * addressed as base + b*stride_n + h*stride_h + w*stride_w (elements), so both the reference layout
+ * [B][H][W] and the frame-major magnitude layout of mfpa_stft_mag (h = bin: stride 1, w = frame: stride
+ * MFPA_MAG_PITCH) work; in == out is allowed.  div_dev may be NULL. */
+int mfpa_unet_forward(mfpa_ctx* ctx, mfpa_unet* unet, const float* in_dev, int64_t in_stride_n, int64_t in_stride_h,
+                      int64_t in_stride_w, const float* div_dev, int B, int H, int W, float* out_dev,
+                      int64_t out_stride_n, int64_t out_stride_h, int64_t out_stride_w, void* stream);
+/* One convolution of the network on caller-owned NHWC bf16 tensors (the unit the parity tests drive):
+ * out[..., coff:coff+cout] = act(conv(in, w) * scale + shift); w_dev [cout][taps][cin] bf16, taps 9 (3x3,
+ * padding 1) or 1; cin, cout multiples of 64.  bn / mt / stages = 0 pick the tile configuration. */
+int mfpa_conv_bf16(mfpa_ctx* ctx, const void* in_dev, int N, int H, int W, int cin, const void* w_dev, int cout,
+                   int taps, const float* scale_dev, const float* shift_dev, int relu, void* out_dev, int ldc,
+                   int coff, int bn, int mt, int stages, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -92,6 +92,13 @@ SIGNATURES = {
     "mfpa_match": (_i, [_vp, _vp, _vp, _i, _i, C.POINTER(MatchParams), _vp, _vp, _i, _vp]),
     "mfpa_dejavu_peaks": (_i, [_vp, _vp, _i, _i, _i, _i, _i, C.c_double, _vp, _vp, _i, _vp, _vp]),
     "mfpa_compact_rows": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _i64, _vp]),
+    "mfpa_unet_num_params": (_i64, []),
+    "mfpa_unet_create": (_i, [_vp, C.POINTER(_vp)]),
+    "mfpa_unet_destroy": (None, [_vp]),
+    "mfpa_unet_load": (_i, [_vp, _vp, _i64]),
+    "mfpa_unet_set_max_chunk": (_i, [_vp, _i]),
+    "mfpa_unet_forward": (_i, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _i, _i, _i, _vp, _i64, _i64, _i64, _vp]),
+    "mfpa_conv_bf16": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp]),
 }
 
 
@@ -475,3 +482,76 @@ class Context:
                                             rows.shape[0], _ptr(offsets))
         check(rc)
         return rows[: int(offsets[-1])].numpy(), offsets.numpy()
+
+
+def unet_param_blob(state_dict):
+    """Flatten a reference ``UNet(1, 1)`` state_dict (training/unet.py:75-95) into the float32 vector
+    ``mfpa_unet_load`` expects: state_dict order, ``num_batches_tracked`` skipped."""
+    import numpy as np
+
+    parts = [v.detach().cpu().float().numpy().ravel() for k, v in state_dict.items()
+             if not k.endswith("num_batches_tracked")]
+    return np.ascontiguousarray(np.concatenate(parts), dtype=np.float32)
+
+
+class UNetDenoiser:
+    """The optional UNet spectrogram denoiser on one Context (tcgen05 implicit-GEMM convolutions)."""
+
+    def __init__(self, ctx: Context, state_dict=None, max_chunk: int | None = None):
+        self.ctx = ctx
+        self._u = C.c_void_p()
+        check(_lib.mfpa_unet_create(ctx.handle, C.byref(self._u)))
+        if max_chunk:
+            check(_lib.mfpa_unet_set_max_chunk(self._u, int(max_chunk)))
+        if state_dict is not None:
+            self.load(state_dict)
+
+    def load(self, state_dict):
+        blob = state_dict if hasattr(state_dict, "ctypes") else unet_param_blob(state_dict)
+        check(_lib.mfpa_unet_load(self._u, blob.ctypes.data_as(C.c_void_p), blob.size))
+
+    def close(self):
+        if getattr(self, "_u", None) and self._u.value:
+            _lib.mfpa_unet_destroy(self._u)
+            self._u = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def forward(self, x, div=None):
+        """x: [B,H,W] (or [B,1,H,W]) float32 cuda -> same shape; ``unet(x / div[b])``."""
+        import torch
+
+        shape = x.shape
+        x3 = x.reshape(shape[0], shape[-2], shape[-1]).contiguous()
+        B, H, W = x3.shape
+        out = torch.empty_like(x3)
+        check(_lib.mfpa_unet_forward(self.ctx.handle, self._u, _ptr(x3), H * W, W, 1, _ptr(div), B, H, W, _ptr(out),
+                                     H * W, W, 1, _stream()))
+        return out.reshape(shape)
+
+    def denoise_mag(self, mag, qmax):
+        """In place on the frame-major magnitudes of ``Context.stft_mag``: mag[i] <- unet(mag[i] / qmax[i])
+        (peak_extractor.py:263-269); returns mag.  The picker must then run without the STFT's statistics
+        (``audfprint_peaks(mag, None, ...)``)."""
+        items, n, pitch = mag.shape
+        assert pitch == MAG_PITCH
+        check(_lib.mfpa_unet_forward(self.ctx.handle, self._u, _ptr(mag), n * pitch, 1, pitch, _ptr(qmax), items, BINS, n,
+                                     _ptr(mag), n * pitch, 1, pitch, _stream()))
+        return mag
+
+
+def conv_bf16(ctx: Context, x, w, scale, shift, relu=True, taps=9, out=None, coff=0, bn=0, mt=0, stages=0):
+    """x [N,H,W,Cin] bf16 cuda, w [Cout,taps,Cin] bf16 cuda -> [N,H,W,Cout] bf16 (or a channel slice of `out`)."""
+    import torch
+
+    N, H, W, cin = x.shape
+    cout = w.shape[0]
+    if out is None:
+        out = torch.empty(N, H, W, cout, dtype=torch.bfloat16, device=x.device)
+    check(_lib.mfpa_conv_bf16(ctx.handle, _ptr(x), N, H, W, cin, _ptr(w), cout, taps, _ptr(scale), _ptr(shift), int(relu),
+                              _ptr(out), out.shape[-1], coff, bn, mt, stages, _stream()))
+    return out

@@ -216,3 +216,45 @@ def planted_queries_device(track_t, track_h, n_queries: int, n_hashes: int = 400
     valid = key != big
     out = torch.stack([torch.where(valid, key >> 32, 0), torch.where(valid, key & 0xFFFFFFFF, 0)], dim=2).to(torch.int32)
     return out.contiguous(), nh, truth.to(torch.int32)
+
+
+def unet_random_params(seed: int = 0):
+    """Random-init parameter vector for ``mfpa_unet_load`` (BASELINE.json configs[3]: "random init"):
+    the layout of the reference ``UNet(1, 1)`` state_dict (training/unet.py:75-95) with
+    U(-1/sqrt(fan_in), 1/sqrt(fan_in)) convolution weights (torch's default bound) and
+    lightly perturbed BatchNorm statistics."""
+    import numpy as np
+
+    rng = np.random.default_rng(seed)
+    widths = (64, 128, 256, 512, 1024)
+    parts = []
+
+    def conv(cin, cout, k, bias):
+        b = 1.0 / np.sqrt(cin * k * k)
+        parts.append(rng.uniform(-b, b, cout * cin * k * k).astype(np.float32))
+        if bias:
+            parts.append(rng.uniform(-b, b, cout).astype(np.float32))
+
+    def bn(c):
+        parts.append(rng.uniform(0.8, 1.2, c).astype(np.float32))          # weight
+        parts.append((0.1 * rng.standard_normal(c)).astype(np.float32))    # bias
+        parts.append((0.1 * rng.standard_normal(c)).astype(np.float32))    # running_mean
+        parts.append(rng.uniform(0.8, 1.2, c).astype(np.float32))          # running_var
+
+    def block(cin, cout):
+        conv(cin, cout, 3, False)
+        bn(cout)
+        conv(cout, cout, 3, False)
+        bn(cout)
+
+    block(1, widths[0])
+    for i in range(1, 5):
+        block(widths[i - 1], widths[i])
+    for i in range(4):
+        cin, cout = widths[4 - i], widths[3 - i]
+        b = 1.0 / np.sqrt(cout * 4)  # ConvTranspose2d fan_in = weight.size(1) * k * k
+        parts.append(rng.uniform(-b, b, cin * cout * 4).astype(np.float32))
+        parts.append(rng.uniform(-b, b, cout).astype(np.float32))
+        block(cin, cout)
+    conv(widths[0], 1, 1, True)
+    return np.concatenate(parts)

@@ -118,3 +118,19 @@ def test_fir_taps_properties():
     for bad in (-0.1, 0.6, 0.0):
         with pytest.raises(ValueError):
             A.lowpass_taps(bad)
+
+
+def test_unet_oracle_reproduces_reference_golden():
+    """oracle/unet_torch.py == the real reference UNet (tests/golden/unet.npz), bit for bit on the CPU
+    for torch.manual_seed(0) weights; state_dict keys (= parameter blob order) identical."""
+    import torch
+
+    from oracle.unet_torch import seeded_unet
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "unet.npz"))
+    torch.set_num_threads(1)
+    net = seeded_unet(0, randomize_bn=False)
+    assert list(net.state_dict().keys()) == [str(k) for k in g["keys"]]
+    with torch.no_grad():
+        y = net(torch.from_numpy(g["x"])).numpy()
+    np.testing.assert_allclose(y, g["y"], rtol=0, atol=1e-6)
