@@ -43,6 +43,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done;
   do {
@@ -123,7 +126,9 @@ struct ConvArgs {
   bf16* out;           // NHWC bf16
   int out_h, out_w;    // spatial size of `out` (mode 1: the skip tensor's size)
   int ldc, coff;       // channels per pixel of `out`, first channel written
-  int cout;            // mode 1: channels per (a, b) phase; GEMM N = 4 * cout
+  int cout;            // output channels (mode 1: channels per (a, b) phase; GEMM N = 4 * cout)
+  int n_total;         // GEMM N (cout, or 4 * cout for the transposed convolution)
+  int N;               // images
   // mode 2: fused 1x1 output convolution (training/unet.py:66-72)
   const float* w_out;  // [64]
   float b_out;
@@ -131,49 +136,67 @@ struct ConvArgs {
   long long of_n, of_h, of_w;  // element strides of out_f32
 };
 
+// Persistent: gridDim.x CTAs walk the (image, pixel tile, channel tile) list with stride gridDim.x.
+// The smem ring runs across tile boundaries (the TMA warp prefetches the next tile while the epilogue
+// drains this one) and, when 2 * MT * BN <= 512 TMEM columns, accumulators are double-buffered so the
+// MMAs of tile i+1 overlap the epilogue of tile i.
 template <int BN, int MT>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int kStageBytes = MT * kATile + BN * 128;
+  constexpr int kAcc = (2 * MT * BN <= 512) ? 2 : 1;   // TMEM accumulator buffers
+  constexpr int kTmemCols = kAcc * MT * BN;
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = (uint64_t*)(smem + (size_t)a.stages * kStageBytes);  // full[S], empty[S], tmem_full
-  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * a.stages + 1);
+  uint64_t* bars = (uint64_t*)(smem + (size_t)a.stages * kStageBytes);  // full[S], empty[S], tmem_full[2], tmem_empty[2]
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * a.stages + 4);
   float* s_scale = (float*)(tmem_slot + 2);
-  float* s_shift = s_scale + BN;
+  float* s_shift = s_scale + a.cout;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN;
   const int tiles_w = (a.W + kTileW - 1) / kTileW;
-  const int w0 = (blockIdx.y % tiles_w) * kTileW, h0 = (blockIdx.y / tiles_w) * (8 * MT);
-  const int img = blockIdx.z;
+  const int tiles_sp = tiles_w * ((a.H + 8 * MT - 1) / (8 * MT));
+  const int tiles_n = a.n_total / BN;
+  const int total = tiles_n * tiles_sp * a.N;
   const int nkb = a.taps * (a.cin / kBlockK);
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (a.stages + s); };
-  const uint32_t tmem_full_bar = bar0 + 8u * (2 * a.stages);
+  auto tmem_full_bar = [&](int b) { return bar0 + 8u * (2 * a.stages + b); };
+  auto tmem_empty_bar = [&](int b) { return bar0 + 8u * (2 * a.stages + 2 + b); };
+  // tile index -> (channel tile fastest, so CTAs running side by side share the activation tile in L2)
+  auto decode = [&](int t, int& n0, int& w0, int& h0, int& img) {
+    n0 = (t % tiles_n) * BN;
+    t /= tiles_n;
+    const int sp = t % tiles_sp;
+    img = t / tiles_sp;
+    w0 = (sp % tiles_w) * kTileW;
+    h0 = (sp / tiles_w) * (8 * MT);
+  };
 
   if (warp == 4 && lane == 0) {
     for (int s = 0; s < a.stages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tmem_full_bar(b), 1);
+      mbar_init(tmem_empty_bar(b), 4);  // one arrival per epilogue warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
   }
   if (warp == 5) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"((uint32_t)(MT * BN))
+                 "r"((uint32_t)kTmemCols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (warp < 4) {
-    for (int i = threadIdx.x; i < BN; i += 128) {
-      const int co = a.mode == kEpiUpscatter ? (n0 + i) % a.cout : n0 + i;
-      s_scale[i] = a.scale[co];
-      s_shift[i] = a.shift[co];
+    for (int i = threadIdx.x; i < a.cout; i += 128) {
+      s_scale[i] = a.scale[i];
+      s_shift[i] = a.shift[i];
     }
   }
   tc_fence_before();
@@ -185,17 +208,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       // ---- TMA producer: one (tap, 64-channel) slice of the pixel tile + the matching weight slice per stage
       const int chunks = a.cin / kBlockK;
-      int kb = 0;
-      for (int tap = 0; tap < a.taps; ++tap) {
-        const int dh = a.taps == 9 ? tap / 3 - 1 : 0, dw = a.taps == 9 ? tap % 3 - 1 : 0;
-        for (int cc = 0; cc < chunks; ++cc, ++kb) {
-          const int s = kb % a.stages;
-          const uint32_t ph = (kb / a.stages) & 1;
-          mbar_wait(empty_bar(s), ph ^ 1);
-          mbar_expect_tx(full_bar(s), kStageBytes);
-          const uint32_t dst = smem_u32(smem + (size_t)s * kStageBytes);
-          tma_load_4d(dst, &tmA, full_bar(s), cc * kBlockK, w0 + dw, h0 + dh, img);
-          tma_load_2d(dst + MT * kATile, &tmB, full_bar(s), tap * a.cin + cc * kBlockK, n0);
+      int it = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        int n0, w0, h0, img;
+        decode(t, n0, w0, h0, img);
+        for (int tap = 0; tap < a.taps; ++tap) {
+          const int dh = a.taps == 9 ? tap / 3 - 1 : 0, dw = a.taps == 9 ? tap % 3 - 1 : 0;
+          for (int cc = 0; cc < chunks; ++cc, ++it) {
+            const int s = it % a.stages;
+            const uint32_t ph = (it / a.stages) & 1;
+            mbar_wait(empty_bar(s), ph ^ 1);
+            mbar_expect_tx(full_bar(s), kStageBytes);
+            const uint32_t dst = smem_u32(smem + (size_t)s * kStageBytes);
+            tma_load_4d(dst, &tmA, full_bar(s), cc * kBlockK, w0 + dw, h0 + dh, img);
+            tma_load_2d(dst + MT * kATile, &tmB, full_bar(s), tap * a.cin + cc * kBlockK, n0);
+          }
         }
       }
     }
@@ -203,90 +230,108 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       // ---- MMA issuer
       constexpr uint32_t idesc = umma_idesc(128, BN);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % a.stages;
-        const uint32_t ph = (kb / a.stages) & 1;
-        mbar_wait(full_bar(s), ph);
+      int it = 0, i = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x, ++i) {
+        const int acc = i % kAcc;
+        const uint32_t acc_ph = (i / kAcc) & 1;
+        mbar_wait(tmem_empty_bar(acc), acc_ph ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + (size_t)s * kStageBytes);
-        const uint32_t sb = sa + MT * kATile;
+        const uint32_t d0 = tmem_base + acc * (MT * BN);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % a.stages;
+          const uint32_t ph = (it / a.stages) & 1;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)s * kStageBytes);
+          const uint32_t sb = sa + MT * kATile;
 #pragma unroll
-        for (int j = 0; j < MT; ++j) {
+          for (int j = 0; j < MT; ++j) {
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            tc_mma(tmem_base + j * BN, umma_desc(sa + j * kATile + k * 32), umma_desc(sb + k * 32), idesc,
-                   (kb > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              tc_mma(d0 + j * BN, umma_desc(sa + j * kATile + k * 32), umma_desc(sb + k * 32), idesc,
+                     (kb > 0 || k > 0) ? 1u : 0u);
+            }
           }
+          tc_commit(empty_bar(s));  // frees the stage when the MMAs above have read it
         }
-        tc_commit(empty_bar(s));  // frees the stage when the MMAs above have read it
+        tc_commit(tmem_full_bar(acc));
       }
-      tc_commit(tmem_full_bar);
     }
   } else {
     // ---- epilogue: warp w owns TMEM lanes 32w..32w+31 = pixels 32w..32w+31 of each 128-pixel sub-tile
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
     const int m = warp * 32 + lane;
+    int i = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++i) {
+      const int acc = i % kAcc;
+      const uint32_t acc_ph = (i / kAcc) & 1;
+      int n0, w0, h0, img;
+      decode(t, n0, w0, h0, img);
+      mbar_wait(tmem_full_bar(acc), acc_ph);
+      tc_fence_after();
 #pragma unroll 1
-    for (int j = 0; j < MT; ++j) {
-      const int h = h0 + 8 * j + (m >> 4), w = w0 + (m & 15);
-      const bool inside = h < a.H && w < a.W;
-      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + j * BN;
-      if (a.mode == kEpiOutc) {
-        float dot = 0.f;
+      for (int j = 0; j < MT; ++j) {
+        const int h = h0 + 8 * j + (m >> 4), w = w0 + (m & 15);
+        const bool inside = h < a.H && w < a.W;
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * (MT * BN) + j * BN;
+        if (a.mode == kEpiOutc) {
+          float dot = 0.f;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          uint32_t v[32];
-          tc_ld32(taddr + c0, v);
+          for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32];
+            tc_ld32(taddr + c0, v);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float y = fmaf(__uint_as_float(v[i]), s_scale[c0 + i], s_shift[c0 + i]);
-            y = fmaxf(y, 0.f);
-            dot = fmaf(y, __ldg(a.w_out + n0 + c0 + i), dot);
-          }
-        }
-        if (inside) a.out_f32[img * a.of_n + h * a.of_h + w * a.of_w] = dot + a.b_out;
-      } else {
-        size_t pix;
-        int cbase;
-        if (a.mode == kEpiUpscatter) {
-          const int phase = n0 / a.cout;  // (a, b) of ConvTranspose2d(k=2, s=2): out[2h+a][2w+b]
-          pix = ((size_t)img * a.out_h + (2 * h + (phase >> 1))) * a.out_w + (2 * w + (phase & 1));
-          cbase = a.coff + n0 % a.cout;
-        } else {
-          pix = ((size_t)img * a.out_h + h) * a.out_w + w;
-          cbase = a.coff + n0;
-        }
-        bf16* dst = a.out + pix * a.ldc + cbase;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          uint32_t v[32];
-          tc_ld32(taddr + c0, v);
-          uint32_t packed[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float y0 = fmaf(__uint_as_float(v[2 * i]), s_scale[c0 + 2 * i], s_shift[c0 + 2 * i]);
-            float y1 = fmaf(__uint_as_float(v[2 * i + 1]), s_scale[c0 + 2 * i + 1], s_shift[c0 + 2 * i + 1]);
-            if (a.relu) {
-              y0 = fmaxf(y0, 0.f);
-              y1 = fmaxf(y1, 0.f);
+            for (int q = 0; q < 32; ++q) {
+              float y = fmaf(__uint_as_float(v[q]), s_scale[n0 + c0 + q], s_shift[n0 + c0 + q]);
+              y = fmaxf(y, 0.f);
+              dot = fmaf(y, __ldg(a.w_out + n0 + c0 + q), dot);
             }
-            __nv_bfloat162 p = __floats2bfloat162_rn(y0, y1);
-            packed[i] = *reinterpret_cast<uint32_t*>(&p);
           }
-          if (inside) {
-            uint4* d4 = reinterpret_cast<uint4*>(dst + c0);
+          if (inside) a.out_f32[img * a.of_n + h * a.of_h + w * a.of_w] = dot + a.b_out;
+        } else {
+#pragma unroll 1
+          for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32];
+            tc_ld32(taddr + c0, v);
+            // output channel / pixel of this 32-column group
+            int co = n0 + c0;
+            size_t pix;
+            if (a.mode == kEpiUpscatter) {
+              const int phase = co / a.cout;  // (a, b) of ConvTranspose2d(k=2, s=2): out[2h+a][2w+b]
+              co -= phase * a.cout;
+              pix = ((size_t)img * a.out_h + (2 * h + (phase >> 1))) * a.out_w + (2 * w + (phase & 1));
+            } else {
+              pix = ((size_t)img * a.out_h + h) * a.out_w + w;
+            }
+            uint32_t packed[16];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) d4[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+            for (int q = 0; q < 16; ++q) {
+              float y0 = fmaf(__uint_as_float(v[2 * q]), s_scale[co + 2 * q], s_shift[co + 2 * q]);
+              float y1 = fmaf(__uint_as_float(v[2 * q + 1]), s_scale[co + 2 * q + 1], s_shift[co + 2 * q + 1]);
+              if (a.relu) {
+                y0 = fmaxf(y0, 0.f);
+                y1 = fmaxf(y1, 0.f);
+              }
+              __nv_bfloat162 pk = __floats2bfloat162_rn(y0, y1);
+              packed[q] = *reinterpret_cast<uint32_t*>(&pk);
+            }
+            if (inside) {
+              uint4* d4 = reinterpret_cast<uint4*>(a.out + pix * a.ldc + a.coff + co);
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                d4[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+            }
           }
         }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 5) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(MT * BN)) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kTmemCols) : "memory");
   }
 }
 
@@ -417,19 +462,23 @@ struct GemmLaunch {
   CUtensorMap tmA, tmB;
   ConvArgs args;
   int bn, mt, n_total, N;
+  int ctas = mfpa::kNumSMs;  // persistent grid size
 };
 
-size_t gemm_smem_bytes(int bn, int mt, int stages) {
-  return 1024 + (size_t)stages * (mt * kATile + bn * 128) + 8 * (2 * stages + 1) + 8 + 2 * bn * sizeof(float);
+size_t gemm_smem_bytes(int mt, int bn, int stages, int cout) {
+  return 1024 + (size_t)stages * (mt * kATile + bn * 128) + 8 * (2 * stages + 4) + 8 + 2 * (size_t)cout * sizeof(float);
 }
 
 template <int BN, int MT>
 int launch_gemm_t(const GemmLaunch& g, cudaStream_t st) {
   MFPA_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  const ConvArgs& a = g.args;
-  const int tiles = ((a.W + kTileW - 1) / kTileW) * ((a.H + 8 * MT - 1) / (8 * MT));
-  dim3 grid(g.n_total / BN, tiles, g.N);
-  conv_gemm_kernel<BN, MT><<<grid, kThreads, gemm_smem_bytes(BN, MT, a.stages), st>>>(g.tmA, g.tmB, a);
+  ConvArgs a = g.args;
+  a.N = g.N;
+  a.n_total = g.n_total;
+  const long long tiles = (long long)((a.W + kTileW - 1) / kTileW) * ((a.H + 8 * MT - 1) / (8 * MT)) * (g.n_total / BN) * g.N;
+  MFPA_REQUIRE(tiles < (1ll << 31), "conv gemm: too many tiles");
+  const int grid = (int)(tiles < g.ctas ? tiles : g.ctas);
+  conv_gemm_kernel<BN, MT><<<grid, kThreads, gemm_smem_bytes(MT, BN, a.stages, a.cout), st>>>(g.tmA, g.tmB, a);
   MFPA_CUDA(cudaGetLastError());
   return MFPA_OK;
 }
@@ -447,11 +496,10 @@ int launch_gemm(const GemmLaunch& g, cudaStream_t st) {
   return MFPA_EINVAL;
 }
 
-int pick_stages(int bn, int mt, int nkb) {
+int pick_stages(int bn, int mt) {
   const int stage = mt * kATile + bn * 128;
-  int s = (int)((200 * 1024) / stage);
-  if (s > 6) s = 6;
-  if (s > nkb) s = nkb;
+  int s = (int)((208 * 1024) / stage);
+  if (s > 8) s = 8;
   return s < 1 ? 1 : s;
 }
 
@@ -557,7 +605,7 @@ int plan_conv(mfpa_unet* u, const ConvBN& c, const bf16* in, int n, int h, int w
   a.W = w;
   a.cin = c.cin;
   a.taps = 9;
-  a.stages = pick_stages(g.bn, g.mt, 9 * c.cin / kBlockK);
+  a.stages = pick_stages(g.bn, g.mt);
   a.mode = mode;
   a.relu = 1;
   a.scale = c.scale;
@@ -576,7 +624,7 @@ int plan_conv(mfpa_unet* u, const ConvBN& c, const bf16* in, int n, int h, int w
 int plan_up(mfpa_unet* u, const UpConv& c, const bf16* in, int n, int h, int w, bf16* out, int out_h, int out_w, int ldc,
             int coff) {
   GemmLaunch g{};
-  g.bn = c.cout >= 256 ? 256 : c.cout;
+  g.bn = 256;  // all four (a, b) phases of 64 channels, or a slice of one phase, per tile
   g.mt = h >= 16 ? 2 : 1;
   g.n_total = 4 * c.cout;
   g.N = n;
@@ -589,7 +637,7 @@ int plan_up(mfpa_unet* u, const UpConv& c, const bf16* in, int n, int h, int w, 
   a.W = w;
   a.cin = c.cin;
   a.taps = 1;
-  a.stages = pick_stages(g.bn, g.mt, c.cin / kBlockK);
+  a.stages = pick_stages(g.bn, g.mt);
   a.mode = kEpiUpscatter;
   a.relu = 0;
   a.scale = c.ones;
@@ -851,8 +899,8 @@ int mfpa_conv_bf16(mfpa_ctx* ctx, const void* in_dev, int N, int H, int W, int c
   a.W = W;
   a.cin = cin;
   a.taps = taps;
-  a.stages = stages > 0 ? stages : pick_stages(g.bn, g.mt, taps * cin / kBlockK);
-  MFPA_REQUIRE(gemm_smem_bytes(g.bn, g.mt, a.stages) <= 227 * 1024, "mfpa_conv_bf16: %d stages do not fit shared memory", a.stages);
+  a.stages = stages > 0 ? stages : pick_stages(g.bn, g.mt);
+  MFPA_REQUIRE(gemm_smem_bytes(g.mt, g.bn, a.stages, cout) <= 227 * 1024, "mfpa_conv_bf16: %d stages do not fit shared memory", a.stages);
   a.mode = kEpiStore;
   a.relu = relu;
   a.scale = scale_dev;
