@@ -300,10 +300,12 @@ int mfpa_unet_forward(mfpa_ctx* ctx, mfpa_unet* unet, const float* in_dev, int64
                       int64_t out_stride_n, int64_t out_stride_h, int64_t out_stride_w, void* stream);
 /* One convolution of the network on caller-owned NHWC bf16 tensors (the unit the parity tests drive):
  * out[..., coff:coff+cout] = act(conv(in, w) * scale + shift); w_dev [cout][taps][cin] bf16, taps 9 (3x3,
- * padding 1) or 1; cin, cout multiples of 64.  bn / mt / stages = 0 pick the tile configuration. */
+ * padding 1) or 1; cin, cout multiples of 64.  bn / mt / stages = 0 pick the tile configuration.
+ * halo_wh > 0 selects the halo-reuse 3x3 kernel with that halo pitch (tile width halo_wh - 2); wres = 1
+ * additionally keeps the weights resident in shared memory (cout == 64 only). */
 int mfpa_conv_bf16(mfpa_ctx* ctx, const void* in_dev, int N, int H, int W, int cin, const void* w_dev, int cout,
                    int taps, const float* scale_dev, const float* shift_dev, int relu, void* out_dev, int ldc,
-                   int coff, int bn, int mt, int stages, void* stream);
+                   int coff, int bn, int mt, int stages, int halo_wh, int wres, void* stream);
 
 #ifdef __cplusplus
 }

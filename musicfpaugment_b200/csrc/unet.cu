@@ -21,6 +21,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -335,49 +336,317 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
+// ------------------------------------------------------------------------------------ halo-reuse 3x3 kernel
+// The per-tap kernel above fetches every activation tile nine times from L2, and L2 -> SM bandwidth
+// (~42 B/clk/SM) is what bounds it.  This variant loads the (th+2) x Wh halo of a tile ONCE per 64-channel
+// chunk and feeds all nine taps from it: with the halo stored one 128-byte swizzled row per pixel, pitch
+// Wh pixels, the operand of tap (kh, kw) is simply the same buffer starting (kh*Wh + kw) rows later - M
+// runs over flat halo positions p = h*Wh + w, rows with w >= Wh-2 are computed and thrown away.  Such a
+// start is 128-byte but not 1024-byte aligned; measured on B200, the tensor core applies the 128-byte
+// swizzle to absolute shared-memory address bits, so the descriptor's base-offset field stays 0 and the
+// pattern TMA wrote (also a function of the absolute address) is read back correctly.
+// WRES keeps the whole weight tensor of a Cout = BN layer resident in shared memory (the 64-channel layers
+// at full resolution, whose weights would otherwise be re-read from L2 for every tile).
+struct HaloArgs {
+  ConvArgs c;
+  int wh;          // halo pitch in pixels (tile width = wh - 2)
+  int th;          // output rows per tile
+  int a_bytes;     // bytes of one halo stage (multiple of 1024)
+  int a_stages, b_stages;
+};
+
+template <int BN, int MT, bool WRES>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const HaloArgs ha) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const ConvArgs& a = ha.c;
+  constexpr int kBBytes = BN * 128;
+  constexpr int kAcc = (2 * MT * BN <= 512) ? 2 : 1;
+  constexpr int kTmemCols = kAcc * MT * BN;
+  const int chunks = a.cin / kBlockK;
+  const int nb = WRES ? 9 * chunks : ha.b_stages;  // weight tiles held in shared memory
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_b = smem + (size_t)ha.a_stages * ha.a_bytes;
+  uint64_t* bars = (uint64_t*)(smem_b + (size_t)nb * kBBytes);
+  // a_full[SA], a_empty[SA], b_full[SB], b_empty[SB], tmem_full[2], tmem_empty[2], wres_full
+  const int SA = ha.a_stages, SB = ha.b_stages;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * SA + 2 * SB + 5);
+  float* s_scale = (float*)(tmem_slot + 2);
+  float* s_shift = s_scale + a.cout;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tw = ha.wh - 2;
+  const int tiles_w = (a.W + tw - 1) / tw;
+  const int tiles_sp = tiles_w * ((a.H + ha.th - 1) / ha.th);
+  const int tiles_n = a.n_total / BN;
+  const int total = tiles_n * tiles_sp * a.N;
+  const uint32_t bar0 = smem_u32(bars);
+  auto a_full = [&](int s) { return bar0 + 8u * s; };
+  auto a_empty = [&](int s) { return bar0 + 8u * (SA + s); };
+  auto b_full = [&](int s) { return bar0 + 8u * (2 * SA + s); };
+  auto b_empty = [&](int s) { return bar0 + 8u * (2 * SA + SB + s); };
+  auto tmem_full_bar = [&](int b) { return bar0 + 8u * (2 * SA + 2 * SB + b); };
+  auto tmem_empty_bar = [&](int b) { return bar0 + 8u * (2 * SA + 2 * SB + 2 + b); };
+  const uint32_t wres_bar = bar0 + 8u * (2 * SA + 2 * SB + 4);
+  auto decode = [&](int t, int& n0, int& w0, int& h0, int& img) {
+    n0 = (t % tiles_n) * BN;
+    t /= tiles_n;
+    const int sp = t % tiles_sp;
+    img = t / tiles_sp;
+    w0 = (sp % tiles_w) * tw;
+    h0 = (sp / tiles_w) * ha.th;
+  };
+
+  if (warp == 4 && lane == 0) {
+    for (int s = 0; s < SA; ++s) {
+      mbar_init(a_full(s), 1);
+      mbar_init(a_empty(s), 1);
+    }
+    for (int s = 0; s < SB; ++s) {
+      mbar_init(b_full(s), 1);
+      mbar_init(b_empty(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tmem_full_bar(b), 1);
+      mbar_init(tmem_empty_bar(b), 4);
+    }
+    mbar_init(wres_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp < 4) {
+    for (int i = threadIdx.x; i < a.cout; i += 128) {
+      s_scale[i] = a.scale[i];
+      s_shift[i] = a.shift[i];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t halo_box_bytes = (uint32_t)(ha.th + 2) * ha.wh * 128u;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      // ---- TMA producer
+      if (WRES) {
+        mbar_expect_tx(wres_bar, (uint32_t)(9 * chunks) * kBBytes);
+        for (int tap = 0; tap < 9; ++tap)
+          for (int cc = 0; cc < chunks; ++cc)
+            tma_load_2d(smem_u32(smem_b + (size_t)(tap * chunks + cc) * kBBytes), &tmB, wres_bar, tap * a.cin + cc * kBlockK, 0);
+      }
+      int ia = 0, ib = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        int n0, w0, h0, img;
+        decode(t, n0, w0, h0, img);
+        for (int cc = 0; cc < chunks; ++cc, ++ia) {
+          const int sa = ia % SA;
+          mbar_wait(a_empty(sa), ((ia / SA) & 1) ^ 1);
+          mbar_expect_tx(a_full(sa), halo_box_bytes);
+          tma_load_4d(smem_u32(smem + (size_t)sa * ha.a_bytes), &tmA, a_full(sa), cc * kBlockK, w0 - 1, h0 - 1, img);
+          if (!WRES) {
+            for (int tap = 0; tap < 9; ++tap, ++ib) {
+              const int sb = ib % SB;
+              mbar_wait(b_empty(sb), ((ib / SB) & 1) ^ 1);
+              mbar_expect_tx(b_full(sb), kBBytes);
+              tma_load_2d(smem_u32(smem_b + (size_t)sb * kBBytes), &tmB, b_full(sb), tap * a.cin + cc * kBlockK, n0);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      // ---- MMA issuer
+      constexpr uint32_t idesc = umma_idesc(128, BN);
+      if (WRES) {
+        mbar_wait(wres_bar, 0);
+        tc_fence_after();
+      }
+      int ia = 0, ib = 0, i = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x, ++i) {
+        const int acc = i % kAcc;
+        mbar_wait(tmem_empty_bar(acc), ((i / kAcc) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d0 = tmem_base + acc * (MT * BN);
+        for (int cc = 0; cc < chunks; ++cc, ++ia) {
+          const int sa = ia % SA;
+          mbar_wait(a_full(sa), (ia / SA) & 1);
+          tc_fence_after();
+          const uint32_t abase = smem_u32(smem + (size_t)sa * ha.a_bytes);
+          for (int tap = 0; tap < 9; ++tap) {
+            uint32_t sbaddr;
+            int sb = 0;
+            if (WRES) {
+              sbaddr = smem_u32(smem_b + (size_t)(tap * chunks + cc) * kBBytes);
+            } else {
+              sb = ib % SB;
+              mbar_wait(b_full(sb), (ib / SB) & 1);
+              tc_fence_after();
+              sbaddr = smem_u32(smem_b + (size_t)sb * kBBytes);
+              ++ib;
+            }
+            const uint32_t arow = abase + (uint32_t)((tap / 3) * ha.wh + tap % 3) * 128u;
+#pragma unroll
+            for (int j = 0; j < MT; ++j) {
+#pragma unroll
+              for (int k = 0; k < kBlockK / 16; ++k) {
+                tc_mma(d0 + j * BN, umma_desc(arow + j * kATile + k * 32), umma_desc(sbaddr + k * 32), idesc,
+                       (cc > 0 || tap > 0 || k > 0) ? 1u : 0u);
+              }
+            }
+            if (!WRES) tc_commit(b_empty(sb));
+          }
+          tc_commit(a_empty(sa));
+        }
+        tc_commit(tmem_full_bar(acc));
+      }
+    }
+  } else {
+    // ---- epilogue: TMEM lane m of sub-tile j = flat halo position j*128 + m
+    int i = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++i) {
+      const int acc = i % kAcc;
+      int n0, w0, h0, img;
+      decode(t, n0, w0, h0, img);
+      mbar_wait(tmem_full_bar(acc), (i / kAcc) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int j = 0; j < MT; ++j) {
+        const int p = j * 128 + warp * 32 + lane;
+        const int hl = p / ha.wh, wl = p - hl * ha.wh;
+        const int h = h0 + hl, w = w0 + wl;
+        const bool inside = wl < tw && hl < ha.th && h < a.H && w < a.W;
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * (MT * BN) + j * BN;
+        if (a.mode == kEpiOutc) {
+          float dot = 0.f;
+#pragma unroll 1
+          for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32];
+            tc_ld32(taddr + c0, v);
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+              float y = fmaf(__uint_as_float(v[q]), s_scale[n0 + c0 + q], s_shift[n0 + c0 + q]);
+              y = fmaxf(y, 0.f);
+              dot = fmaf(y, __ldg(a.w_out + n0 + c0 + q), dot);
+            }
+          }
+          if (inside) a.out_f32[img * a.of_n + h * a.of_h + w * a.of_w] = dot + a.b_out;
+        } else {
+          const size_t pix = ((size_t)img * a.out_h + h) * a.out_w + w;
+#pragma unroll 1
+          for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32];
+            tc_ld32(taddr + c0, v);
+            const int co = n0 + c0;
+            uint32_t packed[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+              float y0 = fmaf(__uint_as_float(v[2 * q]), s_scale[co + 2 * q], s_shift[co + 2 * q]);
+              float y1 = fmaf(__uint_as_float(v[2 * q + 1]), s_scale[co + 2 * q + 1], s_shift[co + 2 * q + 1]);
+              if (a.relu) {
+                y0 = fmaxf(y0, 0.f);
+                y1 = fmaxf(y1, 0.f);
+              }
+              __nv_bfloat162 pk = __floats2bfloat162_rn(y0, y1);
+              packed[q] = *reinterpret_cast<uint32_t*>(&pk);
+            }
+            if (inside) {
+              uint4* d4 = reinterpret_cast<uint4*>(a.out + pix * a.ldc + a.coff + co);
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                d4[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kTmemCols) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------------------------ CUDA-core kernels
 // inc.double_conv.0: Conv2d(1, 64, 3, padding=1, bias=False) + BatchNorm + ReLU (training/unet.py:15-18).
 // in: float32, element strides (in_n, in_h, in_w), optionally divided by div[n] (sgram /= max,
-// peak_extractor.py:263); out: NHWC bf16 [N][H][W][64].  One thread per pixel.
-__global__ void __launch_bounds__(128)
+// peak_extractor.py:263); out: NHWC bf16 [N][H][W][64].  A block stages the 10 x 34 input halo of an
+// 8 x 32 pixel tile in shared memory (read along whichever input dimension has unit stride), then every
+// thread produces 8 channels of a pixel so that a warp stores 4 pixels x 128 contiguous bytes.
+constexpr int kInTh = 8, kInTw = 32;
+__global__ void __launch_bounds__(256)
 conv_in_kernel(const float* __restrict__ in, long long in_n, long long in_h, long long in_w, const float* __restrict__ div,
                int H, int W, const float* __restrict__ wgt /* [9][64] */, const float* __restrict__ scale,
                const float* __restrict__ shift, bf16* __restrict__ out) {
   __shared__ float s_w[9 * 64], s_sc[64], s_sh[64];
+  __shared__ float s_x[kInTh + 2][kInTw + 2 + 1];
   for (int i = threadIdx.x; i < 9 * 64; i += blockDim.x) s_w[i] = wgt[i];
   if (threadIdx.x < 64) {
     s_sc[threadIdx.x] = scale[threadIdx.x];
     s_sh[threadIdx.x] = shift[threadIdx.x];
   }
-  __syncthreads();
-  const int n = blockIdx.z, h = blockIdx.y, w = blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= W) return;
+  const int n = blockIdx.z, h0 = blockIdx.y * kInTh, w0 = blockIdx.x * kInTw;
   const float dv = div ? div[n] : 1.0f;
   const float* base = in + n * in_n;
-  float x[9];
-#pragma unroll
-  for (int t = 0; t < 9; ++t) {
-    const int hh = h + t / 3 - 1, ww = w + t % 3 - 1;
-    x[t] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? base[hh * in_h + ww * in_w] / dv : 0.f;
+  constexpr int kHalo = (kInTh + 2) * (kInTw + 2);
+  for (int i = threadIdx.x; i < kHalo; i += blockDim.x) {
+    int r, c;
+    if (in_h == 1) {  // frame-major magnitudes: consecutive threads walk the bins
+      r = i % (kInTh + 2);
+      c = i / (kInTh + 2);
+    } else {
+      r = i / (kInTw + 2);
+      c = i % (kInTw + 2);
+    }
+    const int hh = h0 + r - 1, ww = w0 + c - 1;
+    s_x[r][c] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? base[hh * in_h + ww * in_w] / dv : 0.f;
   }
-  uint4* dst = reinterpret_cast<uint4*>(out + (((size_t)n * H + h) * W + w) * 64);
+  __syncthreads();
+  const int cg = threadIdx.x & 7;  // channels 8*cg .. 8*cg+7
+  float wr[9][8], sc[8], sh[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    sc[q] = s_sc[8 * cg + q];
+    sh[q] = s_sh[8 * cg + q];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) wr[t][q] = s_w[t * 64 + 8 * cg + q];
+  }
 #pragma unroll 1
-  for (int c0 = 0; c0 < 64; c0 += 8) {
+  for (int it = 0; it < kInTh; ++it) {
+    const int p = it * 32 + (threadIdx.x >> 3);  // 32 pixels (one tile row) per pass
+    const int r = p / kInTw, c = p % kInTw;
+    const int h = h0 + r, w = w0 + c;
+    if (h >= H || w >= W) continue;
+    float x[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) x[t] = s_x[r + t / 3][c + t % 3];
     uint32_t packed[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float acc0 = 0.f, acc1 = 0.f;
+    for (int q = 0; q < 4; ++q) {
+      float a0 = 0.f, a1 = 0.f;
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
-        acc0 = fmaf(x[t], s_w[t * 64 + c0 + 2 * i], acc0);
-        acc1 = fmaf(x[t], s_w[t * 64 + c0 + 2 * i + 1], acc1);
+        a0 = fmaf(x[t], wr[t][2 * q], a0);
+        a1 = fmaf(x[t], wr[t][2 * q + 1], a1);
       }
-      acc0 = fmaxf(fmaf(acc0, s_sc[c0 + 2 * i], s_sh[c0 + 2 * i]), 0.f);
-      acc1 = fmaxf(fmaf(acc1, s_sc[c0 + 2 * i + 1], s_sh[c0 + 2 * i + 1]), 0.f);
-      __nv_bfloat162 p = __floats2bfloat162_rn(acc0, acc1);
-      packed[i] = *reinterpret_cast<uint32_t*>(&p);
+      a0 = fmaxf(fmaf(a0, sc[2 * q], sh[2 * q]), 0.f);
+      a1 = fmaxf(fmaf(a1, sc[2 * q + 1], sh[2 * q + 1]), 0.f);
+      __nv_bfloat162 pk = __floats2bfloat162_rn(a0, a1);
+      packed[q] = *reinterpret_cast<uint32_t*>(&pk);
     }
-    dst[c0 / 8] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+    *reinterpret_cast<uint4*>(out + (((size_t)n * H + h) * W + w) * 64 + 8 * cg) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
   }
 }
 
@@ -432,12 +701,12 @@ EncodeTiledFn encode_fn() {
 }
 
 // NHWC bf16 activation [N][H][W][C] -> 4-D map, box {64, 16, box_h, 1}, 128-byte swizzle, zero OOB fill
-int make_act_map(CUtensorMap* m, const bf16* ptr, int N, int H, int W, int C, int box_h) {
+int make_act_map(CUtensorMap* m, const bf16* ptr, int N, int H, int W, int C, int box_h, int box_w = kTileW) {
   EncodeTiledFn fn = encode_fn();
   MFPA_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)kTileW, (cuuint32_t)box_h, 1};
+  cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -463,7 +732,60 @@ struct GemmLaunch {
   ConvArgs args;
   int bn, mt, n_total, N;
   int ctas = mfpa::kNumSMs;  // persistent grid size
+  // halo-reuse variant (wh > 0)
+  int wh = 0, th = 0, wres = 0, a_stages = 0, b_stages = 0, a_bytes = 0;
 };
+
+// geometry of the halo kernel for pitch wh: rows per tile and bytes of one halo stage
+void halo_geometry(int wh, int mt, int* th, int* a_bytes) {
+  const int tw = wh - 2;
+  *th = (128 * mt - tw) / wh + 1;
+  int rows = (*th + 2) * wh;
+  const int reach = 128 * mt + 2 * wh + 2;  // last row any tap's operand touches
+  if (rows < reach) rows = reach;
+  *a_bytes = (rows * 128 + 1023) / 1024 * 1024;
+}
+size_t halo_smem_bytes(const GemmLaunch& g, int cin, int cout) {
+  const int nb = g.wres ? 9 * (cin / kBlockK) : g.b_stages;
+  return 1024 + (size_t)g.a_stages * g.a_bytes + (size_t)nb * g.bn * 128 + 8 * (2 * g.a_stages + 2 * g.b_stages + 5) + 8 +
+         2 * (size_t)cout * sizeof(float);
+}
+
+template <int BN, int MT, bool WRES>
+int launch_halo_t(const GemmLaunch& g, cudaStream_t st) {
+  MFPA_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BN, MT, WRES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  HaloArgs ha{};
+  ha.c = g.args;
+  ha.c.N = g.N;
+  ha.c.n_total = g.n_total;
+  ha.wh = g.wh;
+  ha.th = g.th;
+  ha.a_bytes = g.a_bytes;
+  ha.a_stages = g.a_stages;
+  ha.b_stages = g.b_stages;
+  const int tw = g.wh - 2;
+  const long long tiles = (long long)((ha.c.W + tw - 1) / tw) * ((ha.c.H + g.th - 1) / g.th) * (g.n_total / BN) * g.N;
+  MFPA_REQUIRE(tiles < (1ll << 31), "conv halo: too many tiles");
+  const int grid = (int)(tiles < g.ctas ? tiles : g.ctas);
+  conv_halo_kernel<BN, MT, WRES><<<grid, kThreads, halo_smem_bytes(g, ha.c.cin, ha.c.cout), st>>>(g.tmA, g.tmB, ha);
+  MFPA_CUDA(cudaGetLastError());
+  return MFPA_OK;
+}
+
+int launch_halo(const GemmLaunch& g, cudaStream_t st) {
+  switch (g.bn * 100 + g.mt * 10 + g.wres) {
+    case 6410: return launch_halo_t<64, 1, false>(g, st);
+    case 6411: return launch_halo_t<64, 1, true>(g, st);
+    case 6420: return launch_halo_t<64, 2, false>(g, st);
+    case 6421: return launch_halo_t<64, 2, true>(g, st);
+    case 12810: return launch_halo_t<128, 1, false>(g, st);
+    case 12820: return launch_halo_t<128, 2, false>(g, st);
+    case 25610: return launch_halo_t<256, 1, false>(g, st);
+    case 25620: return launch_halo_t<256, 2, false>(g, st);
+  }
+  mfpa::set_error("conv halo: unsupported configuration BN=%d MT=%d WRES=%d", g.bn, g.mt, g.wres);
+  return MFPA_EINVAL;
+}
 
 size_t gemm_smem_bytes(int mt, int bn, int stages, int cout) {
   return 1024 + (size_t)stages * (mt * kATile + bn * 128) + 8 * (2 * stages + 4) + 8 + 2 * (size_t)cout * sizeof(float);
@@ -484,6 +806,7 @@ int launch_gemm_t(const GemmLaunch& g, cudaStream_t st) {
 }
 
 int launch_gemm(const GemmLaunch& g, cudaStream_t st) {
+  if (g.wh > 0) return launch_halo(g, st);
   switch (g.bn * 10 + g.mt) {
     case 641: return launch_gemm_t<64, 1>(g, st);
     case 642: return launch_gemm_t<64, 2>(g, st);
@@ -596,7 +919,28 @@ int plan_conv(mfpa_unet* u, const ConvBN& c, const bf16* in, int n, int h, int w
   if (mode == kEpiOutc) g.bn = 64;
   g.n_total = c.cout;
   g.N = n;
-  int rc = make_act_map(&g.tmA, in, n, h, w, c.cin, 8 * g.mt);
+  // Kernel choice (measured on B200, scratch/tune_conv.py): the 64-output-channel layers are bound by
+  // L2 -> SM operand traffic in the per-tap kernel, so they use the halo-reuse kernel with the weights
+  // resident in shared memory; wider layers are weight-traffic bound either way and keep
+  // the per-tap kernel, with 128-pixel tiles where that evens out the last wave.
+  if (c.cout <= 64 && w >= 30) {
+    g.mt = 2;
+    g.wres = c.cout == 64;
+    g.a_stages = 2;
+    g.b_stages = 4;
+    if (g.wres && c.cin > 64) {
+      g.wh = 18;
+    } else {
+      int k = 1;
+      while ((w + k - 1) / k + 2 > 130) ++k;
+      g.wh = (w + k - 1) / k + 2;
+    }
+    halo_geometry(g.wh, g.mt, &g.th, &g.a_bytes);
+    if (halo_smem_bytes(g, c.cin, c.cout) > 227 * 1024) g.wh = 0;  // does not fit: per-tap kernel
+  } else if (c.cout >= 256 && c.cin <= 256 && h * w >= 2048) {
+    g.mt = 1;
+  }
+  int rc = g.wh > 0 ? make_act_map(&g.tmA, in, n, h, w, c.cin, g.th + 2, g.wh) : make_act_map(&g.tmA, in, n, h, w, c.cin, 8 * g.mt);
   if (rc) return rc;
   rc = make_wgt_map(&g.tmB, c.w, c.cout, 9 * c.cin, g.bn);
   if (rc) return rc;
@@ -625,7 +969,7 @@ int plan_up(mfpa_unet* u, const UpConv& c, const bf16* in, int n, int h, int w, 
             int coff) {
   GemmLaunch g{};
   g.bn = 256;  // all four (a, b) phases of 64 channels, or a slice of one phase, per tile
-  g.mt = h >= 16 ? 2 : 1;
+  g.mt = 1;    // 2 x 256 TMEM columns: the (store-heavy) epilogue of one tile overlaps the MMAs of the next
   g.n_total = 4 * c.cout;
   g.N = n;
   int rc = make_act_map(&g.tmA, in, n, h, w, c.cin, 8 * g.mt);
@@ -836,8 +1180,8 @@ int mfpa_unet_forward(mfpa_ctx* ctx, mfpa_unet* u, const float* in_dev, int64_t 
   for (int b0 = 0; b0 < B; b0 += chunk) {
     const int n = (B - b0) < chunk ? (B - b0) : chunk;
     {
-      dim3 grid((W + 127) / 128, H, n);
-      conv_in_kernel<<<grid, 128, 0, st>>>(in_dev + b0 * in_n, in_n, in_h, in_w, div_dev ? div_dev + b0 : nullptr, H, W,
+      dim3 grid((W + kInTw - 1) / kInTw, (H + kInTh - 1) / kInTh, n);
+      conv_in_kernel<<<grid, 256, 0, st>>>(in_dev + b0 * in_n, in_n, in_h, in_w, div_dev ? div_dev + b0 : nullptr, H, W,
                                            u->in_w, u->in_scale, u->in_shift, u->mid[0]);
       MFPA_CUDA(cudaGetLastError());
     }
@@ -880,7 +1224,7 @@ int mfpa_unet_forward(mfpa_ctx* ctx, mfpa_unet* u, const float* in_dev, int64_t 
 // [N][H][W][ldc].  taps = 1 runs a 1x1 convolution (w_dev [cout][cin]).
 int mfpa_conv_bf16(mfpa_ctx* ctx, const void* in_dev, int N, int H, int W, int cin, const void* w_dev, int cout, int taps,
                    const float* scale_dev, const float* shift_dev, int relu, void* out_dev, int ldc, int coff, int bn,
-                   int mt, int stages, void* stream) {
+                   int mt, int stages, int halo_wh, int wres, void* stream) {
   MFPA_REQUIRE(ctx && in_dev && w_dev && out_dev && scale_dev && shift_dev, "mfpa_conv_bf16: null argument");
   MFPA_REQUIRE(cin % 64 == 0 && cout % 64 == 0 && (taps == 9 || taps == 1), "mfpa_conv_bf16: cin/cout must be multiples of 64, taps 1 or 9");
   MFPA_REQUIRE(ldc % 8 == 0 && coff % 8 == 0, "mfpa_conv_bf16: ldc and coff must be multiples of 8");
@@ -890,17 +1234,32 @@ int mfpa_conv_bf16(mfpa_ctx* ctx, const void* in_dev, int N, int H, int W, int c
   MFPA_REQUIRE(cout % g.bn == 0, "mfpa_conv_bf16: cout %d is not a multiple of the N tile %d", cout, g.bn);
   g.n_total = cout;
   g.N = N;
-  int rc = make_act_map(&g.tmA, (const bf16*)in_dev, N, H, W, cin, 8 * g.mt);
+  int rc;
+  ConvArgs& a = g.args;
+  if (halo_wh > 0) {
+    MFPA_REQUIRE(taps == 9 && halo_wh >= 3 && halo_wh <= 256, "mfpa_conv_bf16: the halo kernel needs taps = 9 and 3 <= wh <= 256");
+    MFPA_REQUIRE(!wres || (g.bn == cout && g.bn == 64), "mfpa_conv_bf16: resident weights need cout == bn == 64");
+    g.wh = halo_wh;
+    g.wres = wres ? 1 : 0;
+    halo_geometry(g.wh, g.mt, &g.th, &g.a_bytes);
+    g.a_stages = stages > 0 ? stages : 2;
+    g.b_stages = 4;
+    MFPA_REQUIRE(g.th + 2 <= 256, "mfpa_conv_bf16: halo box too tall");
+    MFPA_REQUIRE(halo_smem_bytes(g, cin, cout) <= 227 * 1024, "mfpa_conv_bf16: halo configuration needs %zu bytes of shared memory",
+                 halo_smem_bytes(g, cin, cout));
+    rc = make_act_map(&g.tmA, (const bf16*)in_dev, N, H, W, cin, g.th + 2, g.wh);
+  } else {
+    rc = make_act_map(&g.tmA, (const bf16*)in_dev, N, H, W, cin, 8 * g.mt);
+  }
   if (rc) return rc;
   rc = make_wgt_map(&g.tmB, (const bf16*)w_dev, cout, taps * cin, g.bn);
   if (rc) return rc;
-  ConvArgs& a = g.args;
   a.H = H;
   a.W = W;
   a.cin = cin;
   a.taps = taps;
   a.stages = stages > 0 ? stages : pick_stages(g.bn, g.mt);
-  MFPA_REQUIRE(gemm_smem_bytes(g.mt, g.bn, a.stages, cout) <= 227 * 1024, "mfpa_conv_bf16: %d stages do not fit shared memory", a.stages);
+  MFPA_REQUIRE(halo_wh > 0 || gemm_smem_bytes(g.mt, g.bn, a.stages, cout) <= 227 * 1024, "mfpa_conv_bf16: %d stages do not fit shared memory", a.stages);
   a.mode = kEpiStore;
   a.relu = relu;
   a.scale = scale_dev;

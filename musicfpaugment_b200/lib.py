@@ -98,7 +98,7 @@ SIGNATURES = {
     "mfpa_unet_load": (_i, [_vp, _vp, _i64]),
     "mfpa_unet_set_max_chunk": (_i, [_vp, _i]),
     "mfpa_unet_forward": (_i, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _i, _i, _i, _vp, _i64, _i64, _i64, _vp]),
-    "mfpa_conv_bf16": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp]),
+    "mfpa_conv_bf16": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
 }
 
 
@@ -544,7 +544,8 @@ class UNetDenoiser:
         return mag
 
 
-def conv_bf16(ctx: Context, x, w, scale, shift, relu=True, taps=9, out=None, coff=0, bn=0, mt=0, stages=0):
+def conv_bf16(ctx: Context, x, w, scale, shift, relu=True, taps=9, out=None, coff=0, bn=0, mt=0, stages=0, halo_wh=0,
+              wres=0):
     """x [N,H,W,Cin] bf16 cuda, w [Cout,taps,Cin] bf16 cuda -> [N,H,W,Cout] bf16 (or a channel slice of `out`)."""
     import torch
 
@@ -553,5 +554,5 @@ def conv_bf16(ctx: Context, x, w, scale, shift, relu=True, taps=9, out=None, cof
     if out is None:
         out = torch.empty(N, H, W, cout, dtype=torch.bfloat16, device=x.device)
     check(_lib.mfpa_conv_bf16(ctx.handle, _ptr(x), N, H, W, cin, _ptr(w), cout, taps, _ptr(scale), _ptr(shift), int(relu),
-                              _ptr(out), out.shape[-1], coff, bn, mt, stages, _stream()))
+                              _ptr(out), out.shape[-1], coff, bn, mt, stages, halo_wh, wres, _stream()))
     return out

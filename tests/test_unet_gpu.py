@@ -58,6 +58,39 @@ def test_conv_gemm_matches_torch(mfpa_ctx, N, H, W, cin, cout, taps, bn, mt, sta
     assert bool((out[..., :64] == 7.0).all()), "channels outside the slice were overwritten"
 
 
+HALO_CASES = [
+    # N, H, W, cin, cout, bn, mt, halo_wh, wres
+    (2, 20, 19, 64, 64, 64, 1, 18, 0),
+    (2, 20, 19, 64, 64, 64, 2, 18, 1),
+    (1, 33, 70, 128, 64, 64, 2, 18, 1),
+    (1, 33, 70, 128, 64, 64, 1, 32, 0),
+    (1, 40, 125, 64, 128, 128, 2, 127, 0),
+    (1, 17, 251, 64, 64, 64, 2, 86, 1),
+    (1, 17, 251, 128, 256, 256, 1, 66, 0),
+    (2, 16, 15, 256, 256, 256, 1, 17, 0),
+]
+
+
+@pytest.mark.parametrize("N,H,W,cin,cout,bn,mt,wh,wres", HALO_CASES)
+def test_conv_halo_kernel_matches_torch(mfpa_ctx, N, H, W, cin, cout, bn, mt, wh, wres):
+    """The halo-reuse 3x3 kernel (one halo load per 64-channel chunk, nine shifted operand views)."""
+    from musicfpaugment_b200 import lib
+
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator(device="cuda").manual_seed(H * 100 + W + cin)
+    x = torch.randn(N, H, W, cin, device="cuda", generator=g).to(torch.bfloat16)
+    w = (torch.randn(cout, 9, cin, device="cuda", generator=g) / (9 * cin) ** 0.5).to(torch.bfloat16)
+    scale = 0.5 + torch.rand(cout, device="cuda", generator=g)
+    shift = 0.2 * torch.randn(cout, device="cuda", generator=g)
+    out = torch.full((N, H, W, cout), 7.0, dtype=torch.bfloat16, device="cuda")
+    lib.conv_bf16(mfpa_ctx, x, w, scale, shift, relu=True, taps=9, out=out, bn=bn, mt=mt, halo_wh=wh, wres=wres)
+    torch.cuda.synchronize()
+    ref = _conv_ref(x, w, scale, shift, True, 9)
+    err = (out.float() - ref).abs()
+    tol = 2.0 ** -7 * ref.abs() + 1e-3
+    assert bool((err <= tol).all()), f"max err {float(err.max())} at ref {float(ref.abs().max())}"
+
+
 def test_unet_forward_matches_fp32_oracle(mfpa_ctx):
     """Whole network vs the fp32 oracle.  Tolerance: 23 bf16-rounded layers -> <= 3 % of the output's
     dynamic range at the worst pixel, <= 0.5 % rms."""
