@@ -68,12 +68,41 @@ class Audfprint_peaks(object):
         self.soundfiledur = 0.0
         if self.denoising:
             assert self.denoising_model in ["demucs", "unet"]
-            raise NotImplementedError(
-                "denoising=True needs the UNet/Demucs forward, which is not built in this round "
-                "(DESIGN.md, out of scope for now); the B200 path has no PyTorch fallback")
+            if self.denoising_model == "demucs":
+                raise NotImplementedError(
+                    "denoising_model='demucs' (training/model.py:163-326) is outside the B200 hot path "
+                    "(SURVEY.md section 8f item 4); only the UNet denoiser is built")
         if self.n_fft != lib.N_FFT or self.n_hop != lib.HOP:
             raise ValueError(f"the CUDA path is built for n_fft={lib.N_FFT}, n_hop={lib.HOP} "
                              f"(testing/parameters.py:17-26), got {self.n_fft}/{self.n_hop}")
+
+    # ---- UNet denoiser (the reference builds it at import time from a hard-coded checkpoint,
+    # peak_extractor.py:23-27; here it is built on first use from the same file, from
+    # $MFPA_UNET_CHECKPOINT, or from a state_dict handed to set_unet_state_dict)
+    UNET_CHECKPOINT = "/workspace/src/training/checkpoints/unet_lr_0.001_BS_128/best_epoch.pt"
+    _unet_state_dict = None
+    _unet = None
+
+    @classmethod
+    def set_unet_state_dict(cls, state_dict) -> None:
+        cls._unet_state_dict = state_dict
+        if cls._unet is not None:
+            cls._unet.close()
+            cls._unet = None
+
+    def _denoiser(self):
+        cls = Audfprint_peaks
+        if cls._unet is None:
+            sd = cls._unet_state_dict
+            if sd is None:
+                import os
+
+                import torch
+
+                path = os.environ.get("MFPA_UNET_CHECKPOINT", cls.UNET_CHECKPOINT)
+                sd = torch.load(path, map_location="cpu")["model_state_dict"]  # FileNotFoundError like the reference
+            cls._unet = lib.UNetDenoiser(self._ctx(), sd)
+        return cls._unet
 
     # ---- parameters -> C struct
     def _afp(self) -> lib.AfpParams:
@@ -111,12 +140,17 @@ class Audfprint_peaks(object):
         ctx = self._ctx()
         x = torch.from_numpy(d).reshape(1, -1).cuda()
         mag, qmax = ctx.stft_mag(x)
-        if not float(qmax[0]) > 0.0:
-            print("find_peaks: Warning: input signal is identically zero.")  # :277-280
-        rec, _ = ctx.audfprint_peaks(mag, qmax, x.shape[1], 1, self._afp())
+        if self.denoising:  # sgram = unet(sgram / max) (:263-269); spec = the float32 network output
+            self._denoiser().denoise_mag(mag, qmax)
+            rec, _ = ctx.audfprint_peaks(mag, None, x.shape[1], 1, self._afp())
+            spec = mag[0, :, : lib.BINS].t().contiguous().cpu().numpy()
+        else:
+            if not float(qmax[0]) > 0.0:
+                print("find_peaks: Warning: input signal is identically zero.")  # :277-280
+            rec, _ = ctx.audfprint_peaks(mag, qmax, x.shape[1], 1, self._afp())
+            spec = ctx.spec_from_mag(mag, qmax, x.shape[1])[0].cpu().numpy()
         peaks, npk = ctx.peaks_list(rec)
         mask = ctx.peaks_mask(rec)[0].cpu().numpy()
-        spec = ctx.spec_from_mag(mag, qmax, x.shape[1])[0].cpu().numpy()
         pk = peaks[0, : int(npk[0])].cpu().numpy()
         return [(int(c), int(b)) for c, b in pk], mask, spec
 
@@ -150,6 +184,11 @@ class Audfprint_peaks(object):
         shifts = self.shifts if shifts is None else shifts
         shifts = 1 if shifts is None or shifts < 2 else int(shifts)
         ctx = self._ctx()
+        if self.denoising:
+            w = waves if isinstance(waves, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(waves, dtype=np.float32))
+            out, nh = ctx.fingerprint_denoised(w.float().contiguous().cuda(), shifts, self._afp(), self._denoiser())
+            out, nh = out.cpu().numpy(), nh.cpu().numpy()
+            return [out[i, : nh[i]].copy() for i in range(len(nh))]
         if isinstance(waves, torch.Tensor) and waves.is_cuda:
             out, nh = ctx.fingerprint(waves.float().contiguous(), shifts, self._afp())
             out, nh = out.cpu().numpy(), nh.cpu().numpy()

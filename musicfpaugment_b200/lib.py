@@ -459,6 +459,18 @@ class Context:
                                     out.shape[1], _ptr(nh), _stream()))
         return out, nh
 
+    def fingerprint_denoised(self, x, shifts: int, params: AfpParams, denoiser):
+        """wavfile2hashes with ``denoising=True, denoising_model="unet"`` (peak_extractor.py:263-269):
+        STFT -> /max -> UNet -> picker -> landmarks -> hashes -> shift merge, all on the device."""
+        B, T = x.shape
+        mag, qmax = self.stft_mag(x, shifts)
+        denoiser.denoise_items(mag, qmax, T, shifts)
+        rec, _ = self.audfprint_peaks(mag, None, T, shifts, params)
+        hashes, nh = self.landmark_hashes(rec, params, sorted_rows=True)
+        if shifts > 1:
+            hashes, nh = self.merge_shifts(hashes, nh, shifts, mag.shape[1])
+        return hashes, nh
+
     def fingerprint_host(self, x, shifts: int, params: AfpParams, rows=None, offsets=None):
         """Host buffers in, host buffers out (CSR).  x: [B,T] float32 numpy array or CPU torch
         tensor (pinned memory makes the chunked copies overlap the kernels).
@@ -532,6 +544,19 @@ class UNetDenoiser:
         check(_lib.mfpa_unet_forward(self.ctx.handle, self._u, _ptr(x3), H * W, W, 1, _ptr(div), B, H, W, _ptr(out),
                                      H * W, W, 1, _stream()))
         return out.reshape(shape)
+
+    def denoise_items(self, mag, qmax, T: int, shifts: int):
+        """denoise_mag for a [B*shifts] item batch: shifted items analyse x[off:] and have one frame
+        fewer (peak_extractor.py:411-413), and the network must see exactly their frames, so each shift
+        goes through the UNet as its own strided sub-batch."""
+        items, n, pitch = mag.shape
+        for s in range(shifts):
+            frames = num_frames(T - shift_offset(s, shifts))
+            sub = mag[s::shifts]
+            div = qmax[s::shifts].contiguous()
+            check(_lib.mfpa_unet_forward(self.ctx.handle, self._u, _ptr(sub), shifts * n * pitch, 1, pitch, _ptr(div),
+                                         sub.shape[0], BINS, frames, _ptr(sub), shifts * n * pitch, 1, pitch, _stream()))
+        return mag
 
     def denoise_mag(self, mag, qmax):
         """In place on the frame-major magnitudes of ``Context.stft_mag``: mag[i] <- unet(mag[i] / qmax[i])

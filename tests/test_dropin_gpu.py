@@ -120,3 +120,41 @@ def test_augmentfp_call_matches_oracle_on_dumped_parameters(mods):
     assert np.abs(y[0].numpy() - ref).max() / np.abs(ref).max() < 1e-4
     yb = a.batch_augment(torch.from_numpy(_queries(3)[:, None, :16000]))
     assert yb.shape == (3, 1, 16000) and torch.isfinite(yb).all()
+
+
+def test_find_peaks_with_unet_denoising(mods):
+    """Audfprint_peaks(params, denoising=True, denoising_model="unet") (peak_extractor.py:263-269): the
+    returned spectrogram is the network output; the picker run on it must agree with the oracle picker
+    fed that same spectrogram, and wavfile2hashes' batched form must equal the per-item chain."""
+    from oracle.unet_torch import seeded_unet
+
+    pe = mods["pe"]
+    net = seeded_unet(0)
+    pe.Audfprint_peaks.set_unet_state_dict(net.state_dict())
+    an = pe.Audfprint_peaks(dict(PRM), denoising=True, denoising_model="unet")
+    X = _queries(2)
+    for x in X:
+        pk, mask, spec = an.find_peaks(x)
+        assert spec.shape == (257, 251) and spec.dtype == np.float32 and mask.shape == (256, 251)
+        # fp32 torch UNet on the oracle's normalised spectrogram: bf16 tolerance (3 % of the range)
+        import torch
+
+        sg = O.normalise(O.stft_mag(x)).astype(np.float32)
+        with torch.no_grad():
+            ref = net(torch.from_numpy(sg)[None, None])[0, 0].numpy()
+        assert np.abs(spec - ref).max() <= 0.03 * (ref.max() - ref.min())
+        opk, omask = O.peaks_from_sgram(O.onset_filter(spec.astype(np.float64)))
+        agree = len(set(pk) & set(opk)) / max(1, len(set(pk) | set(opk)))
+        assert agree >= 0.99, agree
+    # batched hashes (shifts = 4) == per-shift find_peaks -> landmarks -> hashes -> unique/sort
+    an.shifts = 4
+    got = an.waves2hashes(X[:1], shifts=4)[0]
+    rows = []
+    for s in range(4):
+        off = int(s / 4 * 256)
+        pk, _, _ = an.find_peaks(X[0][off:])
+        rows.append(O.landmarks2hashes(O.peaks2landmarks(pk)))
+    want = O.unique_sorted_hashes(np.concatenate(rows))
+    assert np.array_equal(got, want)
+    with pytest.raises(NotImplementedError):
+        pe.Audfprint_peaks(dict(PRM), denoising=True, denoising_model="demucs")

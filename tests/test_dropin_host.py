@@ -64,8 +64,9 @@ def test_analyzer_surface_and_errors(dropin_modules):
 
     assert p.a_dec == O.a_dec() and p.maxpks == 5
     assert a.find_peaks(np.zeros(0, np.float32))[0] == []
-    with pytest.raises(NotImplementedError):
-        pe.Audfprint_peaks(prm, denoising=True, denoising_model="unet")
+    with pytest.raises(NotImplementedError):  # Demucs is outside the hot path; the UNet is built
+        pe.Audfprint_peaks(prm, denoising=True, denoising_model="demucs")
+    assert pe.Audfprint_peaks(prm, denoising=True, denoising_model="unet").denoising
     with pytest.raises(ValueError):
         pe.Audfprint_peaks(dict(prm, n_fft=1024))
 
