@@ -8,14 +8,16 @@
 //   stage 6  HighPassFilter(fc3)
 //   stage 7  PeakNormalization          / peak if > 0                      peak_normalization.py:38-67
 //
-// Long convolutions (stages 1, 2, 6) are overlap-save blocks of one 16384-point complex
-// FFT held entirely in shared memory: the signal block goes into the real part, the
-// filter (FIR taps generated on the fly, or the impulse response) into the imaginary
-// part, one forward transform yields both spectra (split by conjugate symmetry), their
-// product is inverse-transformed in place.  Forward is decimation-in-frequency and the
-// inverse undoes it pass by pass, so no bit-reversal pass is ever needed.  The per-query
-// reductions that gate the next stage (peak of the full convolution, RMS, peak after the
-// mix, clip quantiles, final peak) are produced by the kernel that writes the data.
+// Long convolutions (stages 1, 2, 6) are overlap-save blocks of 16384 REAL samples transformed
+// as one 8192-point complex FFT held in shared memory (even samples in the real part, odd samples
+// in the imaginary part).  A per-query kernel turns the filter (FIR taps generated on the fly, or
+// the impulse response) into its half spectrum once; every signal block then does forward FFT ->
+// one fused pass (split into the real-signal spectrum, multiply by the filter spectrum, re-pack)
+// -> inverse FFT.  Forward is decimation-in-frequency and the inverse undoes it pass by pass, so
+// no bit-reversal pass is ever needed; the filter spectrum is stored in the same digit-reversed
+// order, which makes the fused pass coalesced.  64 KB of shared memory per block lets three blocks
+// share an SM.  The per-query reductions that gate the next stage (peak of the full convolution,
+// RMS, peak after the mix, clip quantiles, final peak) are produced by the kernel that writes the data.
 #include <math.h>
 
 #include "common.cuh"
@@ -24,10 +26,13 @@ namespace mfpa {
 
 namespace {
 
-constexpr int FN = 16384;          // FFT length
-constexpr int FT = 512;            // threads per FFT block
-constexpr int FPAD = FN + FN / 16; // padded smem array (conflict-free radix-16 / radix-4 passes)
-constexpr size_t kConvSmem = sizeof(float2) * (FPAD + 1024) + 64 * sizeof(float);
+constexpr int FN = 16384;          // real samples per overlap-save block
+constexpr int LOGM = 13;
+constexpr int FM = 1 << LOGM;      // complex FFT length (FN / 2)
+constexpr int FT = 256;            // threads per FFT block
+constexpr int FPAD = FM + FM / 16; // padded smem array (radix-16 passes are conflict-free)
+constexpr int kTw = FM / 16;       // twiddle table entries
+constexpr size_t kConvSmem = sizeof(float2) * (FPAD + kTw) + 64 * sizeof(float);
 constexpr float kPi = 3.14159265358979323846f;
 
 struct AugQ {            // per-query derived parameters (device copy)
@@ -79,12 +84,12 @@ template <int S> __device__ __forceinline__ void dft16(float2 (&v)[16]) {
   for (int k1 = 0; k1 < 4; ++k1) dft4<S>(v[4 * k1], v[4 * k1 + 1], v[4 * k1 + 2], v[4 * k1 + 3]);
 }
 
-// One radix-16 pass over sub-transforms of length 16*s.  tw[e] = exp(-2 pi i e / FN), e < 1024;
+// One radix-16 pass over sub-transforms of length 16*s.  tw[e] = exp(-2 pi i e / FM), e < FM/16;
 // the twiddle of element k in a group is tw[j * tw_mul]^k.
 template <bool INV> __device__ __forceinline__ void pass16(float2* buf, const float2* tw, int log2s, int tw_mul, int tid) {
   const int s = 1 << log2s;
 #pragma unroll 1
-  for (int g = 0; g < FN / 16 / FT; ++g) {
+  for (int g = 0; g < FM / 16 / FT; ++g) {
     const int gid = tid + FT * g;
     const int j = gid & (s - 1);
     const int base = ((gid >> log2s) << (log2s + 4)) + j;
@@ -116,32 +121,53 @@ template <bool INV> __device__ __forceinline__ void pass16(float2* buf, const fl
   }
 }
 
-template <int S> __device__ __forceinline__ void pass4(float2* buf, int tid) {
-#pragma unroll 2
-  for (int g = 0; g < FN / 4 / FT; ++g) {
-    const int base = 4 * (tid + FT * g);
-    float2 a = buf[pidx(base)], b = buf[pidx(base + 1)], c = buf[pidx(base + 2)], d = buf[pidx(base + 3)];
-    dft4<S>(a, b, c, d);
-    buf[pidx(base)] = a; buf[pidx(base + 1)] = b; buf[pidx(base + 2)] = c; buf[pidx(base + 3)] = d;
+// final radix-2 pass on adjacent pairs (its own inverse up to the factor 2)
+__device__ __forceinline__ void pass2(float2* buf, int tid) {
+#pragma unroll 4
+  for (int g = 0; g < FM / 2 / FT; ++g) {
+    const int base = 2 * (tid + FT * g);
+    const float2 a = buf[pidx(base)], b = buf[pidx(base + 1)];
+    buf[pidx(base)] = cadd(a, b);
+    buf[pidx(base + 1)] = csub(a, b);
   }
 }
 
-// forward: natural order in, digit-reversed out.  inverse: digit-reversed in, natural out (x FN).
+// forward: natural order in, digit-reversed out.  inverse: digit-reversed in, natural out (x FM).
 __device__ __forceinline__ void fft_forward(float2* buf, const float2* tw, int tid) {
-  pass16<false>(buf, tw, 10, 1, tid);   __syncthreads();
-  pass16<false>(buf, tw, 6, 16, tid);   __syncthreads();
-  pass16<false>(buf, tw, 2, 256, tid);  __syncthreads();
-  pass4<-1>(buf, tid);                  __syncthreads();
+  pass16<false>(buf, tw, LOGM - 4, 1, tid);    __syncthreads();
+  pass16<false>(buf, tw, LOGM - 8, 16, tid);   __syncthreads();
+  pass16<false>(buf, tw, LOGM - 12, 256, tid); __syncthreads();
+  pass2(buf, tid);                             __syncthreads();
 }
 __device__ __forceinline__ void fft_inverse(float2* buf, const float2* tw, int tid) {
-  pass4<1>(buf, tid);                   __syncthreads();
-  pass16<true>(buf, tw, 2, 256, tid);   __syncthreads();
-  pass16<true>(buf, tw, 6, 16, tid);    __syncthreads();
-  pass16<true>(buf, tw, 10, 1, tid);    __syncthreads();
+  pass2(buf, tid);                             __syncthreads();
+  pass16<true>(buf, tw, LOGM - 12, 256, tid);  __syncthreads();
+  pass16<true>(buf, tw, LOGM - 8, 16, tid);    __syncthreads();
+  pass16<true>(buf, tw, LOGM - 4, 1, tid);     __syncthreads();
 }
-// position of frequency k after fft_forward
+// position of frequency k after fft_forward, and the frequency held at position r
 __device__ __forceinline__ int rev_pos(int k) {
-  return ((k & 15) << 10) | (((k >> 4) & 15) << 6) | (((k >> 8) & 15) << 2) | (k >> 12);
+  return ((k & 15) << 9) | (((k >> 4) & 15) << 5) | (((k >> 8) & 15) << 1) | (k >> 12);
+}
+__device__ __forceinline__ int pos_freq(int r) {
+  return (r >> 9) | (((r >> 5) & 15) << 4) | (((r >> 1) & 15) << 8) | ((r & 1) << 12);
+}
+__device__ __forceinline__ float2 conjf2(float2 a) { return make_float2(a.x, -a.y); }
+// W^k = exp(-2 pi i k / FN) = exp(-pi i k / FM)
+__device__ __forceinline__ float2 half_twiddle(int k) {
+  float sn, cs;
+  sincospif((float)k * (1.0f / (float)FM), &sn, &cs);
+  return make_float2(cs, -sn);
+}
+// Z = FFT_FM(even + i odd) of a real signal  ->  its spectrum at k and FM-k (0 < k < FM/2):
+// E = (Z[k] + conj Z[FM-k]) / 2, O = (Z[k] - conj Z[FM-k]) / (2i); X[k] = E + W^k O, X[FM-k] = conj(E - W^k O)
+__device__ __forceinline__ void real_split(float2 z1, float2 z2, float2 wk, float2& xk, float2& xmk) {
+  const float2 e = make_float2(0.5f * (z1.x + z2.x), 0.5f * (z1.y - z2.y));
+  const float2 d = make_float2(z1.x - z2.x, z1.y + z2.y);       // Z[k] - conj Z[FM-k]
+  const float2 o = make_float2(0.5f * d.y, -0.5f * d.x);        // d / (2i)
+  const float2 t = cmul(wk, o);
+  xk = cadd(e, t);
+  xmk = conjf2(csub(e, t));
 }
 
 __device__ __forceinline__ float block_sum(float v, float* red, int tid) {
@@ -182,15 +208,79 @@ struct ConvArgs {
   float* out;                            // [B][T] contiguous
   const float* ir; int ir_stride;        // kModeIR
   const AugQ* q; AugS* st;
-  int T; uint32_t bit; int which;        // which FIR (1 or 3) / which stats slot (0 = a, 1 = b, 2 = v)
+  int T; uint32_t bit; int which;        // which FIR (1, 2 or 3) / which stats slot
+  float2* hspec;                         // [B][FM] filter half spectra, digit-reversed order, entry 0 = (H[0], H[FM])
 };
 
+__device__ __forceinline__ void filter_params(const AugQ& q, int which, int& half, float& c2, float& argscale) {
+  half = which == 1 ? q.half1 : (which == 2 ? q.half2 : q.half3);
+  c2 = which == 1 ? q.c1x2 : (which == 2 ? q.c2x2 : q.c3x2);
+  argscale = which == 1 ? q.arg1 : (which == 2 ? q.arg2 : q.arg3);
+}
+
+// One block per query: half spectrum of the query's filter (zero-padded to FN real samples), scaled by
+// 1/FM (the unscaled inverse transform) and, for the FIRs, by 1/sum(taps) (julius normalises to DC gain 1).
 template <int MODE>
-__global__ void __launch_bounds__(FT, 1) fftconv_kernel(const ConvArgs a, const float2* __restrict__ tw_g) {
+__global__ void __launch_bounds__(FT) filter_spectrum_kernel(const ConvArgs a, const float2* __restrict__ tw_g) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* buf = reinterpret_cast<float2*>(smem_raw);
   float2* tw = buf + FPAD;
-  float* red = reinterpret_cast<float*>(tw + 1024);
+  float* red = reinterpret_cast<float*>(tw + kTw);
+  const int tid = threadIdx.x, qi = blockIdx.x;
+  const AugQ q = a.q[qi];
+  if (!(q.apply & a.bit)) return;
+  int K, half = 0;
+  float c2 = 0.f, argscale = 0.f;
+  if (MODE == kModeIR) {
+    K = q.ir_len;
+  } else {
+    filter_params(q, a.which, half, c2, argscale);
+    K = 2 * half + 1;
+  }
+  for (int i = tid; i < kTw; i += FT) tw[i] = tw_g[i];
+  const float* ir = MODE == kModeIR ? a.ir + (int64_t)qi * a.ir_stride : nullptr;
+  float hs = 0.f;
+  for (int m = tid; m < FM; m += FT) {
+    float h[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int i = 2 * m + e;
+      h[e] = 0.f;
+      if (i < K) h[e] = MODE == kModeIR ? ir[i] : fir_tap(i, half, c2, argscale);
+    }
+    hs += h[0] + h[1];
+    buf[pidx(m)] = make_float2(h[0], h[1]);
+  }
+  float scale = 1.0f / (float)FM;
+  if (MODE != kModeIR) scale /= block_sum(hs, red, tid);
+  __syncthreads();
+  fft_forward(buf, tw, tid);
+  float2* hg = a.hspec + (size_t)qi * FM;
+  for (int j = tid; j < FM / 2; j += FT) {
+    const int r = 2 * j, k = pos_freq(r);
+    if (k == 0) {
+      const float2 z = buf[pidx(0)];
+      hg[0] = make_float2((z.x + z.y) * scale, (z.x - z.y) * scale);
+    } else {
+      const int r2 = rev_pos(FM - k);
+      float2 hk, hmk;
+      real_split(buf[pidx(r)], buf[pidx(r2)], half_twiddle(k), hk, hmk);
+      hg[r] = make_float2(hk.x * scale, hk.y * scale);
+      hg[r2] = make_float2(hmk.x * scale, hmk.y * scale);
+    }
+  }
+  if (tid == 0) {  // k = FM/2 pairs with itself: X = conj(Z)
+    const float2 z = buf[pidx(1)];
+    hg[1] = make_float2(z.x * scale, -z.y * scale);
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(FT, 3) fftconv_kernel(const ConvArgs a, const float2* __restrict__ tw_g) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* buf = reinterpret_cast<float2*>(smem_raw);
+  float2* tw = buf + FPAD;
+  float* red = reinterpret_cast<float*>(tw + kTw);
   const int tid = threadIdx.x, qi = blockIdx.y, blk = blockIdx.x;
   const AugQ q = a.q[qi];
   const float* in = a.in + (int64_t)qi * a.in_stride;
@@ -207,54 +297,64 @@ __global__ void __launch_bounds__(FT, 1) fftconv_kernel(const ConvArgs a, const 
       vss += v * v;
     }
   } else {
-    int K, lead, half = 0;
-    float c2 = 0.f, argscale = 0.f;
+    int K, lead;
     if (MODE == kModeIR) {
       K = q.ir_len; lead = K - 1;
     } else {
-      half = a.which == 1 ? q.half1 : (a.which == 2 ? q.half2 : q.half3);
-      c2 = a.which == 1 ? q.c1x2 : (a.which == 2 ? q.c2x2 : q.c3x2);
-      argscale = a.which == 1 ? q.arg1 : (a.which == 2 ? q.arg2 : q.arg3);
+      const int half = a.which == 1 ? q.half1 : (a.which == 2 ? q.half2 : q.half3);
       K = 2 * half + 1; lead = half;
     }
     const int V = FN - K + 1;
     const int n_total = MODE == kModeIR ? T + K - 1 : T;
     const int n0 = blk * V;
     if (n0 >= n_total) return;  // block-uniform
-    for (int i = tid; i < 1024; i += FT) tw[i] = tw_g[i];
-    const float* ir = MODE == kModeIR ? a.ir + (int64_t)qi * a.ir_stride : nullptr;
-    float hs = 0.f;
-    for (int i = tid; i < FN; i += FT) {
-      const int n = n0 - lead + i;
-      float x, h = 0.f;
-      if (MODE == kModeIR) {
-        x = (n >= 0 && n < T) ? in[n] : 0.f;                      // zero extension
-        if (i < K) h = ir[i];
-      } else {
-        x = in[min(max(n, 0), T - 1)];                            // replicate padding (julius)
-        if (i < K) { h = fir_tap(i, half, c2, argscale); hs += h; }
+    for (int i = tid; i < kTw; i += FT) tw[i] = tw_g[i];
+    for (int m = tid; m < FM; m += FT) {
+      float x[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int n = n0 - lead + 2 * m + e;
+        if (MODE == kModeIR) x[e] = (n >= 0 && n < T) ? in[n] : 0.f;   // zero extension
+        else x[e] = in[min(max(n, 0), T - 1)];                          // replicate padding (julius)
       }
-      buf[pidx(i)] = make_float2(x, h);
+      buf[pidx(m)] = make_float2(x[0], x[1]);
     }
-    float scale = 1.0f / (float)FN;
-    if (MODE != kModeIR) scale /= block_sum(hs, red, tid);         // taps are normalised to sum 1
     __syncthreads();
     fft_forward(buf, tw, tid);
-    // Z = X + iH  ->  Y = X.H = (Z1^2 - conj(Z2)^2) / (4i), Z1 = Z[k], Z2 = Z[N-k]
-    for (int k = tid; k <= FN / 2; k += FT) {
-      const int p1 = pidx(rev_pos(k)), p2 = pidx(rev_pos((FN - k) & (FN - 1)));
-      const float2 z1 = buf[p1], z2 = buf[p2];
-      const float2 c = make_float2(z2.x, -z2.y);
-      const float2 d = csub(cmul(z1, z1), cmul(c, c));
-      const float2 y = make_float2(0.25f * d.y, -0.25f * d.x);    // d / (4i)
-      buf[p1] = y;
-      if (p2 != p1) buf[p2] = make_float2(y.x, -y.y);
+    // split -> multiply by the filter spectrum -> re-pack, pair (k, FM-k) per thread
+    const float2* hg = a.hspec + (size_t)qi * FM;
+    for (int j = tid; j < FM / 2; j += FT) {
+      const int r = 2 * j, k = pos_freq(r);
+      if (k == 0) {
+        const float2 z = buf[pidx(0)], h = hg[0];
+        const float y0 = (z.x + z.y) * h.x, ym = (z.x - z.y) * h.y;
+        buf[pidx(0)] = make_float2(0.5f * (y0 + ym), 0.5f * (y0 - ym));
+      } else {
+        const int r2 = rev_pos(FM - k);
+        const float2 wk = half_twiddle(k);
+        float2 xk, xmk;
+        real_split(buf[pidx(r)], buf[pidx(r2)], wk, xk, xmk);
+        const float2 yk = cmul(xk, hg[r]), ymk = cmul(xmk, hg[r2]);
+        // Zy[k] = Ey + i Oy, Zy[FM-k] = conj(Ey) + i conj(Oy); Ey = (Y[k] + conj Y[FM-k]) / 2,
+        // Oy = (Y[k] - conj Y[FM-k]) / 2 * conj(W^k)
+        const float2 ey = make_float2(0.5f * (yk.x + ymk.x), 0.5f * (yk.y - ymk.y));
+        const float2 oy = cmul(make_float2(0.5f * (yk.x - ymk.x), 0.5f * (yk.y + ymk.y)), conjf2(wk));
+        buf[pidx(r)] = make_float2(ey.x - oy.y, ey.y + oy.x);
+        buf[pidx(r2)] = make_float2(ey.x + oy.y, oy.x - ey.y);
+      }
+    }
+    if (tid == 0) {  // k = FM/2: X = conj(Z), Zy = conj(Y)
+      const float2 z = buf[pidx(1)];
+      const float2 y = cmul(conjf2(z), hg[1]);
+      buf[pidx(1)] = conjf2(y);
     }
     __syncthreads();
     fft_inverse(buf, tw, tid);
     const int n_end = min(n_total, n0 + V);
     for (int n = n0 + tid; n < n_end; n += FT) {
-      const float c = buf[pidx(n - n0 + K - 1)].x * scale;
+      const int jj = n - n0 + K - 1;
+      const float2 pr = buf[pidx(jj >> 1)];
+      const float c = (jj & 1) ? pr.y : pr.x;
       float v;
       if (MODE == kModeHP) v = in[n] - c; else v = c;
       vmax = fmaxf(vmax, fabsf(v));
@@ -592,14 +692,16 @@ __global__ void __launch_bounds__(256) norm_kernel(const float* __restrict__ v, 
 
 static int aug_init_tables(mfpa_ctx* ctx) {
   if (ctx->aug_tw_dev) return MFPA_OK;
-  static float2 tw[1024];
+  static float2 tw[kTw];
   const double pi = 3.14159265358979323846;
-  for (int e = 0; e < 1024; ++e) tw[e] = make_float2((float)cos(2 * pi * e / FN), (float)-sin(2 * pi * e / FN));
+  for (int e = 0; e < kTw; ++e) tw[e] = make_float2((float)cos(2 * pi * e / FM), (float)-sin(2 * pi * e / FM));
   MFPA_CUDA(cudaMalloc(&ctx->aug_tw_dev, sizeof(tw)));
   MFPA_CUDA(cudaMemcpy(ctx->aug_tw_dev, tw, sizeof(tw), cudaMemcpyHostToDevice));
   MFPA_CUDA(cudaFuncSetAttribute(fftconv_kernel<kModeHP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmem));
   MFPA_CUDA(cudaFuncSetAttribute(fftconv_kernel<kModeIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmem));
   MFPA_CUDA(cudaFuncSetAttribute(fftconv_kernel<kModeLP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmem));
+  MFPA_CUDA(cudaFuncSetAttribute(filter_spectrum_kernel<kModeHP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmem));
+  MFPA_CUDA(cudaFuncSetAttribute(filter_spectrum_kernel<kModeIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmem));
   return MFPA_OK;
 }
 
@@ -679,6 +781,8 @@ int launch_augment(mfpa_ctx* ctx, const float* x, int B, int T, int64_t x_stride
   const size_t rows = sizeof(float) * (size_t)B * T;
   if (ctx->aug_a.reserve(rows) || ctx->aug_b.reserve(rows)) return MFPA_ENOMEM;
   if (ctx->aug_small.reserve((sizeof(AugQ) + sizeof(AugS)) * (size_t)B)) return MFPA_ENOMEM;
+  if (ctx->aug_d.reserve(sizeof(float2) * (size_t)B * FM)) return MFPA_ENOMEM;
+  float2* hspec = (float2*)ctx->aug_d.ptr;
   float* bufA = (float*)ctx->aug_a.ptr;
   float* bufB = (float*)ctx->aug_b.ptr;
   AugQ* dq = (AugQ*)ctx->aug_small.ptr;
@@ -689,13 +793,15 @@ int launch_augment(mfpa_ctx* ctx, const float* x, int B, int T, int64_t x_stride
   auto blocks_for = [&](int n_total, int min_v) { return (unsigned)((n_total + min_v - 1) / min_v); };
   // stage 1: x -> A
   {
-    ConvArgs a{x, x_stride, bufA, nullptr, 0, dq, ds, T, MFPA_AUG_HPF1, 1};
+    ConvArgs a{x, x_stride, bufA, nullptr, 0, dq, ds, T, MFPA_AUG_HPF1, 1, hspec};
+    filter_spectrum_kernel<kModeHP><<<B, FT, kConvSmem, st>>>(a, ctx->aug_tw_dev);
     fftconv_kernel<kModeHP><<<dim3(blocks_for(T, min_v1), B), FT, kConvSmem, st>>>(a, ctx->aug_tw_dev);
     MFPA_CUDA(cudaGetLastError());
   }
   // stage 2: A -> B
   {
-    ConvArgs a{bufA, T, bufB, ir, ir_stride, dq, ds, T, MFPA_AUG_IR, 0};
+    ConvArgs a{bufA, T, bufB, ir, ir_stride, dq, ds, T, MFPA_AUG_IR, 0, hspec};
+    filter_spectrum_kernel<kModeIR><<<B, FT, kConvSmem, st>>>(a, ctx->aug_tw_dev);
     fftconv_kernel<kModeIR><<<dim3(blocks_for(T + FN - min_vir, min_vir), B), FT, kConvSmem, st>>>(a, ctx->aug_tw_dev);
     MFPA_CUDA(cudaGetLastError());
   }
@@ -720,14 +826,16 @@ int launch_augment(mfpa_ctx* ctx, const float* x, int B, int T, int64_t x_stride
       float* bufC = (float*)ctx->aug_c.ptr;
       clip_lpf_kernel<<<dim3(gx, B), 256, 0, st>>>(bufA, bufC, dq, ds, T, 1);
       MFPA_CUDA(cudaGetLastError());
-      ConvArgs a{bufC, T, bufB, nullptr, 0, dq, ds, T, MFPA_AUG_LPF, 2};
+      ConvArgs a{bufC, T, bufB, nullptr, 0, dq, ds, T, MFPA_AUG_LPF, 2, hspec};
+      filter_spectrum_kernel<kModeHP><<<B, FT, kConvSmem, st>>>(a, ctx->aug_tw_dev);
       fftconv_kernel<kModeLP><<<dim3(blocks_for(T, FN - 2 * max_half2), B), FT, kConvSmem, st>>>(a, ctx->aug_tw_dev);
       MFPA_CUDA(cudaGetLastError());
     }
   }
   // stage 6: B -> A (v) ; stage 7: A -> out
   {
-    ConvArgs a{bufB, T, bufA, nullptr, 0, dq, ds, T, MFPA_AUG_HPF3, 3};
+    ConvArgs a{bufB, T, bufA, nullptr, 0, dq, ds, T, MFPA_AUG_HPF3, 3, hspec};
+    filter_spectrum_kernel<kModeHP><<<B, FT, kConvSmem, st>>>(a, ctx->aug_tw_dev);
     fftconv_kernel<kModeHP><<<dim3(blocks_for(T, min_v3), B), FT, kConvSmem, st>>>(a, ctx->aug_tw_dev);
     MFPA_CUDA(cudaGetLastError());
     const unsigned gx = (unsigned)((T + 4095) / 4096);
