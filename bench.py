@@ -250,11 +250,27 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
     assert int(offs_host[-1]) == tot_hashes, (int(offs_host[-1]), tot_hashes)
+    # the same call on 16-bit PCM (what a decoded audio file holds): half the bytes over PCIe
+    x16_host = torch.empty(B, T_QUERY, dtype=torch.int16).pin_memory()
+    x16_host.copy_((x * 32767.0).round().clamp_(-32768, 32767).to(torch.int16))
 
-    times = torch.tensor([ms_total, e2e_ms], dtype=torch.float64, device=dev)
+    def e2e16_step():
+        lib.check(L.mfpa_fingerprint_host_pcm16(h, ptr(x16_host), B, T_QUERY, S, C.byref(p), ptr(rows_host), rows_host.shape[0],
+                                                ptr(offs_host)))
+
+    e2e16_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e16_step()
+    torch.cuda.synchronize()
+    e2e16_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    n_rows16 = int(offs_host[-1])
+
+    times = torch.tensor([ms_total, e2e_ms, e2e16_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms = times.tolist()
+    ms_total, e2e_ms, e2e16_ms = times.tolist()
     if rank == 0:
         hbm, how = _peaks()
         ms_step = ms_total / args.steps
@@ -279,6 +295,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": B * T_QUERY * 4, "d2h_bytes_per_step": tot_hashes * 8 + (B + 1) * 8,
                     "api": "mfpa_fingerprint_host (pinned host buffers, chunked copy/compute overlap)"},
+            "e2e_pcm16": {"value": world * B / (e2e16_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e16_ms,
+                          "h2d_bytes_per_step": B * T_QUERY * 2, "d2h_bytes_per_step": n_rows16 * 8 + (B + 1) * 8,
+                          "api": "mfpa_fingerprint_host_pcm16 (int16 PCM host buffers, converted to float32 on the device)"},
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
         }
@@ -287,7 +306,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"{nq} of the same synthetic queries ({args.cpu_queries_per_core} per core), "
                                               f"numpy oracle of wavfile2hashes, {wall:.1f} s wall"}
-    del x, mag, rec, hashes, out, x_host, rows_host
+    del x, mag, rec, hashes, out, x_host, rows_host, x16_host
     torch.cuda.empty_cache()
     # ---- the other BASELINE configs, device-timed (extra keys of the same JSON line)
     extras = {}
@@ -320,7 +339,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                         f"(1000 hashes/track, depth 100) sharded by hash range over {world} GPU(s) (BASELINE.json configs[4])",
             "value": B / (ms * 1e-3), "unit": "queries/s", "ms_per_step": ms, "scaling": "strong",
             "top1_equals_planted_track": top1, "query_hashes": nqh,
-            "collective": "none" if world == 1 else "NCCL all-reduce of per-track counts + all-gather of candidate hit lists"}
+            "collective": "none" if world == 1 else "NCCL reduce-scatter of packed per-track counts (query owners), all-gather of "
+                                                                  "candidates, all-to-all of candidate hit lists, all-gather of result rows"}
     if "unet" in args.also:
         Bu = args.unet_queries
         ms, finite = bench_unet(ctx, lib, dev, rank, Bu, max(2, args.steps // 3), 2, barrier, args.unet_chunk)
@@ -444,6 +464,8 @@ def bench_match(ctx, lib, dev, rank, world, B, n_tracks, steps, warmup, barrier)
     del tt, th
     torch.cuda.empty_cache()
     mp = lib.match_defaults()
+    if world > 1:
+        ctx.set_option(lib.OPT_MATCH_PACKED, 1)  # 16-bit counter pairs: half the bytes through the reduce-scatter
 
     def step():
         if world == 1:

@@ -82,6 +82,11 @@ int mfpa_set_spread_table(mfpa_ctx* ctx, const double* table513_host);
  * float64 picker (the one behind mfpa_audfprint_peaks_from_spec) on the float32 magnitudes instead of
  * the float32 picker; slower, same hashes on every input tested. */
 #define MFPA_OPT_PEAKS_F64 1
+/* MFPA_OPT_MATCH_PACKED (default 0): 1 makes mfpa_match_counts write, and mfpa_match_select read, the
+ * per-(query, track) raw counts as pairs of 16-bit counters: counts_dev is then uint32
+ * [B][(n_tracks + 1) / 2], word j = count[2j] | count[2j+1] << 16.  Summing such rows as uint32 (the
+ * sharded path's NCCL reduction) is exact as long as no total reaches 65536; half the bytes. */
+#define MFPA_OPT_MATCH_PACKED 2
 int mfpa_set_option(mfpa_ctx* ctx, int option, int value);
 
 /* ---- geometry --------------------------------------------------------- */
@@ -164,6 +169,14 @@ int mfpa_fingerprint(mfpa_ctx* ctx, const float* x_dev, int B, int T, int64_t x_
 int mfpa_fingerprint_host(mfpa_ctx* ctx, const float* x_host, int B, int T, int shifts,
                           const mfpa_afp_params* p, int32_t* rows_host, int64_t rows_cap,
                           int64_t* offsets_host);
+
+/* Same, for 16-bit PCM input (what a decoded WAV/MP3 query holds before the reference's loaders turn
+ * it into float32, afp/audfprint/peak_extractor.py:348-389): samples are x / 32768, exactly the
+ * float32 values a host conversion would produce, converted on the device after a copy half the size.
+ * Results are identical to mfpa_fingerprint_host on (float)x / 32768. */
+int mfpa_fingerprint_host_pcm16(mfpa_ctx* ctx, const int16_t* x_host, int B, int T, int shifts,
+                                const mfpa_afp_params* p, int32_t* rows_host, int64_t rows_cap,
+                                int64_t* offsets_host);
 
 /* Ragged [items][cap][2] rows + counts -> CSR on the device: offsets_dev [items+1] int64
  * (exclusive scan of min(n, cap)), rows_dev [>= total][2]. */

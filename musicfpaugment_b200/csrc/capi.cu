@@ -137,7 +137,7 @@ void mfpa_destroy(mfpa_ctx* ctx) {
                     &ctx->aug_small, &ctx->match_a, &ctx->match_b, &ctx->match_c};
   for (Scratch* s : all) s->release();
   for (int b = 0; b < 2; ++b) {
-    ctx->h_x[b].release(); ctx->h_rows[b].release(); ctx->h_csr[b].release(); ctx->h_n[b].release(); ctx->h_off[b].release();
+    ctx->h_x[b].release(); ctx->h_x16[b].release(); ctx->h_rows[b].release(); ctx->h_csr[b].release(); ctx->h_n[b].release(); ctx->h_off[b].release();
     if (ctx->ev_in[b]) cudaEventDestroy(ctx->ev_in[b]);
     if (ctx->ev_run[b]) cudaEventDestroy(ctx->ev_run[b]);
     if (ctx->ev_out[b]) cudaEventDestroy(ctx->ev_out[b]);
@@ -168,6 +168,7 @@ int mfpa_set_option(mfpa_ctx* ctx, int option, int value) {
   MFPA_REQUIRE(ctx != nullptr, "set_option: ctx is NULL");
   switch (option) {
     case MFPA_OPT_PEAKS_F64: ctx->opt_peaks_f64 = value != 0; return MFPA_OK;
+    case MFPA_OPT_MATCH_PACKED: ctx->opt_match_packed = value != 0; return MFPA_OK;
     default: break;
   }
   set_error("set_option: unknown option %d", option);
@@ -289,10 +290,31 @@ int mfpa_compact_rows(mfpa_ctx* ctx, const int32_t* rows_in_dev, const int32_t* 
 // Chunked, double-buffered host path: H2D of chunk i+1 (s_in) overlaps the kernels of
 // chunk i (s_run); compacted rows leave on s_out.  Scratch used by the kernels is only
 // touched from s_run, so chunks never race on it.
-int mfpa_fingerprint_host(mfpa_ctx* ctx, const float* x_host, int B, int T, int shifts,
-                          const mfpa_afp_params* p, int32_t* rows_host, int64_t rows_cap,
-                          int64_t* offsets_host) {
-  MFPA_REQUIRE(ctx && x_host && rows_host && offsets_host, "fingerprint_host: NULL argument");
+__global__ void __launch_bounds__(256) pcm16_to_f32_kernel(const int16_t* __restrict__ in, float* __restrict__ out, int64_t n) {
+  // 8 samples per thread: one 16-byte load, two 16-byte stores; x / 32768 is exact in float32
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i + 8 <= n) {
+    const uint4 v = *reinterpret_cast<const uint4*>(in + i);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    float f[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      f[2 * k] = (float)(int16_t)(w[k] & 0xffffu) * (1.0f / 32768.0f);
+      f[2 * k + 1] = (float)(int16_t)(w[k] >> 16) * (1.0f / 32768.0f);
+    }
+    *reinterpret_cast<float4*>(out + i) = make_float4(f[0], f[1], f[2], f[3]);
+    *reinterpret_cast<float4*>(out + i + 4) = make_float4(f[4], f[5], f[6], f[7]);
+  } else {
+    for (int64_t k = i; k < n; ++k) out[k] = (float)in[k] * (1.0f / 32768.0f);
+  }
+}
+
+static int fingerprint_host_impl(mfpa_ctx* ctx, const void* x_host_v, bool pcm16, int B, int T, int shifts,
+                                 const mfpa_afp_params* p, int32_t* rows_host, int64_t rows_cap,
+                                 int64_t* offsets_host) {
+  const float* x_host = (const float*)x_host_v;
+  const int16_t* x_host16 = (const int16_t*)x_host_v;
+  MFPA_REQUIRE(ctx && x_host_v && rows_host && offsets_host, "fingerprint_host: NULL argument");
   if (int e = check_batch(B, T, shifts)) return e;
   if (int e = check_afp(p)) return e;
   MFPA_REQUIRE(rows_cap >= 0, "fingerprint_host: rows_cap < 0");
@@ -304,6 +326,7 @@ int mfpa_fingerprint_host(mfpa_ctx* ctx, const float* x_host, int B, int T, int 
   if (chunk > B) chunk = B;
   for (int b = 0; b < 2; ++b) {
     if (ctx->h_x[b].reserve(sizeof(float) * (size_t)chunk * T)) return MFPA_ENOMEM;
+    if (pcm16 && ctx->h_x16[b].reserve(sizeof(int16_t) * (size_t)chunk * T + 16)) return MFPA_ENOMEM;
     if (ctx->h_rows[b].reserve(sizeof(int32_t) * 2 * (size_t)chunk * cap)) return MFPA_ENOMEM;
     if (ctx->h_csr[b].reserve(sizeof(int32_t) * 2 * (size_t)chunk * cap)) return MFPA_ENOMEM;
     if (ctx->h_n[b].reserve(sizeof(int32_t) * chunk)) return MFPA_ENOMEM;
@@ -326,8 +349,17 @@ int mfpa_fingerprint_host(mfpa_ctx* ctx, const float* x_host, int B, int T, int 
     if (ci >= 2) {
       MFPA_CUDA(cudaStreamWaitEvent(ctx->s_in, ctx->ev_run[b], 0));
     }
-    MFPA_CUDA(cudaMemcpyAsync(ctx->h_x[b].ptr, x_host + (size_t)q0 * T, sizeof(float) * (size_t)nq * T,
-                              cudaMemcpyHostToDevice, ctx->s_in));
+    if (pcm16) {
+      const int64_t n = (int64_t)nq * T;
+      MFPA_CUDA(cudaMemcpyAsync(ctx->h_x16[b].ptr, x_host16 + (size_t)q0 * T, sizeof(int16_t) * (size_t)n,
+                                cudaMemcpyHostToDevice, ctx->s_in));
+      pcm16_to_f32_kernel<<<(unsigned)((n / 8 + 256) / 256), 256, 0, ctx->s_in>>>((const int16_t*)ctx->h_x16[b].ptr,
+                                                                                 (float*)ctx->h_x[b].ptr, n);
+      MFPA_CUDA(cudaGetLastError());
+    } else {
+      MFPA_CUDA(cudaMemcpyAsync(ctx->h_x[b].ptr, x_host + (size_t)q0 * T, sizeof(float) * (size_t)nq * T,
+                                cudaMemcpyHostToDevice, ctx->s_in));
+    }
     MFPA_CUDA(cudaEventRecord(ctx->ev_in[b], ctx->s_in));
     MFPA_CUDA(cudaStreamWaitEvent(ctx->s_run, ctx->ev_in[b], 0));
     if (ci >= 2) MFPA_CUDA(cudaStreamWaitEvent(ctx->s_run, ctx->ev_out[b], 0));
@@ -365,6 +397,18 @@ int mfpa_fingerprint_host(mfpa_ctx* ctx, const float* x_host, int B, int T, int 
     return MFPA_ECAP;
   }
   return MFPA_OK;
+}
+
+int mfpa_fingerprint_host(mfpa_ctx* ctx, const float* x_host, int B, int T, int shifts,
+                          const mfpa_afp_params* p, int32_t* rows_host, int64_t rows_cap,
+                          int64_t* offsets_host) {
+  return fingerprint_host_impl(ctx, x_host, false, B, T, shifts, p, rows_host, rows_cap, offsets_host);
+}
+
+int mfpa_fingerprint_host_pcm16(mfpa_ctx* ctx, const int16_t* x_host, int B, int T, int shifts,
+                                const mfpa_afp_params* p, int32_t* rows_host, int64_t rows_cap,
+                                int64_t* offsets_host) {
+  return fingerprint_host_impl(ctx, x_host, true, B, T, shifts, p, rows_host, rows_cap, offsets_host);
 }
 
 static int check_augment(mfpa_ctx* ctx, const float* x_dev, int B, int T, int64_t x_stride, int sample_rate,

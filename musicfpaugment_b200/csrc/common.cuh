@@ -61,6 +61,7 @@ struct mfpa_ctx {
   int device = 0;
   int num_sms = mfpa::kNumSMs;
   int opt_peaks_f64 = 0;            // MFPA_OPT_PEAKS_F64
+  int opt_match_packed = 0;         // MFPA_OPT_MATCH_PACKED
   double* spread_dev = nullptr;     // [513] Gaussian table
   float2* tw_dev = nullptr;         // FFT twiddles (stft.cu layout)
   float* win_dev = nullptr;         // [512] analysis window
@@ -82,7 +83,7 @@ struct mfpa_ctx {
   // host-path pipeline (capi.cu): copy-in, compute and copy-out streams, double-buffered chunks
   cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_run[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
-  mfpa::Scratch h_x[2], h_rows[2], h_csr[2], h_n[2], h_off[2];
+  mfpa::Scratch h_x[2], h_x16[2], h_rows[2], h_csr[2], h_n[2], h_off[2];
 };
 
 // ---- kernel launchers implemented in the stage translation units ----------

@@ -38,7 +38,7 @@ struct IndexView {
 // lanes stride the 400-byte bucket row.
 __global__ void __launch_bounds__(kCountThreads) match_counts_kernel(const IndexView ix, const int32_t* __restrict__ hashes,
                                                                     const int32_t* __restrict__ nh, int cap,
-                                                                    int32_t* __restrict__ out) {
+                                                                    int32_t* __restrict__ out, int packed) {
   extern __shared__ unsigned hist[];  // two 16-bit counters per word
   const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int words = (ix.n_tracks + 1) >> 1;
@@ -57,6 +57,11 @@ __global__ void __launch_bounds__(kCountThreads) match_counts_kernel(const Index
     }
   }
   __syncthreads();
+  if (packed) {  // MFPA_OPT_MATCH_PACKED: hand out the 16-bit pairs as they are (half the bytes to all-reduce)
+    unsigned* o = reinterpret_cast<unsigned*>(out) + (int64_t)q * words;
+    for (int i = tid; i < words; i += kCountThreads) o[i] = hist[i];
+    return;
+  }
   int32_t* o = out + (int64_t)q * ix.n_tracks;
   for (int i = tid; i < ix.n_tracks; i += kCountThreads) o[i] = (int)((hist[i >> 1] >> ((i & 1) * 16)) & 0xffffu);
 }
@@ -92,14 +97,17 @@ __device__ __forceinline__ bool before(const Cand& a, const Cand& b) {  // a ran
 
 __global__ void __launch_bounds__(512) match_select_kernel(const int32_t* __restrict__ counts, const uint32_t* __restrict__ hpid,
                                                            int n_tracks, int threshcount, int search_depth,
-                                                           int32_t* __restrict__ cand, int32_t* __restrict__ ncand) {
+                                                           int32_t* __restrict__ cand, int32_t* __restrict__ ncand, int packed) {
   __shared__ int s_int[16];
   __shared__ Cand s_best[16];
   __shared__ Cand s_prev;
   const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int32_t* c = counts + (int64_t)q * n_tracks;
+  const int32_t* c = counts + (int64_t)q * (packed ? (n_tracks + 1) >> 1 : n_tracks);
+  auto count_of = [&](int i) -> int {
+    return packed ? (int)((reinterpret_cast<const unsigned*>(c)[i >> 1] >> ((i & 1) * 16)) & 0xffffu) : c[i];
+  };
   int gt = 0;
-  for (int i = tid; i < n_tracks; i += 512) gt += c[i] > threshcount;
+  for (int i = tid; i < n_tracks; i += 512) gt += count_of(i) > threshcount;
 #pragma unroll
   for (int o = 16; o; o >>= 1) gt += __shfl_xor_sync(kFull, gt, o);
   if (lane == 0) s_int[warp] = gt;
@@ -113,7 +121,7 @@ __global__ void __launch_bounds__(512) match_select_kernel(const int32_t* __rest
     const Cand prev = s_prev;
     Cand best{-1, 1, -1};
     for (int i = tid; i < n_tracks; i += 512) {
-      const int raw = c[i];
+      const int raw = count_of(i);
       if (raw <= 0) continue;
       const Cand x{raw, (long long)hpid[i], i};
       const bool after_prev = prev.hp == 0 || before(prev, x);
@@ -367,8 +375,9 @@ int launch_match_counts(mfpa_ctx* ctx, const int32_t* hashes, const int32_t* nh,
   if (ix.n_tracks <= kMaxTracksSmem) {
     const size_t smem = sizeof(unsigned) * (size_t)((ix.n_tracks + 1) / 2);
     MFPA_CUDA(cudaFuncSetAttribute(match_counts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    match_counts_kernel<<<B, kCountThreads, smem, st>>>(ix, hashes, nh, cap, counts);
+    match_counts_kernel<<<B, kCountThreads, smem, st>>>(ix, hashes, nh, cap, counts, ctx->opt_match_packed);
   } else {
+    MFPA_REQUIRE(!ctx->opt_match_packed, "match_counts: packed counts need n_tracks <= %d", kMaxTracksSmem);
     MFPA_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t)B * ix.n_tracks, st));
     match_counts_global_kernel<<<B, kCountThreads, 0, st>>>(ix, hashes, nh, cap, counts);
   }
@@ -379,7 +388,7 @@ int launch_match_counts(mfpa_ctx* ctx, const int32_t* hashes, const int32_t* nh,
 int launch_match_select(mfpa_ctx* ctx, const int32_t* counts, int B, int threshcount, int search_depth, int32_t* cand,
                         int32_t* ncand, cudaStream_t st) {
   match_select_kernel<<<B, 512, 0, st>>>(counts, ctx->index_hashesperid, ctx->index_ntracks, threshcount, search_depth,
-                                         cand, ncand);
+                                         cand, ncand, ctx->opt_match_packed);
   MFPA_CUDA(cudaGetLastError());
   return MFPA_OK;
 }

@@ -80,6 +80,7 @@ SIGNATURES = {
     "mfpa_merge_shifts": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _vp]),
     "mfpa_fingerprint": (_i, [_vp, _vp, _i, _i, _i64, _i, _P, _vp, _i, _vp, _vp]),
     "mfpa_fingerprint_host": (_i, [_vp, _vp, _i, _i, _i, _P, _vp, _i64, _vp]),
+    "mfpa_fingerprint_host_pcm16": (_i, [_vp, _vp, _i, _i, _i, _P, _vp, _i64, _vp]),
     "mfpa_augment": (_i, [_vp, _vp, _i, _i, _i64, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     "mfpa_augment_fingerprint": (_i, [_vp, _vp, _i, _i, _i64, _i, _vp, _vp, _i, _vp, _i, _P, _vp, _i, _vp, _vp]),
     "mfpa_index_load": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i]),
@@ -113,6 +114,7 @@ _bind(SIGNATURES)
 ALL_SIGNATURES = dict(SIGNATURES)
 
 OPT_PEAKS_F64 = 1
+OPT_MATCH_PACKED = 2
 N_FFT, HOP, BINS, ROWS, MAG_PITCH, MAX_PKS, MAX_SHIFTS, HASHES_PER_FRAME = 512, 256, 257, 256, 264, 5, 8, 15
 
 
@@ -212,6 +214,8 @@ class Context:
 
     def set_option(self, option: int, value: int):
         check(_lib.mfpa_set_option(self._h, option, value))
+        if option == OPT_MATCH_PACKED:
+            self.packed_counts = bool(value)
 
     # ---- S2 --------------------------------------------------------------
     def stft_mag(self, x, shifts: int = 1):
@@ -392,7 +396,8 @@ class Context:
         import torch
 
         B, cap, _ = hashes.shape
-        counts = torch.empty(B, self.n_tracks, dtype=torch.int32, device=hashes.device)
+        width = (self.n_tracks + 1) // 2 if getattr(self, "packed_counts", False) else self.n_tracks
+        counts = torch.empty(B, width, dtype=torch.int32, device=hashes.device)
         check(_lib.mfpa_match_counts(self._h, _ptr(hashes), _ptr(nh), B, cap, _ptr(counts), _stream()))
         return counts
 
@@ -472,26 +477,25 @@ class Context:
         return hashes, nh
 
     def fingerprint_host(self, x, shifts: int, params: AfpParams, rows=None, offsets=None):
-        """Host buffers in, host buffers out (CSR).  x: [B,T] float32 numpy array or CPU torch
-        tensor (pinned memory makes the chunked copies overlap the kernels).
+        """Host buffers in, host buffers out (CSR).  x: [B,T] float32 (or int16 PCM, scaled by 1/32768 on
+        the device) numpy array or CPU torch tensor (pinned memory makes the chunked copies overlap the kernels).
         -> (rows int32 [total,2], offsets int64 [B+1]) as numpy views."""
         import numpy as np
         import torch
 
         if isinstance(x, np.ndarray):
-            x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
-        assert not x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.is_contiguous()
+            x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.int16 if x.dtype == np.int16 else np.float32))
+        assert not x.is_cuda and x.dtype in (torch.float32, torch.int16) and x.dim() == 2 and x.is_contiguous()
+        entry = _lib.mfpa_fingerprint_host_pcm16 if x.dtype == torch.int16 else _lib.mfpa_fingerprint_host
         B, T = x.shape
         if rows is None:
             rows = torch.empty(B * 1024 * shifts, 2, dtype=torch.int32)
         if offsets is None:
             offsets = torch.empty(B + 1, dtype=torch.int64)
-        rc = _lib.mfpa_fingerprint_host(self._h, _ptr(x), B, T, shifts, C.byref(params), _ptr(rows), rows.shape[0],
-                                        _ptr(offsets))
+        rc = entry(self._h, _ptr(x), B, T, shifts, C.byref(params), _ptr(rows), rows.shape[0], _ptr(offsets))
         if rc == -4:  # MFPA_ECAP: offsets are valid, retry with the exact size
             rows = torch.empty(int(offsets[-1]), 2, dtype=torch.int32)
-            rc = _lib.mfpa_fingerprint_host(self._h, _ptr(x), B, T, shifts, C.byref(params), _ptr(rows),
-                                            rows.shape[0], _ptr(offsets))
+            rc = entry(self._h, _ptr(x), B, T, shifts, C.byref(params), _ptr(rows), rows.shape[0], _ptr(offsets))
         check(rc)
         return rows[: int(offsets[-1])].numpy(), offsets.numpy()
 

@@ -248,3 +248,18 @@ def test_float32_picker_equals_float64_picker(mfpa_ctx):
         total += rec32.numel()
         assert int((n32 - n64).abs().sum()) <= 2
     assert same / total >= 0.9995, (same, total)
+
+
+def test_pcm16_host_entry_equals_float_entry(mfpa_ctx):
+    """mfpa_fingerprint_host_pcm16(x) == mfpa_fingerprint_host(float32(x) / 32768), bit for bit."""
+    from musicfpaugment_b200 import lib, synth
+
+    x = synth.music_like(5, seed=21).numpy()
+    x16 = np.clip(np.round(x * 32767.0), -32768, 32767).astype(np.int16)
+    x16[3] = 0  # a silent query
+    p = lib.afp_defaults()
+    for shifts in (1, 4):
+        rows_f, offs_f = mfpa_ctx.fingerprint_host(x16.astype(np.float32) / np.float32(32768.0), shifts, p)
+        rows_i, offs_i = mfpa_ctx.fingerprint_host(x16, shifts, p)
+        assert np.array_equal(offs_f, offs_i) and np.array_equal(rows_f, rows_i)
+        assert offs_i[-1] > 0

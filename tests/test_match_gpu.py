@@ -112,6 +112,38 @@ def test_hash_range_shards_sum_to_the_whole(mfpa_ctx):
     assert torch.equal(nrows_s, nrows_w) and torch.equal(res_s, res_w)
 
 
+def test_packed_counts_option(mfpa_ctx):
+    """MFPA_OPT_MATCH_PACKED: 16-bit counter pairs (what the sharded path reduce-scatters) give the same
+    candidates; adding two shards' packed rows as uint32 equals the packed whole."""
+    from musicfpaugment_b200 import lib, sharded, synth
+
+    table, counts, hpid, th = synth.hash_index(5001, 600, seed=13)  # odd track count: last word half used
+    q, nq, _ = synth.planted_queries(th, 6, n_hashes=300, seed=14)
+    h, n = torch.from_numpy(q).cuda(), torch.from_numpy(nq).cuda()
+    p = lib.match_defaults()
+    mfpa_ctx.index_load(table, counts, hpid)
+    plain = mfpa_ctx.match_counts(h, n)
+    cand0, ncand0 = mfpa_ctx.match_select(plain, p)
+    try:
+        mfpa_ctx.set_option(lib.OPT_MATCH_PACKED, 1)
+        packed = mfpa_ctx.match_counts(h, n)
+        assert packed.shape == (6, 2501)
+        w = packed.cpu().numpy().view(np.uint32)
+        un = np.stack([w & 0xFFFF, w >> 16], axis=-1).reshape(6, -1)[:, :5001]
+        assert np.array_equal(un.astype(np.int32), plain.cpu().numpy())
+        cand1, ncand1 = mfpa_ctx.match_select(packed, p)
+        assert torch.equal(cand0, cand1) and torch.equal(ncand0, ncand1)
+        total = torch.zeros_like(packed)
+        for r in range(2):
+            lo, hi = sharded.hash_range(r, 2)
+            mfpa_ctx.index_load(table[lo:hi], counts[lo:hi], hpid, hash_lo=lo)
+            total += mfpa_ctx.match_counts(h, n)
+        assert torch.equal(total, packed)
+    finally:
+        mfpa_ctx.set_option(lib.OPT_MATCH_PACKED, 0)
+        mfpa_ctx.index_load(table, counts, hpid)
+
+
 def test_match_without_index_raises():
     lib = _lib()
     ctx = lib.Context(0)

@@ -2,8 +2,9 @@
 
 The four matching kernels are replaced by a numpy stand-in built from the oracle (test
 infrastructure only), so what is exercised here is the host logic a real run depends on:
-the hash-range partition of the index, the all-reduce of per-track raw counts, the
-all-gather of the candidates' (track, delta-t) lists and the contiguous query partition.
+the hash-range partition of the index, the reduce-scatter of per-track raw counts (which
+assigns every query an owner rank), the all-gather of the owners' candidates, the all-to-all
+of the candidates' (track, delta-t) lists and the contiguous query partition.
 The same `match_sharded` drives the CUDA kernels over NCCL on the GPU box.
 """
 import os
@@ -116,7 +117,7 @@ def _worker(rank, world, port, out_dir):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         table, counts, hpid, th = synth.hash_index(300, 400, seed=21, depth=20)
-        q, nq, truth = synth.planted_queries(th, 6, n_hashes=200, frac=0.4, seed=22)
+        q, nq, truth = synth.planted_queries(th, 7, n_hashes=200, frac=0.4, seed=22)  # 7: the last sub-batch needs padding
         lo, hi = sharded.hash_range(rank, world)
         ctx = NumpyShardCtx(table, counts, hpid, lo, hi)
         res, nrows = sharded.match_sharded(ctx, torch.from_numpy(q), torch.from_numpy(nq), params=_P, max_rows=8,
