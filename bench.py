@@ -30,6 +30,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# NCCL writes its version banner to stdout when NCCL_DEBUG is set in the environment; stdout carries
+# exactly one JSON line, so anything NCCL has to say goes to stderr.
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 METRIC = "8s_query_fingerprints_per_sec"
 UNIT = "queries/s"
