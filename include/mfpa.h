@@ -291,6 +291,17 @@ int mfpa_dejavu_peaks(mfpa_ctx* ctx, const void* arr_dev, int is_f64, int B, int
                       double amp_min, uint8_t* mask_dev, int32_t* peaks_dev, int cap, int32_t* npeaks_dev,
                       void* stream);
 
+/* Front end of Dejavu's fingerprint() (afp/dejavu/fingerprint.py:60-79):
+ *   mfpa_dejavu_psd: matplotlib.mlab.specgram(x, NFFT=512, Fs, window_hanning, noverlap=256)[0] divided by its
+ *     maximum (:60-68) -> psd_dev float32 [B][257][mfpa_dejavu_num_frames(T)] ((T - 256) / 256 segments, no
+ *     padding; the /Fs and /sum(w^2) factors cancel in the normalisation);
+ *   mfpa_dejavu_log: arr = 10 ln(max(p, max(p) / 1e6)) - mean(...) per item (:77-79), p = psd, or psd^2 when
+ *     `square` (the UNet path squares the network output, :74) -> arr_dev float32 [B][F][N], the array
+ *     mfpa_dejavu_peaks takes. */
+int mfpa_dejavu_num_frames(int n_samples);
+int mfpa_dejavu_psd(mfpa_ctx* ctx, const float* x_dev, int B, int T, int64_t x_stride, float* psd_dev, void* stream);
+int mfpa_dejavu_log(mfpa_ctx* ctx, const float* psd_dev, int B, int F, int N, int square, float* arr_dev, void* stream);
+
 /* ---- optional UNet magnitude-spectrogram denoiser  (training/unet.py:75-108: UNet(1, 1, bilinear=False),
  * eval mode; inserted between `sgram /= max` and the log at afp/audfprint/peak_extractor.py:265-269 and
  * afp/dejavu/fingerprint.py:70-75).  bf16 activations/weights, fp32 accumulation, BatchNorm folded;

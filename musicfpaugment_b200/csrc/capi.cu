@@ -148,6 +148,7 @@ void mfpa_destroy(mfpa_ctx* ctx) {
   if (ctx->spread_dev) cudaFree(ctx->spread_dev);
   if (ctx->tw_dev) cudaFree(ctx->tw_dev);
   if (ctx->win_dev) cudaFree(ctx->win_dev);
+  if (ctx->win_dejavu_dev) cudaFree(ctx->win_dejavu_dev);
   if (ctx->index_table) cudaFree(ctx->index_table);
   if (ctx->index_counts) cudaFree(ctx->index_counts);
   if (ctx->index_hashesperid) cudaFree(ctx->index_hashesperid);
@@ -567,6 +568,22 @@ int mfpa_dejavu_peaks(mfpa_ctx* ctx, const void* arr_dev, int is_f64, int B, int
   DeviceGuard guard(ctx->device);
   return launch_dejavu_peaks(arr_dev, is_f64, B, F, N, neighborhood, amp_min, mask_dev, peaks_dev, cap, npeaks_dev,
                              (cudaStream_t)stream);
+}
+
+int mfpa_dejavu_num_frames(int n_samples) { return dejavu_num_frames(n_samples); }
+
+int mfpa_dejavu_psd(mfpa_ctx* ctx, const float* x_dev, int B, int T, int64_t x_stride, float* psd_dev, void* stream) {
+  MFPA_REQUIRE(ctx && x_dev && psd_dev, "dejavu_psd: NULL argument");
+  MFPA_REQUIRE(B >= 1 && T >= 1 && x_stride >= T, "dejavu_psd: batch %d, n_samples %d, stride %lld", B, T, (long long)x_stride);
+  DeviceGuard guard(ctx->device);
+  return launch_dejavu_psd(ctx, x_dev, B, T, x_stride, psd_dev, (cudaStream_t)stream);
+}
+
+int mfpa_dejavu_log(mfpa_ctx* ctx, const float* psd_dev, int B, int F, int N, int square, float* arr_dev, void* stream) {
+  MFPA_REQUIRE(ctx && psd_dev && arr_dev, "dejavu_log: NULL argument");
+  MFPA_REQUIRE(B >= 1 && F >= 1 && N >= 1, "dejavu_log: bad sizes %d x %d x %d", B, F, N);
+  DeviceGuard guard(ctx->device);
+  return launch_dejavu_log(psd_dev, B, F * N, square, arr_dev, (cudaStream_t)stream);
 }
 
 }  // extern "C"

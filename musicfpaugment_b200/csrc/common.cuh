@@ -65,6 +65,7 @@ struct mfpa_ctx {
   double* spread_dev = nullptr;     // [513] Gaussian table
   float2* tw_dev = nullptr;         // FFT twiddles (stft.cu layout)
   float* win_dev = nullptr;         // [512] analysis window
+  float* win_dejavu_dev = nullptr;  // [512] np.hanning(512) x 1/2 (mlab.window_hanning, afp/dejavu/fingerprint.py:64)
   mfpa::Scratch mag, qmax, rec, fwd, hashes, nh, misc, spec64, xin, out_h, out_n;
   // augmentation / matching state is appended by their translation units
   mfpa::Scratch aug_a, aug_b, aug_c, aug_d, aug_small;
@@ -90,7 +91,10 @@ struct mfpa_ctx {
 namespace mfpa {
 
 int launch_stft_mag(mfpa_ctx* ctx, const float* x, int B, int T, int64_t stride, int shifts,
-                    float* mag, float* qmax, cudaStream_t st);
+                    float* mag, float* qmax, cudaStream_t st, const float* window = nullptr);
+int dejavu_num_frames(int T);
+int launch_dejavu_psd(mfpa_ctx* ctx, const float* x, int B, int T, int64_t stride, float* psd, cudaStream_t st);
+int launch_dejavu_log(const float* psd, int B, int n, int square, float* arr, cudaStream_t st);
 int launch_spec_from_mag(const float* mag, const float* qmax, int B, int T, int shifts,
                          double* spec, cudaStream_t st);
 int launch_peaks_f32(mfpa_ctx* ctx, const float* mag, const float* qmax, int B, int T, int shifts,

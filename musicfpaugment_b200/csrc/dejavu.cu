@@ -131,4 +131,116 @@ int launch_dejavu_peaks(const void* arr, int is_f64, int B, int F, int N, int r,
   return MFPA_OK;
 }
 
+
+// ---- fingerprint() front end (afp/dejavu/fingerprint.py:60-79) --------------------------------
+// mlab.specgram's segments (512 samples every 256, no padding, np.hanning(512)) are exactly the
+// INTERIOR frames 1..n-2 of the audfprint STFT (frame f of that transform covers samples
+// [256 (f-1), 256 (f+1)), reflect padding only touches frames 0 and n-1), so the PSD reuses
+// stft_mag_kernel with the symmetric window table and squares the magnitudes:
+//   psd[k][j] = |X_{j+1}[k]|^2 * (2 if 0 < k < 256 else 1)      (/Fs and /sum(w^2) cancel in "/= max")
+namespace {
+
+__device__ __forceinline__ float block_reduce_max(float v, float* red) {
+  for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = red[0];
+  for (int w = 1; w < (int)blockDim.x / 32; ++w) r = fmaxf(r, red[w]);
+  __syncthreads();
+  return r;
+}
+__device__ __forceinline__ double block_reduce_sum(double v, double* red) {
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double r = 0.0;
+  for (int w = 0; w < (int)blockDim.x / 32; ++w) r += red[w];
+  __syncthreads();
+  return r;
+}
+
+// mag [item][n_stft][264] (frame-major, Dejavu window) -> psd [item][257][nd] normalised by its maximum.
+// One block per item; 32 x 32 tiles go through shared memory so both sides are coalesced.
+__global__ void __launch_bounds__(256) dejavu_psd_kernel(const float* __restrict__ mag, int n_stft, int nd,
+                                                         float* __restrict__ psd) {
+  __shared__ float tile[32][33];
+  __shared__ float red[8];
+  const int item = blockIdx.x, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const float* m = mag + (int64_t)item * n_stft * kPitch;
+  float vmax = 0.f;
+  for (int j = ty; j < nd; j += 8)
+    for (int k = tx; k < kBins; k += 32) {
+      const float a = m[(int64_t)(j + 1) * kPitch + k];
+      vmax = fmaxf(vmax, a * a * ((k > 0 && k < kBins - 1) ? 2.f : 1.f));
+    }
+  vmax = block_reduce_max(vmax, red);
+  float* out = psd + (int64_t)item * kBins * nd;
+  for (int k0 = 0; k0 < kBins; k0 += 32)
+    for (int j0 = 0; j0 < nd; j0 += 32) {
+      for (int i = ty; i < 32; i += 8) {
+        const int j = j0 + i, k = k0 + tx;
+        float v = 0.f;
+        if (j < nd && k < kBins) {
+          const float a = m[(int64_t)(j + 1) * kPitch + k];
+          v = a * a * ((k > 0 && k < kBins - 1) ? 2.f : 1.f) / vmax;   // arr2D /= arr2D.max()
+        }
+        tile[i][tx] = v;
+      }
+      __syncthreads();
+      for (int i = ty; i < 32; i += 8) {
+        const int k = k0 + i, j = j0 + tx;
+        if (k < kBins && j < nd) out[(int64_t)k * nd + j] = tile[tx][i];
+      }
+      __syncthreads();
+    }
+}
+
+// arr = 10 ln(max(p, max(p) / 1e6)) - mean, p = psd or psd^2 (after the UNet, fingerprint.py:74-79)
+__global__ void __launch_bounds__(256) dejavu_log_kernel(const float* __restrict__ psd, int n, int square,
+                                                         float* __restrict__ arr) {
+  __shared__ float redf[8];
+  __shared__ double redd[8];
+  const int item = blockIdx.x;
+  const float* p = psd + (int64_t)item * n;
+  float* o = arr + (int64_t)item * n;
+  float vmax = -INFINITY;
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const float v = square ? p[i] * p[i] : p[i];
+    vmax = fmaxf(vmax, v);
+  }
+  vmax = block_reduce_max(vmax, redf);
+  const float floor_v = vmax / 1e6f;
+  double sum = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const float v = square ? p[i] * p[i] : p[i];
+    const float l = 10.f * logf(fmaxf(v, floor_v));
+    o[i] = l;
+    sum += (double)l;
+  }
+  const float mean = (float)(block_reduce_sum(sum, redd) / (double)n);
+  for (int i = threadIdx.x; i < n; i += 256) o[i] -= mean;
+}
+
+}  // namespace
+
+int dejavu_num_frames(int T) { return T >= kNfft ? (T - kHop) / kHop : 0; }
+
+int launch_dejavu_psd(mfpa_ctx* ctx, const float* x, int B, int T, int64_t stride, float* psd, cudaStream_t st) {
+  const int n_stft = num_frames(T), nd = dejavu_num_frames(T);
+  MFPA_REQUIRE(nd >= 1, "dejavu_psd: %d samples are fewer than one 512-sample segment", T);
+  if (ctx->mag.reserve(sizeof(float) * (size_t)B * n_stft * kPitch) || ctx->qmax.reserve(sizeof(float) * (size_t)B))
+    return MFPA_ENOMEM;
+  if (int e = launch_stft_mag(ctx, x, B, T, stride, 1, (float*)ctx->mag.ptr, (float*)ctx->qmax.ptr, st, ctx->win_dejavu_dev))
+    return e;
+  dejavu_psd_kernel<<<B, 256, 0, st>>>((const float*)ctx->mag.ptr, n_stft, nd, psd);
+  MFPA_CUDA(cudaGetLastError());
+  return MFPA_OK;
+}
+
+int launch_dejavu_log(const float* psd, int B, int n, int square, float* arr, cudaStream_t st) {
+  dejavu_log_kernel<<<B, 256, 0, st>>>(psd, n, square, arr);
+  MFPA_CUDA(cudaGetLastError());
+  return MFPA_OK;
+}
+
 }  // namespace mfpa

@@ -276,11 +276,15 @@ int stft_init_tables(mfpa_ctx* ctx) {
   MFPA_CUDA(cudaMalloc(&ctx->win_dev, sizeof(win)));
   MFPA_CUDA(cudaMemcpy(ctx->tw_dev, tw, sizeof(tw), cudaMemcpyHostToDevice));
   MFPA_CUDA(cudaMemcpy(ctx->win_dev, win, sizeof(win), cudaMemcpyHostToDevice));
+  // np.hanning(512): 0.5 - 0.5*cos(2*pi*n/511) (symmetric; matplotlib.mlab.window_hanning)
+  for (int n = 0; n < kNfft; ++n) win[n] = (float)(0.5 * (0.5 - 0.5 * cos(2 * pi * n / (kNfft - 1))));
+  MFPA_CUDA(cudaMalloc(&ctx->win_dejavu_dev, sizeof(win)));
+  MFPA_CUDA(cudaMemcpy(ctx->win_dejavu_dev, win, sizeof(win), cudaMemcpyHostToDevice));
   return MFPA_OK;
 }
 
 int launch_stft_mag(mfpa_ctx* ctx, const float* x, int B, int T, int64_t stride, int shifts,
-                    float* mag, float* qmax, cudaStream_t st) {
+                    float* mag, float* qmax, cudaStream_t st, const float* window) {
   const int items = B * shifts;
   const int n_max = num_frames(T);
   MFPA_CUDA(cudaMemsetAsync(qmax, 0, sizeof(float) * items, st));
@@ -292,7 +296,7 @@ int launch_stft_mag(mfpa_ctx* ctx, const float* x, int B, int T, int64_t stride,
   for (int sft = 0; sft < shifts; ++sft) so.off[sft] = shift_offset(sft, shifts);
   MFPA_CUDA(cudaFuncSetAttribute(stft_mag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStftSmem));
   stft_mag_kernel<<<blocks, kWarps * 32, kStftSmem, st>>>(x, T, stride, shifts, n_max, (unsigned)total_tiles, so, ctx->tw_dev,
-                                                          ctx->win_dev, mag, qmax);
+                                                          window ? window : ctx->win_dev, mag, qmax);
   MFPA_CUDA(cudaGetLastError());
   return MFPA_OK;
 }

@@ -92,6 +92,9 @@ SIGNATURES = {
     "mfpa_match_align": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, C.POINTER(MatchParams), _vp, _vp, _i, _vp]),
     "mfpa_match": (_i, [_vp, _vp, _vp, _i, _i, C.POINTER(MatchParams), _vp, _vp, _i, _vp]),
     "mfpa_dejavu_peaks": (_i, [_vp, _vp, _i, _i, _i, _i, _i, C.c_double, _vp, _vp, _i, _vp, _vp]),
+    "mfpa_dejavu_num_frames": (_i, [_i]),
+    "mfpa_dejavu_psd": (_i, [_vp, _vp, _i, _i, _i64, _vp, _vp]),
+    "mfpa_dejavu_log": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "mfpa_compact_rows": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _i64, _vp]),
     "mfpa_unet_num_params": (_i64, []),
     "mfpa_unet_create": (_i, [_vp, C.POINTER(_vp)]),
@@ -445,6 +448,27 @@ class Context:
         check(_lib.mfpa_dejavu_peaks(self._h, _ptr(arr), int(arr.dtype == torch.float64), B, F, N, neighborhood,
                                      float(amp_min), _ptr(mask), _ptr(peaks), cap, _ptr(npk), _stream()))
         return mask, peaks, npk
+
+    def dejavu_psd(self, x):
+        """x [B,T] f32 cuda -> mlab.specgram PSD / max, float32 [B,257,(T-256)//256] (fingerprint.py:60-68)."""
+        import torch
+
+        assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
+        B, T = x.shape
+        nd = _lib.mfpa_dejavu_num_frames(T)
+        psd = torch.empty(B, BINS, nd, dtype=torch.float32, device=x.device)
+        check(_lib.mfpa_dejavu_psd(self._h, _ptr(x), B, T, _row_stride(x), _ptr(psd), _stream()))
+        return psd
+
+    def dejavu_log(self, psd, square: bool = False):
+        """10 ln(max(p, max/1e6)) - mean per item (fingerprint.py:77-79); p = psd**2 when `square`."""
+        import torch
+
+        psd = psd.contiguous()
+        B, F, N = psd.shape
+        arr = torch.empty_like(psd)
+        check(_lib.mfpa_dejavu_log(self._h, _ptr(psd), B, F, N, int(square), _ptr(arr), _stream()))
+        return arr
 
     # ---- fused -----------------------------------------------------------
     def fingerprint(self, x, shifts: int, params: AfpParams, out=None, nh=None, cap: int | None = None):

@@ -15,7 +15,10 @@ Contents
 ``augment_np``     numpy/torch-free restatement of the AugmentFP arithmetic
                    (julius low-pass FIR, IR FFT convolution, noise mix, gain,
                    clipping quantiles, peak normalisation).
-``dejavu_np``      numpy restatement of Dejavu's get_2D_peaks.
+``dejavu_np``      numpy restatement of Dejavu's get_2D_peaks and of fingerprint()'s
+                   mlab.specgram front end (pinned against scipy.signal.spectrogram).
+``unet_torch``     fp32 torch restatement of the UNet denoiser (training/unet.py), pinned
+                   bit-for-bit against the real class (tests/golden/unet.npz).
 ``synth``          seeded synthetic inputs.
 ``ref_loader``     imports the *real* reference from /root/reference with
                    stub modules (build container only; it cannot travel).

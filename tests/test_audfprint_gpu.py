@@ -263,3 +263,34 @@ def test_pcm16_host_entry_equals_float_entry(mfpa_ctx):
         rows_i, offs_i = mfpa_ctx.fingerprint_host(x16, shifts, p)
         assert np.array_equal(offs_f, offs_i) and np.array_equal(rows_f, rows_i)
         assert offs_i[-1] > 0
+
+
+def test_picker_edge_cases_on_crafted_sgrams(mfpa_ctx):
+    """SURVEY.md App. E cases on hand-made filtered spectrograms (stage 1 entry, bit-exact): plateaus
+    (locmax keeps the LAST element, sort ties favour the higher bin), more than 5 candidates in a frame,
+    a peak repeated in the same bin of the next frame (backward pass clears the later one), fewer than 10
+    frames (initial threshold from min(10, n) columns), a single frame, and an all-equal spectrogram."""
+    lib = _lib()
+    p = _params(lib)
+    rng = np.random.default_rng(99)
+    cases = []
+    sg = np.zeros((256, 40))
+    sg[10:14, :] = 3.0                       # a 4-bin plateau in every frame
+    sg[100, 5] = sg[100, 6] = 9.0            # same bin, consecutive frames
+    sg[200:206, 20] = [1, 2, 2, 2, 1, 0]     # plateau inside a bump
+    cases.append(sg)
+    sg = rng.standard_normal((256, 30))
+    sg[::8, 3] += 50.0                       # 32 strong candidates in one frame -> top 5 kept
+    cases.append(sg)
+    cases.append(rng.standard_normal((256, 4)))    # fewer than 10 frames
+    cases.append(rng.standard_normal((256, 1)))    # a single frame
+    cases.append(np.full((256, 12), 0.25))         # everything equal
+    cases.append(np.round(rng.standard_normal((256, 64)) * 2) / 2)  # heavy ties
+    for i, sg in enumerate(cases):
+        want, _ = O.peaks_from_sgram(sg)
+        rec, npk = mfpa_ctx.audfprint_peaks_from_spec(torch.from_numpy(np.ascontiguousarray(sg)[None]).cuda(), 1, p)
+        got = _rec_to_pklist(rec[0].cpu().numpy())
+        assert got == want, i
+        h, nh = mfpa_ctx.landmark_hashes(rec, p, sorted_rows=False)
+        wh = O.landmarks2hashes(O.peaks2landmarks(want))
+        assert int(nh[0]) == len(wh) and np.array_equal(h[0, : len(wh)].cpu().numpy(), wh), i

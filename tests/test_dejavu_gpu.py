@@ -37,3 +37,33 @@ def test_batch_vs_oracle_full_size(mfpa_ctx):
             assert np.array_equal(mask[i].cpu().numpy(), m.astype(np.uint8)), (dt, i)
             assert [tuple(r) for r in peaks[i, : int(n[i])].cpu().numpy().tolist()] == pk
             assert len(pk) > 10
+
+
+def test_fingerprint_front_end_vs_oracle(mfpa_ctx):
+    """fingerprint.py:60-79 on the GPU (float32) vs the float64 oracle: PSD/max within 1e-4 of the peak,
+    log array within 1e-3 (10 ln of a 1e-6-floored value), and the peak sets agree >= 99 %."""
+    from musicfpaugment_b200 import synth
+    from oracle import dejavu_np as D
+
+    X = synth.music_like(4, seed=50, device=torch.device("cuda"))
+    psd = mfpa_ctx.dejavu_psd(X)
+    arr = mfpa_ctx.dejavu_log(psd)
+    mask, peaks, n = mfpa_ctx.dejavu_peaks(arr, cap=257 * 249)
+    assert psd.shape == (4, 257, 249)
+    for i in range(4):
+        want_arr, want_psd = D.dejavu_fingerprint_arr(X[i].cpu().numpy())
+        assert np.abs(psd[i].cpu().numpy() - want_psd).max() < 1e-4
+        assert np.abs(arr[i].cpu().numpy() - want_arr).max() < 2e-3
+        want_pk, _ = D.get_2d_peaks(want_arr)
+        got_pk = set(map(tuple, peaks[i, : int(n[i])].cpu().numpy().tolist()))
+        agree = len(got_pk & set(want_pk)) / max(1, len(got_pk | set(want_pk)))
+        assert agree >= 0.99, agree
+        # the peak finder itself is exact on the GPU's own array
+        same_pk, _ = D.get_2d_peaks(arr[i].cpu().numpy())
+        assert got_pk == set(same_pk)
+    # short input: one segment; too short raises
+    assert mfpa_ctx.dejavu_psd(X[:1, :700]).shape == (1, 257, 1)
+    from musicfpaugment_b200 import lib
+
+    with pytest.raises(lib.MfpaError):
+        mfpa_ctx.dejavu_psd(X[:1, :400])

@@ -158,3 +158,28 @@ def test_find_peaks_with_unet_denoising(mods):
     assert np.array_equal(got, want)
     with pytest.raises(NotImplementedError):
         pe.Audfprint_peaks(dict(PRM), denoising=True, denoising_model="demucs")
+
+
+def test_dejavu_fingerprint_drop_in(mods):
+    """afp.dejavu.fingerprint.fingerprint (fingerprint.py:34-91): hashes are generate_hashes of the peaks
+    of the GPU log-spectrogram; with get_masks it also returns the mask and the normalised PSD."""
+    from oracle import dejavu_np as D
+    from oracle.unet_torch import seeded_unet
+
+    fp = mods["fp"]
+    x = _queries(1)[0]
+    hashes, mask, spec = fp.fingerprint(x, get_masks=True)
+    assert mask.shape == spec.shape == (257, 249)
+    want_arr, want_psd = D.dejavu_fingerprint_arr(x)
+    assert np.abs(spec - want_psd).max() < 1e-4
+    want_pk, _ = D.get_2d_peaks(want_arr)
+    got_pk = set(zip(*np.nonzero(mask)))
+    assert len(got_pk & set(want_pk)) / max(1, len(got_pk | set(want_pk))) >= 0.99
+    assert hashes == fp.generate_hashes([(f, t) for f, t in sorted(got_pk)], fan_value=3)
+    assert fp.fingerprint(x) == hashes
+    # denoised: arr2D = unet(arr2D) ** 2 before the log (:70-75)
+    fp.set_unet_state_dict(seeded_unet(0).state_dict())
+    h2, m2, s2 = fp.fingerprint(x, denoising=True, denoising_model="unet", get_masks=True)
+    assert s2.shape == (257, 249) and (s2 >= 0).all() and isinstance(h2, list)
+    with pytest.raises(NotImplementedError):
+        fp.fingerprint(x, denoising=True, denoising_model="demucs")

@@ -134,3 +134,19 @@ def test_unet_oracle_reproduces_reference_golden():
     with torch.no_grad():
         y = net(torch.from_numpy(g["x"])).numpy()
     np.testing.assert_allclose(y, g["y"], rtol=0, atol=1e-6)
+
+
+def test_dejavu_specgram_restatement_matches_scipy_definition():
+    """oracle/dejavu_np.specgram_psd (restating matplotlib.mlab.specgram, not installed) against
+    scipy.signal.spectrogram, an independent implementation of the same one-sided density periodogram."""
+    import scipy.signal
+
+    from musicfpaugment_b200 import synth
+
+    for i, T in enumerate((64000, 5000, 513)):
+        x = synth.music_like(1, seed=40 + i).numpy()[0, :T].astype(np.float64)
+        got = D.specgram_psd(x)
+        _, _, want = scipy.signal.spectrogram(x, fs=8000.0, window=np.hanning(512), nperseg=512, noverlap=256, nfft=512,
+                                              detrend=False, return_onesided=True, scaling="density", mode="psd")
+        assert got.shape == want.shape == (257, (T - 256) // 256)
+        np.testing.assert_allclose(got, want, rtol=1e-10, atol=1e-18)
