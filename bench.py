@@ -549,8 +549,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--also", default="chain,match,unet",
                     help="comma list of the other BASELINE configs to time after the headline: chain, match, unet, or none")
-    ap.add_argument("--unet-queries", type=int, default=128, help="spectrograms per step of the UNet leg")
-    ap.add_argument("--unet-chunk", type=int, default=32, help="images per pass through the UNet (activation arena size)")
+    ap.add_argument("--unet-queries", type=int, default=148, help="spectrograms per step of the UNet leg")
+    ap.add_argument("--unet-chunk", type=int, default=37, help="images per pass through the UNet (activation arena size)")
     ap.add_argument("--tracks", type=int, default=100000, help="tracks in the synthetic index of the match workload")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -313,7 +313,8 @@ int64_t mfpa_unet_num_params(void);
 int mfpa_unet_create(mfpa_ctx* ctx, mfpa_unet** out);
 void mfpa_unet_destroy(mfpa_unet* unet);
 int mfpa_unet_load(mfpa_unet* unet, const float* params_host, int64_t n_floats);
-/* Images per pass through the network (activation arena = ~45 MB per 257x251 image); default 16. */
+/* Images per pass through the network (activation arena = ~45 MB per 257x251 image); default 37 (a
+ * quarter of the 148 SMs: every layer's tile count is then a whole number of waves). */
 int mfpa_unet_set_max_chunk(mfpa_unet* unet, int images);
 /* out[b] = unet(in[b] / div[b]) for B single-channel H x W images.  in/out are float32 device arrays
  * addressed as base + b*stride_n + h*stride_h + w*stride_w (elements), so both the reference layout

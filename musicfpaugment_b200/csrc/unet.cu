@@ -865,7 +865,9 @@ struct mfpa_unet {
   bf16* dec[4] = {nullptr};   // decoder outputs u1..u3 at levels 3..1 (dec[l]), C_l channels
   std::vector<void*> arena;
   std::vector<GemmLaunch> plan;  // in execution order
-  int max_chunk = 16;
+  // images per pass: 37 = 148 / 4, and every level of the 257x251 geometry has a multiple of 4 tiles per
+  // image, so each persistent launch fills a whole number of waves of the 148 SMs
+  int max_chunk = 37;
 };
 
 namespace {
@@ -937,7 +939,7 @@ int plan_conv(mfpa_unet* u, const ConvBN& c, const bf16* in, int n, int h, int w
     }
     halo_geometry(g.wh, g.mt, &g.th, &g.a_bytes);
     if (halo_smem_bytes(g, c.cin, c.cout) > 227 * 1024) g.wh = 0;  // does not fit: per-tap kernel
-  } else if (c.cout >= 256 && c.cin <= 256 && h * w >= 2048) {
+  } else if (c.cout >= 256 && c.cin <= 128 && h * w >= 2048) {
     g.mt = 1;
   }
   int rc = g.wh > 0 ? make_act_map(&g.tmA, in, n, h, w, c.cin, g.th + 2, g.wh) : make_act_map(&g.tmA, in, n, h, w, c.cin, 8 * g.mt);
