@@ -87,6 +87,10 @@ int mfpa_set_spread_table(mfpa_ctx* ctx, const double* table513_host);
  * [B][(n_tracks + 1) / 2], word j = count[2j] | count[2j+1] << 16.  Summing such rows as uint32 (the
  * sharded path's NCCL reduction) is exact as long as no total reaches 65536; half the bytes. */
 #define MFPA_OPT_MATCH_PACKED 2
+/* MFPA_OPT_MATCH_UNFUSED (default 0): mfpa_match normally runs counts + select + collect as one kernel
+ * whose histogram never leaves shared memory (indexes of up to 110000 tracks); 1 forces the four-step
+ * path (the one the sharded matcher drives with collectives in between) for comparison. */
+#define MFPA_OPT_MATCH_UNFUSED 3
 int mfpa_set_option(mfpa_ctx* ctx, int option, int value);
 
 /* ---- geometry --------------------------------------------------------- */

@@ -560,26 +560,24 @@ __global__ void __launch_bounds__(kSelThreads) clip_select_kernel(const float* _
     __syncthreads();
     const unsigned t_lo = thr_key[0], t_hi = thr_key[1];
     __syncthreads();   // sample (= lo_list) is dead from here
-    const int lane = tid & 31;
-    for (int n0 = 0; n0 < T; n0 += kSelThreads) {
-      const int n = n0 + tid;
-      const unsigned k = n < T ? order_key(z[n]) : 0u;
-      const bool is_lo = n < T && k <= t_lo, is_hi = n < T && k >= t_hi;
-      const unsigned b_lo = __ballot_sync(0xffffffffu, is_lo), b_hi = __ballot_sync(0xffffffffu, is_hi);
-      if (b_lo) {
-        unsigned base = 0;
-        if (lane == 0) base = atomicAdd(&cnt[0], __popc(b_lo));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        const unsigned slot = base + __popc(b_lo & ((1u << lane) - 1u));
-        if (is_lo && slot < kSelCap) lo_list[slot] = k;
+    // one pass: the tails are ~1 % of the samples, so a shared-memory atomic per hit is cheaper than
+    // warp compaction on every iteration (list order is irrelevant: the lists are sorted below)
+    auto visit = [&](float v) {
+      const unsigned k = order_key(v);
+      if (k <= t_lo) { const unsigned slot = atomicAdd(&cnt[0], 1u); if (slot < kSelCap) lo_list[slot] = k; }
+      if (k >= t_hi) { const unsigned slot = atomicAdd(&cnt[1], 1u); if (slot < kSelCap) hi_list[slot] = k; }
+    };
+    if ((reinterpret_cast<uintptr_t>(z) & 15) == 0) {
+      const float4* z4 = reinterpret_cast<const float4*>(z);
+      const int n4 = T >> 2;
+#pragma unroll 4
+      for (int i = tid; i < n4; i += kSelThreads) {
+        const float4 v = z4[i];
+        visit(v.x); visit(v.y); visit(v.z); visit(v.w);
       }
-      if (b_hi) {
-        unsigned base = 0;
-        if (lane == 0) base = atomicAdd(&cnt[1], __popc(b_hi));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        const unsigned slot = base + __popc(b_hi & ((1u << lane) - 1u));
-        if (is_hi && slot < kSelCap) hi_list[slot] = k;
-      }
+      for (int n = (n4 << 2) + tid; n < T; n += kSelThreads) visit(z[n]);
+    } else {
+      for (int n = tid; n < T; n += kSelThreads) visit(z[n]);
     }
     __syncthreads();
     const int c_lo = (int)cnt[0], c_hi = (int)cnt[1];
@@ -621,13 +619,20 @@ __global__ void __launch_bounds__(kSelThreads) clip_select_kernel(const float* _
   }
 }
 
-// stage 3b-5: w = clamp((z/peak_z)*gain, lo, hi); u = lowpass(w) with a short FIR (direct form)
+// stage 3b-5: w = clamp((z/peak_z)*gain, lo, hi); u = lowpass(w) with a short FIR (direct form).
+// The tile starts round_up(half, 4) samples before its first output so that 16-byte global loads,
+// shared-memory float4 reads and 16-byte stores all stay aligned; the taps are stored shifted by the
+// same amount and zero-padded to whole float4 groups.  Each thread produces four consecutive outputs
+// from a sliding pair of float4 tile reads: 16 FMAs per two 16-byte shared loads.
 constexpr int kLpMaxHalf = 64;
+constexpr int kLpTile = 1024;
+constexpr int kLpTapsPad = 2 * kLpMaxHalf + 8;
+constexpr int kLpTileLen = kLpTile + kLpTapsPad + 8;
 __global__ void __launch_bounds__(256) clip_lpf_kernel(const float* __restrict__ z_all, float* __restrict__ u_all,
                                                        const AugQ* __restrict__ qs, const AugS* __restrict__ st, int T,
                                                        int materialise_only) {
-  __shared__ float taps[2 * kLpMaxHalf + 1];
-  __shared__ float tile[1024 + 2 * kLpMaxHalf];
+  __shared__ __align__(16) float taps[kLpTapsPad];
+  __shared__ __align__(16) float tile[kLpTileLen];
   __shared__ float red[8];
   const int qi = blockIdx.y, tid = threadIdx.x;
   const AugQ q = qs[qi];
@@ -637,12 +642,22 @@ __global__ void __launch_bounds__(256) clip_lpf_kernel(const float* __restrict__
   const float g = (q.apply & MFPA_AUG_GAIN) ? q.gain : 1.f;
   const bool lp_on = (q.apply & MFPA_AUG_LPF) && !materialise_only;
   const int half = lp_on ? q.half2 : 0;
-  const float* z = z_all + (int64_t)qi * T;
-  float* u = u_all + (int64_t)qi * T;
+  const int half_al = (half + 3) & ~3, shift = half_al - half;
+  const int groups = lp_on ? (2 * half + 1 + shift + 3) >> 2 : 0;   // float4 groups of shifted taps
+  const int64_t row = (int64_t)qi * T;
+  const float* z = z_all + row;
+  float* u = u_all + row;
+  const bool vec_ok = (row & 3) == 0 && (reinterpret_cast<uintptr_t>(z_all) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(u_all) & 15) == 0;
   float hsum = 1.f;
   if (lp_on) {
     float hs = 0.f;
-    for (int i = tid; i < 2 * half + 1; i += 256) { const float h = fir_tap(i, half, q.c2x2, q.arg2); taps[i] = h; hs += h; }
+    for (int i = tid; i < kLpTapsPad; i += 256) {
+      const int k = i - shift;
+      const float h = (k >= 0 && k <= 2 * half) ? fir_tap(k, half, q.c2x2, q.arg2) : 0.f;
+      taps[i] = h;
+      hs += h;
+    }
 #pragma unroll
     for (int o = 16; o; o >>= 1) hs += __shfl_xor_sync(0xffffffffu, hs, o);
     if ((tid & 31) == 0) red[tid >> 5] = hs;
@@ -651,26 +666,56 @@ __global__ void __launch_bounds__(256) clip_lpf_kernel(const float* __restrict__
     for (int w = 0; w < 8; ++w) hsum += red[w];
   }
   const float inv = 1.0f / hsum;
-  for (int n0 = blockIdx.x * 1024; n0 < T; n0 += gridDim.x * 1024) {
+  auto shape = [&](float v) {
+    if (nz_on) v /= peak;
+    v *= g;
+    return fminf(fmaxf(v, s.lo), s.hi);
+  };
+  const int fill4 = (kLpTile + 4 * groups + 4) >> 2;   // float4 slots of the tile that are read
+  const float4* tile4 = reinterpret_cast<const float4*>(tile);
+  const float4* taps4 = reinterpret_cast<const float4*>(taps);
+  for (int n0 = blockIdx.x * kLpTile; n0 < T; n0 += gridDim.x * kLpTile) {
     __syncthreads();
-    for (int i = tid; i < 1024 + 2 * half; i += 256) {
-      const int n = min(max(n0 - half + i, 0), T - 1);
-      float v = z[n];
-      if (nz_on) v /= peak;
-      v *= g;
-      tile[i] = fminf(fmaxf(v, s.lo), s.hi);
+    for (int i4 = tid; i4 < fill4; i4 += 256) {
+      const int n = n0 - half_al + 4 * i4;
+      float4 v;
+      if (vec_ok && n >= 0 && n + 3 < T) {
+        v = *reinterpret_cast<const float4*>(z + n);
+      } else {   // replicate padding (julius pads with the edge sample)
+        v.x = z[min(max(n, 0), T - 1)];
+        v.y = z[min(max(n + 1, 0), T - 1)];
+        v.z = z[min(max(n + 2, 0), T - 1)];
+        v.w = z[min(max(n + 3, 0), T - 1)];
+      }
+      v.x = shape(v.x); v.y = shape(v.y); v.z = shape(v.z); v.w = shape(v.w);
+      reinterpret_cast<float4*>(tile)[i4] = v;
     }
     __syncthreads();
-    for (int i = tid; i < 1024 && n0 + i < T; i += 256) {
-      float acc;
+    const int n = n0 + 4 * tid;
+    if (n < T) {
+      float4 c = tile4[tid], r;
       if (lp_on) {
-        acc = 0.f;
-        for (int k = 0; k <= 2 * half; ++k) acc += taps[k] * tile[i + k];
-        acc *= inv;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        for (int m = 0; m < groups; ++m) {
+          const float4 d = tile4[tid + m + 1], h = taps4[m];
+          a0 = fmaf(h.x, c.x, a0); a0 = fmaf(h.y, c.y, a0); a0 = fmaf(h.z, c.z, a0); a0 = fmaf(h.w, c.w, a0);
+          a1 = fmaf(h.x, c.y, a1); a1 = fmaf(h.y, c.z, a1); a1 = fmaf(h.z, c.w, a1); a1 = fmaf(h.w, d.x, a1);
+          a2 = fmaf(h.x, c.z, a2); a2 = fmaf(h.y, c.w, a2); a2 = fmaf(h.z, d.x, a2); a2 = fmaf(h.w, d.y, a2);
+          a3 = fmaf(h.x, c.w, a3); a3 = fmaf(h.y, d.x, a3); a3 = fmaf(h.z, d.y, a3); a3 = fmaf(h.w, d.z, a3);
+          c = d;
+        }
+        r = make_float4(a0 * inv, a1 * inv, a2 * inv, a3 * inv);
       } else {
-        acc = tile[i];
+        r = c;
       }
-      u[n0 + i] = acc;
+      if (vec_ok && n + 3 < T) {
+        *reinterpret_cast<float4*>(u + n) = r;
+      } else {
+        u[n] = r.x;
+        if (n + 1 < T) u[n + 1] = r.y;
+        if (n + 2 < T) u[n + 2] = r.z;
+        if (n + 3 < T) u[n + 3] = r.w;
+      }
     }
   }
 }
@@ -839,8 +884,10 @@ int launch_augment(mfpa_ctx* ctx, const float* x, int B, int T, int64_t x_stride
     fftconv_kernel<kModeHP><<<dim3(blocks_for(T, min_v3), B), FT, kConvSmem, st>>>(a, ctx->aug_tw_dev);
     MFPA_CUDA(cudaGetLastError());
     const unsigned gx = (unsigned)((T + 4095) / 4096);
-    norm_kernel<<<dim3(gx, B), 256, 0, st>>>(bufA, out, ds, T, final_norm ? 1 : 0);
-    MFPA_CUDA(cudaGetLastError());
+    if (out) {   // out == nullptr: the caller consumes stage 6's output in place (ctx->aug_a)
+      norm_kernel<<<dim3(gx, B), 256, 0, st>>>(bufA, out, ds, T, final_norm ? 1 : 0);
+      MFPA_CUDA(cudaGetLastError());
+    }
   }
   return MFPA_OK;
 }

@@ -170,6 +170,7 @@ int mfpa_set_option(mfpa_ctx* ctx, int option, int value) {
   switch (option) {
     case MFPA_OPT_PEAKS_F64: ctx->opt_peaks_f64 = value != 0; return MFPA_OK;
     case MFPA_OPT_MATCH_PACKED: ctx->opt_match_packed = value != 0; return MFPA_OK;
+    case MFPA_OPT_MATCH_UNFUSED: ctx->opt_match_unfused = value != 0; return MFPA_OK;
     default: break;
   }
   set_error("set_option: unknown option %d", option);
@@ -437,11 +438,12 @@ int mfpa_augment_fingerprint(mfpa_ctx* ctx, const float* x_dev, int B, int T, in
                              int32_t* hashes_dev, int cap, int32_t* nh_dev, void* stream) {
   if (int e = check_augment(ctx, x_dev, B, T, x_stride, sample_rate, params_host)) return e;
   DeviceGuard guard(ctx->device);
-  if (ctx->aug_d.reserve(sizeof(float) * (size_t)B * T)) return MFPA_ENOMEM;
-  float* y = (float*)ctx->aug_d.ptr;
-  if (int e = launch_augment(ctx, x_dev, B, T, x_stride, sample_rate, params_host, ir_dev, ir_stride, noise_dev, y,
+  // PeakNormalization (stage 7) is skipped: the picker divides the magnitudes by their maximum and
+  // works on log differences, so a positive scale of the waveform cancels; the fingerprint stages read
+  // stage 6's output where launch_augment leaves it (ctx->aug_a) and no copy of the waveform is made.
+  if (int e = launch_augment(ctx, x_dev, B, T, x_stride, sample_rate, params_host, ir_dev, ir_stride, noise_dev, nullptr,
                              false, (cudaStream_t)stream)) return e;
-  return mfpa_fingerprint(ctx, y, B, T, T, shifts, p, hashes_dev, cap, nh_dev, stream);
+  return mfpa_fingerprint(ctx, (const float*)ctx->aug_a.ptr, B, T, T, shifts, p, hashes_dev, cap, nh_dev, stream);
 }
 
 void mfpa_match_defaults(mfpa_match_params* p) {
@@ -535,6 +537,27 @@ int mfpa_match(mfpa_ctx* ctx, const int32_t* hashes_dev, const int32_t* nh_dev, 
   DeviceGuard guard(ctx->device);
   cudaStream_t st = (cudaStream_t)stream;
   const int nt = ctx->index_ntracks;
+  if (match_fused_ok(ctx) && !ctx->opt_match_unfused) {
+    // single shard, histogram fits shared memory: counts + select + collect never leave the block
+    const int list_cap = 8192;
+    const int sub = B < 4096 ? B : 4096;
+    if (ctx->match_b.reserve(sizeof(int32_t) * (size_t)sub * (2 * p->search_depth + 2))) return MFPA_ENOMEM;
+    if (ctx->match_c.reserve(sizeof(uint32_t) * (size_t)sub * list_cap)) return MFPA_ENOMEM;
+    int32_t* cand = (int32_t*)ctx->match_b.ptr;
+    int32_t* ncand = cand + (size_t)sub * 2 * p->search_depth;
+    int32_t* nlist = ncand + sub;
+    uint32_t* list = (uint32_t*)ctx->match_c.ptr;
+    for (int q0 = 0; q0 < B; q0 += sub) {
+      const int nq = B - q0 < sub ? B - q0 : sub;
+      const int32_t* hq = hashes_dev + (size_t)q0 * cap * 2;
+      if (int e = launch_match_fused(ctx, hq, nh_dev + q0, nq, cap, p->threshcount, p->search_depth, cand, ncand, list,
+                                     list_cap, nlist, st)) return e;
+      if (int e = launch_match_align(list, nlist, 1, nq, list_cap, cand, ncand, p->search_depth, p->window, p->threshcount,
+                                     p->max_alignments_per_id, results_dev + (size_t)q0 * max_rows * 7, nrows_dev + q0,
+                                     max_rows, st)) return e;
+    }
+    return MFPA_OK;
+  }
   int sub = (int)((int64_t)(256 << 20) / ((int64_t)nt * 4));  // ~256 MiB of dense counts per sub-batch
   if (sub < 1) sub = 1;
   if (sub > B) sub = B;

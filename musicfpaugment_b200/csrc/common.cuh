@@ -62,6 +62,7 @@ struct mfpa_ctx {
   int num_sms = mfpa::kNumSMs;
   int opt_peaks_f64 = 0;            // MFPA_OPT_PEAKS_F64
   int opt_match_packed = 0;         // MFPA_OPT_MATCH_PACKED
+  int opt_match_unfused = 0;        // MFPA_OPT_MATCH_UNFUSED
   double* spread_dev = nullptr;     // [513] Gaussian table
   float2* tw_dev = nullptr;         // FFT twiddles (stft.cu layout)
   float* win_dev = nullptr;         // [512] analysis window
@@ -115,6 +116,10 @@ int launch_augment(mfpa_ctx* ctx, const float* x, int B, int T, int64_t x_stride
                    float* out, bool final_norm, cudaStream_t st);
 int launch_match_counts(mfpa_ctx* ctx, const int32_t* hashes, const int32_t* nh, int B, int cap, int32_t* counts,
                         cudaStream_t st);
+bool match_fused_ok(const mfpa_ctx* ctx);
+int launch_match_fused(mfpa_ctx* ctx, const int32_t* hashes, const int32_t* nh, int B, int cap, int threshcount,
+                       int search_depth, int32_t* cand, int32_t* ncand, uint32_t* list, int list_cap, int32_t* nlist,
+                       cudaStream_t st);
 int launch_match_select(mfpa_ctx* ctx, const int32_t* counts, int B, int threshcount, int search_depth, int32_t* cand,
                         int32_t* ncand, cudaStream_t st);
 int launch_match_collect(mfpa_ctx* ctx, const int32_t* hashes, const int32_t* nh, int B, int cap, const int32_t* cand,

@@ -146,6 +146,154 @@ __global__ void __launch_bounds__(512) match_select_kernel(const int32_t* __rest
   }
 }
 
+// ---- counts + select + collect in one block per query (single shard: no exchange between the steps) ----
+// The packed 16-bit histogram never leaves shared memory: the block counts the query's hits, ranks the
+// candidates straight from the histogram, then re-uses the same words as a "candidate index + 1" map for
+// the second sweep over the (L2-hot) bucket rows that emits the candidates' (index, delta-t) hits.
+// The sweeps are latency-bound gathers, so each warp keeps four bucket rows (16 loads per lane) in flight;
+// the per-row (bucket, count, query time) triples are staged through a small shared-memory cache first.
+constexpr int kFusedRows = 768;
+constexpr int kFusedThreads = 512;
+struct RowCache { int hb[kFusedRows]; int cnt[kFusedRows]; int t[kFusedRows]; };
+
+template <bool COLLECT>
+__device__ __forceinline__ void fused_sweep(const IndexView& ix, const int2* __restrict__ rows, int n, RowCache* rc,
+                                            unsigned* hist, uint32_t* __restrict__ out, int list_cap, int* s_n, int tid) {
+  const int lane = tid & 31, warp = tid >> 5;
+  const uint32_t tmask = (1u << ix.maxtimebits) - 1u;
+  const unsigned short* mark = reinterpret_cast<const unsigned short*>(hist);
+  for (int c0 = 0; c0 < n; c0 += kFusedRows) {
+    const int nc = min(kFusedRows, n - c0);
+    __syncthreads();
+    for (int i = tid; i < nc; i += kFusedThreads) {
+      const int2 row = rows[c0 + i];
+      const int hb = (row.y & ix.hashmask) - ix.hash_lo;
+      const bool in = hb >= 0 && hb < ix.n_buckets;
+      rc->hb[i] = in ? hb : 0;
+      rc->cnt[i] = in ? min(ix.depth, ix.counts[hb]) : 0;
+      rc->t[i] = row.x;
+    }
+    __syncthreads();
+    for (int s0 = 0; s0 < ix.depth; s0 += 128) {   // one trip for depth <= 128 (the reference's is 100)
+      for (int r = warp * 4; r < nc; r += (kFusedThreads / 32) * 4) {
+        uint32_t v[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          const int rr = r + a;
+          const int cnt = rr < nc ? rc->cnt[rr] : 0;
+          const uint32_t* bucket = ix.table + (int64_t)(rr < nc ? rc->hb[rr] : 0) * ix.depth;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int s = s0 + lane + 32 * i;
+            v[a][i] = s < cnt ? __ldg(bucket + s) : 0u;   // 0 = empty slot (stored ids are id + 1 >= 1)
+          }
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int id = (int)(v[a][i] >> ix.maxtimebits) - 1;
+            if (id < 0 || id >= ix.n_tracks) continue;
+            if (!COLLECT) {
+              atomicAdd(&hist[id >> 1], (id & 1) ? 0x10000u : 1u);
+            } else {
+              const unsigned k = mark[id];
+              if (k) {
+                const int dt = (int)(v[a][i] & tmask) - rc->t[r + a];
+                const int pos = atomicAdd(s_n, 1);
+                if (pos < list_cap) out[pos] = ((k - 1u) << 16) | (uint32_t)(dt + kDtOff);
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kFusedThreads, 1)
+match_fused_kernel(const IndexView ix, const int32_t* __restrict__ hashes, const int32_t* __restrict__ nh, int cap,
+                   int threshcount, int search_depth, int32_t* __restrict__ cand, int32_t* __restrict__ ncand,
+                   uint32_t* __restrict__ list, int list_cap, int32_t* __restrict__ nlist) {
+  extern __shared__ __align__(16) unsigned fused_smem[];
+  const int words = (ix.n_tracks + 1) >> 1;
+  unsigned* hist = fused_smem;
+  RowCache* rc = reinterpret_cast<RowCache*>(fused_smem + ((words + 3) & ~3));
+  __shared__ int s_int[16];
+  __shared__ Cand s_best[16];
+  __shared__ Cand s_prev;
+  __shared__ int s_n;
+  const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int2* rows = reinterpret_cast<const int2*>(hashes) + (int64_t)q * cap;
+  const int n = min(nh[q], cap);
+  for (int i = tid; i < words; i += kFusedThreads) hist[i] = 0;
+  if (tid == 0) s_n = 0;
+  fused_sweep<false>(ix, rows, n, rc, hist, nullptr, 0, nullptr, tid);
+
+  // select (_best_count_ids, audfprint_match.py:102-129) on the shared-memory histogram
+  auto count_of = [&](int i) -> int { return (int)((hist[i >> 1] >> ((i & 1) * 16)) & 0xffffu); };
+  int gt = 0;
+  for (int w = tid; w < words; w += kFusedThreads) {
+    const unsigned h2 = hist[w];
+    if (h2) gt += ((int)(h2 & 0xffffu) > threshcount) + ((int)(h2 >> 16) > threshcount);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) gt += __shfl_xor_sync(kFull, gt, o);
+  if (lane == 0) s_int[warp] = gt;
+  __syncthreads();
+  gt = 0;
+  for (int w = 0; w < 16; ++w) gt += s_int[w];
+  const int depth = min(gt, search_depth);
+  if (tid == 0) { ncand[q] = depth; s_prev = Cand{1, 0, 0x7fffffff}; }  // +infinity sentinel (hp = 0)
+  __syncthreads();
+  for (int k = 0; k < depth; ++k) {
+    const Cand prev = s_prev;
+    Cand best{-1, 1, -1};
+    for (int w = tid; w < words; w += kFusedThreads) {
+      const unsigned h2 = hist[w];
+      if (!h2) continue;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int raw = (int)((h2 >> (16 * e)) & 0xffffu), i = 2 * w + e;
+        if (raw <= 0 || i >= ix.n_tracks) continue;
+        const Cand x{raw, (long long)ix.hashesperid[i], i};
+        const bool after_prev = prev.hp == 0 || before(prev, x);
+        if (after_prev && (best.id < 0 || before(x, best))) best = x;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      Cand y;
+      y.raw = __shfl_xor_sync(kFull, best.raw, o); y.hp = __shfl_xor_sync(kFull, best.hp, o); y.id = __shfl_xor_sync(kFull, best.id, o);
+      if (y.id >= 0 && (best.id < 0 || before(y, best))) best = y;
+    }
+    if (lane == 0) s_best[warp] = best;
+    __syncthreads();
+    if (tid == 0) {
+      Cand b = s_best[0];
+      for (int w = 1; w < 16; ++w) if (s_best[w].id >= 0 && (b.id < 0 || before(s_best[w], b))) b = s_best[w];
+      s_prev = b;
+      cand[((int64_t)q * search_depth + k) * 2] = b.id;
+      cand[((int64_t)q * search_depth + k) * 2 + 1] = (int)b.raw;
+    }
+    __syncthreads();
+  }
+  (void)count_of;
+  if (depth == 0) {
+    if (tid == 0) nlist[q] = 0;
+    return;
+  }
+  // the histogram becomes the candidate map: 16-bit slot of track id = candidate index + 1
+  for (int i = tid; i < words; i += kFusedThreads) hist[i] = 0;
+  __syncthreads();
+  const int nc = min(depth, 128);   // align_kernel handles at most 128 candidates (check_match bounds search_depth)
+  for (int k = tid; k < nc; k += kFusedThreads)
+    reinterpret_cast<unsigned short*>(hist)[cand[((int64_t)q * search_depth + k) * 2]] = (unsigned short)(k + 1);
+  fused_sweep<true>(ix, rows, n, rc, hist, list + (int64_t)q * list_cap, list_cap, &s_n, tid);
+  if (tid == 0) nlist[q] = s_n;
+}
+
 // ---- collect -----------------------------------------------------------------------------
 // (candidate index << 16) | (t_ref - t_q + 16384) for every local hit of a candidate track.
 __global__ void __launch_bounds__(256) match_collect_kernel(const IndexView ix, const int32_t* __restrict__ hashes,
@@ -381,6 +529,21 @@ int launch_match_counts(mfpa_ctx* ctx, const int32_t* hashes, const int32_t* nh,
     MFPA_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t)B * ix.n_tracks, st));
     match_counts_global_kernel<<<B, kCountThreads, 0, st>>>(ix, hashes, nh, cap, counts);
   }
+  MFPA_CUDA(cudaGetLastError());
+  return MFPA_OK;
+}
+
+bool match_fused_ok(const mfpa_ctx* ctx) { return ctx->index_ntracks <= kMaxTracksSmem; }
+
+int launch_match_fused(mfpa_ctx* ctx, const int32_t* hashes, const int32_t* nh, int B, int cap, int threshcount,
+                       int search_depth, int32_t* cand, int32_t* ncand, uint32_t* list, int list_cap, int32_t* nlist,
+                       cudaStream_t st) {
+  const IndexView ix = view(ctx);
+  const size_t words = (size_t)((ix.n_tracks + 1) / 2);
+  const size_t smem = sizeof(unsigned) * ((words + 3) & ~(size_t)3) + sizeof(RowCache);
+  MFPA_CUDA(cudaFuncSetAttribute(match_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  match_fused_kernel<<<B, kFusedThreads, smem, st>>>(ix, hashes, nh, cap, threshcount, search_depth, cand, ncand, list,
+                                                     list_cap, nlist);
   MFPA_CUDA(cudaGetLastError());
   return MFPA_OK;
 }

@@ -144,6 +144,39 @@ def test_packed_counts_option(mfpa_ctx):
         mfpa_ctx.index_load(table, counts, hpid)
 
 
+def test_fused_match_equals_four_step_path(mfpa_ctx):
+    """mfpa_match's one-kernel counts+select+collect (histogram kept in shared memory) gives the rows of
+    the four-step path: long queries (more rows than the kernel's row cache), a small index where many
+    tracks pass the count threshold (deep candidate lists), an odd track count, empty queries."""
+    from musicfpaugment_b200 import lib, synth
+
+    table, counts, hpid, th = synth.hash_index(301, 3000, seed=21)   # 301 tracks: every track collects hits
+    q, nq, _ = synth.planted_queries(th, 12, n_hashes=2000, frac=0.2, seed=22)
+    nq[3] = 0
+    nq[7] = 1
+    h, n = torch.from_numpy(q).cuda(), torch.from_numpy(nq).cuda()
+    mfpa_ctx.index_load(table, counts, hpid)
+    p = lib.match_defaults()
+    res_f, nrows_f = mfpa_ctx.match(h, n, p, max_rows=128)
+    try:
+        mfpa_ctx.set_option(lib.OPT_MATCH_UNFUSED, 1)
+        res_u, nrows_u = mfpa_ctx.match(h, n, p, max_rows=128)
+    finally:
+        mfpa_ctx.set_option(lib.OPT_MATCH_UNFUSED, 0)
+    assert torch.equal(nrows_f, nrows_u)
+    assert int(nrows_f[3]) == 0 and int(nrows_f[0]) >= 1
+    _, ncand = mfpa_ctx.match_select(mfpa_ctx.match_counts(h, n), p)
+    assert int(ncand.max()) == p.search_depth   # the candidate lists are as deep as they get
+    for i in range(len(q)):
+        k = int(nrows_f[i])
+        assert torch.equal(res_f[i, :k], res_u[i, :k]), i
+    ht = O.HashTable()
+    ht.table, ht.counts, ht.hashesperid = table, counts, hpid
+    for i in (0, 5):
+        want = O.match_hashes(ht, q[i, : nq[i]])
+        _rows_equal(res_f[i, : int(nrows_f[i])].cpu().numpy(), want)
+
+
 def test_match_without_index_raises():
     lib = _lib()
     ctx = lib.Context(0)
