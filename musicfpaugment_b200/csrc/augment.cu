@@ -49,6 +49,8 @@ struct AugS {            // per-query running statistics (zeroed per call)
   float max_a, max_b;    // peak of stage-1 output / of the FULL stage-2 convolution
   float max_z, max_v;    // peak after the noise mix / after stage 6
   float lo, hi;          // clip thresholds in the gained domain
+  unsigned t_lo_key, t_hi_key;   // tail thresholds placed by clip_sample_kernel (order keys)
+  unsigned cnt_lo, cnt_hi;       // samples beyond them, counted (and listed) by mix_kernel
   float pad[2];
 };
 
@@ -371,50 +373,6 @@ __global__ void __launch_bounds__(FT, 3) fftconv_kernel(const ConvArgs a, const 
   }
 }
 
-// stage 3: z = in/peak_b + (rms/10^(snr/20)) * noise ; statistics: peak of z
-__global__ void __launch_bounds__(256) mix_kernel(const float* __restrict__ in, const float* __restrict__ noise,
-                                                  float* __restrict__ z, const AugQ* __restrict__ qs, AugS* st, int T) {
-  __shared__ float red[8];
-  const int qi = blockIdx.y, tid = threadIdx.x;
-  const AugQ q = qs[qi];
-  AugS* s = st + qi;
-  const bool ir_on = q.apply & MFPA_AUG_IR, nz_on = q.apply & MFPA_AUG_NOISE;
-  const float peak = ir_on ? s->max_b : 1.f;
-  // calculate_rms of the (already peak-normalised) stage-2 output: sqrt(mean(x^2)) (utils.py:23-29)
-  const float rms = sqrtf((float)(s->ss_b / (double)T)) / peak;
-  const float ns = nz_on ? rms / q.snr_div : 0.f;
-  float vmax = 0.f;
-  const int64_t row = (int64_t)qi * T;
-  for (int n = blockIdx.x * blockDim.x * 4 + tid * 4; n < T; n += gridDim.x * blockDim.x * 4) {
-    if (n + 3 < T && ((row + n) & 3) == 0) {
-      float4 v = *reinterpret_cast<const float4*>(in + row + n);
-      if (ir_on) { v.x /= peak; v.y /= peak; v.z /= peak; v.w /= peak; }
-      if (nz_on) {
-        const float4 b = *reinterpret_cast<const float4*>(noise + row + n);
-        v.x += ns * b.x; v.y += ns * b.y; v.z += ns * b.z; v.w += ns * b.w;
-      }
-      *reinterpret_cast<float4*>(z + row + n) = v;
-      vmax = fmaxf(fmaxf(vmax, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
-    } else {
-      for (int m = n; m < min(n + 4, T); ++m) {
-        float v = in[row + m];
-        if (ir_on) v /= peak;
-        if (nz_on) v += ns * noise[row + m];
-        z[row + m] = v;
-        vmax = fmaxf(vmax, fabsf(v));
-      }
-    }
-  }
-#pragma unroll
-  for (int o = 16; o; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-  if ((tid & 31) == 0) red[tid >> 5] = vmax;
-  __syncthreads();
-  if (tid == 0) {
-    for (int w = 1; w < 8; ++w) vmax = fmaxf(vmax, red[w]);
-    atomic_max_pos(&s->max_z, vmax);
-  }
-}
-
 // ---- stage 4: clip thresholds by exact radix select (torch.quantile, linear interpolation) ----
 __device__ __forceinline__ unsigned order_key(float v) {
   const unsigned u = __float_as_uint(v);
@@ -425,8 +383,9 @@ __device__ __forceinline__ float key_value(unsigned k) {
 }
 
 constexpr int kSelThreads = 512;
-constexpr int kSelSample = 2048;   // strided sample that places the tail thresholds
-constexpr int kSelCap = 2048;      // capacity of each tail list
+constexpr int kSelSample = 512;    // strided sample that places the tail thresholds (each sample costs a DRAM sector)
+constexpr int kSelCap = 4096;      // capacity of each tail list
+constexpr int kMixStage = 256;     // per-block staging of the tails in mix_kernel
 
 // ascending bitonic sort of a[0..n), n a power of two <= 2048, by the whole block
 __device__ __forceinline__ void bitonic_sort(unsigned* a, int n, int tid) {
@@ -513,18 +472,140 @@ __device__ void clip_select_general(const float* __restrict__ z, int T, const in
   }
 }
 
-// One block per query: the order statistics sorted[r], sorted[r+1] of torch.quantile's two ranks.
-// Clipping percentiles are small (p <= 0.01 in AugmentFP), so both ranks sit in the tails: a sorted
-// strided sample places two thresholds that provably (checked by counting) bracket the wanted ranks,
-// ONE pass over the query collects the few hundred samples beyond them into shared memory, and a
-// bitonic sort of those lists gives the exact order statistics.  When the count check fails (ranks
-// not in the tails, pathological data) the general radix select runs instead: always exact.
-__global__ void __launch_bounds__(kSelThreads) clip_select_kernel(const float* __restrict__ z_all, const AugQ* __restrict__ qs,
-                                                                  AugS* st, int T) {
+// Exact selection in a shared-memory array: k = sorted(a)[r] and its successor sorted(a)[min(r+1, n-1)],
+// by four 8-bit radix passes (256-bin histogram, digit found by one warp) and one counting pass.  All
+// threads of the block call it; `hist` is 256 words, `sh` 4 words of shared scratch.
+__device__ void smem_select(const unsigned* a, int n, int r, unsigned* hist, unsigned* sh, int tid, unsigned& k_out,
+                            unsigned& k_succ) {
+  unsigned prefix = 0, rank = (unsigned)r;
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    const unsigned himask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+    __syncthreads();
+    if (tid < 256) hist[tid] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += kSelThreads) {
+      const unsigned k = a[i];
+      if ((k & himask) == prefix) atomicAdd(&hist[(k >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (tid < 32) {   // digit d with cum(d-1) <= rank < cum(d); lane owns bins 8*lane .. 8*lane+7
+      unsigned c[8], tot = 0;
+#pragma unroll
+      for (int b = 0; b < 8; ++b) { c[b] = hist[8 * tid + b]; tot += c[b]; }
+      unsigned incl = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, o); if (tid >= o) incl += v; }
+      unsigned acc = incl - tot;
+      if (acc <= rank && rank < incl) {   // exactly one lane
+        int d = 0;
+        for (; d < 8; ++d) { if (acc + c[d] > rank) break; acc += c[d]; }
+        sh[0] = prefix | ((unsigned)(8 * tid + d) << shift);
+        sh[1] = rank - acc;
+      }
+    }
+    __syncthreads();
+    prefix = sh[0];
+    rank = sh[1];
+  }
+  __syncthreads();
+  if (tid == 0) { sh[2] = 0u; sh[3] = 0xffffffffu; }
+  __syncthreads();
+  unsigned c_le = 0, g = 0xffffffffu;
+  for (int i = tid; i < n; i += kSelThreads) {
+    const unsigned k = a[i];
+    if (k <= prefix) ++c_le; else g = min(g, k);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    c_le += __shfl_xor_sync(0xffffffffu, c_le, o);
+    g = min(g, __shfl_xor_sync(0xffffffffu, g, o));
+  }
+  if ((tid & 31) == 0) { atomicAdd(&sh[2], c_le); atomicMin(&sh[3], g); }
+  __syncthreads();
+  k_out = prefix;
+  k_succ = (sh[2] >= (unsigned)r + 2u || r + 1 > n - 1) ? prefix : sh[3];
+  __syncthreads();
+}
+
+// Clip thresholds = the order statistics sorted[r], sorted[r+1] of torch.quantile's two ranks over z.
+// Clipping percentiles are small (p <= 0.01 in AugmentFP), so both ranks sit in the tails and no pass over
+// z is spent on them:
+//   clip_sample_kernel  (before the mix) evaluates z at a strided sample, sorts it and places two tail
+//                       thresholds that bracket the wanted ranks with a > 4 sigma margin;
+//   mix_kernel          lists the few hundred z beyond the thresholds while it writes z, and counts them;
+//   clip_finish_kernel  checks the counts (the proof that the lists hold the wanted ranks), sorts the lists
+//                       and interpolates.  When the check fails (ranks not in the tails, pathological data)
+//                       the general radix select runs over z instead: always exact.
+struct ClipPlan {
+  float pos[2];
+  int r0[2], need_lo, need_hi, s_lo, s_hi;
+  bool fast;
+};
+__device__ __forceinline__ ClipPlan clip_plan(const AugQ& q, int T) {
+  ClipPlan p;
+  // torch.quantile: rank = q * (n - 1) in float32, lo = floor(rank)
+  const float q_hi = 1.0f - q.q_lo;
+  p.pos[0] = q.q_lo * (float)(T - 1);
+  p.pos[1] = q_hi * (float)(T - 1);
+  p.r0[0] = min((int)floorf(p.pos[0]), T - 1);
+  p.r0[1] = min((int)floorf(p.pos[1]), T - 1);
+  p.need_lo = min(p.r0[0] + 2, T);   // smallest elements needed: sorted[0 .. r0[0]+1]
+  p.need_hi = T - p.r0[1];           // largest elements needed: sorted[r0[1] .. T-1]
+  p.s_lo = p.s_hi = 0;
+  p.fast = T >= 4 * kSelSample;
+  if (p.fast) {
+    // sample order statistic whose full-data count exceeds `need` with > 4 sigma margin
+    const float f = (float)kSelSample / (float)T;
+    const float m_lo = p.need_lo * f, m_hi = p.need_hi * f;
+    p.s_lo = (int)ceilf(m_lo + 4.f * sqrtf(m_lo) + 6.f);
+    p.s_hi = (int)ceilf(m_hi + 4.f * sqrtf(m_hi) + 6.f);
+    p.fast = p.s_lo < kSelSample / 8 && p.s_hi < kSelSample / 8;   // expected list length stays well below kSelCap
+  }
+  return p;
+}
+
+// the scale mix_kernel applies to the noise: calculate_rms of the (peak-normalised) stage-2 output over 10^(snr/20)
+__device__ __forceinline__ float mix_noise_scale(const AugQ& q, const AugS& s, int T, float peak) {
+  const float rms = sqrtf((float)(s.ss_b / (double)T)) / peak;
+  return (q.apply & MFPA_AUG_NOISE) ? rms / q.snr_div : 0.f;
+}
+
+__global__ void __launch_bounds__(kSelThreads) clip_sample_kernel(const float* __restrict__ in, const float* __restrict__ noise,
+                                                                  const AugQ* __restrict__ qs, AugS* st, int T) {
+  __shared__ unsigned sample[kSelSample];
+  const int qi = blockIdx.x, tid = threadIdx.x;
+  const AugQ q = qs[qi];
+  AugS* s = st + qi;
+  if (!(q.apply & MFPA_AUG_CLIP)) return;
+  const ClipPlan p = clip_plan(q, T);
+  if (!p.fast) {   // nothing is listed; clip_finish_kernel takes the general path
+    if (tid == 0) { s->t_lo_key = 0u; s->t_hi_key = 0xffffffffu; }
+    return;
+  }
+  const bool ir_on = q.apply & MFPA_AUG_IR, nz_on = q.apply & MFPA_AUG_NOISE;
+  const float peak = ir_on ? s->max_b : 1.f;
+  const float ns = mix_noise_scale(q, *s, T, peak);
+  const int64_t row = (int64_t)qi * T;
+  for (int i = tid; i < kSelSample; i += kSelThreads) {
+    const int n = (int)(((int64_t)i * T) / kSelSample);
+    float v = in[row + n];
+    if (ir_on) v /= peak;
+    if (nz_on) v += ns * noise[row + n];
+    sample[i] = order_key(v);
+  }
+  __shared__ unsigned hist[256], sh[4];
+  unsigned k_lo, k_hi, unused;
+  smem_select(sample, kSelSample, p.s_lo, hist, sh, tid, k_lo, unused);
+  smem_select(sample, kSelSample, kSelSample - 1 - p.s_hi, hist, sh, tid, k_hi, unused);
+  if (tid == 0) { s->t_lo_key = k_lo; s->t_hi_key = k_hi; }
+}
+
+__global__ void __launch_bounds__(kSelThreads) clip_finish_kernel(const float* __restrict__ z_all, const unsigned* __restrict__ lists,
+                                                                  const AugQ* __restrict__ qs, AugS* st, int T) {
   __shared__ unsigned lo_list[kSelCap], hi_list[kSelCap];
-  __shared__ unsigned hist[2][256];   // sample sort reuses lo_list; hist only for the fallback
+  __shared__ unsigned hist[2][256];   // general path only
   __shared__ unsigned sh[8];
-  __shared__ unsigned cnt[2], thr_key[2];
   const int qi = blockIdx.x, tid = threadIdx.x;
   const AugQ q = qs[qi];
   AugS* s = st + qi;
@@ -532,75 +613,19 @@ __global__ void __launch_bounds__(kSelThreads) clip_select_kernel(const float* _
     if (tid == 0) { s->lo = -INFINITY; s->hi = INFINITY; }
     return;
   }
-  const float* z = z_all + (int64_t)qi * T;
-  // torch.quantile: rank = q * (n - 1) in float32, lo = floor(rank)
-  const float q_hi = 1.0f - q.q_lo;
-  const float pos[2] = {q.q_lo * (float)(T - 1), q_hi * (float)(T - 1)};
-  const int r0[2] = {min((int)floorf(pos[0]), T - 1), min((int)floorf(pos[1]), T - 1)};
-  const int need_lo = min(r0[0] + 2, T);   // smallest elements needed: sorted[0 .. r0[0]+1]
-  const int need_hi = T - r0[1];           // largest elements needed: sorted[r0[1] .. T-1]
+  const ClipPlan p = clip_plan(q, T);
+  const int c_lo = (int)s->cnt_lo, c_hi = (int)s->cnt_hi;
+  const bool fast = p.fast && c_lo >= p.need_lo && c_lo <= kSelCap && c_hi >= p.need_hi && c_hi <= kSelCap;
   unsigned kout[2], ksucc[2];
-  bool fast = T >= 4 * kSelSample;
-  int s_lo = 0, s_hi = 0;
   if (fast) {
-    // sample order statistic whose full-data count exceeds `need` with > 4 sigma margin
-    const float f = (float)kSelSample / (float)T;
-    const float m_lo = need_lo * f, m_hi = need_hi * f;
-    s_lo = (int)ceilf(m_lo + 4.f * sqrtf(m_lo) + 6.f);
-    s_hi = (int)ceilf(m_hi + 4.f * sqrtf(m_hi) + 6.f);
-    fast = s_lo < kSelSample / 8 && s_hi < kSelSample / 8;   // expected list length stays well below kSelCap
-  }
-  if (fast) {
-    unsigned* sample = lo_list;   // kSelSample == kSelCap
-    for (int i = tid; i < kSelSample; i += kSelThreads) sample[i] = order_key(z[(int)(((int64_t)i * T) / kSelSample)]);
-    if (tid < 2) cnt[tid] = 0;
-    __syncthreads();
-    bitonic_sort(sample, kSelSample, tid);
-    if (tid == 0) { thr_key[0] = sample[s_lo]; thr_key[1] = sample[kSelSample - 1 - s_hi]; }
-    __syncthreads();
-    const unsigned t_lo = thr_key[0], t_hi = thr_key[1];
-    __syncthreads();   // sample (= lo_list) is dead from here
-    // one pass: the tails are ~1 % of the samples, so a shared-memory atomic per hit is cheaper than
-    // warp compaction on every iteration (list order is irrelevant: the lists are sorted below)
-    auto visit = [&](float v) {
-      const unsigned k = order_key(v);
-      if (k <= t_lo) { const unsigned slot = atomicAdd(&cnt[0], 1u); if (slot < kSelCap) lo_list[slot] = k; }
-      if (k >= t_hi) { const unsigned slot = atomicAdd(&cnt[1], 1u); if (slot < kSelCap) hi_list[slot] = k; }
-    };
-    if ((reinterpret_cast<uintptr_t>(z) & 15) == 0) {
-      const float4* z4 = reinterpret_cast<const float4*>(z);
-      const int n4 = T >> 2;
-#pragma unroll 4
-      for (int i = tid; i < n4; i += kSelThreads) {
-        const float4 v = z4[i];
-        visit(v.x); visit(v.y); visit(v.z); visit(v.w);
-      }
-      for (int n = (n4 << 2) + tid; n < T; n += kSelThreads) visit(z[n]);
-    } else {
-      for (int n = tid; n < T; n += kSelThreads) visit(z[n]);
-    }
-    __syncthreads();
-    const int c_lo = (int)cnt[0], c_hi = (int)cnt[1];
-    fast = c_lo >= need_lo && c_lo <= kSelCap && c_hi >= need_hi && c_hi <= kSelCap;
-    if (fast) {
-      int p_lo = 32, p_hi = 32;
-      while (p_lo < c_lo) p_lo <<= 1;
-      while (p_hi < c_hi) p_hi <<= 1;
-      for (int i = c_lo + tid; i < p_lo; i += kSelThreads) lo_list[i] = 0xffffffffu;   // pad above
-      for (int i = c_hi + tid; i < p_hi; i += kSelThreads) hi_list[i] = 0u;            // pad below
-      __syncthreads();
-      bitonic_sort(lo_list, p_lo, tid);
-      bitonic_sort(hi_list, p_hi, tid);
-      kout[0] = lo_list[r0[0]];
-      ksucc[0] = r0[0] + 1 > T - 1 ? kout[0] : lo_list[r0[0] + 1];
-      const int j = T - 1 - r0[1];          // sorted[r0[1]] is the j-th largest (0-based)
-      kout[1] = hi_list[p_hi - 1 - j];
-      ksucc[1] = j >= 1 ? hi_list[p_hi - j] : kout[1];
-    }
-  }
-  if (!fast) {
-    __syncthreads();
-    clip_select_general(z, T, r0, hist, sh, kout, ksucc);
+    const unsigned* gl = lists + (size_t)qi * 2 * kSelCap;
+    for (int i = tid; i < c_lo; i += kSelThreads) lo_list[i] = gl[i];
+    for (int i = tid; i < c_hi; i += kSelThreads) hi_list[i] = gl[kSelCap + i];
+    // sorted[r0[0]] is rank r0[0] of the low list; sorted[r0[1]] is rank c_hi - (T - r0[1]) of the high list
+    smem_select(lo_list, c_lo, p.r0[0], hist[0], sh, tid, kout[0], ksucc[0]);
+    smem_select(hi_list, c_hi, c_hi - (T - p.r0[1]), hist[0], sh, tid, kout[1], ksucc[1]);
+  } else {
+    clip_select_general(z_all + (int64_t)qi * T, T, p.r0, hist, sh, kout, ksucc);
   }
   if (tid == 0) {
     // elementwise map into the gained domain, monotone so the order statistics carry over
@@ -611,11 +636,91 @@ __global__ void __launch_bounds__(kSelThreads) clip_select_kernel(const float* _
     for (int i = 0; i < 2; ++i) {
       const float va = key_value(kout[i]), vb = key_value(ksucc[i]);
       const float fa = (nz_on ? va / peak : va) * g, fb = (nz_on ? vb / peak : vb) * g;
-      const float w = pos[i] - (float)r0[i];
+      const float w = p.pos[i] - (float)p.r0[i];
       thr[i] = fa + (fb - fa) * w;
     }
     s->lo = thr[0];
     s->hi = thr[1];
+  }
+}
+
+// stage 3: z = in/peak_b + (rms/10^(snr/20)) * noise ; statistics: peak of z, and the tails of z beyond
+// the thresholds clip_sample_kernel placed (lists[query][0 = low, 1 = high][kSelCap] order keys + counts)
+__global__ void __launch_bounds__(256) mix_kernel(const float* __restrict__ in, const float* __restrict__ noise,
+                                                  float* __restrict__ z, const AugQ* __restrict__ qs, AugS* st, int T,
+                                                  unsigned* __restrict__ lists) {
+  __shared__ float red[8];
+  const int qi = blockIdx.y, tid = threadIdx.x;
+  const AugQ q = qs[qi];
+  AugS* s = st + qi;
+  const bool ir_on = q.apply & MFPA_AUG_IR, nz_on = q.apply & MFPA_AUG_NOISE;
+  const float peak = ir_on ? s->max_b : 1.f;
+  const float ns = mix_noise_scale(q, *s, T, peak);
+  const bool clip_on = q.apply & MFPA_AUG_CLIP;
+  const unsigned t_lo = clip_on ? s->t_lo_key : 0u, t_hi = clip_on ? s->t_hi_key : 0xffffffffu;
+  unsigned* ql = lists + (size_t)qi * 2 * kSelCap;
+  // tails are staged per block (shared-memory atomics) and appended to the query's lists with one global
+  // atomic per block and side; a block that outgrows its stage appends the excess directly
+  __shared__ unsigned stage[2][kMixStage];
+  __shared__ unsigned stage_n[2], stage_base[2];
+  if (tid < 2) stage_n[tid] = 0;
+  __syncthreads();
+  auto tail_side = [&](unsigned k, int side) {
+    const unsigned slot = atomicAdd(&stage_n[side], 1u);
+    if (slot < kMixStage) { stage[side][slot] = k; return; }
+    const unsigned g = atomicAdd(side ? &s->cnt_hi : &s->cnt_lo, 1u);
+    if (g < kSelCap) ql[side * kSelCap + g] = k;
+  };
+  auto tail = [&](float v) {
+    const unsigned k = order_key(v);
+    if (k <= t_lo || k >= t_hi) {   // ~1 % of the samples
+      if (!clip_on) return;
+      if (k <= t_lo) tail_side(k, 0);
+      if (k >= t_hi) tail_side(k, 1);
+    }
+  };
+  float vmax = 0.f;
+  const int64_t row = (int64_t)qi * T;
+  for (int n = blockIdx.x * blockDim.x * 4 + tid * 4; n < T; n += gridDim.x * blockDim.x * 4) {
+    if (n + 3 < T && ((row + n) & 3) == 0) {
+      float4 v = *reinterpret_cast<const float4*>(in + row + n);
+      if (ir_on) { v.x /= peak; v.y /= peak; v.z /= peak; v.w /= peak; }
+      if (nz_on) {
+        const float4 b = *reinterpret_cast<const float4*>(noise + row + n);
+        v.x += ns * b.x; v.y += ns * b.y; v.z += ns * b.z; v.w += ns * b.w;
+      }
+      *reinterpret_cast<float4*>(z + row + n) = v;
+      vmax = fmaxf(fmaxf(vmax, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+      tail(v.x); tail(v.y); tail(v.z); tail(v.w);
+    } else {
+      for (int m = n; m < min(n + 4, T); ++m) {
+        float v = in[row + m];
+        if (ir_on) v /= peak;
+        if (nz_on) v += ns * noise[row + m];
+        z[row + m] = v;
+        vmax = fmaxf(vmax, fabsf(v));
+        tail(v);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+  if ((tid & 31) == 0) red[tid >> 5] = vmax;
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < 8; ++w) vmax = fmaxf(vmax, red[w]);
+    atomic_max_pos(&s->max_z, vmax);
+  }
+  if (tid < 2) {
+    const unsigned n = min(stage_n[tid], (unsigned)kMixStage);
+    stage_base[tid] = n ? atomicAdd(tid ? &s->cnt_hi : &s->cnt_lo, n) : 0u;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int side = 0; side < 2; ++side) {
+    const unsigned n = min(stage_n[side], (unsigned)kMixStage), base = stage_base[side];
+    for (unsigned i = tid; i < n; i += 256)
+      if (base + i < kSelCap) ql[side * kSelCap + base + i] = stage[side][i];
   }
 }
 
@@ -853,12 +958,14 @@ int launch_augment(mfpa_ctx* ctx, const float* x, int B, int T, int64_t x_stride
   // stage 3: B -> A (z)
   {
     const unsigned gx = (unsigned)((T + 4095) / 4096);
-    mix_kernel<<<dim3(gx, B), 256, 0, st>>>(bufB, noise, bufA, dq, ds, T);
+    if (ctx->aug_lists.reserve(sizeof(unsigned) * 2 * kSelCap * (size_t)B)) return MFPA_ENOMEM;
+    unsigned* lists = (unsigned*)ctx->aug_lists.ptr;
+    clip_sample_kernel<<<B, kSelThreads, 0, st>>>(bufB, noise, dq, ds, T);
+    mix_kernel<<<dim3(gx, B), 256, 0, st>>>(bufB, noise, bufA, dq, ds, T, lists);
+    // stage 4: clip thresholds from the listed tails of z
+    clip_finish_kernel<<<B, kSelThreads, 0, st>>>(bufA, lists, dq, ds, T);
     MFPA_CUDA(cudaGetLastError());
   }
-  // stage 4: clip thresholds from z
-  clip_select_kernel<<<B, kSelThreads, 0, st>>>(bufA, dq, ds, T);
-  MFPA_CUDA(cudaGetLastError());
   // stage 5: A -> B (u)
   {
     const unsigned gx = (unsigned)((T + 4095) / 4096);

@@ -134,7 +134,7 @@ void mfpa_destroy(mfpa_ctx* ctx) {
   cudaDeviceSynchronize();
   Scratch* all[] = {&ctx->mag, &ctx->qmax, &ctx->rec, &ctx->fwd, &ctx->hashes, &ctx->nh, &ctx->misc, &ctx->spec64,
                     &ctx->xin, &ctx->out_h, &ctx->out_n, &ctx->aug_a, &ctx->aug_b, &ctx->aug_c, &ctx->aug_d,
-                    &ctx->aug_small, &ctx->match_a, &ctx->match_b, &ctx->match_c};
+                    &ctx->aug_small, &ctx->aug_lists, &ctx->match_a, &ctx->match_b, &ctx->match_c};
   for (Scratch* s : all) s->release();
   for (int b = 0; b < 2; ++b) {
     ctx->h_x[b].release(); ctx->h_x16[b].release(); ctx->h_rows[b].release(); ctx->h_csr[b].release(); ctx->h_n[b].release(); ctx->h_off[b].release();
@@ -480,6 +480,10 @@ int mfpa_index_load(mfpa_ctx* ctx, const uint32_t* table_host, const int32_t* co
   MFPA_CUDA(cudaMemcpy(ctx->index_hashesperid, hashesperid_host, sizeof(uint32_t) * (size_t)n_tracks, cudaMemcpyHostToDevice));
   ctx->index_hash_lo = hash_lo; ctx->index_hash_hi = hash_lo + n_buckets; ctx->index_depth = depth;
   ctx->index_ntracks = n_tracks; ctx->index_maxtimebits = maxtimebits; ctx->index_hashmask = (1 << hashbits) - 1;
+  uint32_t hp_min = 0xffffffffu;
+  for (int i = 0; i < n_tracks; ++i)
+    if (hashesperid_host[i] != 0 && hashesperid_host[i] < hp_min) hp_min = hashesperid_host[i];
+  ctx->index_hp_min = hp_min == 0xffffffffu ? 1u : hp_min;
   return MFPA_OK;
 }
 

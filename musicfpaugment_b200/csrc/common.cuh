@@ -69,7 +69,7 @@ struct mfpa_ctx {
   float* win_dejavu_dev = nullptr;  // [512] np.hanning(512) x 1/2 (mlab.window_hanning, afp/dejavu/fingerprint.py:64)
   mfpa::Scratch mag, qmax, rec, fwd, hashes, nh, misc, spec64, xin, out_h, out_n;
   // augmentation / matching state is appended by their translation units
-  mfpa::Scratch aug_a, aug_b, aug_c, aug_d, aug_small;
+  mfpa::Scratch aug_a, aug_b, aug_c, aug_d, aug_small, aug_lists;
   float2* aug_tw_dev = nullptr;     // two-level twiddle tables of the 16384-point FFT (augment.cu)
   void* aug_pinned = nullptr;
   size_t aug_pinned_bytes = 0;
@@ -77,6 +77,7 @@ struct mfpa_ctx {
   uint32_t* index_table = nullptr;
   int32_t* index_counts = nullptr;
   uint32_t* index_hashesperid = nullptr;
+  uint32_t index_hp_min = 1;        // smallest non-zero hashesperid (lets the matcher skip tracks by raw count alone)
   int index_hash_lo = 0, index_hash_hi = 0, index_depth = 0, index_ntracks = 0, index_maxtimebits = 14;
   int index_hashmask = (1 << 20) - 1;
   mfpa::Scratch match_a, match_b, match_c;

@@ -30,6 +30,7 @@ struct IndexView {
   const int32_t* counts;
   const uint32_t* hashesperid;
   int hash_lo, n_buckets, depth, maxtimebits, n_tracks, hashmask;
+  uint32_t hp_min;
 };
 
 // ---- counts ------------------------------------------------------------------------------
@@ -221,6 +222,7 @@ match_fused_kernel(const IndexView ix, const int32_t* __restrict__ hashes, const
   unsigned* hist = fused_smem;
   RowCache* rc = reinterpret_cast<RowCache*>(fused_smem + ((words + 3) & ~3));
   __shared__ int s_int[16];
+  __shared__ float s_flt[16];
   __shared__ Cand s_best[16];
   __shared__ Cand s_prev;
   __shared__ int s_n;
@@ -231,55 +233,135 @@ match_fused_kernel(const IndexView ix, const int32_t* __restrict__ hashes, const
   if (tid == 0) s_n = 0;
   fused_sweep<false>(ix, rows, n, rc, hist, nullptr, 0, nullptr, tid);
 
-  // select (_best_count_ids, audfprint_match.py:102-129) on the shared-memory histogram
   auto count_of = [&](int i) -> int { return (int)((hist[i >> 1] >> ((i & 1) * 16)) & 0xffffu); };
+  // select (_best_count_ids, audfprint_match.py:102-129) on the shared-memory histogram.
+  // depth = min(#{raw > threshcount}, search_depth) tracks are wanted, ranked by raw / hashesperid over ALL
+  // tracks.  Every track with raw > threshcount has a quotient >= m = min of theirs, and there are >= depth of
+  // them, so the wanted tracks all have quotient >= m: one cheap pass finds the count and m, a second lists
+  // the contenders {quotient >= m} (tracks whose raw count is below m * min(hashesperid) are skipped without
+  // touching hashesperid), and the exact ranking runs over that short list.  float32 quotients carry a
+  // relative error < 1e-6; the list is cut at m * (1 - 1e-5) and ranked with exact integer cross products.
+  int* contenders = reinterpret_cast<int*>(rc);                       // the row cache is idle here
+  constexpr int kContCap = (int)(sizeof(RowCache) / sizeof(int));
   int gt = 0;
+  float fmin = INFINITY;
   for (int w = tid; w < words; w += kFusedThreads) {
     const unsigned h2 = hist[w];
-    if (h2) gt += ((int)(h2 & 0xffffu) > threshcount) + ((int)(h2 >> 16) > threshcount);
+    if (!h2) continue;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int raw = (int)((h2 >> (16 * e)) & 0xffffu);
+      if (raw > threshcount) {
+        ++gt;
+        fmin = fminf(fmin, __fdividef((float)raw, (float)__ldg(ix.hashesperid + 2 * w + e)));
+      }
+    }
   }
 #pragma unroll
-  for (int o = 16; o; o >>= 1) gt += __shfl_xor_sync(kFull, gt, o);
-  if (lane == 0) s_int[warp] = gt;
+  for (int o = 16; o; o >>= 1) {
+    gt += __shfl_xor_sync(kFull, gt, o);
+    fmin = fminf(fmin, __shfl_xor_sync(kFull, fmin, o));
+  }
+  if (lane == 0) { s_int[warp] = gt; s_flt[warp] = fmin; }
+  if (tid == 0) s_n = 0;
   __syncthreads();
   gt = 0;
-  for (int w = 0; w < 16; ++w) gt += s_int[w];
+  for (int w = 0; w < 16; ++w) { gt += s_int[w]; fmin = fminf(fmin, s_flt[w]); }
   const int depth = min(gt, search_depth);
-  if (tid == 0) { ncand[q] = depth; s_prev = Cand{1, 0, 0x7fffffff}; }  // +infinity sentinel (hp = 0)
-  __syncthreads();
-  for (int k = 0; k < depth; ++k) {
-    const Cand prev = s_prev;
-    Cand best{-1, 1, -1};
+  const float cut = fmin * 0.99999f;
+  const int raw_min = max(1, (int)floorf(cut * (float)ix.hp_min * 0.99999f));   // raw < raw_min => quotient < cut
+  if (tid == 0) ncand[q] = depth;
+  bool listed = depth > 0;
+  if (listed) {
     for (int w = tid; w < words; w += kFusedThreads) {
       const unsigned h2 = hist[w];
       if (!h2) continue;
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int raw = (int)((h2 >> (16 * e)) & 0xffffu), i = 2 * w + e;
-        if (raw <= 0 || i >= ix.n_tracks) continue;
-        const Cand x{raw, (long long)ix.hashesperid[i], i};
+        if (raw < raw_min) continue;
+        if (__fdividef((float)raw, (float)__ldg(ix.hashesperid + i)) < cut) continue;
+        const int slot = atomicAdd(&s_n, 1);
+        if (slot < kContCap) contenders[slot] = i;
+      }
+    }
+    __syncthreads();
+    listed = s_n <= kContCap;
+  }
+  if (depth > 0 && listed) {
+    const int nc_list = s_n;
+    __syncthreads();
+    if (tid == 0) { s_prev = Cand{1, 0, 0x7fffffff}; s_n = 0; }  // +infinity sentinel (hp = 0)
+    __syncthreads();
+    for (int k = 0; k < depth; ++k) {
+      const Cand prev = s_prev;
+      Cand best{-1, 1, -1};
+      for (int c = tid; c < nc_list; c += kFusedThreads) {
+        const int i = contenders[c];
+        const Cand x{(long long)count_of(i), (long long)ix.hashesperid[i], i};
         const bool after_prev = prev.hp == 0 || before(prev, x);
         if (after_prev && (best.id < 0 || before(x, best))) best = x;
       }
-    }
 #pragma unroll
-    for (int o = 16; o; o >>= 1) {
-      Cand y;
-      y.raw = __shfl_xor_sync(kFull, best.raw, o); y.hp = __shfl_xor_sync(kFull, best.hp, o); y.id = __shfl_xor_sync(kFull, best.id, o);
-      if (y.id >= 0 && (best.id < 0 || before(y, best))) best = y;
+      for (int o = 16; o; o >>= 1) {
+        Cand y;
+        y.raw = __shfl_xor_sync(kFull, best.raw, o); y.hp = __shfl_xor_sync(kFull, best.hp, o); y.id = __shfl_xor_sync(kFull, best.id, o);
+        if (y.id >= 0 && (best.id < 0 || before(y, best))) best = y;
+      }
+      if (lane == 0) s_best[warp] = best;
+      __syncthreads();
+      if (tid == 0) {
+        Cand b = s_best[0];
+        for (int w = 1; w < 16; ++w) if (s_best[w].id >= 0 && (b.id < 0 || before(s_best[w], b))) b = s_best[w];
+        s_prev = b;
+        cand[((int64_t)q * search_depth + k) * 2] = b.id;
+        cand[((int64_t)q * search_depth + k) * 2 + 1] = (int)b.raw;
+      }
+      __syncthreads();
     }
-    if (lane == 0) s_best[warp] = best;
+  } else if (depth > 0) {
+    // more contenders than the list holds: rank by repeated scans of the whole histogram
     __syncthreads();
-    if (tid == 0) {
-      Cand b = s_best[0];
-      for (int w = 1; w < 16; ++w) if (s_best[w].id >= 0 && (b.id < 0 || before(s_best[w], b))) b = s_best[w];
-      s_prev = b;
-      cand[((int64_t)q * search_depth + k) * 2] = b.id;
-      cand[((int64_t)q * search_depth + k) * 2 + 1] = (int)b.raw;
+    if (tid == 0) { s_prev = Cand{1, 0, 0x7fffffff}; s_n = 0; }
+    __syncthreads();
+    for (int k = 0; k < depth; ++k) {
+      const Cand prev = s_prev;
+      Cand best{-1, 1, -1};
+      const float f_hi = prev.hp == 0 ? INFINITY : __fdividef((float)prev.raw, (float)prev.hp) * 1.00001f;
+      float f_lo = cut;
+      for (int w = tid; w < words; w += kFusedThreads) {
+        const unsigned h2 = hist[w];
+        if (!h2) continue;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int raw = (int)((h2 >> (16 * e)) & 0xffffu), i = 2 * w + e;
+          if (raw < raw_min || i >= ix.n_tracks) continue;
+          const unsigned hp = __ldg(ix.hashesperid + i);
+          const float fx = __fdividef((float)raw, (float)hp);
+          if (fx > f_hi || fx < f_lo) continue;
+          const Cand x{raw, (long long)hp, i};
+          const bool after_prev = prev.hp == 0 || before(prev, x);
+          if (after_prev && (best.id < 0 || before(x, best))) { best = x; f_lo = fmaxf(cut, fx * 0.99999f); }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o; o >>= 1) {
+        Cand y;
+        y.raw = __shfl_xor_sync(kFull, best.raw, o); y.hp = __shfl_xor_sync(kFull, best.hp, o); y.id = __shfl_xor_sync(kFull, best.id, o);
+        if (y.id >= 0 && (best.id < 0 || before(y, best))) best = y;
+      }
+      if (lane == 0) s_best[warp] = best;
+      __syncthreads();
+      if (tid == 0) {
+        Cand b = s_best[0];
+        for (int w = 1; w < 16; ++w) if (s_best[w].id >= 0 && (b.id < 0 || before(s_best[w], b))) b = s_best[w];
+        s_prev = b;
+        cand[((int64_t)q * search_depth + k) * 2] = b.id;
+        cand[((int64_t)q * search_depth + k) * 2 + 1] = (int)b.raw;
+      }
+      __syncthreads();
     }
-    __syncthreads();
   }
-  (void)count_of;
   if (depth == 0) {
     if (tid == 0) nlist[q] = 0;
     return;
@@ -512,6 +594,7 @@ IndexView view(const mfpa_ctx* ctx) {
   v.table = ctx->index_table; v.counts = ctx->index_counts; v.hashesperid = ctx->index_hashesperid;
   v.hash_lo = ctx->index_hash_lo; v.n_buckets = ctx->index_hash_hi - ctx->index_hash_lo; v.depth = ctx->index_depth;
   v.maxtimebits = ctx->index_maxtimebits; v.n_tracks = ctx->index_ntracks; v.hashmask = ctx->index_hashmask;
+  v.hp_min = ctx->index_hp_min;
   return v;
 }
 
