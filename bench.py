@@ -33,6 +33,16 @@ sys.path.insert(0, ROOT)
 # NCCL writes its version banner to stdout when NCCL_DEBUG is set in the environment; stdout carries
 # exactly one JSON line, so anything NCCL has to say goes to stderr.
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# ... and because the torch-bundled NCCL still prints its banner with a bare printf on some boxes, file
+# descriptor 1 itself points at stderr for the whole run; the JSON line is written to the saved descriptor.
+_JSON_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    sys.stdout.flush()
+    os.write(_JSON_FD, (json.dumps(line) + "\n").encode())
+
 
 METRIC = "8s_query_fingerprints_per_sec"
 UNIT = "queries/s"
@@ -44,9 +54,9 @@ BYTES_PEAKS = 257 * N_FRAMES * 4 + 256 * N_FRAMES  # S3: magnitudes in, peak mas
 BYTES_FUSED = 256_000                              # S2-S4 fused: waveform in (+ 8 B per hash out)
 BYTES_CHAIN = 544_000                              # S1-S4 fused: x + noise + IR in (+ 8 B per hash out)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at 10 000 queries, shifts=1, from the
-# `ncu --set full` capture summarised in profiles/r01f_summary.txt (scaled by items/10000 for other sizes)
-NCU_TRAFFIC_10K = {"stft_mag": 2.730195e9 + 2.606733e9, "audfprint_peaks": 2.962223e9 + 0.020727e9,
-                   "landmark_hashes(+merge)": 0.020237e9 + 0.000085e9}
+# `ncu --set full` capture summarised in profiles/r01i_summary.txt (scaled by items/10000 for other sizes)
+NCU_TRAFFIC_10K = {"stft_mag": 2.729413e9 + 2.611101e9, "audfprint_peaks": 2.963264e9 + 0.020452e9,
+                   "landmark_hashes(+merge)": 0.020241e9 + 0.000100e9}
 
 
 def _peaks():
@@ -153,7 +163,7 @@ def run_reference(args, rank: int, world: int):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_name(args):
@@ -292,7 +302,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "stage_ms": stage_ms,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm, "unit": "GB/s",
                          "frac": achieved / hbm, "traffic": NCU_TRAFFIC_10K[dom] * items / 10000,
-                         "traffic_source": "profiles/r01f_summary.txt (ncu --set full, dram read+write)", "peak_source": how,
+                         "traffic_source": "profiles/r01i_summary.txt (ncu --set full, dram read+write)", "peak_source": how,
                          "algorithmic_bytes_per_launch": dom_bytes,
                          "whole_path_frac": (BYTES_FUSED * B + 8 * tot_hashes) / (ms_step * 1e-3) / 1e9 / hbm},
             "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
@@ -367,7 +377,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                                               "sample": "3 forwards of the fp32 torch oracle UNet, 1x1x257x251"}
     if rank == 0:
         line.update(extras)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     ctx.close()

@@ -96,27 +96,97 @@ __device__ __forceinline__ bool before(const Cand& a, const Cand& b) {  // a ran
   return l > r || (l == r && a.id > b.id);
 }
 
+// Exact ranking of a short list of contender tracks (shared memory): the first `depth` by `before`, written
+// as (id, raw) pairs to cand_q.  All 512 threads of the block call it.
+template <typename CountOf>
+__device__ __forceinline__ void rank_list(const int* list, int n_list, int depth, CountOf count_of,
+                                          const uint32_t* __restrict__ hpid, int32_t* __restrict__ cand_q,
+                                          Cand* s_best, Cand* s_prev, int tid) {
+  const int lane = tid & 31, warp = tid >> 5;
+  __syncthreads();
+  if (tid == 0) *s_prev = Cand{1, 0, 0x7fffffff};  // +infinity sentinel (hp = 0)
+  __syncthreads();
+  for (int k = 0; k < depth; ++k) {
+    const Cand prev = *s_prev;
+    Cand best{-1, 1, -1};
+    for (int c = tid; c < n_list; c += 512) {
+      const int i = list[c];
+      const Cand x{(long long)count_of(i), (long long)hpid[i], i};
+      const bool after_prev = prev.hp == 0 || before(prev, x);
+      if (after_prev && (best.id < 0 || before(x, best))) best = x;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      Cand y;
+      y.raw = __shfl_xor_sync(kFull, best.raw, o); y.hp = __shfl_xor_sync(kFull, best.hp, o); y.id = __shfl_xor_sync(kFull, best.id, o);
+      if (y.id >= 0 && (best.id < 0 || before(y, best))) best = y;
+    }
+    if (lane == 0) s_best[warp] = best;
+    __syncthreads();
+    if (tid == 0) {
+      Cand b = s_best[0];
+      for (int w = 1; w < 16; ++w) if (s_best[w].id >= 0 && (b.id < 0 || before(s_best[w], b))) b = s_best[w];
+      *s_prev = b;
+      cand_q[2 * k] = b.id;
+      cand_q[2 * k + 1] = (int)b.raw;
+    }
+    __syncthreads();
+  }
+}
+
 __global__ void __launch_bounds__(512) match_select_kernel(const int32_t* __restrict__ counts, const uint32_t* __restrict__ hpid,
                                                            int n_tracks, int threshcount, int search_depth,
-                                                           int32_t* __restrict__ cand, int32_t* __restrict__ ncand, int packed) {
+                                                           int32_t* __restrict__ cand, int32_t* __restrict__ ncand, int packed,
+                                                           uint32_t hp_min) {
+  constexpr int kListCap = 4096;
   __shared__ int s_int[16];
+  __shared__ float s_flt[16];
   __shared__ Cand s_best[16];
   __shared__ Cand s_prev;
+  __shared__ int s_list[kListCap];
+  __shared__ int s_n;
   const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int32_t* c = counts + (int64_t)q * (packed ? (n_tracks + 1) >> 1 : n_tracks);
   auto count_of = [&](int i) -> int {
     return packed ? (int)((reinterpret_cast<const unsigned*>(c)[i >> 1] >> ((i & 1) * 16)) & 0xffffu) : c[i];
   };
+  // the tracks wanted all have quotient raw / hashesperid >= m = min over the tracks with raw > threshcount
+  // (see match_fused_kernel): list those contenders in one more pass over the row and rank the short list
   int gt = 0;
-  for (int i = tid; i < n_tracks; i += 512) gt += count_of(i) > threshcount;
+  float fmin = INFINITY;
+  for (int i = tid; i < n_tracks; i += 512) {
+    const int raw = count_of(i);
+    if (raw > threshcount) { ++gt; fmin = fminf(fmin, __fdividef((float)raw, (float)__ldg(hpid + i))); }
+  }
 #pragma unroll
-  for (int o = 16; o; o >>= 1) gt += __shfl_xor_sync(kFull, gt, o);
-  if (lane == 0) s_int[warp] = gt;
+  for (int o = 16; o; o >>= 1) {
+    gt += __shfl_xor_sync(kFull, gt, o);
+    fmin = fminf(fmin, __shfl_xor_sync(kFull, fmin, o));
+  }
+  if (lane == 0) { s_int[warp] = gt; s_flt[warp] = fmin; }
+  if (tid == 0) s_n = 0;
   __syncthreads();
   gt = 0;
-  for (int w = 0; w < 16; ++w) gt += s_int[w];
+  for (int w = 0; w < 16; ++w) { gt += s_int[w]; fmin = fminf(fmin, s_flt[w]); }
   const int depth = min(gt, search_depth);
-  if (tid == 0) { ncand[q] = depth; s_prev = Cand{1, 0, 0x7fffffff}; }  // +infinity sentinel (hp = 0)
+  if (tid == 0) ncand[q] = depth;
+  if (depth == 0) return;
+  const float cut = fmin * 0.99999f;
+  const int raw_min = max(1, (int)floorf(cut * (float)hp_min * 0.99999f));   // raw < raw_min => quotient < cut
+  for (int i = tid; i < n_tracks; i += 512) {
+    const int raw = count_of(i);
+    if (raw < raw_min) continue;
+    if (__fdividef((float)raw, (float)__ldg(hpid + i)) < cut) continue;
+    const int slot = atomicAdd(&s_n, 1);
+    if (slot < kListCap) s_list[slot] = i;
+  }
+  __syncthreads();
+  if (s_n <= kListCap) {
+    rank_list(s_list, s_n, depth, count_of, hpid, cand + (int64_t)q * search_depth * 2, s_best, &s_prev, tid);
+    return;
+  }
+  // more contenders than the list holds: rank by repeated scans of the whole row
+  if (tid == 0) s_prev = Cand{1, 0, 0x7fffffff};  // +infinity sentinel (hp = 0)
   __syncthreads();
   for (int k = 0; k < depth; ++k) {
     const Cand prev = s_prev;
@@ -290,35 +360,9 @@ match_fused_kernel(const IndexView ix, const int32_t* __restrict__ hashes, const
   }
   if (depth > 0 && listed) {
     const int nc_list = s_n;
+    rank_list(contenders, nc_list, depth, count_of, ix.hashesperid, cand + (int64_t)q * search_depth * 2, s_best, &s_prev, tid);
+    if (tid == 0) s_n = 0;
     __syncthreads();
-    if (tid == 0) { s_prev = Cand{1, 0, 0x7fffffff}; s_n = 0; }  // +infinity sentinel (hp = 0)
-    __syncthreads();
-    for (int k = 0; k < depth; ++k) {
-      const Cand prev = s_prev;
-      Cand best{-1, 1, -1};
-      for (int c = tid; c < nc_list; c += kFusedThreads) {
-        const int i = contenders[c];
-        const Cand x{(long long)count_of(i), (long long)ix.hashesperid[i], i};
-        const bool after_prev = prev.hp == 0 || before(prev, x);
-        if (after_prev && (best.id < 0 || before(x, best))) best = x;
-      }
-#pragma unroll
-      for (int o = 16; o; o >>= 1) {
-        Cand y;
-        y.raw = __shfl_xor_sync(kFull, best.raw, o); y.hp = __shfl_xor_sync(kFull, best.hp, o); y.id = __shfl_xor_sync(kFull, best.id, o);
-        if (y.id >= 0 && (best.id < 0 || before(y, best))) best = y;
-      }
-      if (lane == 0) s_best[warp] = best;
-      __syncthreads();
-      if (tid == 0) {
-        Cand b = s_best[0];
-        for (int w = 1; w < 16; ++w) if (s_best[w].id >= 0 && (b.id < 0 || before(s_best[w], b))) b = s_best[w];
-        s_prev = b;
-        cand[((int64_t)q * search_depth + k) * 2] = b.id;
-        cand[((int64_t)q * search_depth + k) * 2 + 1] = (int)b.raw;
-      }
-      __syncthreads();
-    }
   } else if (depth > 0) {
     // more contenders than the list holds: rank by repeated scans of the whole histogram
     __syncthreads();
@@ -634,7 +678,7 @@ int launch_match_fused(mfpa_ctx* ctx, const int32_t* hashes, const int32_t* nh, 
 int launch_match_select(mfpa_ctx* ctx, const int32_t* counts, int B, int threshcount, int search_depth, int32_t* cand,
                         int32_t* ncand, cudaStream_t st) {
   match_select_kernel<<<B, 512, 0, st>>>(counts, ctx->index_hashesperid, ctx->index_ntracks, threshcount, search_depth,
-                                         cand, ncand, ctx->opt_match_packed);
+                                         cand, ncand, ctx->opt_match_packed, ctx->index_hp_min);
   MFPA_CUDA(cudaGetLastError());
   return MFPA_OK;
 }

@@ -12,8 +12,8 @@ if [ "${2:-}" != "skip-tests" ]; then
 fi
 python bench.py --steps 10 --warmup 3 > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err
 OURS='stft_mag_kernel|peaks_kernel|peaks_fast_kernel|landmark_kernel|merge_shifts_kernel|offsets_scan_kernel|compact_rows_kernel'
-AUG='fftconv_kernel|mix_kernel|clip_select_kernel|clip_lpf_kernel|norm_kernel|filter_spectrum_kernel'
-MAT='match_counts|match_select_kernel|match_collect_kernel|match_align_kernel'
+AUG='fftconv_kernel|mix_kernel|clip_sample_kernel|clip_finish_kernel|clip_lpf_kernel|norm_kernel|filter_spectrum_kernel'
+MAT='match_fused_kernel|match_counts|match_select_kernel|match_collect_kernel|match_align_kernel'
 UNET='conv_gemm_kernel|conv_halo_kernel|conv_in_kernel|maxpool_kernel'
 finish() {  # $1 = report stem, $2 = launch list
   python profiles/summarize.py $OUT/$1.ncu-rep $2 $OUT/$1_summary.txt > /dev/null 2>&1
@@ -27,13 +27,14 @@ ncu --set full --clock-control none --import-source on -k "regex:stft_mag_kernel
     -o $OUT/prof_$TAG -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline --also none > $OUT/ncu_full_$TAG.log 2>&1
 finish prof_$TAG $OUT/launches_$TAG.csv
 # ... the augmentation kernels (second call of the full-chain leg) ...
-ncu --set full --clock-control none --import-source on -k "regex:$AUG" -s 9 -c 9 \
+ncu --set full --clock-control none --import-source on -k "regex:$AUG" -s 10 -c 10 \
     -o $OUT/prof_aug_$TAG -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline --also chain > $OUT/ncu_full_aug_$TAG.log 2>&1
 finish prof_aug_$TAG $OUT/launches_$TAG.csv
 # ... the matching kernels ...
-ncu --set full --clock-control none --import-source on -k "regex:$MAT" -s 4 -c 4 \
+ncu --set full --clock-control none --import-source on -k "regex:$MAT" -s 6 -c 2 \
     -o $OUT/prof_match_$TAG -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline --also match > $OUT/ncu_full_match_$TAG.log 2>&1
 finish prof_match_$TAG $OUT/launches_$TAG.csv
+if [ "${SKIP_UNET:-0}" = "1" ]; then ls -la $OUT > $OUT/ls_$TAG.txt; exit 0; fi
 # ... and the UNet denoiser: per-layer launch list (profiles/unet_layers.py turns it into TFLOP/s per layer)
 # plus a full capture of the tcgen05 GEMM launches of one forward pass
 ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:$UNET" -c 60 --csv \

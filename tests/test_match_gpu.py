@@ -144,16 +144,19 @@ def test_packed_counts_option(mfpa_ctx):
         mfpa_ctx.index_load(table, counts, hpid)
 
 
-def test_fused_match_equals_four_step_path(mfpa_ctx):
+@pytest.mark.parametrize("n_tracks,per_track,n_hashes", [(301, 3000, 2000), (12000, 1500, 4000)])
+def test_fused_match_equals_four_step_path(mfpa_ctx, n_tracks, per_track, n_hashes):
     """mfpa_match's one-kernel counts+select+collect (histogram kept in shared memory) gives the rows of
     the four-step path: long queries (more rows than the kernel's row cache), a small index where many
-    tracks pass the count threshold (deep candidate lists), an odd track count, empty queries."""
+    tracks pass the count threshold (deep candidate lists), an odd track count, empty queries; the second
+    case has more contenders (thousands of tracks above the count threshold) than either kernel's
+    shared-memory list holds, so both rank by repeated scans."""
     from musicfpaugment_b200 import lib, synth
 
-    table, counts, hpid, th = synth.hash_index(301, 3000, seed=21)   # 301 tracks: every track collects hits
-    q, nq, _ = synth.planted_queries(th, 12, n_hashes=2000, frac=0.2, seed=22)
+    table, counts, hpid, th = synth.hash_index(n_tracks, per_track, seed=21)
+    q, nq, _ = synth.planted_queries(th, 12 if n_tracks < 1000 else 5, n_hashes=n_hashes, frac=0.2, seed=22)
     nq[3] = 0
-    nq[7] = 1
+    nq[-1] = 1
     h, n = torch.from_numpy(q).cuda(), torch.from_numpy(nq).cuda()
     mfpa_ctx.index_load(table, counts, hpid)
     p = lib.match_defaults()
@@ -172,7 +175,7 @@ def test_fused_match_equals_four_step_path(mfpa_ctx):
         assert torch.equal(res_f[i, :k], res_u[i, :k]), i
     ht = O.HashTable()
     ht.table, ht.counts, ht.hashesperid = table, counts, hpid
-    for i in (0, 5):
+    for i in (0, 2):
         want = O.match_hashes(ht, q[i, : nq[i]])
         _rows_equal(res_f[i, : int(nrows_f[i])].cpu().numpy(), want)
 
