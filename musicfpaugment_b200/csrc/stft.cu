@@ -111,20 +111,26 @@ __device__ __forceinline__ TileInfo tile_info(unsigned tile, unsigned tiles, con
   return t;
 }
 
-// Stage samples [256*(f0-1), 256*(f0+kTile)) of one item into xs.  Interior tiles whose
-// source is 16-byte aligned go through cp.async (overlapping the previous tile's FFTs);
-// tiles touching either end of the signal apply numpy's reflect padding with plain loads.
+// Stage samples [256*(f0-1), 256*(f0+kTile)) of one item into xs.  Every 16-byte chunk that lies inside
+// the signal goes through cp.async (overlapping the previous tile's FFTs); only the chunks that reach past
+// either end of the signal (numpy's reflect padding: the first and last tile of an item) use plain loads,
+// and only as far as the tile's existing frames read.
 __device__ __forceinline__ void stage_tile(const TileInfo& t, float* xs, int tid) {
   if (t.f0 >= t.n_frames) return;
   const int s0 = kHop * (t.f0 - 1);
-  const bool interior = s0 >= 0 && s0 + (kTile + 1) * kHop <= t.len && ((((uintptr_t)(t.xq + s0)) & 15) == 0);
-  if (interior) {
-    for (int i = tid * 4; i < (kTile + 1) * kHop; i += kWarps * 32 * 4) cp_async16(xs + i, t.xq + s0 + i);
-  } else {
-    for (int i = tid; i < (kTile + 1) * kHop; i += kWarps * 32) {
-      int s = s0 + i;
-      if (s < 0 || s >= t.len) s = reflect_index(s, t.len);
-      xs[i] = __ldg(t.xq + s);
+  const int need = (min(t.n_frames - t.f0, kTile) + 1) * kHop;
+  const bool aligned = (((uintptr_t)(t.xq + s0)) & 15) == 0;   // s0 is a multiple of 256
+  for (int i = tid * 4; i < need; i += kWarps * 32 * 4) {
+    const int s = s0 + i;
+    if (aligned && s >= 0 && s + 4 <= t.len) {
+      cp_async16(xs + i, t.xq + s);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        int ss = s + e;
+        if (ss < 0 || ss >= t.len) ss = reflect_index(ss, t.len);
+        xs[i + e] = __ldg(t.xq + ss);
+      }
     }
   }
 }
