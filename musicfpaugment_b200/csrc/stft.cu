@@ -165,11 +165,13 @@ stft_mag_kernel(const float* __restrict__ x, int T, int64_t x_stride, int shifts
   cp_async_commit();
   for (; tile < total_tiles; tile += gridDim.x, buf ^= 1) {
     const TileInfo ti = tile_info(tile, tiles, x, T, x_stride, shifts, so);
+    // one barrier per tile: it publishes this tile's samples (staged one iteration ago) and proves every
+    // warp is done with the other buffer, which the next tile's copy may then refill under this tile's FFTs
+    cp_async_wait<0>();
+    __syncthreads();
     const unsigned next = tile + gridDim.x;
     if (next < total_tiles) stage_tile(tile_info(next, tiles, x, T, x_stride, shifts, so), xs[buf ^ 1], tid);
     cp_async_commit();
-    cp_async_wait<1>();
-    __syncthreads();
     float vmax = 0.f;
     if (ti.f0 + 2 * warp < ti.n_frames) {  // warp-uniform: at least this warp's first frame exists
       const float* xf = xs[buf] + (2 * warp + half) * kHop + 2 * l16;
@@ -239,7 +241,6 @@ stft_mag_kernel(const float* __restrict__ x, int T, int64_t x_stride, int shifts
 #pragma unroll
     for (int o = 16; o; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
     if (lane == 0 && ti.f0 + 2 * warp < ti.n_frames) atomicMax(reinterpret_cast<int*>(qmax + ti.item), __float_as_int(vmax));
-    __syncthreads();  // everyone is done with xs[buf] before it is refilled two iterations later
   }
   cp_async_wait<0>();
 }
