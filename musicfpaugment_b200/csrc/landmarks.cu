@@ -99,6 +99,92 @@ landmark_kernel(const uint64_t* __restrict__ rec_all, int items, int n_max, int 
   if (lane == 0) nh[item] = written;  // may exceed cap: caller checks
 }
 
+// Same pairing, one lane per PEAK instead of per frame (items of up to kListFrames frames): the warp first
+// compacts the item's records into a (frame, bin)-ordered peak list in shared memory with the list offset of
+// every frame, then each lane walks the list from the first peak of frame c + mindt - which is exactly the
+// reference's scan order (frames ascending, bins ascending) without visiting empty frames - until it has
+// `fanout` pairs or leaves the target zone.  Frames hold ~0.5 peaks on music, so all lanes stay busy and the
+// walk is ~30 list entries instead of 61 records x 5 slots.
+constexpr int kListFrames = 1024;
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+landmark_list_kernel(const uint64_t* __restrict__ rec_all, int items, int n_max, int mindt, int targetdt,
+                     int targetdf, int fanout, int sorted, int32_t* __restrict__ hashes, int cap,
+                     int32_t* __restrict__ nh) {
+  extern __shared__ unsigned lm_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int item = blockIdx.x * kWarpsPerBlock + warp;
+  if (item >= items) return;
+  const int per_warp = kMaxPks * n_max + n_max + 1;
+  unsigned* list = lm_smem + warp * per_warp;                   // (frame << 8) | bin, frame-major
+  int* off = reinterpret_cast<int*>(list + kMaxPks * n_max);    // off[c] = list index of frame c's first peak
+  const uint64_t* rec = rec_all + (int64_t)item * n_max;
+  int2* out = reinterpret_cast<int2*>(hashes) + (int64_t)item * cap;
+
+  int total = 0, scols = 0;
+  for (int base = 0; base < n_max; base += 32) {
+    const int c = base + lane;
+    const uint64_t r = c < n_max ? rec[c] : 0;
+    const int n = min((int)(r & 0xff), kMaxPks);
+    int incl = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(kFull, incl, o);
+      if (lane >= o) incl += t;
+    }
+    const int first = total + incl - n;
+    if (c < n_max) off[c] = first;
+    for (int i = 0; i < n; ++i) list[first + i] = ((unsigned)c << 8) | (unsigned)rec_bin(r, i);
+    const unsigned bal = __ballot_sync(kFull, n != 0);
+    if (bal) scols = base + 32 - __clz(bal);   // column of the final peak + 1 (:325)
+    total += __shfl_sync(kFull, incl, 31);
+  }
+  if (lane == 0) off[n_max] = total;
+  __syncwarp();
+
+  int written = 0;
+  for (int base = 0; base < total; base += 32) {
+    const int i = base + lane;
+    uint32_t hb[kFanMax];
+    int cnt = 0, c = 0;
+    if (i < total) {
+      const unsigned p = list[i];
+      c = (int)(p >> 8);
+      const int b = (int)(p & 255u);
+      const int c_end = min(scols, c + targetdt);
+      for (int j = off[min(max(c + mindt, 0), n_max)]; j < total && cnt < fanout; ++j) {
+        const unsigned p2 = list[j];
+        const int c2 = (int)(p2 >> 8);
+        if (c2 >= c_end) break;
+        const int b2 = (int)(p2 & 255u);
+        if (abs(b2 - b) < targetdf)
+          hb[cnt++] = ((uint32_t)(b & 255) << 12) | ((uint32_t)((b2 - b) & 63) << 6) | (uint32_t)((c2 - c) & 63);
+      }
+      if (sorted && cnt > 1) {  // per-peak hashes ascending; peaks are already in bin order
+        if (hb[0] > hb[1]) { const uint32_t t = hb[0]; hb[0] = hb[1]; hb[1] = t; }
+        if (cnt > 2) {
+          if (hb[1] > hb[2]) { const uint32_t t = hb[1]; hb[1] = hb[2]; hb[2] = t; }
+          if (hb[0] > hb[1]) { const uint32_t t = hb[0]; hb[0] = hb[1]; hb[1] = t; }
+        }
+      }
+    }
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(kFull, incl, o);
+      if (lane >= o) incl += t;
+    }
+    int pos = written + incl - cnt;
+#pragma unroll
+    for (int k = 0; k < kFanMax; ++k)
+      if (k < cnt) {
+        if (pos < cap) out[pos] = make_int2(c, (int)hb[k]);
+        ++pos;
+      }
+    written += __shfl_sync(kFull, incl, 31);
+  }
+  if (lane == 0) nh[item] = written;  // may exceed cap: caller checks
+}
+
 // One block per query: merge `shifts` (time,hash)-sorted lists, drop duplicates.
 // Thread t owns time value t: gathers the <= 15 rows per list with that time,
 // insertion-merges them, then a block scan places each time's run.
@@ -263,8 +349,15 @@ int launch_landmark_hashes(const uint64_t* rec, int items, int n_frames, const m
                            int sorted, int32_t* hashes, int cap, int32_t* nh, cudaStream_t st) {
   MFPA_REQUIRE(p.fanout >= 1 && p.fanout <= kFanMax, "landmarks: fanout %d not in 1..%d", p.fanout, kFanMax);
   const int blocks = (items + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  landmark_kernel<<<blocks, kWarpsPerBlock * 32, 0, st>>>(rec, items, n_frames, p.mindt, p.targetdt, p.targetdf,
-                                                          p.fanout, sorted, hashes, cap, nh);
+  if (n_frames <= kListFrames) {
+    const size_t smem = sizeof(unsigned) * kWarpsPerBlock * ((size_t)kMaxPks * n_frames + n_frames + 1);
+    MFPA_CUDA(cudaFuncSetAttribute(landmark_list_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    landmark_list_kernel<<<blocks, kWarpsPerBlock * 32, smem, st>>>(rec, items, n_frames, p.mindt, p.targetdt, p.targetdf,
+                                                                    p.fanout, sorted, hashes, cap, nh);
+  } else {
+    landmark_kernel<<<blocks, kWarpsPerBlock * 32, 0, st>>>(rec, items, n_frames, p.mindt, p.targetdt, p.targetdf,
+                                                            p.fanout, sorted, hashes, cap, nh);
+  }
   MFPA_CUDA(cudaGetLastError());
   return MFPA_OK;
 }

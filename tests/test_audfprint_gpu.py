@@ -133,6 +133,24 @@ def test_landmark_hashes_bit_exact(mfpa_ctx):
         assert np.array_equal(h_sorted[i, : len(want)].cpu().numpy(), O.unique_sorted_hashes(want))
 
 
+@pytest.mark.parametrize("n_samples", [200000, 300000])
+def test_landmark_hashes_long_items(mfpa_ctx, n_samples):
+    """Items of 782 frames (lane-per-peak list kernel) and 1172 frames (above its shared-memory bound: the
+    lane-per-frame kernel) against the oracle's landmarks, on white noise (dense peaks: 5 per frame)."""
+    lib = _lib()
+    r = np.random.default_rng(n_samples)
+    X = r.standard_normal((2, n_samples)).astype(np.float32)
+    X[1] *= np.linspace(0.0, 1.0, n_samples, dtype=np.float32) ** 2
+    specs = np.stack([O.normalise(O.stft_mag(x)) for x in X])
+    p = _params(lib)
+    rec, _ = mfpa_ctx.audfprint_peaks_from_spec(torch.from_numpy(specs).cuda(), 0, p)
+    h_ref_order, nh = mfpa_ctx.landmark_hashes(rec, p, sorted_rows=False)
+    for i, x in enumerate(X):
+        want = O.landmarks2hashes(O.peaks2landmarks(O.find_peaks(x)[0]))
+        assert int(nh[i]) == len(want) > 1000
+        assert np.array_equal(h_ref_order[i, : len(want)].cpu().numpy(), want)
+
+
 @pytest.mark.parametrize("shifts", [1, 4])
 def test_fingerprint_end_to_end(mfpa_ctx, shifts):
     lib = _lib()
