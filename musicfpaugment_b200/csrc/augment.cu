@@ -285,8 +285,8 @@ __global__ void __launch_bounds__(FT, 3) fftconv_kernel(const ConvArgs a, const 
   float* red = reinterpret_cast<float*>(tw + kTw);
   const int tid = threadIdx.x, qi = blockIdx.y, blk = blockIdx.x;
   const AugQ q = a.q[qi];
-  const float* in = a.in + (int64_t)qi * a.in_stride;
-  float* out = a.out + (int64_t)qi * a.T;
+  const float* __restrict__ in = a.in + (int64_t)qi * a.in_stride;
+  float* __restrict__ out = a.out + (int64_t)qi * a.T;
   const int T = a.T;
   float vmax = 0.f, vss = 0.f;
 
@@ -311,24 +311,42 @@ __global__ void __launch_bounds__(FT, 3) fftconv_kernel(const ConvArgs a, const 
     const int n0 = blk * V;
     if (n0 >= n_total) return;  // block-uniform
     for (int i = tid; i < kTw; i += FT) tw[i] = tw_g[i];
-    for (int m = tid; m < FM; m += FT) {
-      float x[2];
+    // global loads in batches of 16 per thread, issued together ahead of the shared-memory stores
+    constexpr int kLd = 8;
+#pragma unroll 1
+    for (int m0 = tid; m0 < FM; m0 += FT * kLd) {
+      float x[kLd][2];
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int n = n0 - lead + 2 * m + e;
-        if (MODE == kModeIR) x[e] = (n >= 0 && n < T) ? in[n] : 0.f;   // zero extension
-        else x[e] = in[min(max(n, 0), T - 1)];                          // replicate padding (julius)
-      }
-      buf[pidx(m)] = make_float2(x[0], x[1]);
+      for (int u = 0; u < kLd; ++u)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int n = n0 - lead + 2 * (m0 + u * FT) + e;
+          if (MODE == kModeIR) x[u][e] = (n >= 0 && n < T) ? __ldg(in + n) : 0.f;   // zero extension
+          else x[u][e] = __ldg(in + min(max(n, 0), T - 1));                          // replicate padding (julius)
+        }
+#pragma unroll
+      for (int u = 0; u < kLd; ++u) buf[pidx(m0 + u * FT)] = make_float2(x[u][0], x[u][1]);
     }
     __syncthreads();
     fft_forward(buf, tw, tid);
     // split -> multiply by the filter spectrum -> re-pack, pair (k, FM-k) per thread
-    const float2* hg = a.hspec + (size_t)qi * FM;
-    for (int j = tid; j < FM / 2; j += FT) {
+    const float2* __restrict__ hg = a.hspec + (size_t)qi * FM;
+    constexpr int kPw = 4;
+#pragma unroll 1
+    for (int j0 = tid; j0 < FM / 2; j0 += FT * kPw) {
+      float2 h1[kPw], h2[kPw];
+#pragma unroll
+      for (int u = 0; u < kPw; ++u) {   // filter spectrum of the pairs (k, FM-k), fetched ahead of the math
+        const int r = 2 * (j0 + u * FT), k = pos_freq(r);
+        h1[u] = __ldg(hg + r);
+        h2[u] = __ldg(hg + (k == 0 ? 1 : rev_pos(FM - k)));
+      }
+#pragma unroll
+      for (int u = 0; u < kPw; ++u) {
+      const int j = j0 + u * FT;
       const int r = 2 * j, k = pos_freq(r);
       if (k == 0) {
-        const float2 z = buf[pidx(0)], h = hg[0];
+        const float2 z = buf[pidx(0)], h = h1[u];
         const float y0 = (z.x + z.y) * h.x, ym = (z.x - z.y) * h.y;
         buf[pidx(0)] = make_float2(0.5f * (y0 + ym), 0.5f * (y0 - ym));
       } else {
@@ -336,13 +354,14 @@ __global__ void __launch_bounds__(FT, 3) fftconv_kernel(const ConvArgs a, const 
         const float2 wk = half_twiddle(k);
         float2 xk, xmk;
         real_split(buf[pidx(r)], buf[pidx(r2)], wk, xk, xmk);
-        const float2 yk = cmul(xk, hg[r]), ymk = cmul(xmk, hg[r2]);
+        const float2 yk = cmul(xk, h1[u]), ymk = cmul(xmk, h2[u]);
         // Zy[k] = Ey + i Oy, Zy[FM-k] = conj(Ey) + i conj(Oy); Ey = (Y[k] + conj Y[FM-k]) / 2,
         // Oy = (Y[k] - conj Y[FM-k]) / 2 * conj(W^k)
         const float2 ey = make_float2(0.5f * (yk.x + ymk.x), 0.5f * (yk.y - ymk.y));
         const float2 oy = cmul(make_float2(0.5f * (yk.x - ymk.x), 0.5f * (yk.y + ymk.y)), conjf2(wk));
         buf[pidx(r)] = make_float2(ey.x - oy.y, ey.y + oy.x);
         buf[pidx(r2)] = make_float2(ey.x + oy.y, oy.x - ey.y);
+      }
       }
     }
     if (tid == 0) {  // k = FM/2: X = conj(Z), Zy = conj(Y)
@@ -353,14 +372,26 @@ __global__ void __launch_bounds__(FT, 3) fftconv_kernel(const ConvArgs a, const 
     __syncthreads();
     fft_inverse(buf, tw, tid);
     const int n_end = min(n_total, n0 + V);
-    for (int n = n0 + tid; n < n_end; n += FT) {
-      const int jj = n - n0 + K - 1;
-      const float2 pr = buf[pidx(jj >> 1)];
-      const float c = (jj & 1) ? pr.y : pr.x;
-      float v;
-      if (MODE == kModeHP) v = in[n] - c; else v = c;
-      vmax = fmaxf(vmax, fabsf(v));
-      if (n < T) { out[n] = v; vss += v * v; }
+    constexpr int kSt = 8;
+#pragma unroll 1
+    for (int nb = n0 + tid; nb < n_end; nb += FT * kSt) {
+      float xin[kSt];
+      if (MODE == kModeHP) {
+#pragma unroll
+        for (int u = 0; u < kSt; ++u) { const int n = nb + u * FT; xin[u] = n < n_end ? __ldg(in + n) : 0.f; }
+      }
+#pragma unroll
+      for (int u = 0; u < kSt; ++u) {
+        const int n = nb + u * FT;
+        if (n < n_end) {
+          const int jj = n - n0 + K - 1;
+          const float2 pr = buf[pidx(jj >> 1)];
+          const float c = (jj & 1) ? pr.y : pr.x;
+          const float v = MODE == kModeHP ? xin[u] - c : c;
+          vmax = fmaxf(vmax, fabsf(v));
+          if (n < T) { out[n] = v; vss += v * v; }
+        }
+      }
     }
   }
   vmax = block_max(vmax, red, tid);
