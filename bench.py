@@ -483,7 +483,7 @@ def bench_match(ctx, lib, dev, rank, world, B, n_tracks, steps, warmup, barrier)
     def step():
         if world == 1:
             return ctx.match(q, nq, mp, max_rows=4)
-        return sharded.match_sharded(ctx, q, nq, mp, max_rows=4, sub_batch=512)
+        return sharded.match_sharded(ctx, q, nq, mp, max_rows=4, sub_batch=int(os.environ.get("MFPA_MATCH_SUB", "2048")))
 
     for _ in range(warmup):
         res, nrows = step()
