@@ -97,8 +97,8 @@ __device__ __forceinline__ bool before(const Cand& a, const Cand& b) {  // a ran
 }
 
 // Exact ranking of a short list of contender tracks (shared memory): the first `depth` by `before`, written
-// as (id, raw) pairs to cand_q.  All 512 threads of the block call it.
-template <typename CountOf>
+// as (id, raw) pairs to cand_q.  All NT threads of the block call it.
+template <int NT, typename CountOf>
 __device__ __forceinline__ void rank_list(const int* list, int n_list, int depth, CountOf count_of,
                                           const uint32_t* __restrict__ hpid, int32_t* __restrict__ cand_q,
                                           Cand* s_best, Cand* s_prev, int tid) {
@@ -109,7 +109,7 @@ __device__ __forceinline__ void rank_list(const int* list, int n_list, int depth
   for (int k = 0; k < depth; ++k) {
     const Cand prev = *s_prev;
     Cand best{-1, 1, -1};
-    for (int c = tid; c < n_list; c += 512) {
+    for (int c = tid; c < n_list; c += NT) {
       const int i = list[c];
       const Cand x{(long long)count_of(i), (long long)hpid[i], i};
       const bool after_prev = prev.hp == 0 || before(prev, x);
@@ -125,7 +125,7 @@ __device__ __forceinline__ void rank_list(const int* list, int n_list, int depth
     __syncthreads();
     if (tid == 0) {
       Cand b = s_best[0];
-      for (int w = 1; w < 16; ++w) if (s_best[w].id >= 0 && (b.id < 0 || before(s_best[w], b))) b = s_best[w];
+      for (int w = 1; w < NT / 32; ++w) if (s_best[w].id >= 0 && (b.id < 0 || before(s_best[w], b))) b = s_best[w];
       *s_prev = b;
       cand_q[2 * k] = b.id;
       cand_q[2 * k + 1] = (int)b.raw;
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(512) match_select_kernel(const int32_t* __rest
   }
   __syncthreads();
   if (s_n <= kListCap) {
-    rank_list(s_list, s_n, depth, count_of, hpid, cand + (int64_t)q * search_depth * 2, s_best, &s_prev, tid);
+    rank_list<512>(s_list, s_n, depth, count_of, hpid, cand + (int64_t)q * search_depth * 2, s_best, &s_prev, tid);
     return;
   }
   // more contenders than the list holds: rank by repeated scans of the whole row
@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(512) match_select_kernel(const int32_t* __rest
 // The sweeps are latency-bound gathers, so each warp keeps four bucket rows (16 loads per lane) in flight;
 // the per-row (bucket, count, query time) triples are staged through a small shared-memory cache first.
 constexpr int kFusedRows = 768;
-constexpr int kFusedThreads = 512;
+constexpr int kFusedThreads = 1024;
 struct RowCache { int hb[kFusedRows]; int cnt[kFusedRows]; int t[kFusedRows]; };
 
 template <bool COLLECT>
@@ -291,9 +291,10 @@ match_fused_kernel(const IndexView ix, const int32_t* __restrict__ hashes, const
   const int words = (ix.n_tracks + 1) >> 1;
   unsigned* hist = fused_smem;
   RowCache* rc = reinterpret_cast<RowCache*>(fused_smem + ((words + 3) & ~3));
-  __shared__ int s_int[16];
-  __shared__ float s_flt[16];
-  __shared__ Cand s_best[16];
+  constexpr int kFusedWarps = kFusedThreads / 32;
+  __shared__ int s_int[kFusedWarps];
+  __shared__ float s_flt[kFusedWarps];
+  __shared__ Cand s_best[kFusedWarps];
   __shared__ Cand s_prev;
   __shared__ int s_n;
   const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -336,7 +337,7 @@ match_fused_kernel(const IndexView ix, const int32_t* __restrict__ hashes, const
   if (tid == 0) s_n = 0;
   __syncthreads();
   gt = 0;
-  for (int w = 0; w < 16; ++w) { gt += s_int[w]; fmin = fminf(fmin, s_flt[w]); }
+  for (int w = 0; w < kFusedWarps; ++w) { gt += s_int[w]; fmin = fminf(fmin, s_flt[w]); }
   const int depth = min(gt, search_depth);
   const float cut = fmin * 0.99999f;
   const int raw_min = max(1, (int)floorf(cut * (float)ix.hp_min * 0.99999f));   // raw < raw_min => quotient < cut
@@ -360,7 +361,7 @@ match_fused_kernel(const IndexView ix, const int32_t* __restrict__ hashes, const
   }
   if (depth > 0 && listed) {
     const int nc_list = s_n;
-    rank_list(contenders, nc_list, depth, count_of, ix.hashesperid, cand + (int64_t)q * search_depth * 2, s_best, &s_prev, tid);
+    rank_list<kFusedThreads>(contenders, nc_list, depth, count_of, ix.hashesperid, cand + (int64_t)q * search_depth * 2, s_best, &s_prev, tid);
     if (tid == 0) s_n = 0;
     __syncthreads();
   } else if (depth > 0) {
@@ -398,7 +399,7 @@ match_fused_kernel(const IndexView ix, const int32_t* __restrict__ hashes, const
       __syncthreads();
       if (tid == 0) {
         Cand b = s_best[0];
-        for (int w = 1; w < 16; ++w) if (s_best[w].id >= 0 && (b.id < 0 || before(s_best[w], b))) b = s_best[w];
+        for (int w = 1; w < kFusedWarps; ++w) if (s_best[w].id >= 0 && (b.id < 0 || before(s_best[w], b))) b = s_best[w];
         s_prev = b;
         cand[((int64_t)q * search_depth + k) * 2] = b.id;
         cand[((int64_t)q * search_depth + k) * 2 + 1] = (int)b.raw;
