@@ -211,10 +211,13 @@ typedef struct mfpa_aug_params {
   int32_t ir_len;     /* valid samples of this query's impulse response (<= ir_stride) */
 } mfpa_aug_params;
 
-/* Longest FIR the CUDA path accepts (taps = 2*int(4*sr/fc)+1 <= this). */
-#define MFPA_AUG_MAX_TAPS 8193
-/* Longest impulse response, in samples. */
-#define MFPA_AUG_MAX_IR 8192
+/* Longest FIR the CUDA path accepts (taps = 2*int(4*sr/fc)+1 <= this: cut-offs down to 0.061 Hz at
+ * 8 kHz).  Filters of up to 8193 taps (fc >= 7.8 Hz at 8 kHz) take one overlap-save block per 8192+
+ * outputs; longer ones - the reference draws the loudspeaker cut-off mel-uniformly from [0, 150] Hz, so
+ * about 6 % of its default draws - run as uniformly partitioned overlap-save. */
+#define MFPA_AUG_MAX_TAPS 1048577
+/* Longest impulse response, in samples (32 s at 8 kHz); above 8192 samples: partitioned as well. */
+#define MFPA_AUG_MAX_IR 262144
 
 /* AugmentFP.__call__ / batch_augment on dumped parameters, per-query semantics (the
  * reference drivers call it with B = 1; Clipping's quantiles are per query).

@@ -42,7 +42,10 @@ struct AugQ {            // per-query derived parameters (device copy)
   float arg1, arg2, arg3;         // float(2*cutoff*pi)
   float snr_div;                  // 10^(snr_db/20)
   float gain, q_lo;
+  uint32_t long_mask;             // stages whose filter is longer than one overlap-save block takes (kLong* bits)
+  uint32_t pad_;                  // sizeof == 64: the AugS array (doubles) follows the AugQ array in one allocation
 };
+static_assert(sizeof(AugQ) % 8 == 0, "AugS follows AugQ[B] and holds doubles");
 
 struct AugS {            // per-query running statistics (zeroed per call)
   double ss_a, ss_b;     // sum of squares of the stage-1 / stage-2 output (first T samples)
@@ -220,6 +223,11 @@ __device__ __forceinline__ void filter_params(const AugQ& q, int which, int& hal
   argscale = which == 1 ? q.arg1 : (which == 2 ? q.arg2 : q.arg3);
 }
 
+enum { kLongHP1 = 1u, kLongIR = 2u, kLongLP = 4u, kLongHP3 = 8u };
+template <int MODE> __device__ __forceinline__ uint32_t long_bit(int which) {
+  return MODE == kModeIR ? kLongIR : (which == 1 ? kLongHP1 : (which == 2 ? kLongLP : kLongHP3));
+}
+
 // One block per query: half spectrum of the query's filter (zero-padded to FN real samples), scaled by
 // 1/FM (the unscaled inverse transform) and, for the FIRs, by 1/sum(taps) (julius normalises to DC gain 1).
 template <int MODE>
@@ -230,7 +238,7 @@ __global__ void __launch_bounds__(FT) filter_spectrum_kernel(const ConvArgs a, c
   float* red = reinterpret_cast<float*>(tw + kTw);
   const int tid = threadIdx.x, qi = blockIdx.x;
   const AugQ q = a.q[qi];
-  if (!(q.apply & a.bit)) return;
+  if (!(q.apply & a.bit) || (q.long_mask & long_bit<MODE>(a.which))) return;
   int K, half = 0;
   float c2 = 0.f, argscale = 0.f;
   if (MODE == kModeIR) {
@@ -289,6 +297,7 @@ __global__ void __launch_bounds__(FT, 3) fftconv_kernel(const ConvArgs a, const 
   float* __restrict__ out = a.out + (int64_t)qi * a.T;
   const int T = a.T;
   float vmax = 0.f, vss = 0.f;
+  if ((q.apply & a.bit) && (q.long_mask & long_bit<MODE>(a.which))) return;   // partconv_kernel's query
 
   if (!(q.apply & a.bit)) {
     // transform not applied to this query: pass the samples through, still report statistics
@@ -500,6 +509,196 @@ __device__ void clip_select_general(const float* __restrict__ z, int T, const in
   for (int i = 0; i < 2; ++i) {
     const bool same = cnt_le[i] >= (unsigned)r0[i] + 2u || r0[i] + 1 > T - 1;
     ksucc[i] = same ? kout[i] : min_gt[i];
+  }
+}
+
+// ---- filters longer than one block: uniformly partitioned overlap-save ------------------------------
+// A low cut-off makes the windowed-sinc FIR arbitrarily long (taps = 2 int(4 sr / fc) + 1: 16 001 taps at
+// 4 Hz, more than the signal below 1 Hz) and real room responses run to several seconds.  Such a filter is
+// cut into P partitions of S = FN/2 taps; with c[n] = sum_k h[k] xe[n + D - k] (xe = padded input, D = half
+// for the centred FIRs, 0 for the causal response),
+//     c[n] = sum_p sum_{k<S} h_p[k] xe[n + D - pS - k],
+// so output block b (n in [bS, (b+1)S)) is ONE inverse transform of  sum_p H_p * X_{b-p},  where X_j is
+// the spectrum of the FN input samples starting at jS + D - S + 1.  Three kernels over the list of long
+// queries: partition spectra H_p, input-block spectra X_j (each computed once, kept in HBM in the
+// transform's digit-reversed order), and the accumulate + inverse + epilogue kernel.
+constexpr int kPartS = FN / 2;
+
+struct PartArgs {
+  ConvArgs c;
+  const int* list;      // [n_long] query indices
+  float2* hparts;       // [n_long][p_cap][FM]
+  float2* xspec;        // [n_long][nb_in_cap][FM]
+  int p_cap, nb_in_cap;
+};
+
+template <int MODE>
+__device__ __forceinline__ void part_geometry(const AugQ& q, int which, int T, int& K, int& half, int& D, int& P,
+                                              int& n_total) {
+  if (MODE == kModeIR) { K = q.ir_len; half = 0; D = 0; n_total = T + K - 1; }
+  else { half = which == 1 ? q.half1 : (which == 2 ? q.half2 : q.half3); K = 2 * half + 1; D = half; n_total = T; }
+  P = (K + kPartS - 1) / kPartS;
+}
+
+// grid (p_cap, n_long): spectrum of partition p (taps [pS, (p+1)S) zero-padded to FN), scaled like filter_spectrum_kernel
+template <int MODE>
+__global__ void __launch_bounds__(FT) part_filter_kernel(const PartArgs a, const float2* __restrict__ tw_g) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* buf = reinterpret_cast<float2*>(smem_raw);
+  float2* tw = buf + FPAD;
+  float* red = reinterpret_cast<float*>(tw + kTw);
+  const int tid = threadIdx.x, li = blockIdx.y, qi = a.list[li], p = blockIdx.x;
+  const AugQ q = a.c.q[qi];
+  int K, half, D, P, n_total;
+  part_geometry<MODE>(q, a.c.which, a.c.T, K, half, D, P, n_total);
+  if (p >= P) return;
+  float c2 = 0.f, argscale = 0.f;
+  int hh;
+  if (MODE != kModeIR) filter_params(q, a.c.which, hh, c2, argscale);
+  for (int i = tid; i < kTw; i += FT) tw[i] = tw_g[i];
+  const float* ir = MODE == kModeIR ? a.c.ir + (int64_t)qi * a.c.ir_stride : nullptr;
+  float scale = 1.0f / (float)FM;
+  if (MODE != kModeIR) {   // julius normalises by the sum of ALL taps
+    float hs = 0.f;
+    for (int i = tid; i < K; i += FT) hs += fir_tap(i, half, c2, argscale);
+    scale /= block_sum(hs, red, tid);
+  }
+  for (int m = tid; m < FM; m += FT) {
+    float h[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int i = p * kPartS + 2 * m + e;
+      h[e] = 0.f;
+      if (2 * m + e < kPartS && i < K) h[e] = MODE == kModeIR ? ir[i] : fir_tap(i, half, c2, argscale);
+    }
+    buf[pidx(m)] = make_float2(h[0], h[1]);
+  }
+  __syncthreads();
+  fft_forward(buf, tw, tid);
+  float2* hg = a.hparts + ((size_t)li * a.p_cap + p) * FM;
+  for (int j = tid; j < FM / 2; j += FT) {
+    const int r = 2 * j, k = pos_freq(r);
+    if (k == 0) {
+      const float2 z = buf[pidx(0)];
+      hg[0] = make_float2((z.x + z.y) * scale, (z.x - z.y) * scale);
+    } else {
+      const int r2 = rev_pos(FM - k);
+      float2 hk, hmk;
+      real_split(buf[pidx(r)], buf[pidx(r2)], half_twiddle(k), hk, hmk);
+      hg[r] = make_float2(hk.x * scale, hk.y * scale);
+      hg[r2] = make_float2(hmk.x * scale, hmk.y * scale);
+    }
+  }
+  if (tid == 0) {
+    const float2 z = buf[pidx(1)];
+    hg[1] = make_float2(z.x * scale, -z.y * scale);
+  }
+}
+
+// grid (nb_in_cap, n_long): Z_j = FFT_FM of the packed input block j - (P-1)
+template <int MODE>
+__global__ void __launch_bounds__(FT, 3) part_forward_kernel(const PartArgs a, const float2* __restrict__ tw_g) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* buf = reinterpret_cast<float2*>(smem_raw);
+  float2* tw = buf + FPAD;
+  const int tid = threadIdx.x, li = blockIdx.y, qi = a.list[li], jb = blockIdx.x;
+  const AugQ q = a.c.q[qi];
+  int K, half, D, P, n_total;
+  part_geometry<MODE>(q, a.c.which, a.c.T, K, half, D, P, n_total);
+  const int nb_out = (n_total + kPartS - 1) / kPartS;
+  if (jb >= nb_out + P - 1) return;
+  const int T = a.c.T;
+  const float* __restrict__ in = a.c.in + (int64_t)qi * a.c.in_stride;
+  const int64_t s0 = (int64_t)(jb - (P - 1)) * kPartS + D - kPartS + 1;
+  for (int i = tid; i < kTw; i += FT) tw[i] = tw_g[i];
+  for (int m = tid; m < FM; m += FT) {
+    float x[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int64_t n = s0 + 2 * m + e;
+      if (MODE == kModeIR) x[e] = (n >= 0 && n < T) ? __ldg(in + n) : 0.f;                  // zero extension
+      else x[e] = __ldg(in + (n < 0 ? 0 : (n > T - 1 ? T - 1 : n)));                         // replicate padding (julius)
+    }
+    buf[pidx(m)] = make_float2(x[0], x[1]);
+  }
+  __syncthreads();
+  fft_forward(buf, tw, tid);
+  float2* zg = a.xspec + ((size_t)li * a.nb_in_cap + jb) * FM;
+  for (int m = tid; m < FM; m += FT) zg[m] = buf[pidx(m)];
+}
+
+// grid (nb_out_max, n_long): Y = sum_p H_p X_{b-p} -> inverse transform -> the same epilogue as fftconv_kernel
+template <int MODE>
+__global__ void __launch_bounds__(FT, 3) part_conv_kernel(const PartArgs a, const float2* __restrict__ tw_g) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* buf = reinterpret_cast<float2*>(smem_raw);
+  float2* tw = buf + FPAD;
+  float* red = reinterpret_cast<float*>(tw + kTw);
+  const int tid = threadIdx.x, li = blockIdx.y, qi = a.list[li], b = blockIdx.x;
+  const AugQ q = a.c.q[qi];
+  int K, half, D, P, n_total;
+  part_geometry<MODE>(q, a.c.which, a.c.T, K, half, D, P, n_total);
+  const int nb_out = (n_total + kPartS - 1) / kPartS;
+  if (b >= nb_out) return;
+  const int T = a.c.T;
+  const float* __restrict__ in = a.c.in + (int64_t)qi * a.c.in_stride;
+  float* __restrict__ out = a.c.out + (int64_t)qi * T;
+  for (int i = tid; i < kTw; i += FT) tw[i] = tw_g[i];
+  const float2* __restrict__ hq = a.hparts + (size_t)li * a.p_cap * FM;
+  const float2* __restrict__ zq = a.xspec + (size_t)li * a.nb_in_cap * FM;
+  for (int j = tid; j < FM / 2; j += FT) {
+    const int r = 2 * j, k = pos_freq(r);
+    if (k == 0) {
+      float y0 = 0.f, ym = 0.f;
+      for (int p = 0; p < P; ++p) {
+        const float2 z = __ldg(zq + (size_t)(b - p + P - 1) * FM), h = __ldg(hq + (size_t)p * FM);
+        y0 += (z.x + z.y) * h.x;
+        ym += (z.x - z.y) * h.y;
+      }
+      buf[pidx(0)] = make_float2(0.5f * (y0 + ym), 0.5f * (y0 - ym));
+    } else {
+      const int r2 = rev_pos(FM - k);
+      const float2 wk = half_twiddle(k);
+      float2 yk = make_float2(0.f, 0.f), ymk = make_float2(0.f, 0.f);
+      for (int p = 0; p < P; ++p) {
+        const float2* z = zq + (size_t)(b - p + P - 1) * FM;
+        const float2* h = hq + (size_t)p * FM;
+        float2 xk, xmk;
+        real_split(__ldg(z + r), __ldg(z + r2), wk, xk, xmk);
+        yk = cadd(yk, cmul(xk, __ldg(h + r)));
+        ymk = cadd(ymk, cmul(xmk, __ldg(h + r2)));
+      }
+      const float2 ey = make_float2(0.5f * (yk.x + ymk.x), 0.5f * (yk.y - ymk.y));
+      const float2 oy = cmul(make_float2(0.5f * (yk.x - ymk.x), 0.5f * (yk.y + ymk.y)), conjf2(wk));
+      buf[pidx(r)] = make_float2(ey.x - oy.y, ey.y + oy.x);
+      buf[pidx(r2)] = make_float2(ey.x + oy.y, oy.x - ey.y);
+    }
+  }
+  if (tid == 0) {  // k = FM/2: X = conj(Z), Zy = conj(Y)
+    float2 y = make_float2(0.f, 0.f);
+    for (int p = 0; p < P; ++p)
+      y = cadd(y, cmul(conjf2(__ldg(zq + (size_t)(b - p + P - 1) * FM + 1)), __ldg(hq + (size_t)p * FM + 1)));
+    buf[pidx(1)] = conjf2(y);
+  }
+  __syncthreads();
+  fft_inverse(buf, tw, tid);
+  float vmax = 0.f, vss = 0.f;
+  const int n_end = min(n_total, (b + 1) * kPartS);
+  for (int n = b * kPartS + tid; n < n_end; n += FT) {
+    const int jj = n - b * kPartS + kPartS - 1;
+    const float2 pr = buf[pidx(jj >> 1)];
+    const float c = (jj & 1) ? pr.y : pr.x;
+    const float v = MODE == kModeHP ? in[n] - c : c;
+    vmax = fmaxf(vmax, fabsf(v));
+    if (n < T) { out[n] = v; vss += v * v; }
+  }
+  vmax = block_max(vmax, red, tid);
+  vss = block_sum(vss, red, tid);
+  if (tid == 0) {
+    AugS* s = a.c.st + qi;
+    if (MODE == kModeHP && a.c.which == 1) { atomic_max_pos(&s->max_a, vmax); atomicAdd(&s->ss_a, (double)vss); }
+    else if (MODE == kModeIR) { atomic_max_pos(&s->max_b, vmax); atomicAdd(&s->ss_b, (double)vss); }
+    else if (MODE == kModeHP && a.c.which == 3) atomic_max_pos(&s->max_v, vmax);
   }
 }
 
@@ -883,6 +1082,15 @@ static int aug_init_tables(mfpa_ctx* ctx) {
   MFPA_CUDA(cudaFuncSetAttribute(fftconv_kernel<kModeLP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmem));
   MFPA_CUDA(cudaFuncSetAttribute(filter_spectrum_kernel<kModeHP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmem));
   MFPA_CUDA(cudaFuncSetAttribute(filter_spectrum_kernel<kModeIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmem));
+  MFPA_CUDA(cudaFuncSetAttribute(part_filter_kernel<kModeHP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmem));
+  MFPA_CUDA(cudaFuncSetAttribute(part_filter_kernel<kModeIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmem));
+  MFPA_CUDA(cudaFuncSetAttribute(part_filter_kernel<kModeLP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmem));
+  MFPA_CUDA(cudaFuncSetAttribute(part_forward_kernel<kModeHP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmem));
+  MFPA_CUDA(cudaFuncSetAttribute(part_forward_kernel<kModeIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmem));
+  MFPA_CUDA(cudaFuncSetAttribute(part_forward_kernel<kModeLP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmem));
+  MFPA_CUDA(cudaFuncSetAttribute(part_conv_kernel<kModeHP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmem));
+  MFPA_CUDA(cudaFuncSetAttribute(part_conv_kernel<kModeIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmem));
+  MFPA_CUDA(cudaFuncSetAttribute(part_conv_kernel<kModeLP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmem));
   return MFPA_OK;
 }
 
@@ -905,7 +1113,9 @@ int launch_augment(mfpa_ctx* ctx, const float* x, int B, int T, int64_t x_stride
                    bool final_norm, cudaStream_t st) {
   if (int e = aug_init_tables(ctx)) return e;
   // ---- derive per-query parameters on the host
-  const size_t need = sizeof(AugQ) * (size_t)B;
+  const size_t need = (sizeof(AugQ) + 4 * sizeof(int)) * (size_t)B;
+  if (ctx->aug_copy_done) MFPA_CUDA(cudaEventSynchronize((cudaEvent_t)ctx->aug_copy_done));   // previous call's H2D of this buffer
+  else { cudaEvent_t ev; MFPA_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); ctx->aug_copy_done = ev; }
   if (ctx->aug_pinned_bytes < need) {
     if (ctx->aug_pinned) cudaFreeHost(ctx->aug_pinned);
     ctx->aug_pinned = nullptr;
@@ -913,8 +1123,15 @@ int launch_augment(mfpa_ctx* ctx, const float* x, int B, int T, int64_t x_stride
     MFPA_CUDA(cudaMallocHost(&ctx->aug_pinned, ctx->aug_pinned_bytes));
   }
   AugQ* hq = (AugQ*)ctx->aug_pinned;
+  int* hlist[4];   // queries whose stage-1 / IR / stage-5 / stage-6 filter needs the partitioned path
+  int nlong[4] = {0, 0, 0, 0}, max_k[4] = {0, 0, 0, 0};
+  for (int l = 0; l < 4; ++l) hlist[l] = reinterpret_cast<int*>(hq + B) + (size_t)l * B;
+  constexpr int kFastTaps = FN / 2 + 1;   // one overlap-save block keeps >= FN/2 valid outputs
   int min_v1 = FN, min_v3 = FN, min_vir = FN, max_half2 = 0;
   bool any_long_lp = false;
+  auto note_long = [&](int l, uint32_t bit, int K, AugQ& q, int i) {
+    q.long_mask |= bit; hlist[l][nlong[l]++] = i; max_k[l] = K > max_k[l] ? K : max_k[l];
+  };
   for (int i = 0; i < B; ++i) {
     const mfpa_aug_params& p = pp[i];
     AugQ q{};
@@ -926,7 +1143,8 @@ int launch_augment(mfpa_ctx* ctx, const float* x, int B, int T, int64_t x_stride
       MFPA_REQUIRE(2 * (int64_t)q.half1 + 1 <= MFPA_AUG_MAX_TAPS, "augment: query %d: high-pass cut-off %g Hz needs %lld taps "
                    "(limit %d)", i, (double)p.fc1_hz, 2ll * q.half1 + 1, MFPA_AUG_MAX_TAPS);
       q.c1x2 = (float)(2.0 * c); q.arg1 = (float)(2.0 * c * 3.14159265358979323846);
-      min_v1 = FN - 2 * q.half1 < min_v1 ? FN - 2 * q.half1 : min_v1;
+      if (2 * q.half1 + 1 > kFastTaps) note_long(0, kLongHP1, 2 * q.half1 + 1, q, i);
+      else min_v1 = FN - 2 * q.half1 < min_v1 ? FN - 2 * q.half1 : min_v1;
     }
     if (p.apply & MFPA_AUG_LPF) {
       q.half2 = fir_half(p.fc2_hz, sample_rate, "low-pass", i, &c);
@@ -935,7 +1153,8 @@ int launch_augment(mfpa_ctx* ctx, const float* x, int B, int T, int64_t x_stride
                    "(limit %d)", i, (double)p.fc2_hz, 2ll * q.half2 + 1, MFPA_AUG_MAX_TAPS);
       q.c2x2 = (float)(2.0 * c); q.arg2 = (float)(2.0 * c * 3.14159265358979323846);
       if (q.half2 > kLpMaxHalf) any_long_lp = true;
-      max_half2 = q.half2 > max_half2 ? q.half2 : max_half2;
+      if (2 * q.half2 + 1 > kFastTaps) note_long(2, kLongLP, 2 * q.half2 + 1, q, i);
+      else max_half2 = q.half2 > max_half2 ? q.half2 : max_half2;
     }
     if (p.apply & MFPA_AUG_HPF3) {
       q.half3 = fir_half(p.fc3_hz, sample_rate, "microphone high-pass", i, &c);
@@ -943,14 +1162,16 @@ int launch_augment(mfpa_ctx* ctx, const float* x, int B, int T, int64_t x_stride
       MFPA_REQUIRE(2 * (int64_t)q.half3 + 1 <= MFPA_AUG_MAX_TAPS, "augment: query %d: high-pass cut-off %g Hz needs %lld taps "
                    "(limit %d)", i, (double)p.fc3_hz, 2ll * q.half3 + 1, MFPA_AUG_MAX_TAPS);
       q.c3x2 = (float)(2.0 * c); q.arg3 = (float)(2.0 * c * 3.14159265358979323846);
-      min_v3 = FN - 2 * q.half3 < min_v3 ? FN - 2 * q.half3 : min_v3;
+      if (2 * q.half3 + 1 > kFastTaps) note_long(3, kLongHP3, 2 * q.half3 + 1, q, i);
+      else min_v3 = FN - 2 * q.half3 < min_v3 ? FN - 2 * q.half3 : min_v3;
     }
     if (p.apply & MFPA_AUG_IR) {
       MFPA_REQUIRE(ir != nullptr, "augment: query %d applies an impulse response but ir_dev is NULL", i);
       MFPA_REQUIRE(p.ir_len >= 1 && p.ir_len <= ir_stride && p.ir_len <= MFPA_AUG_MAX_IR,
                    "augment: query %d: ir_len %d not in [1, min(ir_stride %d, %d)]", i, p.ir_len, ir_stride, MFPA_AUG_MAX_IR);
       q.ir_len = p.ir_len;
-      min_vir = FN - p.ir_len + 1 < min_vir ? FN - p.ir_len + 1 : min_vir;
+      if (p.ir_len > FN / 2) note_long(1, kLongIR, p.ir_len, q, i);
+      else min_vir = FN - p.ir_len + 1 < min_vir ? FN - p.ir_len + 1 : min_vir;
     }
     if (p.apply & MFPA_AUG_NOISE) MFPA_REQUIRE(noise != nullptr, "augment: query %d mixes noise but noise_dev is NULL", i);
     q.snr_div = powf(10.0f, p.snr_db / 20.0f);
@@ -970,6 +1191,38 @@ int launch_augment(mfpa_ctx* ctx, const float* x, int B, int T, int64_t x_stride
   AugS* ds = (AugS*)(dq + B);
   MFPA_CUDA(cudaMemcpyAsync(dq, hq, sizeof(AugQ) * (size_t)B, cudaMemcpyHostToDevice, st));
   MFPA_CUDA(cudaMemsetAsync(ds, 0, sizeof(AugS) * (size_t)B, st));
+  int* dlist = nullptr;
+  if (nlong[0] + nlong[1] + nlong[2] + nlong[3]) {
+    if (ctx->aug_long.reserve(sizeof(int) * 4 * (size_t)B)) return MFPA_ENOMEM;
+    dlist = (int*)ctx->aug_long.ptr;
+    MFPA_CUDA(cudaMemcpyAsync(dlist, hlist[0], sizeof(int) * 4 * (size_t)B, cudaMemcpyHostToDevice, st));
+  }
+  MFPA_CUDA(cudaEventRecord((cudaEvent_t)ctx->aug_copy_done, st));
+  // partitioned overlap-save for the queries of list l (filters longer than one block takes)
+  auto run_long = [&](int l, int mode, ConvArgs c) -> int {
+    if (!nlong[l]) return MFPA_OK;
+    const int P = (max_k[l] + kPartS - 1) / kPartS;
+    const int n_total = mode == kModeIR ? T + max_k[l] - 1 : T;
+    const int nb_out = (n_total + kPartS - 1) / kPartS, nb_in = nb_out + P - 1;
+    if (ctx->aug_part.reserve(sizeof(float2) * FM * (size_t)nlong[l] * (P + nb_in))) return MFPA_ENOMEM;
+    PartArgs a{c, dlist + (size_t)l * B, (float2*)ctx->aug_part.ptr, (float2*)ctx->aug_part.ptr + (size_t)nlong[l] * P * FM, P, nb_in};
+    const dim3 gf(P, nlong[l]), gi(nb_in, nlong[l]), go(nb_out, nlong[l]);
+    if (mode == kModeHP) {
+      part_filter_kernel<kModeHP><<<gf, FT, kConvSmem, st>>>(a, ctx->aug_tw_dev);
+      part_forward_kernel<kModeHP><<<gi, FT, kConvSmem, st>>>(a, ctx->aug_tw_dev);
+      part_conv_kernel<kModeHP><<<go, FT, kConvSmem, st>>>(a, ctx->aug_tw_dev);
+    } else if (mode == kModeIR) {
+      part_filter_kernel<kModeIR><<<gf, FT, kConvSmem, st>>>(a, ctx->aug_tw_dev);
+      part_forward_kernel<kModeIR><<<gi, FT, kConvSmem, st>>>(a, ctx->aug_tw_dev);
+      part_conv_kernel<kModeIR><<<go, FT, kConvSmem, st>>>(a, ctx->aug_tw_dev);
+    } else {
+      part_filter_kernel<kModeLP><<<gf, FT, kConvSmem, st>>>(a, ctx->aug_tw_dev);
+      part_forward_kernel<kModeLP><<<gi, FT, kConvSmem, st>>>(a, ctx->aug_tw_dev);
+      part_conv_kernel<kModeLP><<<go, FT, kConvSmem, st>>>(a, ctx->aug_tw_dev);
+    }
+    MFPA_CUDA(cudaGetLastError());
+    return MFPA_OK;
+  };
 
   auto blocks_for = [&](int n_total, int min_v) { return (unsigned)((n_total + min_v - 1) / min_v); };
   // stage 1: x -> A
@@ -978,6 +1231,7 @@ int launch_augment(mfpa_ctx* ctx, const float* x, int B, int T, int64_t x_stride
     filter_spectrum_kernel<kModeHP><<<B, FT, kConvSmem, st>>>(a, ctx->aug_tw_dev);
     fftconv_kernel<kModeHP><<<dim3(blocks_for(T, min_v1), B), FT, kConvSmem, st>>>(a, ctx->aug_tw_dev);
     MFPA_CUDA(cudaGetLastError());
+    if (int e = run_long(0, kModeHP, a)) return e;
   }
   // stage 2: A -> B
   {
@@ -985,6 +1239,7 @@ int launch_augment(mfpa_ctx* ctx, const float* x, int B, int T, int64_t x_stride
     filter_spectrum_kernel<kModeIR><<<B, FT, kConvSmem, st>>>(a, ctx->aug_tw_dev);
     fftconv_kernel<kModeIR><<<dim3(blocks_for(T + FN - min_vir, min_vir), B), FT, kConvSmem, st>>>(a, ctx->aug_tw_dev);
     MFPA_CUDA(cudaGetLastError());
+    if (int e = run_long(1, kModeIR, a)) return e;
   }
   // stage 3: B -> A (z)
   {
@@ -1013,6 +1268,7 @@ int launch_augment(mfpa_ctx* ctx, const float* x, int B, int T, int64_t x_stride
       filter_spectrum_kernel<kModeHP><<<B, FT, kConvSmem, st>>>(a, ctx->aug_tw_dev);
       fftconv_kernel<kModeLP><<<dim3(blocks_for(T, FN - 2 * max_half2), B), FT, kConvSmem, st>>>(a, ctx->aug_tw_dev);
       MFPA_CUDA(cudaGetLastError());
+      if (int e = run_long(2, kModeLP, a)) return e;
     }
   }
   // stage 6: B -> A (v) ; stage 7: A -> out
@@ -1021,6 +1277,7 @@ int launch_augment(mfpa_ctx* ctx, const float* x, int B, int T, int64_t x_stride
     filter_spectrum_kernel<kModeHP><<<B, FT, kConvSmem, st>>>(a, ctx->aug_tw_dev);
     fftconv_kernel<kModeHP><<<dim3(blocks_for(T, min_v3), B), FT, kConvSmem, st>>>(a, ctx->aug_tw_dev);
     MFPA_CUDA(cudaGetLastError());
+    if (int e = run_long(3, kModeHP, a)) return e;
     const unsigned gx = (unsigned)((T + 4095) / 4096);
     if (out) {   // out == nullptr: the caller consumes stage 6's output in place (ctx->aug_a)
       norm_kernel<<<dim3(gx, B), 256, 0, st>>>(bufA, out, ds, T, final_norm ? 1 : 0);

@@ -134,7 +134,7 @@ void mfpa_destroy(mfpa_ctx* ctx) {
   cudaDeviceSynchronize();
   Scratch* all[] = {&ctx->mag, &ctx->qmax, &ctx->rec, &ctx->fwd, &ctx->hashes, &ctx->nh, &ctx->misc, &ctx->spec64,
                     &ctx->xin, &ctx->out_h, &ctx->out_n, &ctx->aug_a, &ctx->aug_b, &ctx->aug_c, &ctx->aug_d,
-                    &ctx->aug_small, &ctx->aug_lists, &ctx->match_a, &ctx->match_b, &ctx->match_c};
+                    &ctx->aug_small, &ctx->aug_lists, &ctx->aug_long, &ctx->aug_part, &ctx->match_a, &ctx->match_b, &ctx->match_c};
   for (Scratch* s : all) s->release();
   for (int b = 0; b < 2; ++b) {
     ctx->h_x[b].release(); ctx->h_x16[b].release(); ctx->h_rows[b].release(); ctx->h_csr[b].release(); ctx->h_n[b].release(); ctx->h_off[b].release();
@@ -154,6 +154,7 @@ void mfpa_destroy(mfpa_ctx* ctx) {
   if (ctx->index_hashesperid) cudaFree(ctx->index_hashesperid);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->aug_pinned) cudaFreeHost(ctx->aug_pinned);
+  if (ctx->aug_copy_done) cudaEventDestroy((cudaEvent_t)ctx->aug_copy_done);
   if (ctx->aug_tw_dev) cudaFree(ctx->aug_tw_dev);
   delete ctx;
 }

@@ -69,9 +69,10 @@ struct mfpa_ctx {
   float* win_dejavu_dev = nullptr;  // [512] np.hanning(512) x 1/2 (mlab.window_hanning, afp/dejavu/fingerprint.py:64)
   mfpa::Scratch mag, qmax, rec, fwd, hashes, nh, misc, spec64, xin, out_h, out_n;
   // augmentation / matching state is appended by their translation units
-  mfpa::Scratch aug_a, aug_b, aug_c, aug_d, aug_small, aug_lists;
+  mfpa::Scratch aug_a, aug_b, aug_c, aug_d, aug_small, aug_lists, aug_long, aug_part;
   float2* aug_tw_dev = nullptr;     // two-level twiddle tables of the 16384-point FFT (augment.cu)
   void* aug_pinned = nullptr;
+  void* aug_copy_done = nullptr;    // cudaEvent_t: the last H2D copy out of aug_pinned
   size_t aug_pinned_bytes = 0;
   // index shard (match.cu)
   uint32_t* index_table = nullptr;

@@ -61,8 +61,6 @@ def _golden_cases():
 def test_golden_cases(mfpa_ctx):
     lib = _lib()
     for i, x, prm, ref in _golden_cases():
-        if prm.get("fc1") is not None and prm["fc1"] < 4.0:
-            continue  # FIR longer than MFPA_AUG_MAX_TAPS: covered by test_too_long_filter_is_rejected
         arr, ir, noise = _pack(lib, [prm], len(x))
         out = mfpa_ctx.augment(torch.from_numpy(x[None]).cuda(), arr, ir, noise).cpu().numpy()[0]
         assert _rel(out, ref) < TOL, (i, _rel(out, ref))
@@ -106,10 +104,40 @@ def test_random_chains_vs_oracle(mfpa_ctx):
         assert _rel(out[i], ref) < TOL, (i, _rel(out[i], ref), sorted(prms[i]))
 
 
+def test_long_filters_and_long_impulse_responses(mfpa_ctx):
+    """Filters longer than one overlap-save block (the partitioned path): loudspeaker cut-offs of 5, 2.5 and
+    0.7 Hz (12 801, 25 601 and 91 429 taps - the last one longer than the signal), a 2 Hz microphone
+    high-pass, impulse responses of 8193, 20 000 and 70 000 samples (longer than the signal), a long
+    "low-pass", all mixed in one batch with ordinary queries so both paths run in the same launch."""
+    from musicfpaugment_b200 import synth
+
+    lib = _lib()
+    B, T = 8, 32000
+    x = synth.music_like(B, n_samples=T, seed=51).numpy()
+    r = np.random.default_rng(52)   # slowly decaying responses: the tail past 8192 samples matters
+    irs = (r.standard_normal((B, 70000)) * (np.exp(-np.arange(70000) / 9000.0) + 0.02)[None]).astype(np.float32)
+    nz = synth.rms_noise(B, n_samples=T, seed=53).numpy()
+    prms = [
+        {"fc1": 5.0, "ir": irs[0][:8193], "noise": nz[0], "snr_db": 3.0, "gain_factor": 1.2, "clip_p": 0.004, "fc2": 3500.0, "fc3": 60.0},
+        {"fc1": 2.5, "ir": irs[1][:20000], "fc3": 2.0},
+        {"fc1": 0.7, "noise": nz[2], "snr_db": -4.0, "clip_p": 0.009},
+        {"fc1": 90.0, "ir": irs[3][:70000], "fc2": 3900.0},
+        {"fc1": 40.0, "ir": irs[4][:4000], "fc3": 100.0},            # ordinary query between the long ones
+        {"ir": irs[5][:16385]},
+        {"fc2": 6.0, "clip_p": 0.002},                                # 10 667-tap "low-pass"
+        {},
+    ]
+    arr, ir, noise = _pack(lib, prms, T)
+    out = mfpa_ctx.augment(torch.from_numpy(x).cuda(), arr, ir, noise).cpu().numpy()
+    for i in range(B):
+        ref = A.augment_chain(x[i], prms[i])
+        assert _rel(out[i], ref) < TOL, (i, _rel(out[i], ref), sorted(prms[i]))
+
+
 def test_too_long_filter_and_bad_cutoffs_are_rejected(mfpa_ctx):
     lib = _lib()
     x = torch.zeros(1, 8000, device="cuda")
-    for fc in (3.0, 0.0, -5.0, 4100.0):
+    for fc in (0.05, 0.0, -5.0, 4100.0):
         arr = np.zeros(1, dtype=lib.AUG_DTYPE)
         arr["apply"], arr["fc1_hz"] = lib.AUG_HPF1 | lib.AUG_NORM, fc
         with pytest.raises(lib.MfpaError):
