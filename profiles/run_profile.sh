@@ -11,7 +11,7 @@ if [ "${2:-}" != "skip-tests" ]; then
   python -m pytest tests -m gpu -q 2>&1 | tail -15 > $OUT/pytest_$TAG.log
 fi
 python bench.py --steps 10 --warmup 3 > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err
-OURS='stft_mag_kernel|peaks_kernel|peaks_fast_kernel|landmark_kernel|merge_shifts_kernel|offsets_scan_kernel|compact_rows_kernel'
+OURS='stft_mag_kernel|peaks_kernel|peaks_fast_kernel|landmark_kernel|landmark_list_kernel|merge_shifts_kernel|offsets_scan_kernel|compact_rows_kernel'
 AUG='fftconv_kernel|mix_kernel|clip_sample_kernel|clip_finish_kernel|clip_lpf_kernel|norm_kernel|filter_spectrum_kernel'
 MAT='match_fused_kernel|match_counts|match_select_kernel|match_collect_kernel|match_align_kernel'
 UNET='conv_gemm_kernel|conv_halo_kernel|conv_in_kernel|maxpool_kernel'
@@ -23,7 +23,7 @@ finish() {  # $1 = report stem, $2 = launch list
 ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:$OURS|$AUG|$MAT" -c 400 --csv \
     --log-file $OUT/launches_$TAG.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --also chain,match > $OUT/ncu_bench_$TAG.log 2>&1
 # full capture: the three headline kernels (after the 3 warm-up steps) ...
-ncu --set full --clock-control none --import-source on -k "regex:stft_mag_kernel|peaks_fast_kernel|landmark_kernel" -s 9 -c 3 \
+ncu --set full --clock-control none --import-source on -k "regex:stft_mag_kernel|peaks_fast_kernel|landmark_list_kernel" -s 9 -c 3 \
     -o $OUT/prof_$TAG -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline --also none > $OUT/ncu_full_$TAG.log 2>&1
 finish prof_$TAG $OUT/launches_$TAG.csv
 # ... the augmentation kernels (second call of the full-chain leg) ...
