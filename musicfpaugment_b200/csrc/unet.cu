@@ -585,7 +585,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // peak_extractor.py:263); out: NHWC bf16 [N][H][W][64].  A block stages the 10 x 34 input halo of an
 // 8 x 32 pixel tile in shared memory (read along whichever input dimension has unit stride), then every
 // thread produces 8 channels of a pixel so that a warp stores 4 pixels x 128 contiguous bytes.
-constexpr int kInTh = 8, kInTw = 32;
+constexpr int kInTh = 32, kInTw = 32;   // 32 rows per block: the 576 weights each thread keeps in registers are loaded once per 32 pixel rows
 __global__ void __launch_bounds__(256)
 conv_in_kernel(const float* __restrict__ in, long long in_n, long long in_h, long long in_w, const float* __restrict__ div,
                int H, int W, const float* __restrict__ wgt /* [9][64] */, const float* __restrict__ scale,
