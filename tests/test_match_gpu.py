@@ -180,6 +180,53 @@ def test_fused_match_equals_four_step_path(mfpa_ctx, n_tracks, per_track, n_hash
         _rows_equal(res_f[i, : int(nrows_f[i])].cpu().numpy(), want)
 
 
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_candidate_ranking_with_uneven_hashesperid(mfpa_ctx, seed):
+    """_best_count_ids ranks by raw / hashesperid over ALL tracks (audfprint_match.py:110-129): with track
+    lengths spread over two orders of magnitude a short track with few hits outranks long tracks with many,
+    which is what the contender-list shortcut (quotient >= the smallest quotient among tracks above the
+    count threshold; tracks skipped by raw count < m * min(hashesperid)) must get right.  One-kernel
+    matcher, four-step path and the oracle must agree on candidates and result rows."""
+    from musicfpaugment_b200 import lib, synth
+
+    r = np.random.default_rng(100 + seed)
+    n_tracks = [257, 1500, 4001][seed - 1]
+    table, counts, hpid, th = synth.hash_index(n_tracks, 2500, seed=40 + seed)
+    hpid = r.integers(1, 6000, size=n_tracks).astype(np.uint32)        # weights only: any positive value is legal
+    hpid[r.integers(0, n_tracks, size=8)] = 1                           # a few extremely "short" tracks
+    q, nq, _ = synth.planted_queries(th, 6, n_hashes=1200, frac=0.25, seed=50 + seed)
+    h, n = torch.from_numpy(q).cuda(), torch.from_numpy(nq).cuda()
+    mfpa_ctx.index_load(table, counts, hpid)
+    p = lib.match_defaults()
+    res_f, nrows_f = mfpa_ctx.match(h, n, p, max_rows=128)
+    cand_d, ncand_d = mfpa_ctx.match_select(mfpa_ctx.match_counts(h, n), p)   # dense-row selection
+    try:
+        mfpa_ctx.set_option(lib.OPT_MATCH_UNFUSED, 1)
+        res_u, nrows_u = mfpa_ctx.match(h, n, p, max_rows=128)
+    finally:
+        mfpa_ctx.set_option(lib.OPT_MATCH_UNFUSED, 0)
+    assert torch.equal(nrows_f, nrows_u)
+    ht = O.HashTable()
+    ht.table, ht.counts, ht.hashesperid = table, counts, hpid
+    for i in range(len(q)):
+        k = int(nrows_f[i])
+        assert torch.equal(res_f[i, :k], res_u[i, :k]), i
+        # candidates: exact rational order, ties -> higher id first
+        hits = ht.get_hits(q[i, : nq[i]])
+        raw = np.bincount(hits[:, 0], minlength=n_tracks).astype(np.int64)
+        ids = np.nonzero(raw)[0]
+        depth = min(int((raw > p.threshcount).sum()), p.search_depth)
+        assert int(ncand_d[i]) == depth
+        from fractions import Fraction
+        order = sorted(ids.tolist(), key=lambda t: (Fraction(int(raw[t]), int(hpid[t])), t), reverse=True)[:depth]
+        assert cand_d[i, :depth, 0].cpu().tolist() == order, i
+        assert cand_d[i, :depth, 1].cpu().tolist() == [int(raw[t]) for t in order]
+        want = O.match_hashes(ht, q[i, : nq[i]])
+        assert k == len(want), i
+        if k:
+            _rows_equal(res_f[i, :k].cpu().numpy(), want)
+
+
 def test_match_without_index_raises():
     lib = _lib()
     ctx = lib.Context(0)
