@@ -230,6 +230,27 @@ int mfpa_augment(mfpa_ctx* ctx, const float* x_dev, int B, int T, int64_t x_stri
                  const mfpa_aug_params* params_host, const float* ir_dev, int ir_stride,
                  const float* noise_dev, float* out_dev, void* stream);
 
+/* ---- noise preparation ahead of the chain
+ * AddBackgroundNoise.random_background (augmentation/transformations/background_noise.py:64-141):
+ * a query's noise row is the concatenation of pieces cut from randomly chosen background files
+ * (a mix-up pair contributes samplePairing = (a + b) / 2, :11-12), each piece RMS-normalised
+ * (x / (rms + 1e-8), augmentation/utils.py:189-205), the concatenation RMS-normalised again.
+ * The random choices stay on the host (the drop-in draws them in the reference's RNG order);
+ * the arithmetic runs here on a device-resident bank of decoded background audio.
+ * bank_dev: float32 [bank_len], every background file back to back at the target sample rate.
+ * pieces_host [n_pieces]: the pieces of all B rows; every row must be covered exactly once
+ * (pieces of a row tile [0, T)).  out_dev [B][T] contiguous. */
+typedef struct mfpa_noise_piece {
+  int64_t src_a;    /* first sample of the piece in bank_dev */
+  int64_t src_b;    /* second source of a mix-up pair, or -1 */
+  int32_t query;    /* row of out_dev */
+  int32_t dst;      /* first sample in the row */
+  int32_t len;      /* samples (>= 1) */
+  int32_t reserved;
+} mfpa_noise_piece;
+int mfpa_noise_assemble(mfpa_ctx* ctx, const float* bank_dev, int64_t bank_len, const mfpa_noise_piece* pieces_host,
+                        int n_pieces, int B, int T, float* out_dev, void* stream);
+
 /* Fused S1-S4 (BASELINE.json config 3): augment, then fingerprint the degraded queries
  * without leaving the device.  The final peak normalisation is skipped on this path
  * (the spectrogram is divided by its own maximum, peak_extractor.py:263). */

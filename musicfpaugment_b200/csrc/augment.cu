@@ -20,6 +20,8 @@
 // RMS, peak after the mix, clip quantiles, final peak) are produced by the kernel that writes the data.
 #include <math.h>
 
+#include <vector>
+
 #include "common.cuh"
 
 namespace mfpa {
@@ -1068,7 +1070,91 @@ __global__ void __launch_bounds__(256) norm_kernel(const float* __restrict__ v, 
   }
 }
 
+// ---- noise rows from a device-resident bank (random_background, background_noise.py:64-141) ----
+struct NoiseStat { double ss; };   // per piece: sum of squares of the (paired) piece
+
+// grid (chunks, n_pieces): copy the piece (or the mean of a mix-up pair) into its row, sum of squares per piece
+__global__ void __launch_bounds__(256) noise_gather_kernel(const float* __restrict__ bank, const mfpa_noise_piece* __restrict__ pieces,
+                                                           int T, float* __restrict__ out, double* __restrict__ piece_ss) {
+  __shared__ float red[8];
+  const mfpa_noise_piece p = pieces[blockIdx.y];
+  const float* a = bank + p.src_a;
+  const float* b = p.src_b >= 0 ? bank + p.src_b : nullptr;
+  float* o = out + (int64_t)p.query * T + p.dst;
+  float ss = 0.f;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < p.len; i += gridDim.x * 256) {
+    float v = __ldg(a + i);
+    if (b) v = (v + __ldg(b + i)) / 2.0f;   // samplePairing (:11-12)
+    o[i] = v;
+    ss += v * v;
+  }
+#pragma unroll
+  for (int k = 16; k; k >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, k);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    atomicAdd(piece_ss + blockIdx.y, (double)t);
+  }
+}
+
+// one thread per piece: sum of squares of the row after every piece was RMS-normalised
+__global__ void noise_total_kernel(const mfpa_noise_piece* __restrict__ pieces, int n_pieces, const double* __restrict__ piece_ss,
+                                   double* __restrict__ row_ss) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pieces) return;
+  const mfpa_noise_piece p = pieces[i];
+  const float rms = sqrtf((float)(piece_ss[i] / (double)p.len));
+  const float s = 1.0f / (rms + 1e-8f);
+  atomicAdd(row_ss + p.query, piece_ss[i] * (double)s * (double)s);
+}
+
+// grid (chunks, n_pieces): x / (rms_piece + 1e-8) / (rms_row + 1e-8)   (rms_normalize twice, utils.py:189-205)
+__global__ void __launch_bounds__(256) noise_scale_kernel(const mfpa_noise_piece* __restrict__ pieces, int T,
+                                                          const double* __restrict__ piece_ss, const double* __restrict__ row_ss,
+                                                          float* __restrict__ out) {
+  const mfpa_noise_piece p = pieces[blockIdx.y];
+  const float rms_p = sqrtf((float)(piece_ss[blockIdx.y] / (double)p.len));
+  const float rms_r = sqrtf((float)(row_ss[p.query] / (double)T));
+  const float dp = rms_p + 1e-8f, dr = rms_r + 1e-8f;
+  float* o = out + (int64_t)p.query * T + p.dst;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < p.len; i += gridDim.x * 256) o[i] = (o[i] / dp) / dr;
+}
+
 }  // namespace
+
+int launch_noise_assemble(mfpa_ctx* ctx, const float* bank, int64_t bank_len, const mfpa_noise_piece* pieces, int n_pieces,
+                          int B, int T, float* out, cudaStream_t st) {
+  // validate on the host: sources inside the bank, every row tiled exactly once
+  std::vector<int64_t> covered((size_t)B, 0);
+  int max_len = 1;
+  for (int i = 0; i < n_pieces; ++i) {
+    const mfpa_noise_piece& p = pieces[i];
+    MFPA_REQUIRE(p.query >= 0 && p.query < B && p.len >= 1 && p.dst >= 0 && (int64_t)p.dst + p.len <= T,
+                 "noise_assemble: piece %d: row %d, dst %d, len %d outside [0, %d) x [0, %d)", i, p.query, p.dst, p.len, B, T);
+    MFPA_REQUIRE(p.src_a >= 0 && p.src_a + p.len <= bank_len && (p.src_b < 0 || p.src_b + p.len <= bank_len),
+                 "noise_assemble: piece %d reads outside the bank (%lld samples)", i, (long long)bank_len);
+    covered[p.query] += p.len;
+    max_len = p.len > max_len ? p.len : max_len;
+  }
+  for (int q = 0; q < B; ++q)
+    MFPA_REQUIRE(covered[q] == T, "noise_assemble: row %d is covered by %lld samples, not %d", q, (long long)covered[q], T);
+  const size_t bytes = sizeof(mfpa_noise_piece) * (size_t)n_pieces + sizeof(double) * ((size_t)n_pieces + B);
+  if (ctx->aug_noise.reserve(bytes)) return MFPA_ENOMEM;
+  double* piece_ss = (double*)ctx->aug_noise.ptr;
+  double* row_ss = piece_ss + n_pieces;
+  mfpa_noise_piece* dp = (mfpa_noise_piece*)(row_ss + B);
+  MFPA_CUDA(cudaMemcpyAsync(dp, pieces, sizeof(mfpa_noise_piece) * (size_t)n_pieces, cudaMemcpyHostToDevice, st));
+  MFPA_CUDA(cudaStreamSynchronize(st));   // pieces_host is caller-owned pageable memory
+  MFPA_CUDA(cudaMemsetAsync(piece_ss, 0, sizeof(double) * ((size_t)n_pieces + B), st));
+  const dim3 grid((unsigned)((max_len + 4095) / 4096), (unsigned)n_pieces);
+  noise_gather_kernel<<<grid, 256, 0, st>>>(bank, dp, T, out, piece_ss);
+  noise_total_kernel<<<(n_pieces + 255) / 256, 256, 0, st>>>(dp, n_pieces, piece_ss, row_ss);
+  noise_scale_kernel<<<grid, 256, 0, st>>>(dp, T, piece_ss, row_ss, out);
+  MFPA_CUDA(cudaGetLastError());
+  return MFPA_OK;
+}
 
 static int aug_init_tables(mfpa_ctx* ctx) {
   if (ctx->aug_tw_dev) return MFPA_OK;

@@ -134,7 +134,7 @@ void mfpa_destroy(mfpa_ctx* ctx) {
   cudaDeviceSynchronize();
   Scratch* all[] = {&ctx->mag, &ctx->qmax, &ctx->rec, &ctx->fwd, &ctx->hashes, &ctx->nh, &ctx->misc, &ctx->spec64,
                     &ctx->xin, &ctx->out_h, &ctx->out_n, &ctx->aug_a, &ctx->aug_b, &ctx->aug_c, &ctx->aug_d,
-                    &ctx->aug_small, &ctx->aug_lists, &ctx->aug_long, &ctx->aug_part, &ctx->match_a, &ctx->match_b, &ctx->match_c};
+                    &ctx->aug_small, &ctx->aug_lists, &ctx->aug_long, &ctx->aug_part, &ctx->aug_noise, &ctx->match_a, &ctx->match_b, &ctx->match_c};
   for (Scratch* s : all) s->release();
   for (int b = 0; b < 2; ++b) {
     ctx->h_x[b].release(); ctx->h_x16[b].release(); ctx->h_rows[b].release(); ctx->h_csr[b].release(); ctx->h_n[b].release(); ctx->h_off[b].release();
@@ -431,6 +431,14 @@ int mfpa_augment(mfpa_ctx* ctx, const float* x_dev, int B, int T, int64_t x_stri
   DeviceGuard guard(ctx->device);
   return launch_augment(ctx, x_dev, B, T, x_stride, sample_rate, params_host, ir_dev, ir_stride, noise_dev, out_dev,
                         true, (cudaStream_t)stream);
+}
+
+int mfpa_noise_assemble(mfpa_ctx* ctx, const float* bank_dev, int64_t bank_len, const mfpa_noise_piece* pieces_host,
+                        int n_pieces, int B, int T, float* out_dev, void* stream) {
+  MFPA_REQUIRE(ctx && bank_dev && pieces_host && out_dev, "noise_assemble: NULL argument");
+  MFPA_REQUIRE(bank_len >= 1 && n_pieces >= 1 && B >= 1 && T >= 1, "noise_assemble: bad sizes");
+  DeviceGuard guard(ctx->device);
+  return launch_noise_assemble(ctx, bank_dev, bank_len, pieces_host, n_pieces, B, T, out_dev, (cudaStream_t)stream);
 }
 
 int mfpa_augment_fingerprint(mfpa_ctx* ctx, const float* x_dev, int B, int T, int64_t x_stride, int sample_rate,

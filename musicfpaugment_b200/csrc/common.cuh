@@ -69,7 +69,7 @@ struct mfpa_ctx {
   float* win_dejavu_dev = nullptr;  // [512] np.hanning(512) x 1/2 (mlab.window_hanning, afp/dejavu/fingerprint.py:64)
   mfpa::Scratch mag, qmax, rec, fwd, hashes, nh, misc, spec64, xin, out_h, out_n;
   // augmentation / matching state is appended by their translation units
-  mfpa::Scratch aug_a, aug_b, aug_c, aug_d, aug_small, aug_lists, aug_long, aug_part;
+  mfpa::Scratch aug_a, aug_b, aug_c, aug_d, aug_small, aug_lists, aug_long, aug_part, aug_noise;
   float2* aug_tw_dev = nullptr;     // two-level twiddle tables of the 16384-point FFT (augment.cu)
   void* aug_pinned = nullptr;
   void* aug_copy_done = nullptr;    // cudaEvent_t: the last H2D copy out of aug_pinned
@@ -116,6 +116,8 @@ int launch_compact_rows(const int32_t* rows_in, const int32_t* n, int items, int
 int launch_augment(mfpa_ctx* ctx, const float* x, int B, int T, int64_t x_stride, int sample_rate,
                    const mfpa_aug_params* params_host, const float* ir, int ir_stride, const float* noise,
                    float* out, bool final_norm, cudaStream_t st);
+int launch_noise_assemble(mfpa_ctx* ctx, const float* bank, int64_t bank_len, const mfpa_noise_piece* pieces, int n_pieces,
+                          int B, int T, float* out, cudaStream_t st);
 int launch_match_counts(mfpa_ctx* ctx, const int32_t* hashes, const int32_t* nh, int B, int cap, int32_t* counts,
                         cudaStream_t st);
 bool match_fused_ok(const mfpa_ctx* ctx);

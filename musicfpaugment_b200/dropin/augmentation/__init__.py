@@ -190,6 +190,9 @@ class AddBackgroundNoise(_Transform):
             raise ValueError("min_snr_in_db must not be greater than max_snr_in_db")
         self.min_snr_in_db, self.max_snr_in_db = min_snr_in_db, max_snr_in_db
         self.audio = Audio(sample_rate=sample_rate, mono=True)
+        # background audio decoded once into a device-resident bank; noise rows are assembled on the GPU
+        self.device_bank = torch.cuda.is_available()   # parameter draws alone (no GPU) keep the host assembly
+        self._bank_index, self._bank_new, self._bank_keep, self._bank_len, self._bank_dev = {}, [], [], 0, None
 
     def random_background(self, target_num_samples: int) -> torch.Tensor:
         """background_noise.py:64-141 — pieces from random scenes/files until the length is reached,
@@ -219,8 +222,90 @@ class AddBackgroundNoise(_Transform):
             pieces.append(piece)
         return audio.rms_normalize(torch.cat([audio.rms_normalize(p) for p in pieces], dim=1))
 
+    # ---- device path: the same draws, the arithmetic in mfpa_noise_assemble -------------
+    def _bank_entry(self, path):
+        """(offset in the bank, length) of a background file decoded once at the target rate; None when the
+        file's own rate differs (the reference resamples each excerpt separately, so excerpts of a resampled
+        whole would not be the same numbers - such files stay on the host path)."""
+        key = id(path) if isinstance(path, dict) else str(path)
+        ent = self._bank_index.get(key)
+        if ent is None:
+            _, sr = self.audio._meta(path)
+            if sr != self.audio.sample_rate:
+                ent = False
+            else:
+                wav = self.audio(path)[0].contiguous()
+                ent = (self._bank_len, wav.shape[0])
+                self._bank_new.append(wav)
+                self._bank_len += wav.shape[0]
+            self._bank_index[key] = ent
+            if isinstance(path, dict):
+                self._bank_keep.append(path)   # id() keys stay valid only while the object lives
+        return ent or None
+
+    def _bank(self):
+        if self._bank_new:
+            parts = ([self._bank_dev] if self._bank_dev is not None else []) + [w.cuda() for w in self._bank_new]
+            self._bank_dev, self._bank_new = torch.cat(parts), []
+        return self._bank_dev
+
+    def _draw_pieces(self, row: int, target_num_samples: int):
+        """random_background's control flow (background_noise.py:64-141) with the same RNG calls, producing
+        mfpa_noise_piece rows instead of audio; None if a chosen file cannot come from the bank (the draws
+        made so far are then replayed on the host path by the caller, which restores the RNG state)."""
+        pieces, missing, audio = [], target_num_samples, self.audio
+        while missing > 0:
+            scene = random.choice(list(self.background_paths_to_update.keys()))
+            path = random.choice(self.background_paths_to_update[str(scene)])
+            dst = target_num_samples - missing
+            if isinstance(path, (list, tuple)) and len(path) == 2:  # mix-up pair (:80-113)
+                ea, eb = self._bank_entry(path[0]), self._bank_entry(path[1])
+                if ea is None or eb is None:
+                    return None
+                n_bg = min(audio.get_num_samples(path[0]), audio.get_num_samples(path[1]))
+                if n_bg >= missing:
+                    o1 = random.randint(0, n_bg - missing)
+                    o2 = random.randint(0, n_bg - missing)
+                    pieces.append((ea[0] + o1, eb[0] + o2, row, dst, missing))
+                    missing = 0
+                else:  # sic: path[0] twice, whole file (App. B.5)
+                    pieces.append((ea[0], ea[0], row, dst, ea[1]))
+                    missing -= n_bg
+            else:
+                e = self._bank_entry(path)
+                if e is None:
+                    return None
+                n_bg = audio.get_num_samples(path)
+                if n_bg >= missing:
+                    off = random.randint(0, n_bg - missing)
+                    pieces.append((e[0] + off, -1, row, dst, missing))
+                    missing = 0
+                else:
+                    pieces.append((e[0], -1, row, dst, e[1]))
+                    missing -= n_bg
+        return pieces
+
+    def random_backgrounds_device(self, n: int, target_num_samples: int):
+        """n noise rows [n, 1, T] on the GPU, or None when some source file is not at the target rate."""
+        state = random.getstate()
+        rows = []
+        for r in range(n):
+            pcs = self._draw_pieces(r, target_num_samples)
+            if pcs is None or sum(p[4] for p in pcs) != target_num_samples:   # a short whole-file piece overshoots: host path
+                random.setstate(state)
+                return None
+            rows.extend(pcs)
+        arr = np.zeros(len(rows), dtype=lib.NOISE_PIECE_DTYPE)
+        for i, (a, b, q, dst, ln) in enumerate(rows):
+            arr[i] = (a, b, q, dst, ln, 0)
+        out = runtime.get_context().noise_assemble(self._bank(), arr, n, target_num_samples)
+        return out.unsqueeze(1)
+
     def randomize_parameters(self, n, num_samples):
-        self.transform_parameters["background"] = torch.stack([self.random_background(num_samples) for _ in range(n)])
+        bg = self.random_backgrounds_device(n, num_samples) if self.device_bank else None
+        if bg is None:
+            bg = torch.stack([self.random_background(num_samples) for _ in range(n)])
+        self.transform_parameters["background"] = bg
         if self.min_snr_in_db == self.max_snr_in_db:
             self.transform_parameters["snr_in_db"] = torch.full((n,), float(self.min_snr_in_db), dtype=torch.float32)
         else:
@@ -308,8 +393,9 @@ class Compose:
                 ir[torch.from_numpy(sel)] = prm["ir"][:, 0, :]
                 arr["ir_len"][sel] = prm["ir"].shape[-1]  # zero-padded to the longest, like pad_sequence (:65-69)
             elif isinstance(t, AddBackgroundNoise):
-                noise = torch.zeros(batch_size, num_samples)
-                noise[torch.from_numpy(sel)] = prm["background"][:, 0, :]
+                bg = prm["background"][:, 0, :]
+                noise = torch.zeros(batch_size, num_samples, device=bg.device)   # the device bank leaves it on the GPU
+                noise[torch.from_numpy(sel).to(bg.device)] = bg
                 arr["snr_db"][sel] = prm["snr_in_db"].numpy()
             elif isinstance(t, Gain):
                 arr["gain_factor"][sel] = prm["gain_factors"].reshape(-1).numpy()

@@ -43,6 +43,8 @@ AUG_HPF1, AUG_IR, AUG_NOISE, AUG_GAIN, AUG_CLIP, AUG_LPF, AUG_HPF3, AUG_NORM = 1
 AUG_ALL = 255
 AUG_DTYPE = [("apply", "<u4"), ("fc1_hz", "<f4"), ("fc2_hz", "<f4"), ("fc3_hz", "<f4"), ("snr_db", "<f4"),
              ("gain_factor", "<f4"), ("clip_p", "<f4"), ("ir_len", "<i4")]
+# mfpa_noise_piece
+NOISE_PIECE_DTYPE = [("src_a", "<i8"), ("src_b", "<i8"), ("query", "<i4"), ("dst", "<i4"), ("len", "<i4"), ("reserved", "<i4")]
 
 
 class MatchParams(C.Structure):
@@ -82,6 +84,7 @@ SIGNATURES = {
     "mfpa_fingerprint_host": (_i, [_vp, _vp, _i, _i, _i, _P, _vp, _i64, _vp]),
     "mfpa_fingerprint_host_pcm16": (_i, [_vp, _vp, _i, _i, _i, _P, _vp, _i64, _vp]),
     "mfpa_augment": (_i, [_vp, _vp, _i, _i, _i64, _i, _vp, _vp, _i, _vp, _vp, _vp]),
+    "mfpa_noise_assemble": (_i, [_vp, _vp, _i64, _vp, _i, _i, _i, _vp, _vp]),
     "mfpa_augment_fingerprint": (_i, [_vp, _vp, _i, _i, _i64, _i, _vp, _vp, _i, _vp, _i, _P, _vp, _i, _vp, _vp]),
     "mfpa_index_load": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i]),
     "mfpa_match_defaults": (None, [C.POINTER(MatchParams)]),
@@ -335,6 +338,19 @@ class Context:
         out = torch.empty(B, T, dtype=torch.float32, device=x.device)
         check(_lib.mfpa_augment(self._h, _ptr(x), B, T, _row_stride(x), sample_rate, params.ctypes.data_as(C.c_void_p),
                                 _ptr(ir), ir.shape[1] if ir is not None else 0, _ptr(noise), _ptr(out), _stream()))
+        return out
+
+    def noise_assemble(self, bank, pieces, B: int, T: int):
+        """AddBackgroundNoise.random_background for a batch (background_noise.py:64-141) from a device bank:
+        bank f32 [bank_len] cuda; pieces: numpy structured array (NOISE_PIECE_DTYPE) -> [B,T] f32 cuda."""
+        import numpy as np
+        import torch
+
+        assert bank.is_cuda and bank.dtype == torch.float32 and bank.dim() == 1 and bank.is_contiguous()
+        pieces = np.ascontiguousarray(pieces, dtype=NOISE_PIECE_DTYPE)
+        out = torch.empty(B, T, dtype=torch.float32, device=bank.device)
+        check(_lib.mfpa_noise_assemble(self._h, _ptr(bank), bank.numel(), pieces.ctypes.data_as(C.c_void_p), len(pieces),
+                                       B, T, _ptr(out), _stream()))
         return out
 
     def augment_fingerprint(self, x, params, ir, noise, shifts: int, afp: AfpParams, sample_rate: int = 8000):

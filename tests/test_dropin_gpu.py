@@ -112,7 +112,7 @@ def test_augmentfp_call_matches_oracle_on_dumped_parameters(mods):
     assert y.shape == (1, 32000) and not y.is_cuda
     t = a.augmentation_pipeline.transforms
     prm = dict(fc1=float(t[0].transform_parameters["cutoff_freq"][0]), ir=t[1].transform_parameters["ir"][0, 0].numpy(),
-               noise=t[2].transform_parameters["background"][0, 0].numpy(), snr_db=float(t[2].transform_parameters["snr_in_db"][0]),
+               noise=t[2].transform_parameters["background"][0, 0].cpu().numpy(), snr_db=float(t[2].transform_parameters["snr_in_db"][0]),
                gain_factor=float(t[3].transform_parameters["gain_factors"].reshape(-1)[0]),
                clip_p=float(t[4].transform_parameters["percentile_threshold"].reshape(-1)[0]),
                fc2=float(t[5].transform_parameters["cutoff_freq"][0]), fc3=float(t[6].transform_parameters["cutoff_freq"][0]))
@@ -120,6 +120,37 @@ def test_augmentfp_call_matches_oracle_on_dumped_parameters(mods):
     assert np.abs(y[0].numpy() - ref).max() / np.abs(ref).max() < 1e-4
     yb = a.batch_augment(torch.from_numpy(_queries(3)[:, None, :16000]))
     assert yb.shape == (3, 1, 16000) and torch.isfinite(yb).all()
+
+
+def test_noise_rows_from_the_device_bank_equal_the_host_assembly(mods):
+    """AddBackgroundNoise.random_background (background_noise.py:64-141): with the same `random` seed the
+    device path (piece descriptors -> mfpa_noise_assemble on a bank of decoded files) gives the rows the
+    host path builds with torch: single files longer and shorter than the query (several pieces per row),
+    a mix-up pair, and both RMS normalisations."""
+    import random
+
+    aug = mods["aug"]
+    g = torch.Generator().manual_seed(11)
+    mk = lambda n, a=1.0: {"samples": a * torch.randn(1, n, generator=g), "sample_rate": 8000}
+    pair = [mk(70000, 0.3), mk(90000, 2.0)]
+    bg = {"street": [mk(90000), mk(5000, 0.1), mk(20000, 3.0)], "cafe": [pair, mk(64000)], "rain": [mk(1234)]}
+    t = aug.AddBackgroundNoise(bg, min_snr_in_db=0.0, max_snr_in_db=10.0, p=1.0, sample_rate=8000)
+    assert t.device_bank
+    T, n = 64000, 24
+    random.seed(5)
+    dev = t.random_backgrounds_device(n, T)
+    state_after_device = random.getstate()
+    assert dev is not None and dev.is_cuda and dev.shape == (n, 1, T)
+    random.seed(5)
+    host = torch.stack([t.random_background(T) for _ in range(n)])
+    assert random.getstate() == state_after_device          # the same number of draws
+    err = (dev.cpu() - host).abs().max().item()
+    assert err < 2e-6 * host.abs().max().item(), err
+    rms = dev.square().mean(dim=-1).sqrt()
+    assert torch.allclose(rms, torch.ones_like(rms), atol=1e-5)
+    # a file at another sample rate is not bankable: the transform falls back to the host assembly
+    t2 = aug.AddBackgroundNoise({"x": [{"samples": torch.randn(1, 200000, generator=g), "sample_rate": 16000}]}, p=1.0, sample_rate=8000)
+    assert t2.random_backgrounds_device(2, 8000) is None
 
 
 def test_find_peaks_with_unet_denoising(mods):
