@@ -263,10 +263,10 @@ __device__ __forceinline__ void fused_sweep(const IndexView& ix, const int2* __r
         for (int a = 0; a < 4; ++a) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const int id = (int)(v[a][i] >> ix.maxtimebits) - 1;
-            if (id < 0 || id >= ix.n_tracks) continue;
+            const unsigned id = (v[a][i] >> ix.maxtimebits) - 1u;   // empty slot -> 0xffffffff
+            if (id >= (unsigned)ix.n_tracks) continue;
             if (!COLLECT) {
-              atomicAdd(&hist[id >> 1], (id & 1) ? 0x10000u : 1u);
+              atomicAdd(&hist[id >> 1], 1u << ((id & 1u) << 4));
             } else {
               const unsigned k = mark[id];
               if (k) {
@@ -316,16 +316,16 @@ match_fused_kernel(const IndexView ix, const int32_t* __restrict__ hashes, const
   constexpr int kContCap = (int)(sizeof(RowCache) / sizeof(int));
   int gt = 0;
   float fmin = INFINITY;
-  for (int w = tid; w < words; w += kFusedThreads) {
-    const unsigned h2 = hist[w];
-    if (!h2) continue;
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const int raw = (int)((h2 >> (16 * e)) & 0xffffu);
-      if (raw > threshcount) {
-        ++gt;
-        fmin = fminf(fmin, __fdividef((float)raw, (float)__ldg(ix.hashesperid + 2 * w + e)));
-      }
+  // uniform trip count so the (rare) tracks above the count threshold can be handled behind a warp vote:
+  // the common iteration is one shared-memory load and two compares
+  for (int w0 = 0; w0 < words; w0 += kFusedThreads) {
+    const int w = w0 + tid;
+    const unsigned h2 = w < words ? hist[w] : 0u;
+    const int r0 = (int)(h2 & 0xffffu), r1 = (int)(h2 >> 16);
+    const bool hit = r0 > threshcount || r1 > threshcount;
+    if (__any_sync(kFull, hit)) {
+      if (r0 > threshcount) { ++gt; fmin = fminf(fmin, __fdividef((float)r0, (float)__ldg(ix.hashesperid + 2 * w))); }
+      if (r1 > threshcount) { ++gt; fmin = fminf(fmin, __fdividef((float)r1, (float)__ldg(ix.hashesperid + 2 * w + 1))); }
     }
   }
 #pragma unroll
@@ -344,16 +344,19 @@ match_fused_kernel(const IndexView ix, const int32_t* __restrict__ hashes, const
   if (tid == 0) ncand[q] = depth;
   bool listed = depth > 0;
   if (listed) {
-    for (int w = tid; w < words; w += kFusedThreads) {
-      const unsigned h2 = hist[w];
-      if (!h2) continue;
+    for (int w0 = 0; w0 < words; w0 += kFusedThreads) {
+      const int w = w0 + tid;
+      const unsigned h2 = w < words ? hist[w] : 0u;
+      const int r0 = (int)(h2 & 0xffffu), r1 = (int)(h2 >> 16);
+      if (__any_sync(kFull, r0 >= raw_min || r1 >= raw_min)) {
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int raw = (int)((h2 >> (16 * e)) & 0xffffu), i = 2 * w + e;
-        if (raw < raw_min) continue;
-        if (__fdividef((float)raw, (float)__ldg(ix.hashesperid + i)) < cut) continue;
-        const int slot = atomicAdd(&s_n, 1);
-        if (slot < kContCap) contenders[slot] = i;
+        for (int e = 0; e < 2; ++e) {
+          const int raw = e ? r1 : r0, i = 2 * w + e;
+          if (raw < raw_min) continue;
+          if (__fdividef((float)raw, (float)__ldg(ix.hashesperid + i)) < cut) continue;
+          const int slot = atomicAdd(&s_n, 1);
+          if (slot < kContCap) contenders[slot] = i;
+        }
       }
     }
     __syncthreads();
