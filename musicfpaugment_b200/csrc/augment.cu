@@ -429,20 +429,6 @@ constexpr int kSelSample = 512;    // strided sample that places the tail thresh
 constexpr int kSelCap = 4096;      // capacity of each tail list
 constexpr int kMixStage = 256;     // per-block staging of the tails in mix_kernel
 
-// ascending bitonic sort of a[0..n), n a power of two <= 2048, by the whole block
-__device__ __forceinline__ void bitonic_sort(unsigned* a, int n, int tid) {
-  for (int k = 2; k <= n; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = tid; i < (n >> 1); i += kSelThreads) {
-        const int l = ((i & ~(j - 1)) << 1) | (i & (j - 1)), r = l | j;
-        const unsigned x = a[l], y = a[r];
-        if ((x > y) == ((l & k) == 0)) { a[l] = y; a[r] = x; }
-      }
-      __syncthreads();
-    }
-  }
-}
-
 // General exact radix select (any rank): sorted[r] for two ranks at once, 8 bits per pass, then one
 // more pass for the successors sorted[r+1].  Fallback of clip_select_kernel.
 __device__ void clip_select_general(const float* __restrict__ z, int T, const int (&r0)[2], unsigned (&hist)[2][256],

@@ -476,7 +476,7 @@ __global__ void __launch_bounds__(256) match_align_kernel(const uint32_t* __rest
   uint32_t* keys = sm;                    // [kAlignCap] sorted hits
   uint32_t* bin_key = sm + kAlignCap;     // [kAlignCap] run starts: key of each distinct (cand, dt)
   int* bin_cnt = reinterpret_cast<int*>(sm + 2 * kAlignCap);  // [kAlignCap]
-  __shared__ int s_total, s_nbins, s_rows, s_seg[130];
+  __shared__ int s_total, s_rows, s_seg[130];
   const int q = blockIdx.x, tid = threadIdx.x;
   const int nc = min(ncand[q], min(search_depth, 128));
   if (tid == 0) { s_total = 0; s_rows = 0; }
@@ -528,7 +528,6 @@ __global__ void __launch_bounds__(256) match_align_kernel(const uint32_t* __rest
       if (nb == 0 || bin_key[nb - 1] != keys[i]) { bin_key[nb] = keys[i]; bin_cnt[nb] = 0; ++nb; }
       ++bin_cnt[nb - 1];
     }
-    s_nbins = nb;
     // segment boundaries per candidate
     int b = 0;
     for (int c = 0; c < nc; ++c) {
