@@ -134,6 +134,29 @@ def test_long_filters_and_long_impulse_responses(mfpa_ctx):
         assert _rel(out[i], ref) < TOL, (i, _rel(out[i], ref), sorted(prms[i]))
 
 
+def test_partition_boundaries_and_short_signals(mfpa_ctx):
+    """Either side of the fast/partitioned switch (8193 vs 8205 taps; 8192- vs 8193-sample responses) and
+    signals much shorter than one partition with filters many times their length."""
+    lib = _lib()
+    for T, seed in ((20000, 61), (3000, 62), (257, 63)):
+        r = np.random.default_rng(seed)
+        x = r.standard_normal((6, T)).astype(np.float32) * 0.3
+        ir = (r.standard_normal((6, 8193)) * np.exp(-np.arange(8193) / 3000.0)[None]).astype(np.float32)
+        prms = [
+            {"fc1": 7.8125},                      # half = 4096: 8193 taps, the longest single-block filter
+            {"fc1": 7.8},                         # half = 4102: 8205 taps, two partitions
+            {"ir": ir[2][:8192]},
+            {"ir": ir[3][:8193]},
+            {"fc1": 2.0, "ir": ir[4][:8193], "fc3": 3.0, "clip_p": 0.005},
+            {"fc3": 0.5},                         # 128 001 taps
+        ]
+        arr, ird, noise = _pack(lib, prms, T)
+        out = mfpa_ctx.augment(torch.from_numpy(x).cuda(), arr, ird, noise).cpu().numpy()
+        for i in range(6):
+            ref = A.augment_chain(x[i], prms[i])
+            assert _rel(out[i], ref) < TOL, (T, i, _rel(out[i], ref), sorted(prms[i]))
+
+
 def test_too_long_filter_and_bad_cutoffs_are_rejected(mfpa_ctx):
     lib = _lib()
     x = torch.zeros(1, 8000, device="cuda")
