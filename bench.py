@@ -364,11 +364,11 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             extras["full_chain"]["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                                                     "sample": f"{nq} queries (2 per core), numpy oracle of the chain + wavfile2hashes"}
     if "match" in args.also:
-        ms, top1, nqh = bench_match(ctx, lib, dev, rank, world, B, args.tracks, max(2, args.steps // 2), 3, barrier)
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        ms, top1, nqh, rep = bench_match(ctx, lib, dev, rank, world, B, args.tracks, max(2, args.steps // 2), 3, barrier)
+        t = torch.tensor([ms, rep[0] if rep else 0.0], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+        ms, ms_rep = float(t[0].item()), float(t[1].item())
         extras["match"] = {
             "workload": f"{B} planted 400-hash queries (the same batch on every rank) vs a synthetic {args.tracks}-track index "
                         f"(1000 hashes/track, depth 100) sharded by hash range over {world} GPU(s) (BASELINE.json configs[4])",
@@ -376,6 +376,12 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "top1_equals_planted_track": top1, "query_hashes": nqh,
             "collective": "none" if world == 1 else "NCCL reduce-scatter of packed per-track counts (query owners), all-gather of "
                                                                   "candidates, all-to-all of candidate hit lists, all-gather of result rows"}
+        if rep:
+            extras["match"]["replicated_index"] = {
+                "workload": "the same queries against the whole index replicated on every rank, queries sharded "
+                            "(sharded.match_replicated: no data-path collective, result rows all-gathered)",
+                "value": B / (ms_rep * 1e-3), "unit": "queries/s", "ms_per_step": ms_rep, "scaling": "strong",
+                "rows_equal_hash_range_mode": rep[1]}
     if "unet" in args.also:
         Bu = args.unet_queries
         ms, finite = bench_unet(ctx, lib, dev, rank, Bu, max(2, args.steps // 3), 2, barrier, args.unet_chunk)
@@ -517,7 +523,25 @@ def bench_match(ctx, lib, dev, rank, world, B, n_tracks, steps, warmup, barrier)
     barrier()
     ms = e0.elapsed_time(e1) / steps
     top1 = float(((nrows > 0) & (res[:, 0, 0] == truth)).float().mean().item())
-    return ms, top1, int(nq.sum().item())
+    rep = None
+    if world > 1:
+        # throughput mode: the whole index on every rank, queries sharded, rows all-gathered
+        ctx.set_option(lib.OPT_MATCH_PACKED, 0)
+        table, counts, hpid, _, _ = synth.hash_index_device(n_tracks, 1000, seed=5000, device=dev)
+        ctx.index_load(table.cpu().numpy().view("uint32"), counts.cpu().numpy(), hpid.cpu().numpy().astype("uint32"))
+        del table
+        torch.cuda.empty_cache()
+        for _ in range(warmup):
+            res2, nrows2 = sharded.match_replicated(ctx, q, nq, mp, max_rows=4)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            res2, nrows2 = sharded.match_replicated(ctx, q, nq, mp, max_rows=4)
+        e1.record()
+        barrier()
+        same = bool(torch.equal(nrows2, nrows) and torch.equal(res2[:, 0, :4], res[:, 0, :4]))
+        rep = (e0.elapsed_time(e1) / steps, same)
+    return ms, top1, int(nq.sum().item()), rep
 
 
 UNET_GFLOP = 93.40  # per 257x251 spectrogram, SURVEY.md App. A.8

@@ -104,3 +104,33 @@ def match_sharded(ctx, hashes, nh, params=None, max_rows: int = 16, list_cap: in
             r, n = _all_gather_rows(r_m, world, group), _all_gather_rows(n_m, world, group)
         res[q0:q0 + n_real], nrows[q0:q0 + n_real] = r[:n_real], n[:n_real]
     return res, nrows
+
+
+def match_replicated(ctx, hashes, nh, params=None, max_rows: int = 16, group=None):
+    """match_hashes for a batch every rank holds, against an index REPLICATED on every rank (each `ctx` holds
+    the whole table: the reference's 2^20 x 100 table is 419 MB).  Queries are the independent units: rank r
+    matches its `query_slice` with the one-kernel matcher and the result rows are all-gathered - no collective
+    on the data path.  This is the throughput mode; `match_sharded` (hash-range shards, histograms summed over
+    NCCL) is the capacity mode for indexes that do not fit one GPU.  Returns (results [B,max_rows,7],
+    nrows [B]) identical on every rank."""
+    import torch
+    import torch.distributed as dist
+
+    from . import lib
+
+    params = params or lib.match_defaults()
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    B = hashes.shape[0]
+    if world == 1:
+        return ctx.match(hashes, nh, params, max_rows)
+    per = -(-B // world)
+    lo, hi = query_slice(B, rank, world)
+    res = torch.zeros(per, max_rows, 7, dtype=torch.int32, device=hashes.device)
+    nrows = torch.zeros(per, dtype=torch.int32, device=hashes.device)
+    if hi > lo:
+        r, n = ctx.match(hashes[lo:hi], nh[lo:hi], params, max_rows)
+        res[: hi - lo], nrows[: hi - lo] = r, n
+    res_all, nrows_all = _all_gather_rows(res, world, group), _all_gather_rows(nrows, world, group)
+    return res_all[:B], nrows_all[:B]
+

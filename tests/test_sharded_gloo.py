@@ -106,6 +106,14 @@ class NumpyShardCtx:
         return res, nrows
 
 
+    def match(self, hashes, nh, p, max_rows):
+        """lib.Context.match (one shard holds the whole index): the four steps back to back."""
+        counts = self.match_counts(hashes, nh)
+        cand, ncand = self.match_select(counts, p)
+        lst, nlist = self.match_collect(hashes, nh, cand, ncand, p, 4096)
+        return self.match_align(lst[None], nlist[None], cand, ncand, p, max_rows)
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -126,6 +134,10 @@ def _worker(rank, world, port, out_dir):
         gathered = [torch.zeros_like(res) for _ in range(world)]
         dist.all_gather(gathered, res)
         assert all(torch.equal(gathered[0], g) for g in gathered)
+        # throughput mode: the whole index on every rank, queries sharded, rows all-gathered - same rows
+        full = NumpyShardCtx(table, counts, hpid, 0, 1 << 20)
+        res_r, nrows_r = sharded.match_replicated(full, torch.from_numpy(q), torch.from_numpy(nq), params=_P, max_rows=8)
+        assert res_r.shape == res.shape and torch.equal(nrows_r, nrows) and torch.equal(res_r, res)
         # query-sharded fingerprint slices cover the batch exactly once
         mine = torch.zeros(11, dtype=torch.int32)
         a, b = sharded.query_slice(11, rank, world)
