@@ -34,39 +34,8 @@ struct IndexView {
 };
 
 // ---- counts ------------------------------------------------------------------------------
-// One block per query.  Every query hash that falls in this shard contributes the first
-// min(depth, counts[h]) entries of its bucket (hash_table.py:235-236).  One warp per hash,
-// lanes stride the 400-byte bucket row.
-__global__ void __launch_bounds__(kCountThreads) match_counts_kernel(const IndexView ix, const int32_t* __restrict__ hashes,
-                                                                    const int32_t* __restrict__ nh, int cap,
-                                                                    int32_t* __restrict__ out, int packed) {
-  extern __shared__ unsigned hist[];  // two 16-bit counters per word
-  const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int words = (ix.n_tracks + 1) >> 1;
-  for (int i = tid; i < words; i += kCountThreads) hist[i] = 0;
-  __syncthreads();
-  const int2* rows = reinterpret_cast<const int2*>(hashes) + (int64_t)q * cap;
-  const int n = min(nh[q], cap);
-  for (int r = warp; r < n; r += kCountThreads / 32) {
-    const int h = (rows[r].y & ix.hashmask) - ix.hash_lo;
-    if (h < 0 || h >= ix.n_buckets) continue;  // warp-uniform
-    const int cnt = min(ix.depth, ix.counts[h]);
-    const uint32_t* bucket = ix.table + (int64_t)h * ix.depth;
-    for (int s = lane; s < cnt; s += 32) {
-      const int id = (int)(bucket[s] >> ix.maxtimebits) - 1;
-      if (id >= 0 && id < ix.n_tracks) atomicAdd(&hist[id >> 1], (id & 1) ? 0x10000u : 1u);
-    }
-  }
-  __syncthreads();
-  if (packed) {  // MFPA_OPT_MATCH_PACKED: hand out the 16-bit pairs as they are (half the bytes to all-reduce)
-    unsigned* o = reinterpret_cast<unsigned*>(out) + (int64_t)q * words;
-    for (int i = tid; i < words; i += kCountThreads) o[i] = hist[i];
-    return;
-  }
-  int32_t* o = out + (int64_t)q * ix.n_tracks;
-  for (int i = tid; i < ix.n_tracks; i += kCountThreads) o[i] = (int)((hist[i >> 1] >> ((i & 1) * 16)) & 0xffffu);
-}
-
+// (the shared-memory histogram version is match_counts_sweep_kernel, next to the sweep it shares with the
+// one-kernel matcher)
 // Fallback for indexes with more tracks than the shared-memory histogram holds: atomics on the dense row.
 __global__ void __launch_bounds__(kCountThreads) match_counts_global_kernel(const IndexView ix, const int32_t* __restrict__ hashes,
                                                                            const int32_t* __restrict__ nh, int cap,
@@ -281,6 +250,31 @@ __device__ __forceinline__ void fused_sweep(const IndexView& ix, const int2* __r
     }
   }
   __syncthreads();
+}
+
+// counts step of the sharded path: the same first sweep, histogram written out as a dense row (int32, or the
+// 16-bit pairs as they are under MFPA_OPT_MATCH_PACKED: half the bytes to reduce-scatter).  One block per
+// query; every query hash that falls in this shard contributes the first min(depth, counts[h]) entries of
+// its bucket (hash_table.py:235-236).
+__global__ void __launch_bounds__(kFusedThreads, 1)
+match_counts_sweep_kernel(const IndexView ix, const int32_t* __restrict__ hashes, const int32_t* __restrict__ nh, int cap,
+                          int32_t* __restrict__ out, int packed) {
+  extern __shared__ __align__(16) unsigned fused_smem[];
+  const int words = (ix.n_tracks + 1) >> 1;
+  unsigned* hist = fused_smem;
+  RowCache* rc = reinterpret_cast<RowCache*>(fused_smem + ((words + 3) & ~3));
+  const int q = blockIdx.x, tid = threadIdx.x;
+  const int2* rows = reinterpret_cast<const int2*>(hashes) + (int64_t)q * cap;
+  const int n = min(nh[q], cap);
+  for (int i = tid; i < words; i += kFusedThreads) hist[i] = 0;
+  fused_sweep<false>(ix, rows, n, rc, hist, nullptr, 0, nullptr, tid);
+  if (packed) {
+    unsigned* o = reinterpret_cast<unsigned*>(out) + (int64_t)q * words;
+    for (int i = tid; i < words; i += kFusedThreads) o[i] = hist[i];
+    return;
+  }
+  int32_t* o = out + (int64_t)q * ix.n_tracks;
+  for (int i = tid; i < ix.n_tracks; i += kFusedThreads) o[i] = (int)((hist[i >> 1] >> ((i & 1) * 16)) & 0xffffu);
 }
 
 __global__ void __launch_bounds__(kFusedThreads, 1)
@@ -651,9 +645,10 @@ int launch_match_counts(mfpa_ctx* ctx, const int32_t* hashes, const int32_t* nh,
                         cudaStream_t st) {
   const IndexView ix = view(ctx);
   if (ix.n_tracks <= kMaxTracksSmem) {
-    const size_t smem = sizeof(unsigned) * (size_t)((ix.n_tracks + 1) / 2);
-    MFPA_CUDA(cudaFuncSetAttribute(match_counts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    match_counts_kernel<<<B, kCountThreads, smem, st>>>(ix, hashes, nh, cap, counts, ctx->opt_match_packed);
+    const size_t words = (size_t)((ix.n_tracks + 1) / 2);
+    const size_t smem = sizeof(unsigned) * ((words + 3) & ~(size_t)3) + sizeof(RowCache);
+    MFPA_CUDA(cudaFuncSetAttribute(match_counts_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    match_counts_sweep_kernel<<<B, kFusedThreads, smem, st>>>(ix, hashes, nh, cap, counts, ctx->opt_match_packed);
   } else {
     MFPA_REQUIRE(!ctx->opt_match_packed, "match_counts: packed counts need n_tracks <= %d", kMaxTracksSmem);
     MFPA_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t)B * ix.n_tracks, st));
