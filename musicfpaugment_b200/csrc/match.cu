@@ -277,6 +277,35 @@ match_counts_sweep_kernel(const IndexView ix, const int32_t* __restrict__ hashes
   for (int i = tid; i < ix.n_tracks; i += kFusedThreads) o[i] = (int)((hist[i >> 1] >> ((i & 1) * 16)) & 0xffffu);
 }
 
+// collect step of the sharded path with the same machinery: the shared-memory words hold the track ->
+// (candidate index + 1) map, the second sweep emits the candidates' (index, delta-t) hits of this shard.
+__global__ void __launch_bounds__(kFusedThreads, 1)
+match_collect_sweep_kernel(const IndexView ix, const int32_t* __restrict__ hashes, const int32_t* __restrict__ nh, int cap,
+                           const int32_t* __restrict__ cand, const int32_t* __restrict__ ncand, int search_depth,
+                           uint32_t* __restrict__ list, int list_cap, int32_t* __restrict__ nlist) {
+  extern __shared__ __align__(16) unsigned fused_smem[];
+  __shared__ int s_n;
+  const int words = (ix.n_tracks + 1) >> 1;
+  unsigned* hist = fused_smem;
+  RowCache* rc = reinterpret_cast<RowCache*>(fused_smem + ((words + 3) & ~3));
+  const int q = blockIdx.x, tid = threadIdx.x;
+  const int nc = min(ncand[q], min(search_depth, 128));
+  if (nc <= 0) {   // block-uniform
+    if (tid == 0) nlist[q] = 0;
+    return;
+  }
+  for (int i = tid; i < words; i += kFusedThreads) hist[i] = 0;
+  if (tid == 0) s_n = 0;
+  __syncthreads();
+  for (int k = tid; k < nc; k += kFusedThreads) {
+    const int id = cand[((int64_t)q * search_depth + k) * 2];
+    if (id >= 0 && id < ix.n_tracks) reinterpret_cast<unsigned short*>(hist)[id] = (unsigned short)(k + 1);
+  }
+  const int2* rows = reinterpret_cast<const int2*>(hashes) + (int64_t)q * cap;
+  fused_sweep<true>(ix, rows, min(nh[q], cap), rc, hist, list + (int64_t)q * list_cap, list_cap, &s_n, tid);
+  if (tid == 0) nlist[q] = s_n;
+}
+
 __global__ void __launch_bounds__(kFusedThreads, 1)
 match_fused_kernel(const IndexView ix, const int32_t* __restrict__ hashes, const int32_t* __restrict__ nh, int cap,
                    int threshcount, int search_depth, int32_t* __restrict__ cand, int32_t* __restrict__ ncand,
@@ -684,7 +713,15 @@ int launch_match_select(mfpa_ctx* ctx, const int32_t* counts, int B, int threshc
 int launch_match_collect(mfpa_ctx* ctx, const int32_t* hashes, const int32_t* nh, int B, int cap, const int32_t* cand,
                          const int32_t* ncand, int search_depth, uint32_t* list, int list_cap, int32_t* nlist,
                          cudaStream_t st) {
-  match_collect_kernel<<<B, 256, 0, st>>>(view(ctx), hashes, nh, cap, cand, ncand, search_depth, list, list_cap, nlist);
+  const IndexView ix = view(ctx);
+  if (ix.n_tracks <= kMaxTracksSmem) {
+    const size_t words = (size_t)((ix.n_tracks + 1) / 2);
+    const size_t smem = sizeof(unsigned) * ((words + 3) & ~(size_t)3) + sizeof(RowCache);
+    MFPA_CUDA(cudaFuncSetAttribute(match_collect_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    match_collect_sweep_kernel<<<B, kFusedThreads, smem, st>>>(ix, hashes, nh, cap, cand, ncand, search_depth, list, list_cap, nlist);
+  } else {
+    match_collect_kernel<<<B, 256, 0, st>>>(ix, hashes, nh, cap, cand, ncand, search_depth, list, list_cap, nlist);
+  }
   MFPA_CUDA(cudaGetLastError());
   return MFPA_OK;
 }
