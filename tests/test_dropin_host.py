@@ -157,6 +157,41 @@ def test_augmentfp_parameter_draws(dropin_modules):
         pipe(torch.zeros(4, 16000))
 
 
+def test_noise_piece_descriptors_describe_random_background(dropin_modules):
+    """The device path of AddBackgroundNoise draws mfpa_noise_piece rows with random_background's RNG calls
+    (background_noise.py:64-141).  Assembled here in numpy (gather, mix-up mean, both RMS normalisations -
+    what mfpa_noise_assemble does on the GPU), the descriptors must give the rows the host path builds, and
+    consume exactly the same random draws."""
+    import random
+
+    aug = dropin_modules["aug"]
+    g = torch.Generator().manual_seed(7)
+    mk = lambda n, a=1.0: {"samples": a * torch.randn(1, n, generator=g), "sample_rate": 8000}
+    bg = {"a": [mk(30000), mk(700, 0.2), mk(9000, 4.0)], "b": [[mk(26000, 0.5), mk(40000)], mk(25000)]}
+    t = aug.AddBackgroundNoise(bg, p=1.0, sample_rate=8000)
+    T, n = 24000, 16
+    random.seed(3)
+    rows = []
+    for r in range(n):
+        pcs = t._draw_pieces(r, T)
+        assert pcs is not None and sum(p[4] for p in pcs) == T
+        rows.append(pcs)
+    state = random.getstate()
+    bank = torch.cat(t._bank_new).numpy().astype(np.float64)
+    random.seed(3)
+    for r in range(n):
+        host = t.random_background(T)[0].numpy()
+        out = np.zeros(T)
+        for a, b, q, dst, ln in rows[r]:
+            assert q == r
+            piece = bank[a: a + ln] if b < 0 else (bank[a: a + ln] + bank[b: b + ln]) / 2
+            out[dst: dst + ln] = piece / (np.sqrt(np.mean(piece ** 2)) + 1e-8)
+        out = out / (np.sqrt(np.mean(out ** 2)) + 1e-8)
+        assert np.abs(out - host).max() < 1e-5 * np.abs(host).max(), r
+    assert random.getstate() == state
+    assert any(len(pcs) > 1 for pcs in rows) and any(p[1] >= 0 for pcs in rows for p in pcs)   # multi-piece rows, mix-up pairs
+
+
 @pytest.mark.skipif(not os.path.isdir("/root/reference/augmentation"), reason="reference mount absent")
 def test_parameter_draws_match_reference_rng_order(dropin_modules):
     """With the same seeds the drop-in draws exactly the reference's parameters for the
