@@ -54,9 +54,9 @@ BYTES_PEAKS = 257 * N_FRAMES * 4 + 256 * N_FRAMES  # S3: magnitudes in, peak mas
 BYTES_FUSED = 256_000                              # S2-S4 fused: waveform in (+ 8 B per hash out)
 BYTES_CHAIN = 544_000                              # S1-S4 fused: x + noise + IR in (+ 8 B per hash out)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at 10 000 queries, shifts=1, from the
-# `ncu --set full` capture summarised in profiles/r01j_summary.txt (scaled by items/10000 for other sizes)
-NCU_TRAFFIC_10K = {"stft_mag": 2.692708e9 + 2.607187e9, "audfprint_peaks": 2.963529e9 + 0.020143e9,
-                   "landmark_hashes(+merge)": 0.020156e9 + 0.000074e9}
+# `ncu --set full` capture summarised in profiles/r01k_summary.txt (scaled by items/10000 for other sizes)
+NCU_TRAFFIC_10K = {"stft_mag": 2.692782e9 + 2.607007e9, "audfprint_peaks": 2.963450e9 + 0.020312e9,
+                   "landmark_hashes(+merge)": 0.020157e9 + 0.000076e9}
 
 
 def _measured(keys, default):
@@ -324,7 +324,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "stage_ms": stage_ms,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm, "unit": "GB/s",
                          "frac": achieved / hbm, "traffic": NCU_TRAFFIC_10K[dom] * items / 10000,
-                         "traffic_source": "profiles/r01j_summary.txt (ncu --set full, dram read+write)", "peak_source": how,
+                         "traffic_source": "profiles/r01k_summary.txt (ncu --set full, dram read+write)", "peak_source": how,
                          "algorithmic_bytes_per_launch": dom_bytes,
                          "whole_path_frac": (BYTES_FUSED * B + 8 * tot_hashes) / (ms_step * 1e-3) / 1e9 / hbm},
             "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,

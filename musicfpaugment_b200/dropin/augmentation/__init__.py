@@ -163,15 +163,47 @@ class ApplyImpulseResponse(_Transform):
         if len(self.ir_paths) == 0:
             raise EmptyPathException("There are no supported audio files found.")
         self.audio = Audio(sample_rate=sample_rate, mono=True)
+        # every response is decoded once; with a GPU they also live in a zero-padded device matrix, so a
+        # batch's [n, 1, Lmax] tensor is an index gather on the device instead of n decodes + one H2D copy
+        self.device_bank = torch.cuda.is_available()
+        self._decoded: Dict[Any, torch.Tensor] = {}
+        self._keep: List[Any] = []
+        self._row: Dict[Any, int] = {}
+        self._bank_dev: Optional[torch.Tensor] = None
+
+    def _decode(self, path) -> torch.Tensor:
+        key = id(path) if isinstance(path, dict) else str(path)
+        ir = self._decoded.get(key)
+        if ir is None:
+            ir = self._decoded[key] = self.audio(path)[0].contiguous()
+            self._row[key] = len(self._row)
+            if isinstance(path, dict):
+                self._keep.append(path)   # id() keys stay valid only while the object lives
+            self._bank_dev = None         # rebuilt on next use
+        return ir
+
+    def _bank(self) -> torch.Tensor:
+        if self._bank_dev is None:
+            rows = sorted(self._row, key=self._row.get)
+            lmax = max(len(self._decoded[k]) for k in rows)
+            m = torch.zeros(len(rows), lmax)
+            for r, k in enumerate(rows):
+                m[r, : len(self._decoded[k])] = self._decoded[k]
+            self._bank_dev = m.cuda()
+        return self._bank_dev
 
     def randomize_parameters(self, n, num_samples):
         """impulse_response.py:57-71 — random.choices, pad_sequence to the longest."""
         paths = random.choices(self.ir_paths, k=n)
-        irs = [self.audio(p)[0] for p in paths]
+        irs = [self._decode(p) for p in paths]
         lmax = max(len(i) for i in irs)
-        ir = torch.zeros(n, 1, lmax)
-        for k, i in enumerate(irs):
-            ir[k, 0, : len(i)] = i
+        if self.device_bank:
+            idx = torch.tensor([self._row[id(p) if isinstance(p, dict) else str(p)] for p in paths], device="cuda")
+            ir = self._bank()[idx, :lmax].unsqueeze(1)
+        else:
+            ir = torch.zeros(n, 1, lmax)
+            for k, i in enumerate(irs):
+                ir[k, 0, : len(i)] = i
         self.transform_parameters["ir"] = ir
         self.transform_parameters["ir_lengths"] = [len(i) for i in irs]
         self.transform_parameters["ir_paths"] = paths
@@ -389,8 +421,9 @@ class Compose:
             if slot:
                 arr[slot][sel] = prm["cutoff_freq"].numpy()
             elif isinstance(t, ApplyImpulseResponse):
-                ir = torch.zeros(batch_size, prm["ir"].shape[-1])
-                ir[torch.from_numpy(sel)] = prm["ir"][:, 0, :]
+                irs = prm["ir"][:, 0, :]
+                ir = torch.zeros(batch_size, irs.shape[-1], device=irs.device)   # the device bank leaves it on the GPU
+                ir[torch.from_numpy(sel).to(irs.device)] = irs
                 arr["ir_len"][sel] = prm["ir"].shape[-1]  # zero-padded to the longest, like pad_sequence (:65-69)
             elif isinstance(t, AddBackgroundNoise):
                 bg = prm["background"][:, 0, :]

@@ -111,7 +111,7 @@ def test_augmentfp_call_matches_oracle_on_dumped_parameters(mods):
     y = a(x.unsqueeze(0))
     assert y.shape == (1, 32000) and not y.is_cuda
     t = a.augmentation_pipeline.transforms
-    prm = dict(fc1=float(t[0].transform_parameters["cutoff_freq"][0]), ir=t[1].transform_parameters["ir"][0, 0].numpy(),
+    prm = dict(fc1=float(t[0].transform_parameters["cutoff_freq"][0]), ir=t[1].transform_parameters["ir"][0, 0].cpu().numpy(),
                noise=t[2].transform_parameters["background"][0, 0].cpu().numpy(), snr_db=float(t[2].transform_parameters["snr_in_db"][0]),
                gain_factor=float(t[3].transform_parameters["gain_factors"].reshape(-1)[0]),
                clip_p=float(t[4].transform_parameters["percentile_threshold"].reshape(-1)[0]),
