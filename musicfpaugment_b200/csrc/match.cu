@@ -23,6 +23,8 @@ constexpr unsigned kFull = 0xffffffffu;
 constexpr int kCountThreads = 512;
 constexpr int kMaxTracksSmem = 110000;  // packed 16-bit counters: 220 KB of shared memory
 constexpr int kAlignCap = 8192;         // hits of all candidates of one query that align_kernel can sort
+constexpr int kAlignSmall = 1024;       // ... in its first pass (most queries: a few hundred hits)
+constexpr int kAlignPending = -3;       // nrows marker: query left for the full-capacity pass
 constexpr int kDtOff = 16384;
 
 struct IndexView {
@@ -494,13 +496,17 @@ __global__ void __launch_bounds__(256) match_align_kernel(const uint32_t* __rest
                                                           int n_lists, int B, int list_cap, const int32_t* __restrict__ cand,
                                                           const int32_t* __restrict__ ncand, int search_depth, int window,
                                                           int threshcount, int max_align, int32_t* __restrict__ results,
-                                                          int32_t* __restrict__ nrows, int max_rows) {
+                                                          int32_t* __restrict__ nrows, int max_rows, int acap, int pass) {
+  // Two passes over the batch: pass 0 runs every query with room for acap = kAlignSmall hits (12 KB of shared
+  // memory: eight blocks per SM) and marks the few queries that need more as pending; pass 1 gives those the
+  // full kAlignCap (96 KB) and leaves the others alone.
   extern __shared__ uint32_t sm[];
-  uint32_t* keys = sm;                    // [kAlignCap] sorted hits
-  uint32_t* bin_key = sm + kAlignCap;     // [kAlignCap] run starts: key of each distinct (cand, dt)
-  int* bin_cnt = reinterpret_cast<int*>(sm + 2 * kAlignCap);  // [kAlignCap]
+  uint32_t* keys = sm;                    // [acap] sorted hits
+  uint32_t* bin_key = sm + acap;          // [acap] run starts: key of each distinct (cand, dt)
+  int* bin_cnt = reinterpret_cast<int*>(sm + 2 * acap);  // [acap]
   __shared__ int s_total, s_rows, s_seg[130];
   const int q = blockIdx.x, tid = threadIdx.x;
+  if (pass == 1 && nrows[q] != kAlignPending) return;
   const int nc = min(ncand[q], min(search_depth, 128));
   if (tid == 0) { s_total = 0; s_rows = 0; }
   __syncthreads();
@@ -514,12 +520,13 @@ __global__ void __launch_bounds__(256) match_align_kernel(const uint32_t* __rest
     if (tid == 0) { s_base = s_total; s_total += min(n, list_cap); }
     __syncthreads();
     for (int i = tid; i < min(n, list_cap); i += 256)
-      if (s_base + i < kAlignCap) keys[s_base + i] = src[i];
+      if (s_base + i < acap) keys[s_base + i] = src[i];
     __syncthreads();
   }
   const int total = s_total;
-  if (overflow || total > kAlignCap) {
-    if (tid == 0) nrows[q] = -1;  // capacity exceeded: the host wrapper raises
+  if (overflow || total > acap) {
+    // pass 0: try again with the full capacity; pass 1 (or a shard list that overflowed): the host wrapper raises
+    if (tid == 0) nrows[q] = (!overflow && pass == 0 && total <= kAlignCap) ? kAlignPending : -1;
     return;
   }
   if (nc == 0 || total == 0) {
@@ -729,10 +736,14 @@ int launch_match_collect(mfpa_ctx* ctx, const int32_t* hashes, const int32_t* nh
 int launch_match_align(const uint32_t* lists, const int32_t* nlists, int n_lists, int B, int list_cap, const int32_t* cand,
                        const int32_t* ncand, int search_depth, int window, int threshcount, int max_align,
                        int32_t* results, int32_t* nrows, int max_rows, cudaStream_t st) {
-  const size_t smem = sizeof(uint32_t) * 3 * kAlignCap;
-  MFPA_CUDA(cudaFuncSetAttribute(match_align_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  match_align_kernel<<<B, 256, smem, st>>>(lists, nlists, n_lists, B, list_cap, cand, ncand, search_depth, window,
-                                           threshcount, max_align, results, nrows, max_rows);
+  MFPA_CUDA(cudaFuncSetAttribute(match_align_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(sizeof(uint32_t) * 3 * kAlignCap)));
+  match_align_kernel<<<B, 256, sizeof(uint32_t) * 3 * kAlignSmall, st>>>(lists, nlists, n_lists, B, list_cap, cand, ncand,
+                                                                         search_depth, window, threshcount, max_align,
+                                                                         results, nrows, max_rows, kAlignSmall, 0);
+  match_align_kernel<<<B, 256, sizeof(uint32_t) * 3 * kAlignCap, st>>>(lists, nlists, n_lists, B, list_cap, cand, ncand,
+                                                                       search_depth, window, threshcount, max_align,
+                                                                       results, nrows, max_rows, kAlignCap, 1);
   MFPA_CUDA(cudaGetLastError());
   return MFPA_OK;
 }
