@@ -91,6 +91,9 @@ int mfpa_set_spread_table(mfpa_ctx* ctx, const double* table513_host);
  * whose histogram never leaves shared memory (indexes of up to 110000 tracks); 1 forces the four-step
  * path (the one the sharded matcher drives with collectives in between) for comparison. */
 #define MFPA_OPT_MATCH_UNFUSED 3
+/* MFPA_OPT_PART_BUDGET_MB (default 2048): device scratch, in MiB, that the partitioned long-filter path of
+ * mfpa_augment may use for block spectra; queries with long filters are processed in groups that fit. */
+#define MFPA_OPT_PART_BUDGET_MB 4
 int mfpa_set_option(mfpa_ctx* ctx, int option, int value);
 
 /* ---- geometry --------------------------------------------------------- */

@@ -1276,9 +1276,16 @@ int launch_augment(mfpa_ctx* ctx, const float* x, int B, int T, int64_t x_stride
     const int P = (max_k[l] + kPartS - 1) / kPartS;
     const int n_total = mode == kModeIR ? T + max_k[l] - 1 : T;
     const int nb_out = (n_total + kPartS - 1) / kPartS, nb_in = nb_out + P - 1;
-    if (ctx->aug_part.reserve(sizeof(float2) * FM * (size_t)nlong[l] * (P + nb_in))) return MFPA_ENOMEM;
-    PartArgs a{c, dlist + (size_t)l * B, (float2*)ctx->aug_part.ptr, (float2*)ctx->aug_part.ptr + (size_t)nlong[l] * P * FM, P, nb_in};
-    const dim3 gf(P, nlong[l]), gi(nb_in, nlong[l]), go(nb_out, nlong[l]);
+    // spectra scratch is (P + nb_in) x 64 KB per query: run the list in groups that keep it under the budget
+    // (MFPA_OPT_PART_BUDGET_MB, 2 GiB by default)
+    const size_t per_query = sizeof(float2) * FM * (size_t)(P + nb_in);
+    int group = (int)(((size_t)ctx->opt_part_budget_mb << 20) / per_query);
+    group = group < 1 ? 1 : (group > nlong[l] ? nlong[l] : group);
+    if (ctx->aug_part.reserve(per_query * (size_t)group)) return MFPA_ENOMEM;
+    for (int g0 = 0; g0 < nlong[l]; g0 += group) {
+    const int ng = nlong[l] - g0 < group ? nlong[l] - g0 : group;
+    PartArgs a{c, dlist + (size_t)l * B + g0, (float2*)ctx->aug_part.ptr, (float2*)ctx->aug_part.ptr + (size_t)ng * P * FM, P, nb_in};
+    const dim3 gf(P, ng), gi(nb_in, ng), go(nb_out, ng);
     if (mode == kModeHP) {
       part_filter_kernel<kModeHP><<<gf, FT, kConvSmem, st>>>(a, ctx->aug_tw_dev);
       part_forward_kernel<kModeHP><<<gi, FT, kConvSmem, st>>>(a, ctx->aug_tw_dev);
@@ -1293,6 +1300,7 @@ int launch_augment(mfpa_ctx* ctx, const float* x, int B, int T, int64_t x_stride
       part_conv_kernel<kModeLP><<<go, FT, kConvSmem, st>>>(a, ctx->aug_tw_dev);
     }
     MFPA_CUDA(cudaGetLastError());
+    }
     return MFPA_OK;
   };
 

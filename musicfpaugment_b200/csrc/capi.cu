@@ -172,6 +172,10 @@ int mfpa_set_option(mfpa_ctx* ctx, int option, int value) {
     case MFPA_OPT_PEAKS_F64: ctx->opt_peaks_f64 = value != 0; return MFPA_OK;
     case MFPA_OPT_MATCH_PACKED: ctx->opt_match_packed = value != 0; return MFPA_OK;
     case MFPA_OPT_MATCH_UNFUSED: ctx->opt_match_unfused = value != 0; return MFPA_OK;
+    case MFPA_OPT_PART_BUDGET_MB:
+      MFPA_REQUIRE(value >= 1, "set_option: MFPA_OPT_PART_BUDGET_MB %d < 1", value);
+      ctx->opt_part_budget_mb = value;
+      return MFPA_OK;
     default: break;
   }
   set_error("set_option: unknown option %d", option);
@@ -418,6 +422,7 @@ static int check_augment(mfpa_ctx* ctx, const float* x_dev, int B, int T, int64_
                          const mfpa_aug_params* params_host) {
   MFPA_REQUIRE(ctx && x_dev && params_host, "augment: NULL argument");
   MFPA_REQUIRE(B >= 1 && T >= 2, "augment: batch %d, n_samples %d", B, T);
+  MFPA_REQUIRE(B <= 65535, "augment: batch %d > 65535 (one grid row per query); split the batch", B);
   MFPA_REQUIRE(x_stride >= T, "augment: row stride %lld < n_samples %d", (long long)x_stride, T);
   MFPA_REQUIRE(sample_rate > 0, "augment: sample_rate %d", sample_rate);
   return MFPA_OK;

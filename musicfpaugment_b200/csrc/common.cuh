@@ -63,6 +63,7 @@ struct mfpa_ctx {
   int opt_peaks_f64 = 0;            // MFPA_OPT_PEAKS_F64
   int opt_match_packed = 0;         // MFPA_OPT_MATCH_PACKED
   int opt_match_unfused = 0;        // MFPA_OPT_MATCH_UNFUSED
+  int opt_part_budget_mb = 2048;    // MFPA_OPT_PART_BUDGET_MB
   double* spread_dev = nullptr;     // [513] Gaussian table
   float2* tw_dev = nullptr;         // FFT twiddles (stft.cu layout)
   float* win_dev = nullptr;         // [512] analysis window

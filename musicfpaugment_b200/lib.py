@@ -122,6 +122,7 @@ ALL_SIGNATURES = dict(SIGNATURES)
 OPT_PEAKS_F64 = 1
 OPT_MATCH_PACKED = 2
 OPT_MATCH_UNFUSED = 3
+OPT_PART_BUDGET_MB = 4
 N_FFT, HOP, BINS, ROWS, MAG_PITCH, MAX_PKS, MAX_SHIFTS, HASHES_PER_FRAME = 512, 256, 257, 256, 264, 5, 8, 15
 
 

@@ -132,6 +132,13 @@ def test_long_filters_and_long_impulse_responses(mfpa_ctx):
     for i in range(B):
         ref = A.augment_chain(x[i], prms[i])
         assert _rel(out[i], ref) < TOL, (i, _rel(out[i], ref), sorted(prms[i]))
+    # a 1 MiB scratch budget makes the long queries run one per group: same numbers
+    try:
+        mfpa_ctx.set_option(lib.OPT_PART_BUDGET_MB, 1)
+        out1 = mfpa_ctx.augment(torch.from_numpy(x).cuda(), arr, ir, noise).cpu().numpy()
+    finally:
+        mfpa_ctx.set_option(lib.OPT_PART_BUDGET_MB, 2048)
+    assert _rel(out1, out) < 1e-6   # (block sums arrive through atomics: the last bits are not ordered)
 
 
 def test_partition_boundaries_and_short_signals(mfpa_ctx):
