@@ -1059,16 +1059,16 @@ __global__ void __launch_bounds__(256) norm_kernel(const float* __restrict__ v, 
 // ---- noise rows from a device-resident bank (random_background, background_noise.py:64-141) ----
 struct NoiseStat { double ss; };   // per piece: sum of squares of the (paired) piece
 
-// grid (chunks, n_pieces): copy the piece (or the mean of a mix-up pair) into its row, sum of squares per piece
+// grid (n_pieces, chunks): copy the piece (or the mean of a mix-up pair) into its row, sum of squares per piece
 __global__ void __launch_bounds__(256) noise_gather_kernel(const float* __restrict__ bank, const mfpa_noise_piece* __restrict__ pieces,
                                                            int T, float* __restrict__ out, double* __restrict__ piece_ss) {
   __shared__ float red[8];
-  const mfpa_noise_piece p = pieces[blockIdx.y];
+  const mfpa_noise_piece p = pieces[blockIdx.x];
   const float* a = bank + p.src_a;
   const float* b = p.src_b >= 0 ? bank + p.src_b : nullptr;
   float* o = out + (int64_t)p.query * T + p.dst;
   float ss = 0.f;
-  for (int i = blockIdx.x * 256 + threadIdx.x; i < p.len; i += gridDim.x * 256) {
+  for (int i = blockIdx.y * 256 + threadIdx.x; i < p.len; i += gridDim.y * 256) {
     float v = __ldg(a + i);
     if (b) v = (v + __ldg(b + i)) / 2.0f;   // samplePairing (:11-12)
     o[i] = v;
@@ -1081,7 +1081,7 @@ __global__ void __launch_bounds__(256) noise_gather_kernel(const float* __restri
   if (threadIdx.x == 0) {
     float t = 0.f;
     for (int w = 0; w < 8; ++w) t += red[w];
-    atomicAdd(piece_ss + blockIdx.y, (double)t);
+    atomicAdd(piece_ss + blockIdx.x, (double)t);
   }
 }
 
@@ -1096,16 +1096,16 @@ __global__ void noise_total_kernel(const mfpa_noise_piece* __restrict__ pieces, 
   atomicAdd(row_ss + p.query, piece_ss[i] * (double)s * (double)s);
 }
 
-// grid (chunks, n_pieces): x / (rms_piece + 1e-8) / (rms_row + 1e-8)   (rms_normalize twice, utils.py:189-205)
+// grid (n_pieces, chunks): x / (rms_piece + 1e-8) / (rms_row + 1e-8)   (rms_normalize twice, utils.py:189-205)
 __global__ void __launch_bounds__(256) noise_scale_kernel(const mfpa_noise_piece* __restrict__ pieces, int T,
                                                           const double* __restrict__ piece_ss, const double* __restrict__ row_ss,
                                                           float* __restrict__ out) {
-  const mfpa_noise_piece p = pieces[blockIdx.y];
-  const float rms_p = sqrtf((float)(piece_ss[blockIdx.y] / (double)p.len));
+  const mfpa_noise_piece p = pieces[blockIdx.x];
+  const float rms_p = sqrtf((float)(piece_ss[blockIdx.x] / (double)p.len));
   const float rms_r = sqrtf((float)(row_ss[p.query] / (double)T));
   const float dp = rms_p + 1e-8f, dr = rms_r + 1e-8f;
   float* o = out + (int64_t)p.query * T + p.dst;
-  for (int i = blockIdx.x * 256 + threadIdx.x; i < p.len; i += gridDim.x * 256) o[i] = (o[i] / dp) / dr;
+  for (int i = blockIdx.y * 256 + threadIdx.x; i < p.len; i += gridDim.y * 256) o[i] = (o[i] / dp) / dr;
 }
 
 }  // namespace
@@ -1134,7 +1134,7 @@ int launch_noise_assemble(mfpa_ctx* ctx, const float* bank, int64_t bank_len, co
   MFPA_CUDA(cudaMemcpyAsync(dp, pieces, sizeof(mfpa_noise_piece) * (size_t)n_pieces, cudaMemcpyHostToDevice, st));
   MFPA_CUDA(cudaStreamSynchronize(st));   // pieces_host is caller-owned pageable memory
   MFPA_CUDA(cudaMemsetAsync(piece_ss, 0, sizeof(double) * ((size_t)n_pieces + B), st));
-  const dim3 grid((unsigned)((max_len + 4095) / 4096), (unsigned)n_pieces);
+  const dim3 grid((unsigned)n_pieces, (unsigned)((max_len + 4095) / 4096));   // pieces on x: no 65535 limit
   noise_gather_kernel<<<grid, 256, 0, st>>>(bank, dp, T, out, piece_ss);
   noise_total_kernel<<<(n_pieces + 255) / 256, 256, 0, st>>>(dp, n_pieces, piece_ss, row_ss);
   noise_scale_kernel<<<grid, 256, 0, st>>>(dp, T, piece_ss, row_ss, out);

@@ -605,6 +605,7 @@ int mfpa_dejavu_peaks(mfpa_ctx* ctx, const void* arr_dev, int is_f64, int B, int
                       double amp_min, uint8_t* mask_dev, int32_t* peaks_dev, int cap, int32_t* npeaks_dev, void* stream) {
   MFPA_REQUIRE(ctx && arr_dev && mask_dev, "dejavu_peaks: NULL argument");
   MFPA_REQUIRE(B >= 1 && F >= 1 && N >= 1, "dejavu_peaks: bad sizes %d x %d x %d", B, F, N);
+  MFPA_REQUIRE(B <= 65535, "dejavu_peaks: batch %d > 65535 (one grid layer per spectrogram); split the batch", B);
   MFPA_REQUIRE((peaks_dev == nullptr) == (npeaks_dev == nullptr) && (peaks_dev == nullptr || cap >= 1), "dejavu_peaks: peaks/npeaks/cap mismatch");
   DeviceGuard guard(ctx->device);
   return launch_dejavu_peaks(arr_dev, is_f64, B, F, N, neighborhood, amp_min, mask_dev, peaks_dev, cap, npeaks_dev,
