@@ -491,7 +491,8 @@ def bench_full_chain(ctx, lib, dev, rank, B, shifts, steps, warmup, barrier):
 
 def bench_match(ctx, lib, dev, rank, world, B, n_tracks, steps, warmup, barrier):
     """BASELINE configs[4]: match B planted 400-hash queries against a synthetic n_tracks-track index
-    sharded by hash range over the ranks; per-track histograms summed with an NCCL all-reduce."""
+    sharded by hash range over the ranks; per-track histograms summed with an NCCL reduce-scatter; at N > 1
+    the replicated-index mode is timed as well."""
     import torch
 
     from musicfpaugment_b200 import sharded, synth

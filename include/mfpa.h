@@ -289,8 +289,9 @@ int mfpa_get_hits(mfpa_ctx* ctx, const int32_t* hashes_dev, int n, int32_t* hits
                   int64_t* nhits_dev, void* stream);
 
 /* The four steps of match_hashes for a batch of B queries (hashes_dev [B][cap][2], nh_dev [B]).
- * Multi-GPU (index sharded by hash range): all-reduce(sum) counts_dev between steps 1 and 2,
- * all-gather list_dev/nlist_dev between steps 3 and 4; single GPU: call mfpa_match.
+ * Multi-GPU (index sharded by hash range): sum counts_dev over the shards between steps 1 and 2 (all-reduce,
+ * or reduce-scatter to the rank that owns the query), bring every shard's list_dev/nlist_dev of a query
+ * together between steps 3 and 4 (all-gather / all-to-all); single GPU: call mfpa_match.
  *  1 counts : counts_dev [B][n_tracks] int32 raw hit counts from this shard's buckets
  *  2 select : cand_dev [B][search_depth][2] (id, raw) in _best_count_ids order, ncand_dev [B]
  *  3 collect: list_dev [B][list_cap] uint32 = (candidate index << 16) | (t_ref - t_q + 16384),

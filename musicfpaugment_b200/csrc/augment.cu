@@ -430,7 +430,7 @@ constexpr int kSelCap = 4096;      // capacity of each tail list
 constexpr int kMixStage = 256;     // per-block staging of the tails in mix_kernel
 
 // General exact radix select (any rank): sorted[r] for two ranks at once, 8 bits per pass, then one
-// more pass for the successors sorted[r+1].  Fallback of clip_select_kernel.
+// more pass for the successors sorted[r+1].  Fallback of clip_finish_kernel.
 __device__ void clip_select_general(const float* __restrict__ z, int T, const int (&r0)[2], unsigned (&hist)[2][256],
                                     unsigned* sh, unsigned (&kout)[2], unsigned (&ksucc)[2]) {
   unsigned* sel_prefix = sh;      // [2]

@@ -4,15 +4,17 @@
 //
 // Index layout is the reference's own (hash_table.py:53-68): table[bucket][depth] uint32,
 // entry = ((id + 1) << maxtimebits) + time, counts[bucket] int32 (may exceed depth).
-// A context holds the buckets [hash_lo, hash_lo + n_buckets) only; queries are matched in
-// four steps so that the two reductions the algorithm needs can cross GPUs with plain
-// NCCL collectives between them:
-//   counts   per-(query, track) raw hit counts from the local buckets (shared-memory histogram,
-//            dense int32 row out)                        -> all-reduce(sum) across shards
-//   select   candidates: top min(#{raw > 5}, 100) by raw / hashesperid (:110-129)
-//   collect  (candidate, delta-t) of every local hit of a candidate -> all-gather across shards
+// A context holds the buckets [hash_lo, hash_lo + n_buckets) only.  With the whole index in one context
+// mfpa_match runs counts + select + collect as ONE kernel whose per-track histogram never leaves shared
+// memory (match_fused_kernel) followed by the align kernel.  For an index sharded by hash range the same
+// four steps are separate kernels, so that the two reductions the algorithm needs can cross GPUs with
+// plain NCCL collectives between them (musicfpaugment_b200/sharded.py):
+//   counts   per-(query, track) raw hit counts from the local buckets (shared-memory histogram, dense
+//            int32 or 16-bit-packed row out)            -> reduce-scatter(sum) to the query's owner rank
+//   select   candidates: top min(#{raw > 5}, 100) by raw / hashesperid (:110-129) -> all-gather
+//   collect  (candidate, delta-t) of every local hit of a candidate -> all-to-all to the owners
 //   align    per candidate delta-t histogram, local-max modes > 5, +-window sum (:266-316), rows
-//            ordered by filtered count descending (:341)
+//            ordered by filtered count descending (:341)  -> all-gather of the rows
 #include "common.cuh"
 
 namespace mfpa {
