@@ -18,6 +18,11 @@
 // order, which makes the fused pass coalesced.  64 KB of shared memory per block lets three blocks
 // share an SM.  The per-query reductions that gate the next stage (peak of the full convolution,
 // RMS, peak after the mix, clip quantiles, final peak) are produced by the kernel that writes the data.
+// Filters longer than one block takes (FIRs above 8193 taps, responses above 8192 samples) run as uniformly
+// partitioned overlap-save on the same transform (part_* kernels below).  The clip quantiles cost no pass
+// over the signal: a sampled pair of tail thresholds, the tails listed by the mix kernel, a shared-memory
+// radix select (clip_sample / mix / clip_finish).  The file also holds the noise-row assembly that runs
+// ahead of the chain (mfpa_noise_assemble).
 #include <math.h>
 
 #include <vector>

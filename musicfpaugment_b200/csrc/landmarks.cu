@@ -4,9 +4,12 @@
 // landmarks2hashes (:40-58) and the concatenate/unique/sort tail of wavfile2hashes (:437-460).
 //
 // Input is the packed per-frame record array produced by peaks.cu
-// (byte 0 = count, bytes 1..5 = bins ascending).  One warp handles one item,
-// one lane one start frame; the pairing window (frames c+2 .. c+62) is read as
-// consecutive 8-byte records so every step of the window is one coalesced load.
+// (byte 0 = count, bytes 1..5 = bins ascending).  One warp handles one item.
+// landmark_list_kernel (items of up to 1024 frames): the warp compacts the records into a
+// (frame, bin)-ordered peak list in shared memory and every lane pairs one PEAK by walking the
+// list - the reference's scan order without the empty frames.  landmark_kernel (longer items):
+// one lane per start frame; the pairing window (frames c+2 .. c+62) is read as consecutive
+// 8-byte records so every step of the window is one coalesced load.
 #include "common.cuh"
 
 namespace mfpa {
