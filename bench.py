@@ -199,12 +199,19 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     import torch
     import torch.distributed as dist
 
-    from musicfpaugment_b200 import lib, synth
+    # libmfpa.so is a build artefact: (re)build it from the sources if it is missing or stale - rank 0 of the
+    # node does it, the others wait at the rendezvous below (a no-op when the source stamp is current)
+    if local_rank == 0:
+        from musicfpaugment_b200 import build as _build
 
+        _build.build()
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        dist.barrier()
+    from musicfpaugment_b200 import lib, synth
+
     ctx = lib.Context(local_rank, spread_table=np.exp(-0.5 * ((np.arange(-256, 257) / 30.0) ** 2)))
     p = lib.afp_defaults()
     B, S = args.queries, args.shifts

@@ -12,6 +12,18 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
 
 
+def pytest_sessionstart(session):
+    """libmfpa.so is a build artefact (git-ignored): make sure the one in the tree matches the sources
+    before any test imports the binding.  build() is a no-op when its source stamp is current; nvcc
+    cross-compiles, so this works on the CPU-only box too."""
+    try:
+        from musicfpaugment_b200 import build
+
+        build.build()
+    except Exception as e:  # the tests that need the library will say so themselves
+        print(f"conftest: could not build libmfpa.so: {e}", file=sys.stderr)
+
+
 @pytest.fixture(scope="session")
 def mfpa_ctx():
     """One libmfpa context on cuda:0 with the numpy-computed spreading table."""
