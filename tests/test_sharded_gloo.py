@@ -151,8 +151,9 @@ def _worker(rank, world, port, out_dir):
 
 
 @pytest.mark.timeout(300)
-def test_match_sharded_world2_equals_single_table(tmp_path):
-    world = 2
+@pytest.mark.parametrize("world", [2, 3])
+def test_match_sharded_equals_single_table(tmp_path, world):
+    """world 3: uneven hash ranges (2^20 / 3), 7 queries padded to sub-batches of 3, owners of 1-2 queries."""
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     g = np.load(tmp_path / "out.npz")
     table, counts, hpid, _ = synth.hash_index(300, 400, seed=21, depth=20)
