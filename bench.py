@@ -333,6 +333,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                          "frac": achieved / hbm, "traffic": NCU_TRAFFIC_10K[dom] * items / 10000,
                          "traffic_source": "profiles/r01k_summary.txt (ncu --set full, dram read+write)", "peak_source": how,
                          "algorithmic_bytes_per_launch": dom_bytes,
+                         "frac_of_nominal_8000_gbs": achieved / 8000.0,   # also against the spec-sheet figure
                          "whole_path_frac": (BYTES_FUSED * B + 8 * tot_hashes) / (ms_step * 1e-3) / 1e9 / hbm},
             "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": B * T_QUERY * 4, "d2h_bytes_per_step": tot_hashes * 8 + (B + 1) * 8,
