@@ -112,6 +112,16 @@ int mfpa_shift_offset(int shift, int shifts); /* peak_extractor.py:412 */
 int mfpa_stft_mag(mfpa_ctx* ctx, const float* x_dev, int B, int T, int64_t x_stride, int shifts,
                   float* mag_dev, float* qmax_dev, void* stream);
 
+/* The module's public function: stft(signal, n_fft, hop_length, window) (afp/audfprint/stft.py:15-62), any
+ * n_fft / hop / window, computed in float64 like the reference (np.pad reflect by n_fft/2, frames of
+ * len(window) samples every `hop`, times the window, rfft of n_fft points).
+ * x_dev: T float64 samples; window_dev: win_len float64 values;
+ * out_dev: complex128 [n_fft/2 + 1][n_frames] (interleaved re, im), n_frames = 1 + (T + 2 (n_fft/2) - win_len) / hop
+ * as returned by mfpa_stft_num_frames.  Not the throughput path (that is mfpa_stft_mag). */
+int mfpa_stft_num_frames(int n_samples, int n_fft, int hop, int win_len);
+int mfpa_stft_complex(mfpa_ctx* ctx, const double* x_dev, int T, int n_fft, int hop, const double* window_dev,
+                      int win_len, double* out_dev, void* stream);
+
 /* Normalised spectrogram in the reference's layout: spec[item][257][n_frames_max]
  * float64 = mag/qmax — the `spec` returned by find_peaks (peak_extractor.py:271,311). */
 int mfpa_spec_from_mag(mfpa_ctx* ctx, const float* mag_dev, const float* qmax_dev, int B, int T,

@@ -10,13 +10,14 @@
 //
 // Long convolutions (stages 1, 2, 6) are overlap-save blocks of 16384 REAL samples transformed
 // as one 8192-point complex FFT held in shared memory (even samples in the real part, odd samples
-// in the imaginary part).  A per-query kernel turns the filter (FIR taps generated on the fly, or
-// the impulse response) into its half spectrum once; every signal block then does forward FFT ->
-// one fused pass (split into the real-signal spectrum, multiply by the filter spectrum, re-pack)
-// -> inverse FFT.  Forward is decimation-in-frequency and the inverse undoes it pass by pass, so
-// no bit-reversal pass is ever needed; the filter spectrum is stored in the same digit-reversed
-// order, which makes the fused pass coalesced.  64 KB of shared memory per block lets three blocks
-// share an SM.  The per-query reductions that gate the next stage (peak of the full convolution,
+// in the imaginary part; fftconv_core.cuh: planar layout, two butterflies per thread in packed
+// FADD2/FMUL2/FFMA2 arithmetic).  A per-query kernel turns the filter (FIR taps generated on the
+// fly, or the impulse response) into its "double pairs" once; every signal block then does
+// forward FFT -> one fused pass (split into the real-signal spectrum, multiply by the filter,
+// re-pack) -> inverse FFT.  Forward is decimation-in-frequency and the inverse undoes it pass by
+// pass, so no bit-reversal pass is ever needed; the filter is stored in the order the fused pass
+// reads it (coalesced 16-byte loads).  Block starts and filter delays are kept multiples of four
+// samples so the waveform is read and written with 16-byte accesses.  The per-query reductions that gate the next stage (peak of the full convolution,
 // RMS, peak after the mix, clip quantiles, final peak) are produced by the kernel that writes the data.
 // Filters longer than one block takes (FIRs above 8193 taps, responses above 8192 samples) run as uniformly
 // partitioned overlap-save on the same transform (part_* kernels below).  The clip quantiles cost no pass
@@ -28,18 +29,19 @@
 #include <vector>
 
 #include "common.cuh"
+#include "fftconv_core.cuh"
 
 namespace mfpa {
 
 namespace {
 
-constexpr int FN = 16384;          // real samples per overlap-save block
-constexpr int LOGM = 13;
-constexpr int FM = 1 << LOGM;      // complex FFT length (FN / 2)
-constexpr int FT = 256;            // threads per FFT block
-constexpr int FPAD = FM + FM / 16; // padded smem array (radix-16 passes are conflict-free)
-constexpr int kTw = FM / 16;       // twiddle table entries
-constexpr size_t kConvSmem = sizeof(float2) * (FPAD + kTw) + 64 * sizeof(float);
+using fc::FN;
+using fc::FM;
+using fc::FT;
+using fc::FPADF;
+using fc::c2;
+constexpr int kTwFloats = 2 * fc::kTwA + 2 * fc::kTwB;   // pass-A and pass-B twiddle tables, planar
+constexpr size_t kConvSmem = sizeof(float) * (fc::kPlaneFloats + 64);
 constexpr float kPi = 3.14159265358979323846f;
 
 struct AugQ {            // per-query derived parameters (device copy)
@@ -64,122 +66,28 @@ struct AugS {            // per-query running statistics (zeroed per call)
   float pad[2];
 };
 
-__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ int pidx(int i) { return i + (i >> 4); }
-
-// 4-point DFT with kernel e^{S i 2 pi nk/4}; S = -1 forward, +1 inverse (unscaled).
-template <int S> __device__ __forceinline__ void dft4(float2& a, float2& b, float2& c, float2& d) {
-  const float2 s0 = cadd(a, c), s1 = csub(a, c), s2 = cadd(b, d), s3 = csub(b, d);
-  const float2 t = S < 0 ? make_float2(s3.y, -s3.x) : make_float2(-s3.y, s3.x);
-  a = cadd(s0, s2); c = csub(s0, s2); b = cadd(s1, t); d = csub(s1, t);
-}
-
-// 16-point DFT, natural order in; output X[k] lands in v[4*(k&3) + (k>>2)].
-template <int S> __device__ __forceinline__ void dft16(float2 (&v)[16]) {
-  constexpr float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f, h = 0.70710678118654752440f;
-#pragma unroll
-  for (int n2 = 0; n2 < 4; ++n2) dft4<S>(v[n2], v[4 + n2], v[8 + n2], v[12 + n2]);
-  // v[4*k1 + n2] *= W16^(n2*k1)
-  const float sg = S < 0 ? -1.f : 1.f;
-  v[5] = cmul(v[5], make_float2(c1, sg * s1));
-  v[6] = cmul(v[6], make_float2(h, sg * h));
-  v[7] = cmul(v[7], make_float2(s1, sg * c1));
-  v[9] = cmul(v[9], make_float2(h, sg * h));
-  v[10] = S < 0 ? make_float2(v[10].y, -v[10].x) : make_float2(-v[10].y, v[10].x);
-  v[11] = cmul(v[11], make_float2(-h, sg * h));
-  v[13] = cmul(v[13], make_float2(s1, sg * c1));
-  v[14] = cmul(v[14], make_float2(-h, sg * h));
-  v[15] = cmul(v[15], make_float2(-c1, sg * -s1));
-#pragma unroll
-  for (int k1 = 0; k1 < 4; ++k1) dft4<S>(v[4 * k1], v[4 * k1 + 1], v[4 * k1 + 2], v[4 * k1 + 3]);
-}
-
-// One radix-16 pass over sub-transforms of length 16*s.  tw[e] = exp(-2 pi i e / FM), e < FM/16;
-// the twiddle of element k in a group is tw[j * tw_mul]^k.
-template <bool INV> __device__ __forceinline__ void pass16(float2* buf, const float2* tw, int log2s, int tw_mul, int tid) {
-  const int s = 1 << log2s;
-#pragma unroll 1
-  for (int g = 0; g < FM / 16 / FT; ++g) {
-    const int gid = tid + FT * g;
-    const int j = gid & (s - 1);
-    const int base = ((gid >> log2s) << (log2s + 4)) + j;
-    float2 v[16];
-#pragma unroll
-    for (int t = 0; t < 16; ++t) v[t] = buf[pidx(base + (t << log2s))];
-    float2 w1 = tw[j * tw_mul];
-    if (INV) w1.y = -w1.y;
-    // powers w^2 .. w^15 with multiplication depth <= 4
-    float2 w[16];
-    w[1] = w1; w[2] = cmul(w1, w1); w[3] = cmul(w[2], w1); w[4] = cmul(w[2], w[2]);
-    w[5] = cmul(w[4], w1); w[6] = cmul(w[3], w[3]); w[7] = cmul(w[4], w[3]); w[8] = cmul(w[4], w[4]);
-    w[9] = cmul(w[8], w1); w[10] = cmul(w[5], w[5]); w[11] = cmul(w[8], w[3]); w[12] = cmul(w[6], w[6]);
-    w[13] = cmul(w[8], w[5]); w[14] = cmul(w[7], w[7]); w[15] = cmul(w[8], w[7]);
-    if (INV) {
-#pragma unroll
-      for (int t = 1; t < 16; ++t) v[t] = cmul(v[t], w[t]);
-      dft16<1>(v);
-#pragma unroll
-      for (int k = 0; k < 16; ++k) buf[pidx(base + (k << log2s))] = v[4 * (k & 3) + (k >> 2)];
-    } else {
-      dft16<-1>(v);
-#pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        const float2 x = v[4 * (k & 3) + (k >> 2)];
-        buf[pidx(base + (k << log2s))] = k ? cmul(x, w[k]) : x;
-      }
-    }
+// shared-memory carve-up of the convolution kernels
+struct ConvSmem {
+  float *re, *im, *twa_re, *twa_im, *twb_re, *twb_im, *red;
+  __device__ explicit ConvSmem(float* s)
+      : re(s), im(s + FPADF), twa_re(s + 2 * FPADF), twa_im(twa_re + fc::kTwA), twb_re(twa_im + fc::kTwA),
+        twb_im(twb_re + fc::kTwB), red(twb_im + fc::kTwB) {}
+  __device__ void load_tables(const float* __restrict__ tw_g, int tid) const {
+    for (int i = tid; i < kTwFloats; i += FT) twa_re[i] = __ldg(tw_g + i);
   }
-}
+};
 
-// final radix-2 pass on adjacent pairs (its own inverse up to the factor 2)
-__device__ __forceinline__ void pass2(float2* buf, int tid) {
-#pragma unroll 4
-  for (int g = 0; g < FM / 2 / FT; ++g) {
-    const int base = 2 * (tid + FT * g);
-    const float2 a = buf[pidx(base)], b = buf[pidx(base + 1)];
-    buf[pidx(base)] = cadd(a, b);
-    buf[pidx(base + 1)] = csub(a, b);
-  }
+// forward: natural order in, digit-reversed out.  inverse: digit-reversed in, natural out (x FM).  Both end
+// with a barrier; the caller provides the one that publishes the input.
+__device__ __forceinline__ void fft_forward(const ConvSmem& s, int tid) {
+  fc::pass_a<false>(s.re, s.im, s.twa_re, s.twa_im, tid); __syncthreads();
+  fc::pass_b<false>(s.re, s.im, s.twb_re, s.twb_im, tid); __syncthreads();
+  fc::pass_last_fwd(s.re, s.im, tid);                     __syncthreads();
 }
-
-// forward: natural order in, digit-reversed out.  inverse: digit-reversed in, natural out (x FM).
-__device__ __forceinline__ void fft_forward(float2* buf, const float2* tw, int tid) {
-  pass16<false>(buf, tw, LOGM - 4, 1, tid);    __syncthreads();
-  pass16<false>(buf, tw, LOGM - 8, 16, tid);   __syncthreads();
-  pass16<false>(buf, tw, LOGM - 12, 256, tid); __syncthreads();
-  pass2(buf, tid);                             __syncthreads();
-}
-__device__ __forceinline__ void fft_inverse(float2* buf, const float2* tw, int tid) {
-  pass2(buf, tid);                             __syncthreads();
-  pass16<true>(buf, tw, LOGM - 12, 256, tid);  __syncthreads();
-  pass16<true>(buf, tw, LOGM - 8, 16, tid);    __syncthreads();
-  pass16<true>(buf, tw, LOGM - 4, 1, tid);     __syncthreads();
-}
-// position of frequency k after fft_forward, and the frequency held at position r
-__device__ __forceinline__ int rev_pos(int k) {
-  return ((k & 15) << 9) | (((k >> 4) & 15) << 5) | (((k >> 8) & 15) << 1) | (k >> 12);
-}
-__device__ __forceinline__ int pos_freq(int r) {
-  return (r >> 9) | (((r >> 5) & 15) << 4) | (((r >> 1) & 15) << 8) | ((r & 1) << 12);
-}
-__device__ __forceinline__ float2 conjf2(float2 a) { return make_float2(a.x, -a.y); }
-// W^k = exp(-2 pi i k / FN) = exp(-pi i k / FM)
-__device__ __forceinline__ float2 half_twiddle(int k) {
-  float sn, cs;
-  sincospif((float)k * (1.0f / (float)FM), &sn, &cs);
-  return make_float2(cs, -sn);
-}
-// Z = FFT_FM(even + i odd) of a real signal  ->  its spectrum at k and FM-k (0 < k < FM/2):
-// E = (Z[k] + conj Z[FM-k]) / 2, O = (Z[k] - conj Z[FM-k]) / (2i); X[k] = E + W^k O, X[FM-k] = conj(E - W^k O)
-__device__ __forceinline__ void real_split(float2 z1, float2 z2, float2 wk, float2& xk, float2& xmk) {
-  const float2 e = make_float2(0.5f * (z1.x + z2.x), 0.5f * (z1.y - z2.y));
-  const float2 d = make_float2(z1.x - z2.x, z1.y + z2.y);       // Z[k] - conj Z[FM-k]
-  const float2 o = make_float2(0.5f * d.y, -0.5f * d.x);        // d / (2i)
-  const float2 t = cmul(wk, o);
-  xk = cadd(e, t);
-  xmk = conjf2(csub(e, t));
+__device__ __forceinline__ void fft_inverse(const ConvSmem& s, int tid) {
+  fc::pass_last_inv(s.re, s.im, tid);                     __syncthreads();
+  fc::pass_b<true>(s.re, s.im, s.twb_re, s.twb_im, tid);  __syncthreads();
+  fc::pass_a<true>(s.re, s.im, s.twa_re, s.twa_im, tid);  __syncthreads();
 }
 
 __device__ __forceinline__ float block_sum(float v, float* red, int tid) {
@@ -221,7 +129,7 @@ struct ConvArgs {
   const float* ir; int ir_stride;        // kModeIR
   const AugQ* q; AugS* st;
   int T; uint32_t bit; int which;        // which FIR (1, 2 or 3) / which stats slot
-  float2* hspec;                         // [B][FM] filter half spectra, digit-reversed order, entry 0 = (H[0], H[FM])
+  float4* hspec;                         // [B][2][FM/4] filter double pairs (fc::dp_index): plane 0 = S, plane 1 = R
 };
 
 __device__ __forceinline__ void filter_params(const AugQ& q, int which, int& half, float& c2, float& argscale) {
@@ -235,76 +143,82 @@ template <int MODE> __device__ __forceinline__ uint32_t long_bit(int which) {
   return MODE == kModeIR ? kLongIR : (which == 1 ? kLongHP1 : (which == 2 ? kLongLP : kLongHP3));
 }
 
-// One block per query: half spectrum of the query's filter (zero-padded to FN real samples), scaled by
-// 1/FM (the unscaled inverse transform) and, for the FIRs, by 1/sum(taps) (julius normalises to DC gain 1).
-template <int MODE>
-__global__ void __launch_bounds__(FT) filter_spectrum_kernel(const ConvArgs a, const float2* __restrict__ tw_g) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float2* buf = reinterpret_cast<float2*>(smem_raw);
-  float2* tw = buf + FPAD;
-  float* red = reinterpret_cast<float*>(tw + kTw);
-  const int tid = threadIdx.x, qi = blockIdx.x;
-  const AugQ q = a.q[qi];
-  if (!(q.apply & a.bit) || (q.long_mask & long_bit<MODE>(a.which))) return;
-  int K, half = 0;
-  float c2 = 0.f, argscale = 0.f;
-  if (MODE == kModeIR) {
-    K = q.ir_len;
-  } else {
-    filter_params(q, a.which, half, c2, argscale);
-    K = 2 * half + 1;
-  }
-  for (int i = tid; i < kTw; i += FT) tw[i] = tw_g[i];
-  const float* ir = MODE == kModeIR ? a.ir + (int64_t)qi * a.ir_stride : nullptr;
-  float hs = 0.f;
-  for (int m = tid; m < FM; m += FT) {
-    float h[2];
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const int i = 2 * m + e;
-      h[e] = 0.f;
-      if (i < K) h[e] = MODE == kModeIR ? ir[i] : fir_tap(i, half, c2, argscale);
-    }
-    hs += h[0] + h[1];
-    buf[pidx(m)] = make_float2(h[0], h[1]);
-  }
-  float scale = 1.0f / (float)FM;
-  if (MODE != kModeIR) scale /= block_sum(hs, red, tid);
-  __syncthreads();
-  fft_forward(buf, tw, tid);
-  float2* hg = a.hspec + (size_t)qi * FM;
-  for (int j = tid; j < FM / 2; j += FT) {
-    const int r = 2 * j, k = pos_freq(r);
-    if (k == 0) {
-      const float2 z = buf[pidx(0)];
-      hg[0] = make_float2((z.x + z.y) * scale, (z.x - z.y) * scale);
-    } else {
-      const int r2 = rev_pos(FM - k);
-      float2 hk, hmk;
-      real_split(buf[pidx(r)], buf[pidx(r2)], half_twiddle(k), hk, hmk);
-      hg[r] = make_float2(hk.x * scale, hk.y * scale);
-      hg[r2] = make_float2(hmk.x * scale, hmk.y * scale);
-    }
-  }
-  if (tid == 0) {  // k = FM/2 pairs with itself: X = conj(Z)
-    const float2 z = buf[pidx(1)];
-    hg[1] = make_float2(z.x * scale, -z.y * scale);
+using fc::ConvGeom;
+using fc::conv_geom;
+
+__device__ __forceinline__ void store_filter_pairs(const ConvSmem& s, float scale, float4* __restrict__ hs,
+                                                   float4* __restrict__ hr, int tid) {
+  fc::filter_pairs_store(s.re, s.im, scale, hs, hr, tid);
+}
+__device__ __forceinline__ void apply_filter_pairs(const ConvSmem& s, const float4* __restrict__ hs,
+                                                   const float4* __restrict__ hr, int tid) {
+  fc::filter_pairs_apply(s.re, s.im, hs, hr, tid);
+}
+
+// Packs FN real samples v(i), i = 0 .. FN-1, into the planes (even samples -> re, odd -> im): thread tid
+// provides float4 number tid + FT u through `quad(i4)`.
+template <typename F> __device__ __forceinline__ void fill_planes(const ConvSmem& s, int tid, F quad) {
+#pragma unroll 4
+  for (int u = 0; u < FN / 4 / FT; ++u) {
+    const int i4 = tid + FT * u;
+    const float4 v = quad(i4);
+    const int o = fc::padi(2 * i4);
+    *reinterpret_cast<float2*>(s.re + o) = make_float2(v.x, v.z);
+    *reinterpret_cast<float2*>(s.im + o) = make_float2(v.y, v.w);
   }
 }
 
+// One block per query: double pairs of the query's filter (zero-padded to FN real samples), scaled by
+// 1/FM (the unscaled inverse transform) and, for the FIRs, by 1/sum(taps) (julius normalises to DC gain 1).
 template <int MODE>
-__global__ void __launch_bounds__(FT, 3) fftconv_kernel(const ConvArgs a, const float2* __restrict__ tw_g) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float2* buf = reinterpret_cast<float2*>(smem_raw);
-  float2* tw = buf + FPAD;
-  float* red = reinterpret_cast<float*>(tw + kTw);
+__global__ void __launch_bounds__(FT, 2) filter_spectrum_kernel(const ConvArgs a, const float* __restrict__ tw_g) {
+  extern __shared__ __align__(16) float smem_f[];
+  const ConvSmem s(smem_f);
+  const int tid = threadIdx.x, qi = blockIdx.x;
+  const AugQ q = a.q[qi];
+  if (!(q.apply & a.bit) || (q.long_mask & long_bit<MODE>(a.which))) return;
+  int half = 0;
+  float c2 = 0.f, argscale = 0.f;
+  if (MODE != kModeIR) filter_params(q, a.which, half, c2, argscale);
+  const ConvGeom g = conv_geom(MODE == kModeIR, half, q.ir_len, a.T);
+  s.load_tables(tw_g, tid);
+  const float* ir = MODE == kModeIR ? a.ir + (int64_t)qi * a.ir_stride : nullptr;
+  float hsum = 0.f;
+  fill_planes(s, tid, [&](int i4) {
+    float h[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int i = 4 * i4 + e;
+      h[e] = 0.f;
+      if (i < g.K) {
+        if (MODE == kModeIR) h[e] = ir[i];
+        else if (i >= g.zeros) h[e] = fir_tap(i - g.zeros, half, c2, argscale);
+      }
+      hsum += h[e];
+    }
+    return make_float4(h[0], h[1], h[2], h[3]);
+  });
+  float scale = 1.0f / (float)FM;
+  if (MODE != kModeIR) scale /= block_sum(hsum, s.red, tid);
+  __syncthreads();
+  fft_forward(s, tid);
+  float4* hs = a.hspec + (size_t)qi * (FM / 2);
+  store_filter_pairs(s, scale, hs, hs + FM / 4, tid);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(FT, 2) fftconv_kernel(const ConvArgs a, const float* __restrict__ tw_g) {
+  extern __shared__ __align__(16) float smem_f[];
+  const ConvSmem s(smem_f);
   const int tid = threadIdx.x, qi = blockIdx.y, blk = blockIdx.x;
   const AugQ q = a.q[qi];
   const float* __restrict__ in = a.in + (int64_t)qi * a.in_stride;
   float* __restrict__ out = a.out + (int64_t)qi * a.T;
   const int T = a.T;
   float vmax = 0.f, vss = 0.f;
-  if ((q.apply & a.bit) && (q.long_mask & long_bit<MODE>(a.which))) return;   // partconv_kernel's query
+  if ((q.apply & a.bit) && (q.long_mask & long_bit<MODE>(a.which))) return;   // part_conv_kernel's query
+  // 16-byte accesses need aligned rows (the in-block offsets are multiples of 4 samples by construction)
+  const bool vec_in = ((reinterpret_cast<uintptr_t>(in) & 15) == 0), vec_out = ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
 
   if (!(q.apply & a.bit)) {
     // transform not applied to this query: pass the samples through, still report statistics
@@ -315,108 +229,70 @@ __global__ void __launch_bounds__(FT, 3) fftconv_kernel(const ConvArgs a, const 
       vss += v * v;
     }
   } else {
-    int K, lead;
-    if (MODE == kModeIR) {
-      K = q.ir_len; lead = K - 1;
-    } else {
-      const int half = a.which == 1 ? q.half1 : (a.which == 2 ? q.half2 : q.half3);
-      K = 2 * half + 1; lead = half;
-    }
-    const int V = FN - K + 1;
-    const int n_total = MODE == kModeIR ? T + K - 1 : T;
-    const int n0 = blk * V;
-    if (n0 >= n_total) return;  // block-uniform
-    for (int i = tid; i < kTw; i += FT) tw[i] = tw_g[i];
-    // global loads in batches of 16 per thread, issued together ahead of the shared-memory stores
-    constexpr int kLd = 8;
-#pragma unroll 1
-    for (int m0 = tid; m0 < FM; m0 += FT * kLd) {
-      float x[kLd][2];
+    const int half = MODE == kModeIR ? 0 : (a.which == 1 ? q.half1 : (a.which == 2 ? q.half2 : q.half3));
+    const ConvGeom g = conv_geom(MODE == kModeIR, half, q.ir_len, T);
+    const int n0 = blk * g.V;
+    if (n0 >= g.n_total) return;  // block-uniform
+    s.load_tables(tw_g, tid);
+    const int s0 = n0 - g.lead;
+    fill_planes(s, tid, [&](int i4) {
+      const int n = s0 + 4 * i4;
+      if (vec_in && n >= 0 && n + 3 < T) return __ldg(reinterpret_cast<const float4*>(in + n));
+      float x[4];
 #pragma unroll
-      for (int u = 0; u < kLd; ++u)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int n = n0 - lead + 2 * (m0 + u * FT) + e;
-          if (MODE == kModeIR) x[u][e] = (n >= 0 && n < T) ? __ldg(in + n) : 0.f;   // zero extension
-          else x[u][e] = __ldg(in + min(max(n, 0), T - 1));                          // replicate padding (julius)
-        }
-#pragma unroll
-      for (int u = 0; u < kLd; ++u) buf[pidx(m0 + u * FT)] = make_float2(x[u][0], x[u][1]);
-    }
+      for (int e = 0; e < 4; ++e) {
+        const int ne = n + e;
+        if (MODE == kModeIR) x[e] = (ne >= 0 && ne < T) ? __ldg(in + ne) : 0.f;   // zero extension
+        else x[e] = __ldg(in + min(max(ne, 0), T - 1));                           // replicate padding (julius)
+      }
+      return make_float4(x[0], x[1], x[2], x[3]);
+    });
     __syncthreads();
-    fft_forward(buf, tw, tid);
-    // split -> multiply by the filter spectrum -> re-pack, pair (k, FM-k) per thread
-    const float2* __restrict__ hg = a.hspec + (size_t)qi * FM;
-    constexpr int kPw = 4;
-#pragma unroll 1
-    for (int j0 = tid; j0 < FM / 2; j0 += FT * kPw) {
-      float2 h1[kPw], h2[kPw];
-#pragma unroll
-      for (int u = 0; u < kPw; ++u) {   // filter spectrum of the pairs (k, FM-k), fetched ahead of the math
-        const int r = 2 * (j0 + u * FT), k = pos_freq(r);
-        h1[u] = __ldg(hg + r);
-        h2[u] = __ldg(hg + (k == 0 ? 1 : rev_pos(FM - k)));
-      }
-#pragma unroll
-      for (int u = 0; u < kPw; ++u) {
-      const int j = j0 + u * FT;
-      const int r = 2 * j, k = pos_freq(r);
-      if (k == 0) {
-        const float2 z = buf[pidx(0)], h = h1[u];
-        const float y0 = (z.x + z.y) * h.x, ym = (z.x - z.y) * h.y;
-        buf[pidx(0)] = make_float2(0.5f * (y0 + ym), 0.5f * (y0 - ym));
-      } else {
-        const int r2 = rev_pos(FM - k);
-        const float2 wk = half_twiddle(k);
-        float2 xk, xmk;
-        real_split(buf[pidx(r)], buf[pidx(r2)], wk, xk, xmk);
-        const float2 yk = cmul(xk, h1[u]), ymk = cmul(xmk, h2[u]);
-        // Zy[k] = Ey + i Oy, Zy[FM-k] = conj(Ey) + i conj(Oy); Ey = (Y[k] + conj Y[FM-k]) / 2,
-        // Oy = (Y[k] - conj Y[FM-k]) / 2 * conj(W^k)
-        const float2 ey = make_float2(0.5f * (yk.x + ymk.x), 0.5f * (yk.y - ymk.y));
-        const float2 oy = cmul(make_float2(0.5f * (yk.x - ymk.x), 0.5f * (yk.y + ymk.y)), conjf2(wk));
-        buf[pidx(r)] = make_float2(ey.x - oy.y, ey.y + oy.x);
-        buf[pidx(r2)] = make_float2(ey.x + oy.y, oy.x - ey.y);
-      }
-      }
-    }
-    if (tid == 0) {  // k = FM/2: X = conj(Z), Zy = conj(Y)
-      const float2 z = buf[pidx(1)];
-      const float2 y = cmul(conjf2(z), hg[1]);
-      buf[pidx(1)] = conjf2(y);
-    }
+    fft_forward(s, tid);
+    const float4* hs = a.hspec + (size_t)qi * (FM / 2);
+    apply_filter_pairs(s, hs, hs + FM / 4, tid);
     __syncthreads();
-    fft_inverse(buf, tw, tid);
-    const int n_end = min(n_total, n0 + V);
-    constexpr int kSt = 8;
-#pragma unroll 1
-    for (int nb = n0 + tid; nb < n_end; nb += FT * kSt) {
-      float xin[kSt];
+    fft_inverse(s, tid);
+    const int n_end = min(g.n_total, n0 + g.V);
+    const int e_base = g.off >> 1;   // output n0 + 4 g4 + e sits at packed index e_base + 2 g4 (+1), re / im alternating
+#pragma unroll 2
+    for (int g4 = tid; n0 + 4 * g4 < n_end; g4 += FT) {
+      const int n = n0 + 4 * g4;
+      const int o = fc::padi(e_base + 2 * g4);
+      const float2 cr = *reinterpret_cast<const float2*>(s.re + o), ci = *reinterpret_cast<const float2*>(s.im + o);
+      float v[4] = {cr.x, ci.x, cr.y, ci.y};
+      const bool full = n + 3 < n_end;
       if (MODE == kModeHP) {
+        if (full && vec_in) {
+          const float4 x = __ldg(reinterpret_cast<const float4*>(in + n));
+          v[0] = x.x - v[0]; v[1] = x.y - v[1]; v[2] = x.z - v[2]; v[3] = x.w - v[3];
+        } else {
 #pragma unroll
-        for (int u = 0; u < kSt; ++u) { const int n = nb + u * FT; xin[u] = n < n_end ? __ldg(in + n) : 0.f; }
-      }
-#pragma unroll
-      for (int u = 0; u < kSt; ++u) {
-        const int n = nb + u * FT;
-        if (n < n_end) {
-          const int jj = n - n0 + K - 1;
-          const float2 pr = buf[pidx(jj >> 1)];
-          const float c = (jj & 1) ? pr.y : pr.x;
-          const float v = MODE == kModeHP ? xin[u] - c : c;
-          vmax = fmaxf(vmax, fabsf(v));
-          if (n < T) { out[n] = v; vss += v * v; }
+          for (int e = 0; e < 4; ++e) v[e] = (n + e < n_end ? __ldg(in + n + e) : 0.f) - v[e];
         }
+      }
+      if (full && n + 3 < T) {
+        vmax = fmaxf(fmaxf(vmax, fmaxf(fabsf(v[0]), fabsf(v[1]))), fmaxf(fabsf(v[2]), fabsf(v[3])));
+        vss = fmaf(v[0], v[0], fmaf(v[1], v[1], fmaf(v[2], v[2], fmaf(v[3], v[3], vss))));
+        if (vec_out) *reinterpret_cast<float4*>(out + n) = make_float4(v[0], v[1], v[2], v[3]);
+        else { out[n] = v[0]; out[n + 1] = v[1]; out[n + 2] = v[2]; out[n + 3] = v[3]; }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (n + e < n_end) {
+            vmax = fmaxf(vmax, fabsf(v[e]));
+            if (n + e < T) { out[n + e] = v[e]; vss += v[e] * v[e]; }
+          }
       }
     }
   }
-  vmax = block_max(vmax, red, tid);
-  vss = block_sum(vss, red, tid);
+  vmax = block_max(vmax, s.red, tid);
+  vss = block_sum(vss, s.red, tid);
   if (tid == 0) {
-    AugS* s = a.st + qi;
-    if (MODE == kModeHP && a.which == 1) { atomic_max_pos(&s->max_a, vmax); atomicAdd(&s->ss_a, (double)vss); }
-    else if (MODE == kModeIR) { atomic_max_pos(&s->max_b, vmax); atomicAdd(&s->ss_b, (double)vss); }
-    else if (MODE == kModeHP && a.which == 3) atomic_max_pos(&s->max_v, vmax);
+    AugS* st = a.st + qi;
+    if (MODE == kModeHP && a.which == 1) { atomic_max_pos(&st->max_a, vmax); atomicAdd(&st->ss_a, (double)vss); }
+    else if (MODE == kModeIR) { atomic_max_pos(&st->max_b, vmax); atomicAdd(&st->ss_b, (double)vss); }
+    else if (MODE == kModeHP && a.which == 3) atomic_max_pos(&st->max_v, vmax);
   }
 }
 
@@ -513,15 +389,15 @@ __device__ void clip_select_general(const float* __restrict__ z, int T, const in
 //     c[n] = sum_p sum_{k<S} h_p[k] xe[n + D - pS - k],
 // so output block b (n in [bS, (b+1)S)) is ONE inverse transform of  sum_p H_p * X_{b-p},  where X_j is
 // the spectrum of the FN input samples starting at jS + D - S + 1.  Three kernels over the list of long
-// queries: partition spectra H_p, input-block spectra X_j (each computed once, kept in HBM in the
-// transform's digit-reversed order), and the accumulate + inverse + epilogue kernel.
+// queries: partition double pairs (S, R of fftconv_core.cuh), input-block transforms (each computed once, kept
+// in HBM as two planes in the transform's digit-reversed order), and the accumulate + inverse + epilogue kernel.
 constexpr int kPartS = FN / 2;
 
 struct PartArgs {
   ConvArgs c;
   const int* list;      // [n_long] query indices
-  float2* hparts;       // [n_long][p_cap][FM]
-  float2* xspec;        // [n_long][nb_in_cap][FM]
+  float4* hparts;       // [n_long][p_cap][2][FM/4] double pairs of every partition
+  float* xspec;         // [n_long][nb_in_cap][2][FM] planes of every input-block transform
   int p_cap, nb_in_cap;
 };
 
@@ -533,13 +409,11 @@ __device__ __forceinline__ void part_geometry(const AugQ& q, int which, int T, i
   P = (K + kPartS - 1) / kPartS;
 }
 
-// grid (p_cap, n_long): spectrum of partition p (taps [pS, (p+1)S) zero-padded to FN), scaled like filter_spectrum_kernel
+// grid (p_cap, n_long): double pairs of partition p (taps [pS, (p+1)S) zero-padded to FN), scaled like filter_spectrum_kernel
 template <int MODE>
-__global__ void __launch_bounds__(FT) part_filter_kernel(const PartArgs a, const float2* __restrict__ tw_g) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float2* buf = reinterpret_cast<float2*>(smem_raw);
-  float2* tw = buf + FPAD;
-  float* red = reinterpret_cast<float*>(tw + kTw);
+__global__ void __launch_bounds__(FT, 2) part_filter_kernel(const PartArgs a, const float* __restrict__ tw_g) {
+  extern __shared__ __align__(16) float smem_f[];
+  const ConvSmem s(smem_f);
   const int tid = threadIdx.x, li = blockIdx.y, qi = a.list[li], p = blockIdx.x;
   const AugQ q = a.c.q[qi];
   int K, half, D, P, n_total;
@@ -548,52 +422,35 @@ __global__ void __launch_bounds__(FT) part_filter_kernel(const PartArgs a, const
   float c2 = 0.f, argscale = 0.f;
   int hh;
   if (MODE != kModeIR) filter_params(q, a.c.which, hh, c2, argscale);
-  for (int i = tid; i < kTw; i += FT) tw[i] = tw_g[i];
+  s.load_tables(tw_g, tid);
   const float* ir = MODE == kModeIR ? a.c.ir + (int64_t)qi * a.c.ir_stride : nullptr;
   float scale = 1.0f / (float)FM;
   if (MODE != kModeIR) {   // julius normalises by the sum of ALL taps
     float hs = 0.f;
     for (int i = tid; i < K; i += FT) hs += fir_tap(i, half, c2, argscale);
-    scale /= block_sum(hs, red, tid);
+    scale /= block_sum(hs, s.red, tid);
   }
-  for (int m = tid; m < FM; m += FT) {
-    float h[2];
+  fill_planes(s, tid, [&](int i4) {
+    float h[4];
 #pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const int i = p * kPartS + 2 * m + e;
+    for (int e = 0; e < 4; ++e) {
+      const int j = 4 * i4 + e, i = p * kPartS + j;
       h[e] = 0.f;
-      if (2 * m + e < kPartS && i < K) h[e] = MODE == kModeIR ? ir[i] : fir_tap(i, half, c2, argscale);
+      if (j < kPartS && i < K) h[e] = MODE == kModeIR ? ir[i] : fir_tap(i, half, c2, argscale);
     }
-    buf[pidx(m)] = make_float2(h[0], h[1]);
-  }
+    return make_float4(h[0], h[1], h[2], h[3]);
+  });
   __syncthreads();
-  fft_forward(buf, tw, tid);
-  float2* hg = a.hparts + ((size_t)li * a.p_cap + p) * FM;
-  for (int j = tid; j < FM / 2; j += FT) {
-    const int r = 2 * j, k = pos_freq(r);
-    if (k == 0) {
-      const float2 z = buf[pidx(0)];
-      hg[0] = make_float2((z.x + z.y) * scale, (z.x - z.y) * scale);
-    } else {
-      const int r2 = rev_pos(FM - k);
-      float2 hk, hmk;
-      real_split(buf[pidx(r)], buf[pidx(r2)], half_twiddle(k), hk, hmk);
-      hg[r] = make_float2(hk.x * scale, hk.y * scale);
-      hg[r2] = make_float2(hmk.x * scale, hmk.y * scale);
-    }
-  }
-  if (tid == 0) {
-    const float2 z = buf[pidx(1)];
-    hg[1] = make_float2(z.x * scale, -z.y * scale);
-  }
+  fft_forward(s, tid);
+  float4* hs = a.hparts + ((size_t)li * a.p_cap + p) * (FM / 2);
+  store_filter_pairs(s, scale, hs, hs + FM / 4, tid);
 }
 
-// grid (nb_in_cap, n_long): Z_j = FFT_FM of the packed input block j - (P-1)
+// grid (nb_in_cap, n_long): transform of the packed input block j - (P-1)
 template <int MODE>
-__global__ void __launch_bounds__(FT, 3) part_forward_kernel(const PartArgs a, const float2* __restrict__ tw_g) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float2* buf = reinterpret_cast<float2*>(smem_raw);
-  float2* tw = buf + FPAD;
+__global__ void __launch_bounds__(FT, 2) part_forward_kernel(const PartArgs a, const float* __restrict__ tw_g) {
+  extern __shared__ __align__(16) float smem_f[];
+  const ConvSmem s(smem_f);
   const int tid = threadIdx.x, li = blockIdx.y, qi = a.list[li], jb = blockIdx.x;
   const AugQ q = a.c.q[qi];
   int K, half, D, P, n_total;
@@ -603,30 +460,33 @@ __global__ void __launch_bounds__(FT, 3) part_forward_kernel(const PartArgs a, c
   const int T = a.c.T;
   const float* __restrict__ in = a.c.in + (int64_t)qi * a.c.in_stride;
   const int64_t s0 = (int64_t)(jb - (P - 1)) * kPartS + D - kPartS + 1;
-  for (int i = tid; i < kTw; i += FT) tw[i] = tw_g[i];
-  for (int m = tid; m < FM; m += FT) {
-    float x[2];
+  s.load_tables(tw_g, tid);
+  fill_planes(s, tid, [&](int i4) {
+    float x[4];
 #pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const int64_t n = s0 + 2 * m + e;
+    for (int e = 0; e < 4; ++e) {
+      const int64_t n = s0 + 4 * i4 + e;
       if (MODE == kModeIR) x[e] = (n >= 0 && n < T) ? __ldg(in + n) : 0.f;                  // zero extension
       else x[e] = __ldg(in + (n < 0 ? 0 : (n > T - 1 ? T - 1 : n)));                         // replicate padding (julius)
     }
-    buf[pidx(m)] = make_float2(x[0], x[1]);
-  }
+    return make_float4(x[0], x[1], x[2], x[3]);
+  });
   __syncthreads();
-  fft_forward(buf, tw, tid);
-  float2* zg = a.xspec + ((size_t)li * a.nb_in_cap + jb) * FM;
-  for (int m = tid; m < FM; m += FT) zg[m] = buf[pidx(m)];
+  fft_forward(s, tid);
+  float* zg = a.xspec + ((size_t)li * a.nb_in_cap + jb) * (2 * FM);
+  for (int i = tid; i < FM / 2; i += FT) {
+    const int o = fc::padi(2 * i);
+    *reinterpret_cast<float2*>(zg + 2 * i) = *reinterpret_cast<const float2*>(s.re + o);
+    *reinterpret_cast<float2*>(zg + FM + 2 * i) = *reinterpret_cast<const float2*>(s.im + o);
+  }
 }
 
-// grid (nb_out_max, n_long): Y = sum_p H_p X_{b-p} -> inverse transform -> the same epilogue as fftconv_kernel
+// grid (nb_out_max, n_long): sum_p (filter pairs of p) x (transform of block b - p) -> inverse transform -> the
+// same epilogue as fftconv_kernel
 template <int MODE>
-__global__ void __launch_bounds__(FT, 3) part_conv_kernel(const PartArgs a, const float2* __restrict__ tw_g) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float2* buf = reinterpret_cast<float2*>(smem_raw);
-  float2* tw = buf + FPAD;
-  float* red = reinterpret_cast<float*>(tw + kTw);
+__global__ void __launch_bounds__(FT, 2) part_conv_kernel(const PartArgs a, const float* __restrict__ tw_g) {
+  extern __shared__ __align__(16) float smem_f[];
+  const ConvSmem s(smem_f);
   const int tid = threadIdx.x, li = blockIdx.y, qi = a.list[li], b = blockIdx.x;
   const AugQ q = a.c.q[qi];
   int K, half, D, P, n_total;
@@ -636,62 +496,69 @@ __global__ void __launch_bounds__(FT, 3) part_conv_kernel(const PartArgs a, cons
   const int T = a.c.T;
   const float* __restrict__ in = a.c.in + (int64_t)qi * a.c.in_stride;
   float* __restrict__ out = a.c.out + (int64_t)qi * T;
-  for (int i = tid; i < kTw; i += FT) tw[i] = tw_g[i];
-  const float2* __restrict__ hq = a.hparts + (size_t)li * a.p_cap * FM;
-  const float2* __restrict__ zq = a.xspec + (size_t)li * a.nb_in_cap * FM;
-  for (int j = tid; j < FM / 2; j += FT) {
-    const int r = 2 * j, k = pos_freq(r);
-    if (k == 0) {
-      float y0 = 0.f, ym = 0.f;
-      for (int p = 0; p < P; ++p) {
-        const float2 z = __ldg(zq + (size_t)(b - p + P - 1) * FM), h = __ldg(hq + (size_t)p * FM);
-        y0 += (z.x + z.y) * h.x;
-        ym += (z.x - z.y) * h.y;
+  s.load_tables(tw_g, tid);
+  const float4* __restrict__ hq = a.hparts + (size_t)li * a.p_cap * (FM / 2);
+  const float* __restrict__ zq = a.xspec + (size_t)li * a.nb_in_cap * (2 * FM);
+  {
+    const int m = tid, mbar = fc::partner_block(m);
+    float sw, cw;
+    sincospif((float)fc::block_c(m) * (1.0f / (float)FM), &sw, &cw);
+#pragma unroll 1
+    for (int d2 = 0; d2 < 8; ++d2) {
+      if (m == 0 && d2 == 0) {
+        fc::SpecAcc acc = fc::spec_acc_zero();
+        for (int p = 0; p < P; ++p) {
+          const float* z = zq + (size_t)(b - p + P - 1) * (2 * FM);
+          const float4 vs = __ldg(hq + (size_t)p * (FM / 2)), vr = __ldg(hq + (size_t)p * (FM / 2) + FM / 4);
+          fc::Specials sp;
+          sp.a0 = vs.x; sp.a1 = vs.y; sp.bre = vs.z; sp.bim = vs.w;
+          sp.sre = vr.x; sp.sim = vr.y; sp.rre = vr.z; sp.rim = vr.w;
+          const float z8[8] = {z[0], z[FM], z[1], z[FM + 1], z[16], z[FM + 16], z[17], z[FM + 17]};
+          fc::specials_accumulate(acc, z8, sp);
+        }
+        fc::specials_finish(s.re, s.im, acc);
+        continue;
       }
-      buf[pidx(0)] = make_float2(0.5f * (y0 + ym), 0.5f * (y0 - ym));
-    } else {
-      const int r2 = rev_pos(FM - k);
-      const float2 wk = half_twiddle(k);
-      float2 yk = make_float2(0.f, 0.f), ymk = make_float2(0.f, 0.f);
+      // unpadded plane offsets of the two slots, and their padded shared-memory twins
+      const int ua = 32 * m + 2 * d2, ub = 32 * mbar + 2 * ((m == 0 ? 16 : 15) - d2);
+      const c2 wv = fc::dp_twiddle(cw, sw, d2);
+      const int i = fc::dp_index(m, d2);
+      const float2 zero = make_float2(0.f, 0.f);
+      c2 ey = fc::mk(zero, zero), dy = fc::mk(zero, zero);
       for (int p = 0; p < P; ++p) {
-        const float2* z = zq + (size_t)(b - p + P - 1) * FM;
-        const float2* h = hq + (size_t)p * FM;
-        float2 xk, xmk;
-        real_split(__ldg(z + r), __ldg(z + r2), wk, xk, xmk);
-        yk = cadd(yk, cmul(xk, __ldg(h + r)));
-        ymk = cadd(ymk, cmul(xmk, __ldg(h + r2)));
+        const float* z = zq + (size_t)(b - p + P - 1) * (2 * FM);
+        const float4 vs = __ldg(hq + (size_t)p * (FM / 2) + i), vr = __ldg(hq + (size_t)p * (FM / 2) + FM / 4 + i);
+        c2 ep, f;
+        fc::dp_split(fc::cld(z, z + FM, ua), fc::cld(z, z + FM, ub), wv, ep, f);
+        const c2 S = fc::mk(fc::f2(vs.x, vs.y), fc::f2(vs.z, vs.w)), R = fc::mk(fc::f2(vr.x, vr.y), fc::f2(vr.z, vr.w));
+        ey = fc::cmac(R, f, fc::cmac(S, ep, ey));
+        dy = fc::cmac(S, f, fc::cmac(R, ep, dy));
       }
-      const float2 ey = make_float2(0.5f * (yk.x + ymk.x), 0.5f * (yk.y - ymk.y));
-      const float2 oy = cmul(make_float2(0.5f * (yk.x - ymk.x), 0.5f * (yk.y + ymk.y)), conjf2(wk));
-      buf[pidx(r)] = make_float2(ey.x - oy.y, ey.y + oy.x);
-      buf[pidx(r2)] = make_float2(ey.x + oy.y, oy.x - ey.y);
+      c2 za, zb;
+      fc::dp_repack(ey, dy, wv, za, zb);
+      fc::cst(s.re, s.im, fc::padi(ua), za);
+      fc::cst(s.re, s.im, fc::padi(ub), zb);
     }
   }
-  if (tid == 0) {  // k = FM/2: X = conj(Z), Zy = conj(Y)
-    float2 y = make_float2(0.f, 0.f);
-    for (int p = 0; p < P; ++p)
-      y = cadd(y, cmul(conjf2(__ldg(zq + (size_t)(b - p + P - 1) * FM + 1)), __ldg(hq + (size_t)p * FM + 1)));
-    buf[pidx(1)] = conjf2(y);
-  }
   __syncthreads();
-  fft_inverse(buf, tw, tid);
+  fft_inverse(s, tid);
   float vmax = 0.f, vss = 0.f;
   const int n_end = min(n_total, (b + 1) * kPartS);
   for (int n = b * kPartS + tid; n < n_end; n += FT) {
     const int jj = n - b * kPartS + kPartS - 1;
-    const float2 pr = buf[pidx(jj >> 1)];
-    const float c = (jj & 1) ? pr.y : pr.x;
+    const int o = fc::padi(jj >> 1);
+    const float c = (jj & 1) ? s.im[o] : s.re[o];
     const float v = MODE == kModeHP ? in[n] - c : c;
     vmax = fmaxf(vmax, fabsf(v));
     if (n < T) { out[n] = v; vss += v * v; }
   }
-  vmax = block_max(vmax, red, tid);
-  vss = block_sum(vss, red, tid);
+  vmax = block_max(vmax, s.red, tid);
+  vss = block_sum(vss, s.red, tid);
   if (tid == 0) {
-    AugS* s = a.c.st + qi;
-    if (MODE == kModeHP && a.c.which == 1) { atomic_max_pos(&s->max_a, vmax); atomicAdd(&s->ss_a, (double)vss); }
-    else if (MODE == kModeIR) { atomic_max_pos(&s->max_b, vmax); atomicAdd(&s->ss_b, (double)vss); }
-    else if (MODE == kModeHP && a.c.which == 3) atomic_max_pos(&s->max_v, vmax);
+    AugS* st = a.c.st + qi;
+    if (MODE == kModeHP && a.c.which == 1) { atomic_max_pos(&st->max_a, vmax); atomicAdd(&st->ss_a, (double)vss); }
+    else if (MODE == kModeIR) { atomic_max_pos(&st->max_b, vmax); atomicAdd(&st->ss_b, (double)vss); }
+    else if (MODE == kModeHP && a.c.which == 3) atomic_max_pos(&st->max_v, vmax);
   }
 }
 
@@ -1148,10 +1015,18 @@ int launch_noise_assemble(mfpa_ctx* ctx, const float* bank, int64_t bank_len, co
 }
 
 static int aug_init_tables(mfpa_ctx* ctx) {
-  if (ctx->aug_tw_dev) return MFPA_OK;
-  static float2 tw[kTw];
+  if ((const float*)ctx->aug_tw_dev) return MFPA_OK;
+  // planar tables of fftconv_core.cuh: exp(-2 pi i e / FM), e < 512, then exp(-2 pi i e / 512), e < 32
+  static float tw[kTwFloats];
   const double pi = 3.14159265358979323846;
-  for (int e = 0; e < kTw; ++e) tw[e] = make_float2((float)cos(2 * pi * e / FM), (float)-sin(2 * pi * e / FM));
+  for (int e = 0; e < fc::kTwA; ++e) {
+    tw[e] = (float)cos(2 * pi * e / FM);
+    tw[fc::kTwA + e] = (float)-sin(2 * pi * e / FM);
+  }
+  for (int e = 0; e < fc::kTwB; ++e) {
+    tw[2 * fc::kTwA + e] = (float)cos(2 * pi * e / 512);
+    tw[2 * fc::kTwA + fc::kTwB + e] = (float)-sin(2 * pi * e / 512);
+  }
   MFPA_CUDA(cudaMalloc(&ctx->aug_tw_dev, sizeof(tw)));
   MFPA_CUDA(cudaMemcpy(ctx->aug_tw_dev, tw, sizeof(tw), cudaMemcpyHostToDevice));
   MFPA_CUDA(cudaFuncSetAttribute(fftconv_kernel<kModeHP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmem));
@@ -1204,7 +1079,14 @@ int launch_augment(mfpa_ctx* ctx, const float* x, int B, int T, int64_t x_stride
   int nlong[4] = {0, 0, 0, 0}, max_k[4] = {0, 0, 0, 0};
   for (int l = 0; l < 4; ++l) hlist[l] = reinterpret_cast<int*>(hq + B) + (size_t)l * B;
   constexpr int kFastTaps = FN / 2 + 1;   // one overlap-save block keeps >= FN/2 valid outputs
-  int min_v1 = FN, min_v3 = FN, min_vir = FN, max_half2 = 0;
+  // grid width of each convolution stage: the most blocks any query needs (pass-through queries: T / FN)
+  const int nb_pass = (T + FN - 1) / FN;
+  int nb1 = nb_pass, nb2 = nb_pass, nb3 = nb_pass, nbir = nb_pass;
+  auto blocks_of = [&](bool causal, int half, int ir_len) {
+    const ConvGeom g = conv_geom(causal, half, ir_len, T);
+    return (g.n_total + g.V - 1) / g.V;
+  };
+  auto up = [](int& a, int b) { if (b > a) a = b; };
   bool any_long_lp = false;
   auto note_long = [&](int l, uint32_t bit, int K, AugQ& q, int i) {
     q.long_mask |= bit; hlist[l][nlong[l]++] = i; max_k[l] = K > max_k[l] ? K : max_k[l];
@@ -1221,7 +1103,7 @@ int launch_augment(mfpa_ctx* ctx, const float* x, int B, int T, int64_t x_stride
                    "(limit %d)", i, (double)p.fc1_hz, 2ll * q.half1 + 1, MFPA_AUG_MAX_TAPS);
       q.c1x2 = (float)(2.0 * c); q.arg1 = (float)(2.0 * c * 3.14159265358979323846);
       if (2 * q.half1 + 1 > kFastTaps) note_long(0, kLongHP1, 2 * q.half1 + 1, q, i);
-      else min_v1 = FN - 2 * q.half1 < min_v1 ? FN - 2 * q.half1 : min_v1;
+      else up(nb1, blocks_of(false, q.half1, 0));
     }
     if (p.apply & MFPA_AUG_LPF) {
       q.half2 = fir_half(p.fc2_hz, sample_rate, "low-pass", i, &c);
@@ -1231,7 +1113,7 @@ int launch_augment(mfpa_ctx* ctx, const float* x, int B, int T, int64_t x_stride
       q.c2x2 = (float)(2.0 * c); q.arg2 = (float)(2.0 * c * 3.14159265358979323846);
       if (q.half2 > kLpMaxHalf) any_long_lp = true;
       if (2 * q.half2 + 1 > kFastTaps) note_long(2, kLongLP, 2 * q.half2 + 1, q, i);
-      else max_half2 = q.half2 > max_half2 ? q.half2 : max_half2;
+      else up(nb2, blocks_of(false, q.half2, 0));
     }
     if (p.apply & MFPA_AUG_HPF3) {
       q.half3 = fir_half(p.fc3_hz, sample_rate, "microphone high-pass", i, &c);
@@ -1240,7 +1122,7 @@ int launch_augment(mfpa_ctx* ctx, const float* x, int B, int T, int64_t x_stride
                    "(limit %d)", i, (double)p.fc3_hz, 2ll * q.half3 + 1, MFPA_AUG_MAX_TAPS);
       q.c3x2 = (float)(2.0 * c); q.arg3 = (float)(2.0 * c * 3.14159265358979323846);
       if (2 * q.half3 + 1 > kFastTaps) note_long(3, kLongHP3, 2 * q.half3 + 1, q, i);
-      else min_v3 = FN - 2 * q.half3 < min_v3 ? FN - 2 * q.half3 : min_v3;
+      else up(nb3, blocks_of(false, q.half3, 0));
     }
     if (p.apply & MFPA_AUG_IR) {
       MFPA_REQUIRE(ir != nullptr, "augment: query %d applies an impulse response but ir_dev is NULL", i);
@@ -1248,7 +1130,7 @@ int launch_augment(mfpa_ctx* ctx, const float* x, int B, int T, int64_t x_stride
                    "augment: query %d: ir_len %d not in [1, min(ir_stride %d, %d)]", i, p.ir_len, ir_stride, MFPA_AUG_MAX_IR);
       q.ir_len = p.ir_len;
       if (p.ir_len > FN / 2) note_long(1, kLongIR, p.ir_len, q, i);
-      else min_vir = FN - p.ir_len + 1 < min_vir ? FN - p.ir_len + 1 : min_vir;
+      else up(nbir, blocks_of(true, 0, p.ir_len));
     }
     if (p.apply & MFPA_AUG_NOISE) MFPA_REQUIRE(noise != nullptr, "augment: query %d mixes noise but noise_dev is NULL", i);
     q.snr_div = powf(10.0f, p.snr_db / 20.0f);
@@ -1261,7 +1143,7 @@ int launch_augment(mfpa_ctx* ctx, const float* x, int B, int T, int64_t x_stride
   if (ctx->aug_a.reserve(rows) || ctx->aug_b.reserve(rows)) return MFPA_ENOMEM;
   if (ctx->aug_small.reserve((sizeof(AugQ) + sizeof(AugS)) * (size_t)B)) return MFPA_ENOMEM;
   if (ctx->aug_d.reserve(sizeof(float2) * (size_t)B * FM)) return MFPA_ENOMEM;
-  float2* hspec = (float2*)ctx->aug_d.ptr;
+  float4* hspec = (float4*)ctx->aug_d.ptr;
   float* bufA = (float*)ctx->aug_a.ptr;
   float* bufB = (float*)ctx->aug_b.ptr;
   AugQ* dq = (AugQ*)ctx->aug_small.ptr;
@@ -1289,40 +1171,40 @@ int launch_augment(mfpa_ctx* ctx, const float* x, int B, int T, int64_t x_stride
     if (ctx->aug_part.reserve(per_query * (size_t)group)) return MFPA_ENOMEM;
     for (int g0 = 0; g0 < nlong[l]; g0 += group) {
     const int ng = nlong[l] - g0 < group ? nlong[l] - g0 : group;
-    PartArgs a{c, dlist + (size_t)l * B + g0, (float2*)ctx->aug_part.ptr, (float2*)ctx->aug_part.ptr + (size_t)ng * P * FM, P, nb_in};
+    PartArgs a{c, dlist + (size_t)l * B + g0, (float4*)ctx->aug_part.ptr,
+               (float*)((float2*)ctx->aug_part.ptr + (size_t)ng * P * FM), P, nb_in};
     const dim3 gf(P, ng), gi(nb_in, ng), go(nb_out, ng);
     if (mode == kModeHP) {
-      part_filter_kernel<kModeHP><<<gf, FT, kConvSmem, st>>>(a, ctx->aug_tw_dev);
-      part_forward_kernel<kModeHP><<<gi, FT, kConvSmem, st>>>(a, ctx->aug_tw_dev);
-      part_conv_kernel<kModeHP><<<go, FT, kConvSmem, st>>>(a, ctx->aug_tw_dev);
+      part_filter_kernel<kModeHP><<<gf, FT, kConvSmem, st>>>(a, (const float*)ctx->aug_tw_dev);
+      part_forward_kernel<kModeHP><<<gi, FT, kConvSmem, st>>>(a, (const float*)ctx->aug_tw_dev);
+      part_conv_kernel<kModeHP><<<go, FT, kConvSmem, st>>>(a, (const float*)ctx->aug_tw_dev);
     } else if (mode == kModeIR) {
-      part_filter_kernel<kModeIR><<<gf, FT, kConvSmem, st>>>(a, ctx->aug_tw_dev);
-      part_forward_kernel<kModeIR><<<gi, FT, kConvSmem, st>>>(a, ctx->aug_tw_dev);
-      part_conv_kernel<kModeIR><<<go, FT, kConvSmem, st>>>(a, ctx->aug_tw_dev);
+      part_filter_kernel<kModeIR><<<gf, FT, kConvSmem, st>>>(a, (const float*)ctx->aug_tw_dev);
+      part_forward_kernel<kModeIR><<<gi, FT, kConvSmem, st>>>(a, (const float*)ctx->aug_tw_dev);
+      part_conv_kernel<kModeIR><<<go, FT, kConvSmem, st>>>(a, (const float*)ctx->aug_tw_dev);
     } else {
-      part_filter_kernel<kModeLP><<<gf, FT, kConvSmem, st>>>(a, ctx->aug_tw_dev);
-      part_forward_kernel<kModeLP><<<gi, FT, kConvSmem, st>>>(a, ctx->aug_tw_dev);
-      part_conv_kernel<kModeLP><<<go, FT, kConvSmem, st>>>(a, ctx->aug_tw_dev);
+      part_filter_kernel<kModeLP><<<gf, FT, kConvSmem, st>>>(a, (const float*)ctx->aug_tw_dev);
+      part_forward_kernel<kModeLP><<<gi, FT, kConvSmem, st>>>(a, (const float*)ctx->aug_tw_dev);
+      part_conv_kernel<kModeLP><<<go, FT, kConvSmem, st>>>(a, (const float*)ctx->aug_tw_dev);
     }
     MFPA_CUDA(cudaGetLastError());
     }
     return MFPA_OK;
   };
 
-  auto blocks_for = [&](int n_total, int min_v) { return (unsigned)((n_total + min_v - 1) / min_v); };
   // stage 1: x -> A
   {
     ConvArgs a{x, x_stride, bufA, nullptr, 0, dq, ds, T, MFPA_AUG_HPF1, 1, hspec};
-    filter_spectrum_kernel<kModeHP><<<B, FT, kConvSmem, st>>>(a, ctx->aug_tw_dev);
-    fftconv_kernel<kModeHP><<<dim3(blocks_for(T, min_v1), B), FT, kConvSmem, st>>>(a, ctx->aug_tw_dev);
+    filter_spectrum_kernel<kModeHP><<<B, FT, kConvSmem, st>>>(a, (const float*)ctx->aug_tw_dev);
+    fftconv_kernel<kModeHP><<<dim3((unsigned)nb1, B), FT, kConvSmem, st>>>(a, (const float*)ctx->aug_tw_dev);
     MFPA_CUDA(cudaGetLastError());
     if (int e = run_long(0, kModeHP, a)) return e;
   }
   // stage 2: A -> B
   {
     ConvArgs a{bufA, T, bufB, ir, ir_stride, dq, ds, T, MFPA_AUG_IR, 0, hspec};
-    filter_spectrum_kernel<kModeIR><<<B, FT, kConvSmem, st>>>(a, ctx->aug_tw_dev);
-    fftconv_kernel<kModeIR><<<dim3(blocks_for(T + FN - min_vir, min_vir), B), FT, kConvSmem, st>>>(a, ctx->aug_tw_dev);
+    filter_spectrum_kernel<kModeIR><<<B, FT, kConvSmem, st>>>(a, (const float*)ctx->aug_tw_dev);
+    fftconv_kernel<kModeIR><<<dim3((unsigned)nbir, B), FT, kConvSmem, st>>>(a, (const float*)ctx->aug_tw_dev);
     MFPA_CUDA(cudaGetLastError());
     if (int e = run_long(1, kModeIR, a)) return e;
   }
@@ -1350,8 +1232,8 @@ int launch_augment(mfpa_ctx* ctx, const float* x, int B, int T, int64_t x_stride
       clip_lpf_kernel<<<dim3(gx, B), 256, 0, st>>>(bufA, bufC, dq, ds, T, 1);
       MFPA_CUDA(cudaGetLastError());
       ConvArgs a{bufC, T, bufB, nullptr, 0, dq, ds, T, MFPA_AUG_LPF, 2, hspec};
-      filter_spectrum_kernel<kModeHP><<<B, FT, kConvSmem, st>>>(a, ctx->aug_tw_dev);
-      fftconv_kernel<kModeLP><<<dim3(blocks_for(T, FN - 2 * max_half2), B), FT, kConvSmem, st>>>(a, ctx->aug_tw_dev);
+      filter_spectrum_kernel<kModeHP><<<B, FT, kConvSmem, st>>>(a, (const float*)ctx->aug_tw_dev);
+      fftconv_kernel<kModeLP><<<dim3((unsigned)nb2, B), FT, kConvSmem, st>>>(a, (const float*)ctx->aug_tw_dev);
       MFPA_CUDA(cudaGetLastError());
       if (int e = run_long(2, kModeLP, a)) return e;
     }
@@ -1359,8 +1241,8 @@ int launch_augment(mfpa_ctx* ctx, const float* x, int B, int T, int64_t x_stride
   // stage 6: B -> A (v) ; stage 7: A -> out
   {
     ConvArgs a{bufB, T, bufA, nullptr, 0, dq, ds, T, MFPA_AUG_HPF3, 3, hspec};
-    filter_spectrum_kernel<kModeHP><<<B, FT, kConvSmem, st>>>(a, ctx->aug_tw_dev);
-    fftconv_kernel<kModeHP><<<dim3(blocks_for(T, min_v3), B), FT, kConvSmem, st>>>(a, ctx->aug_tw_dev);
+    filter_spectrum_kernel<kModeHP><<<B, FT, kConvSmem, st>>>(a, (const float*)ctx->aug_tw_dev);
+    fftconv_kernel<kModeHP><<<dim3((unsigned)nb3, B), FT, kConvSmem, st>>>(a, (const float*)ctx->aug_tw_dev);
     MFPA_CUDA(cudaGetLastError());
     if (int e = run_long(3, kModeHP, a)) return e;
     const unsigned gx = (unsigned)((T + 4095) / 4096);

@@ -191,6 +191,24 @@ int mfpa_stft_mag(mfpa_ctx* ctx, const float* x_dev, int B, int T, int64_t x_str
   return launch_stft_mag(ctx, x_dev, B, T, x_stride, shifts, mag_dev, qmax_dev, (cudaStream_t)stream);
 }
 
+int mfpa_stft_num_frames(int n_samples, int n_fft, int hop, int win_len) {
+  if (n_samples < 1 || n_fft < 2 || hop < 1 || win_len < 1) return 0;
+  const int64_t padded = (int64_t)n_samples + 2 * (n_fft / 2);
+  if (padded < win_len) return 0;
+  return (int)(1 + (padded - win_len) / hop);
+}
+
+int mfpa_stft_complex(mfpa_ctx* ctx, const double* x_dev, int T, int n_fft, int hop, const double* window_dev,
+                      int win_len, double* out_dev, void* stream) {
+  MFPA_REQUIRE(ctx && x_dev && window_dev && out_dev, "stft_complex: NULL argument");
+  MFPA_REQUIRE(T >= 1 && n_fft >= 2 && n_fft <= 8192 && hop >= 1 && win_len >= 1, "stft_complex: T %d, n_fft %d, hop %d, window %d",
+               T, n_fft, hop, win_len);
+  const int n_frames = mfpa_stft_num_frames(T, n_fft, hop, win_len);
+  MFPA_REQUIRE(n_frames >= 1, "stft_complex: signal of %d samples is shorter than one window of %d", T, win_len);
+  DeviceGuard guard(ctx->device);
+  return launch_stft_complex(x_dev, T, n_fft, hop, window_dev, win_len, n_frames, out_dev, (cudaStream_t)stream);
+}
+
 int mfpa_spec_from_mag(mfpa_ctx* ctx, const float* mag_dev, const float* qmax_dev, int B, int T,
                        int shifts, double* spec_dev, void* stream) {
   MFPA_REQUIRE(ctx && mag_dev && qmax_dev && spec_dev, "spec_from_mag: NULL argument");

@@ -71,7 +71,7 @@ struct mfpa_ctx {
   mfpa::Scratch mag, qmax, rec, fwd, hashes, nh, misc, spec64, xin, out_h, out_n;
   // augmentation / matching state is appended by their translation units
   mfpa::Scratch aug_a, aug_b, aug_c, aug_d, aug_small, aug_lists, aug_long, aug_part, aug_noise;
-  float2* aug_tw_dev = nullptr;     // two-level twiddle tables of the 16384-point FFT (augment.cu)
+  float2* aug_tw_dev = nullptr;     // planar twiddle tables of the 8192-point FFT (augment.cu, fftconv_core.cuh)
   void* aug_pinned = nullptr;
   void* aug_copy_done = nullptr;    // cudaEvent_t: the last H2D copy out of aug_pinned
   size_t aug_pinned_bytes = 0;
@@ -96,6 +96,8 @@ namespace mfpa {
 
 int launch_stft_mag(mfpa_ctx* ctx, const float* x, int B, int T, int64_t stride, int shifts,
                     float* mag, float* qmax, cudaStream_t st, const float* window = nullptr);
+int launch_stft_complex(const double* x, int T, int n_fft, int hop, const double* win, int win_len, int n_frames,
+                        double* out, cudaStream_t st);
 int dejavu_num_frames(int T);
 int launch_dejavu_psd(mfpa_ctx* ctx, const float* x, int B, int T, int64_t stride, float* psd, cudaStream_t st);
 int launch_dejavu_log(const float* psd, int B, int n, int square, float* arr, cudaStream_t st);

@@ -269,6 +269,39 @@ __global__ void spec_from_mag_kernel(const float* __restrict__ mag, const float*
   }
 }
 
+
+// ---- complex STFT in float64 (afp/audfprint/stft.py:15-62: the module's public function) -------------
+// One block per frame, one thread per bin: a direct DFT of the windowed frame with an exact-to-rounding
+// float64 twiddle table.  Not on the throughput path (find_peaks uses stft_mag_kernel); it exists so that
+// stft.stft() keeps its meaning - complex128 [n_fft/2 + 1][frames] - for callers of the module.
+__global__ void __launch_bounds__(256) stft_complex_kernel(const double* __restrict__ x, int T, int n_fft, int hop,
+                                                           const double* __restrict__ win, int L, int n_frames,
+                                                           double2* __restrict__ out) {
+  extern __shared__ __align__(16) double sm_d[];
+  double2* tw = reinterpret_cast<double2*>(sm_d);   // [n_fft]
+  double* fr = sm_d + 2 * n_fft;                    // [L] windowed frame
+  const int f = blockIdx.x, pad = n_fft / 2;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) fr[i] = x[reflect_index(f * hop + i - pad, T)] * win[i];
+  for (int m = threadIdx.x; m < n_fft; m += blockDim.x) {
+    double sn, cs;
+    sincospi(2.0 * (double)m / (double)n_fft, &sn, &cs);
+    tw[m] = make_double2(cs, -sn);
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k <= n_fft / 2; k += blockDim.x) {
+    double re = 0.0, im = 0.0;
+    int idx = 0;
+    for (int n = 0; n < L; ++n) {
+      const double2 w = tw[idx];
+      re += fr[n] * w.x;
+      im += fr[n] * w.y;
+      idx += k;
+      if (idx >= n_fft) idx -= n_fft;
+    }
+    out[(int64_t)k * n_frames + f] = make_double2(re, im);
+  }
+}
+
 }  // namespace
 
 int stft_init_tables(mfpa_ctx* ctx) {
@@ -319,6 +352,17 @@ int launch_spec_from_mag(const float* mag, const float* qmax, int B, int T, int 
                                                       n_max, spec + (int64_t)i0 * kBins * n_max, i0);
     MFPA_CUDA(cudaGetLastError());
   }
+  return MFPA_OK;
+}
+
+int launch_stft_complex(const double* x, int T, int n_fft, int hop, const double* win, int win_len, int n_frames,
+                        double* out, cudaStream_t st) {
+  const int L = win_len < n_fft ? win_len : n_fft;   // np.fft.rfft(frames, n_fft) crops / zero-pads the frame
+  const size_t smem = sizeof(double) * (2 * (size_t)n_fft + L);
+  MFPA_REQUIRE(smem <= 200 * 1024, "stft_complex: n_fft %d too large for one block's shared memory", n_fft);
+  MFPA_CUDA(cudaFuncSetAttribute(stft_complex_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  stft_complex_kernel<<<n_frames, 256, smem, st>>>(x, T, n_fft, hop, win, L, n_frames, reinterpret_cast<double2*>(out));
+  MFPA_CUDA(cudaGetLastError());
   return MFPA_OK;
 }
 

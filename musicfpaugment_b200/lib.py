@@ -73,6 +73,8 @@ SIGNATURES = {
     "mfpa_num_frames": (_i, [_i]),
     "mfpa_shift_offset": (_i, [_i, _i]),
     "mfpa_stft_mag": (_i, [_vp, _vp, _i, _i, _i64, _i, _vp, _vp, _vp]),
+    "mfpa_stft_num_frames": (_i, [_i, _i, _i, _i]),
+    "mfpa_stft_complex": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp]),
     "mfpa_spec_from_mag": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "mfpa_audfprint_peaks": (_i, [_vp, _vp, _vp, _i, _i, _i, _P, _vp, _vp, _vp]),
     "mfpa_audfprint_peaks_from_spec": (_i, [_vp, _vp, _i, _i, _i, _P, _vp, _vp, _vp]),
@@ -237,6 +239,18 @@ class Context:
         qmax = torch.empty(B * shifts, dtype=torch.float32, device=x.device)
         check(_lib.mfpa_stft_mag(self._h, _ptr(x), B, T, _row_stride(x), shifts, _ptr(mag), _ptr(qmax), _stream()))
         return mag, qmax
+
+    def stft_complex(self, x, n_fft: int, hop: int, window):
+        """stft.stft (afp/audfprint/stft.py:15-62): x float64 [T] cuda, window float64 [L] cuda ->
+        complex128 [n_fft/2+1, frames] cuda."""
+        import torch
+
+        assert x.is_cuda and x.dtype == torch.float64 and x.dim() == 1 and x.is_contiguous()
+        assert window.is_cuda and window.dtype == torch.float64 and window.dim() == 1 and window.is_contiguous()
+        n = _lib.mfpa_stft_num_frames(x.numel(), n_fft, hop, window.numel())
+        out = torch.empty(n_fft // 2 + 1, max(n, 0), dtype=torch.complex128, device=x.device)
+        check(_lib.mfpa_stft_complex(self._h, _ptr(x), x.numel(), n_fft, hop, _ptr(window), window.numel(), _ptr(out), _stream()))
+        return out
 
     def spec_from_mag(self, mag, qmax, T: int, shifts: int = 1):
         import torch
