@@ -94,7 +94,30 @@ int mfpa_set_spread_table(mfpa_ctx* ctx, const double* table513_host);
 /* MFPA_OPT_PART_BUDGET_MB (default 2048): device scratch, in MiB, that the partitioned long-filter path of
  * mfpa_augment may use for block spectra; queries with long filters are processed in groups that fit. */
 #define MFPA_OPT_PART_BUDGET_MB 4
+/* MFPA_OPT_CONV_OCC (default 3): resident blocks per SM the FFT-convolution kernels of mfpa_augment are compiled
+ * for - 3 (80 registers per thread, 24 warps per SM) or 2 (up to 128 registers); a tuning knob, same results. */
+#define MFPA_OPT_CONV_OCC 5
+/* MFPA_OPT_STAGE_TIMES (default 0): 1 makes mfpa_augment_fingerprint and mfpa_fingerprint stamp a CUDA event at the
+ * start of every stage on the caller's stream (setting the option also clears the record); mfpa_stage_times then
+ * returns the mean duration of each stage over the last (up to 16) calls - how bench.py times the dominant kernel
+ * live inside its timed region. */
+#define MFPA_OPT_STAGE_TIMES 6
 int mfpa_set_option(mfpa_ctx* ctx, int option, int value);
+#define MFPA_STAGE_HPF1_FILTER 0  /* filter_spectrum_kernel (loudspeaker high-pass) */
+#define MFPA_STAGE_HPF1_CONV 1    /* fftconv_kernel */
+#define MFPA_STAGE_IR_FILTER 2
+#define MFPA_STAGE_IR_CONV 3
+#define MFPA_STAGE_MIX 4          /* clip_sample + mix + clip_finish */
+#define MFPA_STAGE_CLIP_LPF 5
+#define MFPA_STAGE_HPF3_FILTER 6
+#define MFPA_STAGE_HPF3_CONV 7    /* (+ final normalisation in mfpa_augment) */
+#define MFPA_STAGE_STFT 8
+#define MFPA_STAGE_PEAKS 9
+#define MFPA_STAGE_LANDMARKS 10   /* landmarks + hashes (+ shift merge) */
+#define MFPA_N_STAGES 11
+/* ms_out[MFPA_N_STAGES]: mean milliseconds per stage (0 for stages that did not run); returns the number of calls
+ * averaged, or a negative error.  Synchronises with the recorded events. */
+int mfpa_stage_times(mfpa_ctx* ctx, float* ms_out);
 
 /* ---- geometry --------------------------------------------------------- */
 int mfpa_num_frames(int n_samples);           /* afp/audfprint/stft.py:50-53 */
@@ -271,6 +294,34 @@ int mfpa_augment_fingerprint(mfpa_ctx* ctx, const float* x_dev, int B, int T, in
                              const mfpa_aug_params* params_host, const float* ir_dev, int ir_stride,
                              const float* noise_dev, int shifts, const mfpa_afp_params* p,
                              int32_t* hashes_dev, int cap, int32_t* nh_dev, void* stream);
+
+/* Host-buffer form of mfpa_augment_fingerprint: the call a user of testing/generate_queries.py +
+ * audfprint_exps.py makes once per batch instead of looping AugmentFP.__call__ (augmentation/__init__.py:95-97)
+ * and wavfile2hashes (peak_extractor.py:426-460) over files.  Only the QUERIES stream from the host (pinned
+ * memory lets the copies overlap the kernels), chunked and double-buffered like mfpa_fingerprint_host; the
+ * degradation sources are device-resident:
+ *   impulse responses  ir_dev + (ir_offsets_host ? ir_offsets_host[q] : q * ir_stride), params_host[q].ir_len samples
+ *                      (ir_bank_len = samples in ir_dev when offsets are given)
+ *   noise              noise_dev [B][T] rows as random_background() leaves them, OR a bank of decoded background
+ *                      audio + the pieces of every row (mfpa_noise_assemble, assembled chunk by chunk; pieces
+ *                      grouped by query, queries ascending).
+ * Output is CSR like mfpa_fingerprint_host. */
+typedef struct mfpa_chain_inputs {
+  const float* x_host;              /* [B][T] float32 ... */
+  const int16_t* x_pcm16_host;      /* ... or [B][T] 16-bit PCM, samples x / 32768 (exactly one of the two) */
+  const float* ir_dev;              /* NULL when no query has MFPA_AUG_IR */
+  int64_t ir_bank_len;
+  const int64_t* ir_offsets_host;   /* [B] or NULL */
+  int32_t ir_stride;
+  int32_t n_pieces;
+  const float* noise_dev;           /* [B][T] or NULL */
+  const float* noise_bank_dev;      /* with pieces_host */
+  int64_t noise_bank_len;
+  const mfpa_noise_piece* pieces_host;
+} mfpa_chain_inputs;
+int mfpa_augment_fingerprint_host(mfpa_ctx* ctx, const mfpa_chain_inputs* in, int B, int T, int sample_rate,
+                                  const mfpa_aug_params* params_host, int shifts, const mfpa_afp_params* p,
+                                  int32_t* rows_host, int64_t rows_cap, int64_t* offsets_host);
 
 /* ---- S5: landmark-hash matching  (HashTable.get_hits hash_table.py:220-246,
  * Matcher._best_count_ids / _approx_match_counts / match_hashes audfprint_match.py:102-129,235-349)

@@ -52,8 +52,9 @@ struct AugQ {            // per-query derived parameters (device copy)
   float snr_div;                  // 10^(snr_db/20)
   float gain, q_lo;
   uint32_t long_mask;             // stages whose filter is longer than one overlap-save block takes (kLong* bits)
-  uint32_t pad_;                  // sizeof == 64: the AugS array (doubles) follows the AugQ array in one allocation
-};
+  uint32_t pad_;
+  int64_t ir_off;                 // first sample of this query's impulse response in the ir buffer
+};                                // sizeof % 8 == 0: the AugS array (doubles) follows the AugQ array in one allocation
 static_assert(sizeof(AugQ) % 8 == 0, "AugS follows AugQ[B] and holds doubles");
 
 struct AugS {            // per-query running statistics (zeroed per call)
@@ -129,7 +130,8 @@ struct ConvArgs {
   const float* ir; int ir_stride;        // kModeIR
   const AugQ* q; AugS* st;
   int T; uint32_t bit; int which;        // which FIR (1, 2 or 3) / which stats slot
-  float4* hspec;                         // [B][2][FM/4] filter double pairs (fc::dp_index): plane 0 = S, plane 1 = R
+  float4* hspec;
+  int highpass;                          // centred FIR: 1 = the filter is delta - lowpass (x - lowpass(x), pass_filters.py:149-155)                         // [B][2][FM/4] filter double pairs (fc::dp_index): plane 0 = S, plane 1 = R
 };
 
 __device__ __forceinline__ void filter_params(const AugQ& q, int which, int& half, float& c2, float& argscale) {
@@ -157,14 +159,21 @@ __device__ __forceinline__ void apply_filter_pairs(const ConvSmem& s, const floa
 
 // Packs FN real samples v(i), i = 0 .. FN-1, into the planes (even samples -> re, odd -> im): thread tid
 // provides float4 number tid + FT u through `quad(i4)`.
-template <typename F> __device__ __forceinline__ void fill_planes(const ConvSmem& s, int tid, F quad) {
-#pragma unroll 4
-  for (int u = 0; u < FN / 4 / FT; ++u) {
-    const int i4 = tid + FT * u;
-    const float4 v = quad(i4);
-    const int o = fc::padi(2 * i4);
-    *reinterpret_cast<float2*>(s.re + o) = make_float2(v.x, v.z);
-    *reinterpret_cast<float2*>(s.im + o) = make_float2(v.y, v.w);
+template <int BATCH, typename F> __device__ __forceinline__ void fill_planes(const ConvSmem& s, int tid, F quad) {
+  // BATCH global loads are issued together ahead of their shared-memory stores;
+  // padi(2 (tid + FT u)) = padi(2 tid) + 544 u
+  const int o0 = fc::padi(2 * tid);
+#pragma unroll 1
+  for (int u0 = 0; u0 < FN / 4 / FT; u0 += BATCH) {
+    float4 v[BATCH];
+#pragma unroll
+    for (int u = 0; u < BATCH; ++u) v[u] = quad(tid + FT * (u0 + u));
+#pragma unroll
+    for (int u = 0; u < BATCH; ++u) {
+      const int o = o0 + 544 * (u0 + u);
+      *reinterpret_cast<float2*>(s.re + o) = make_float2(v[u].x, v[u].z);
+      *reinterpret_cast<float2*>(s.im + o) = make_float2(v[u].y, v[u].w);
+    }
   }
 }
 
@@ -182,9 +191,9 @@ __global__ void __launch_bounds__(FT, 2) filter_spectrum_kernel(const ConvArgs a
   if (MODE != kModeIR) filter_params(q, a.which, half, c2, argscale);
   const ConvGeom g = conv_geom(MODE == kModeIR, half, q.ir_len, a.T);
   s.load_tables(tw_g, tid);
-  const float* ir = MODE == kModeIR ? a.ir + (int64_t)qi * a.ir_stride : nullptr;
+  const float* ir = MODE == kModeIR ? a.ir + q.ir_off : nullptr;
   float hsum = 0.f;
-  fill_planes(s, tid, [&](int i4) {
+  fill_planes<1>(s, tid, [&](int i4) {
     float h[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -195,19 +204,27 @@ __global__ void __launch_bounds__(FT, 2) filter_spectrum_kernel(const ConvArgs a
         else if (i >= g.zeros) h[e] = fir_tap(i - g.zeros, half, c2, argscale);
       }
       hsum += h[e];
+      if (MODE != kModeIR && a.highpass) h[e] = -h[e];
     }
     return make_float4(h[0], h[1], h[2], h[3]);
   });
   float scale = 1.0f / (float)FM;
-  if (MODE != kModeIR) scale /= block_sum(hsum, s.red, tid);
+  if (MODE != kModeIR) {
+    const float sum = block_sum(hsum, s.red, tid);   // ends with a barrier: the planes are complete
+    scale /= sum;
+    // x - lowpass(x) = (delta - lowpass) * x: the unit tap sits at the filter's delay g.lead (a multiple of 4),
+    // worth `sum` before the normalisation by 1 / sum
+    if (a.highpass && tid == 0) s.re[fc::padi(g.lead >> 1)] += sum;
+  }
   __syncthreads();
   fft_forward(s, tid);
   float4* hs = a.hspec + (size_t)qi * (FM / 2);
   store_filter_pairs(s, scale, hs, hs + FM / 4, tid);
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(FT, 2) fftconv_kernel(const ConvArgs a, const float* __restrict__ tw_g) {
+// OCC = blocks per SM the register allocation aims at: 2 (up to 128 registers) or 3 (80 registers, 24 warps)
+template <int MODE, int OCC>
+__global__ void __launch_bounds__(FT, OCC) fftconv_kernel(const ConvArgs a, const float* __restrict__ tw_g) {
   extern __shared__ __align__(16) float smem_f[];
   const ConvSmem s(smem_f);
   const int tid = threadIdx.x, qi = blockIdx.y, blk = blockIdx.x;
@@ -233,45 +250,48 @@ __global__ void __launch_bounds__(FT, 2) fftconv_kernel(const ConvArgs a, const 
     const ConvGeom g = conv_geom(MODE == kModeIR, half, q.ir_len, T);
     const int n0 = blk * g.V;
     if (n0 >= g.n_total) return;  // block-uniform
+    const float4* hs = a.hspec + (size_t)qi * (FM / 2);
+    // the filter's double pairs are read between the two transforms: pull this thread's 16 into L2 now
+#pragma unroll
+    for (int d2 = 0; d2 < 8; ++d2) {
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(hs + fc::dp_index(tid, d2)));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(hs + FM / 4 + fc::dp_index(tid, d2)));
+    }
     s.load_tables(tw_g, tid);
     const int s0 = n0 - g.lead;
-    fill_planes(s, tid, [&](int i4) {
-      const int n = s0 + 4 * i4;
-      if (vec_in && n >= 0 && n + 3 < T) return __ldg(reinterpret_cast<const float4*>(in + n));
-      float x[4];
+    if (vec_in && s0 >= 0 && s0 + FN <= T) {   // interior block: sixteen 16-byte loads in flight per thread
+      const float4* src = reinterpret_cast<const float4*>(in + s0);
+      fill_planes<16>(s, tid, [&](int i4) { return __ldg(src + i4); });
+    } else {
+      fill_planes<4>(s, tid, [&](int i4) {
+        const int n = s0 + 4 * i4;
+        if (vec_in && n >= 0 && n + 3 < T) return __ldg(reinterpret_cast<const float4*>(in + n));
+        float x[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int ne = n + e;
-        if (MODE == kModeIR) x[e] = (ne >= 0 && ne < T) ? __ldg(in + ne) : 0.f;   // zero extension
-        else x[e] = __ldg(in + min(max(ne, 0), T - 1));                           // replicate padding (julius)
-      }
-      return make_float4(x[0], x[1], x[2], x[3]);
-    });
+        for (int e = 0; e < 4; ++e) {
+          const int ne = n + e;
+          if (MODE == kModeIR) x[e] = (ne >= 0 && ne < T) ? __ldg(in + ne) : 0.f;   // zero extension
+          else x[e] = __ldg(in + min(max(ne, 0), T - 1));                           // replicate padding (julius)
+        }
+        return make_float4(x[0], x[1], x[2], x[3]);
+      });
+    }
     __syncthreads();
     fft_forward(s, tid);
-    const float4* hs = a.hspec + (size_t)qi * (FM / 2);
     apply_filter_pairs(s, hs, hs + FM / 4, tid);
     __syncthreads();
     fft_inverse(s, tid);
+    // y[n0 + 4 g4 + e] sits at packed index e_base + 2 g4 (+1), re / im alternating; a high-pass needs no second
+    // look at x: its filter is delta - lowpass (filter_spectrum_kernel)
     const int n_end = min(g.n_total, n0 + g.V);
-    const int e_base = g.off >> 1;   // output n0 + 4 g4 + e sits at packed index e_base + 2 g4 (+1), re / im alternating
-#pragma unroll 2
+    const int e_base = g.off >> 1;
+#pragma unroll 4
     for (int g4 = tid; n0 + 4 * g4 < n_end; g4 += FT) {
       const int n = n0 + 4 * g4;
       const int o = fc::padi(e_base + 2 * g4);
       const float2 cr = *reinterpret_cast<const float2*>(s.re + o), ci = *reinterpret_cast<const float2*>(s.im + o);
-      float v[4] = {cr.x, ci.x, cr.y, ci.y};
-      const bool full = n + 3 < n_end;
-      if (MODE == kModeHP) {
-        if (full && vec_in) {
-          const float4 x = __ldg(reinterpret_cast<const float4*>(in + n));
-          v[0] = x.x - v[0]; v[1] = x.y - v[1]; v[2] = x.z - v[2]; v[3] = x.w - v[3];
-        } else {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) v[e] = (n + e < n_end ? __ldg(in + n + e) : 0.f) - v[e];
-        }
-      }
-      if (full && n + 3 < T) {
+      const float v[4] = {cr.x, ci.x, cr.y, ci.y};
+      if (n + 3 < n_end && n + 3 < T) {
         vmax = fmaxf(fmaxf(vmax, fmaxf(fabsf(v[0]), fabsf(v[1]))), fmaxf(fabsf(v[2]), fabsf(v[3])));
         vss = fmaf(v[0], v[0], fmaf(v[1], v[1], fmaf(v[2], v[2], fmaf(v[3], v[3], vss))));
         if (vec_out) *reinterpret_cast<float4*>(out + n) = make_float4(v[0], v[1], v[2], v[3]);
@@ -290,9 +310,9 @@ __global__ void __launch_bounds__(FT, 2) fftconv_kernel(const ConvArgs a, const 
   vss = block_sum(vss, s.red, tid);
   if (tid == 0) {
     AugS* st = a.st + qi;
-    if (MODE == kModeHP && a.which == 1) { atomic_max_pos(&st->max_a, vmax); atomicAdd(&st->ss_a, (double)vss); }
+    if (MODE != kModeIR && a.which == 1) { atomic_max_pos(&st->max_a, vmax); atomicAdd(&st->ss_a, (double)vss); }
     else if (MODE == kModeIR) { atomic_max_pos(&st->max_b, vmax); atomicAdd(&st->ss_b, (double)vss); }
-    else if (MODE == kModeHP && a.which == 3) atomic_max_pos(&st->max_v, vmax);
+    else if (MODE != kModeIR && a.which == 3) atomic_max_pos(&st->max_v, vmax);
   }
 }
 
@@ -423,14 +443,14 @@ __global__ void __launch_bounds__(FT, 2) part_filter_kernel(const PartArgs a, co
   int hh;
   if (MODE != kModeIR) filter_params(q, a.c.which, hh, c2, argscale);
   s.load_tables(tw_g, tid);
-  const float* ir = MODE == kModeIR ? a.c.ir + (int64_t)qi * a.c.ir_stride : nullptr;
+  const float* ir = MODE == kModeIR ? a.c.ir + q.ir_off : nullptr;
   float scale = 1.0f / (float)FM;
   if (MODE != kModeIR) {   // julius normalises by the sum of ALL taps
     float hs = 0.f;
     for (int i = tid; i < K; i += FT) hs += fir_tap(i, half, c2, argscale);
     scale /= block_sum(hs, s.red, tid);
   }
-  fill_planes(s, tid, [&](int i4) {
+  fill_planes<1>(s, tid, [&](int i4) {
     float h[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -461,7 +481,7 @@ __global__ void __launch_bounds__(FT, 2) part_forward_kernel(const PartArgs a, c
   const float* __restrict__ in = a.c.in + (int64_t)qi * a.c.in_stride;
   const int64_t s0 = (int64_t)(jb - (P - 1)) * kPartS + D - kPartS + 1;
   s.load_tables(tw_g, tid);
-  fill_planes(s, tid, [&](int i4) {
+  fill_planes<1>(s, tid, [&](int i4) {
     float x[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -503,8 +523,10 @@ __global__ void __launch_bounds__(FT, 2) part_conv_kernel(const PartArgs a, cons
     const int m = tid, mbar = fc::partner_block(m);
     float sw, cw;
     sincospif((float)fc::block_c(m) * (1.0f / (float)FM), &sw, &cw);
+    c2 wv = fc::dp_twiddle0(cw, sw);
 #pragma unroll 1
     for (int d2 = 0; d2 < 8; ++d2) {
+      if (d2) wv = fc::dp_twiddle_next(wv);
       if (m == 0 && d2 == 0) {
         fc::SpecAcc acc = fc::spec_acc_zero();
         for (int p = 0; p < P; ++p) {
@@ -521,7 +543,6 @@ __global__ void __launch_bounds__(FT, 2) part_conv_kernel(const PartArgs a, cons
       }
       // unpadded plane offsets of the two slots, and their padded shared-memory twins
       const int ua = 32 * m + 2 * d2, ub = 32 * mbar + 2 * ((m == 0 ? 16 : 15) - d2);
-      const c2 wv = fc::dp_twiddle(cw, sw, d2);
       const int i = fc::dp_index(m, d2);
       const float2 zero = make_float2(0.f, 0.f);
       c2 ey = fc::mk(zero, zero), dy = fc::mk(zero, zero);
@@ -680,8 +701,8 @@ __global__ void __launch_bounds__(kSelThreads) clip_sample_kernel(const float* _
   for (int i = tid; i < kSelSample; i += kSelThreads) {
     const int n = (int)(((int64_t)i * T) / kSelSample);
     float v = in[row + n];
-    if (ir_on) v /= peak;
-    if (nz_on) v += ns * noise[row + n];
+    if (ir_on) v *= 1.0f / peak;
+    if (nz_on) v = fmaf(ns, noise[row + n], v);
     sample[i] = order_key(v);
   }
   __shared__ unsigned hist[256], sh[4];
@@ -761,23 +782,28 @@ __global__ void __launch_bounds__(256) mix_kernel(const float* __restrict__ in, 
     const unsigned g = atomicAdd(side ? &s->cnt_hi : &s->cnt_lo, 1u);
     if (g < kSelCap) ql[side * kSelCap + g] = k;
   };
+  // the order keys are monotone in the value, so the common case is two float compares
+  const float f_lo = clip_on ? key_value(t_lo) : -INFINITY, f_hi = clip_on ? key_value(t_hi) : INFINITY;
   auto tail = [&](float v) {
-    const unsigned k = order_key(v);
-    if (k <= t_lo || k >= t_hi) {   // ~1 % of the samples
+    if (v <= f_lo || v >= f_hi) {   // ~1 % of the samples
       if (!clip_on) return;
+      const unsigned k = order_key(v);
       if (k <= t_lo) tail_side(k, 0);
       if (k >= t_hi) tail_side(k, 1);
     }
   };
   float vmax = 0.f;
   const int64_t row = (int64_t)qi * T;
+  // x / peak as x * (1 / peak): one rounding more than the reference's division, four IEEE divisions less per
+  // 16 bytes (this kernel is issue-bound, not bandwidth-bound, with them)
+  const float rpeak = ir_on ? 1.0f / peak : 1.f;
   for (int n = blockIdx.x * blockDim.x * 4 + tid * 4; n < T; n += gridDim.x * blockDim.x * 4) {
     if (n + 3 < T && ((row + n) & 3) == 0) {
       float4 v = *reinterpret_cast<const float4*>(in + row + n);
-      if (ir_on) { v.x /= peak; v.y /= peak; v.z /= peak; v.w /= peak; }
+      if (ir_on) { v.x *= rpeak; v.y *= rpeak; v.z *= rpeak; v.w *= rpeak; }
       if (nz_on) {
         const float4 b = *reinterpret_cast<const float4*>(noise + row + n);
-        v.x += ns * b.x; v.y += ns * b.y; v.z += ns * b.z; v.w += ns * b.w;
+        v.x = fmaf(ns, b.x, v.x); v.y = fmaf(ns, b.y, v.y); v.z = fmaf(ns, b.z, v.z); v.w = fmaf(ns, b.w, v.w);
       }
       *reinterpret_cast<float4*>(z + row + n) = v;
       vmax = fmaxf(fmaxf(vmax, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
@@ -785,8 +811,8 @@ __global__ void __launch_bounds__(256) mix_kernel(const float* __restrict__ in, 
     } else {
       for (int m = n; m < min(n + 4, T); ++m) {
         float v = in[row + m];
-        if (ir_on) v /= peak;
-        if (nz_on) v += ns * noise[row + m];
+        if (ir_on) v *= rpeak;
+        if (nz_on) v = fmaf(ns, noise[row + m], v);
         z[row + m] = v;
         vmax = fmaxf(vmax, fabsf(v));
         tail(v);
@@ -861,11 +887,8 @@ __global__ void __launch_bounds__(256) clip_lpf_kernel(const float* __restrict__
     for (int w = 0; w < 8; ++w) hsum += red[w];
   }
   const float inv = 1.0f / hsum;
-  auto shape = [&](float v) {
-    if (nz_on) v /= peak;
-    v *= g;
-    return fminf(fmaxf(v, s.lo), s.hi);
-  };
+  const float pre = nz_on ? g / peak : g;   // (z / peak) * gain in one multiply
+  auto shape = [&](float v) { return fminf(fmaxf(v * pre, s.lo), s.hi); };
   const int fill4 = (kLpTile + 4 * groups + 4) >> 2;   // float4 slots of the tile that are read
   const float4* tile4 = reinterpret_cast<const float4*>(tile);
   const float4* taps4 = reinterpret_cast<const float4*>(taps);
@@ -983,7 +1006,7 @@ __global__ void __launch_bounds__(256) noise_scale_kernel(const mfpa_noise_piece
 }  // namespace
 
 int launch_noise_assemble(mfpa_ctx* ctx, const float* bank, int64_t bank_len, const mfpa_noise_piece* pieces, int n_pieces,
-                          int B, int T, float* out, cudaStream_t st) {
+                          int B, int T, float* out, cudaStream_t st, bool pieces_pinned) {
   // validate on the host: sources inside the bank, every row tiled exactly once
   std::vector<int64_t> covered((size_t)B, 0);
   int max_len = 1;
@@ -1004,7 +1027,7 @@ int launch_noise_assemble(mfpa_ctx* ctx, const float* bank, int64_t bank_len, co
   double* row_ss = piece_ss + n_pieces;
   mfpa_noise_piece* dp = (mfpa_noise_piece*)(row_ss + B);
   MFPA_CUDA(cudaMemcpyAsync(dp, pieces, sizeof(mfpa_noise_piece) * (size_t)n_pieces, cudaMemcpyHostToDevice, st));
-  MFPA_CUDA(cudaStreamSynchronize(st));   // pieces_host is caller-owned pageable memory
+  if (!pieces_pinned) MFPA_CUDA(cudaStreamSynchronize(st));   // pieces_host is caller-owned pageable memory
   MFPA_CUDA(cudaMemsetAsync(piece_ss, 0, sizeof(double) * ((size_t)n_pieces + B), st));
   const dim3 grid((unsigned)n_pieces, (unsigned)((max_len + 4095) / 4096));   // pieces on x: no 65535 limit
   noise_gather_kernel<<<grid, 256, 0, st>>>(bank, dp, T, out, piece_ss);
@@ -1029,9 +1052,10 @@ static int aug_init_tables(mfpa_ctx* ctx) {
   }
   MFPA_CUDA(cudaMalloc(&ctx->aug_tw_dev, sizeof(tw)));
   MFPA_CUDA(cudaMemcpy(ctx->aug_tw_dev, tw, sizeof(tw), cudaMemcpyHostToDevice));
-  MFPA_CUDA(cudaFuncSetAttribute(fftconv_kernel<kModeHP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmem));
-  MFPA_CUDA(cudaFuncSetAttribute(fftconv_kernel<kModeIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmem));
-  MFPA_CUDA(cudaFuncSetAttribute(fftconv_kernel<kModeLP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmem));
+  MFPA_CUDA(cudaFuncSetAttribute(fftconv_kernel<kModeHP, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmem));
+  MFPA_CUDA(cudaFuncSetAttribute(fftconv_kernel<kModeIR, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmem));
+  MFPA_CUDA(cudaFuncSetAttribute(fftconv_kernel<kModeHP, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmem));
+  MFPA_CUDA(cudaFuncSetAttribute(fftconv_kernel<kModeIR, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmem));
   MFPA_CUDA(cudaFuncSetAttribute(filter_spectrum_kernel<kModeHP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmem));
   MFPA_CUDA(cudaFuncSetAttribute(filter_spectrum_kernel<kModeIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmem));
   MFPA_CUDA(cudaFuncSetAttribute(part_filter_kernel<kModeHP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmem));
@@ -1062,7 +1086,7 @@ static int fir_half(float fc_hz, int sample_rate, const char* name, int qi, doub
 
 int launch_augment(mfpa_ctx* ctx, const float* x, int B, int T, int64_t x_stride, int sample_rate,
                    const mfpa_aug_params* pp, const float* ir, int ir_stride, const float* noise, float* out,
-                   bool final_norm, cudaStream_t st) {
+                   bool final_norm, cudaStream_t st, const int64_t* ir_offsets, int64_t ir_bank_len) {
   if (int e = aug_init_tables(ctx)) return e;
   // ---- derive per-query parameters on the host
   const size_t need = (sizeof(AugQ) + 4 * sizeof(int)) * (size_t)B;
@@ -1126,8 +1150,16 @@ int launch_augment(mfpa_ctx* ctx, const float* x, int B, int T, int64_t x_stride
     }
     if (p.apply & MFPA_AUG_IR) {
       MFPA_REQUIRE(ir != nullptr, "augment: query %d applies an impulse response but ir_dev is NULL", i);
-      MFPA_REQUIRE(p.ir_len >= 1 && p.ir_len <= ir_stride && p.ir_len <= MFPA_AUG_MAX_IR,
-                   "augment: query %d: ir_len %d not in [1, min(ir_stride %d, %d)]", i, p.ir_len, ir_stride, MFPA_AUG_MAX_IR);
+      if (ir_offsets) {   // responses addressed inside a device-resident bank
+        MFPA_REQUIRE(p.ir_len >= 1 && p.ir_len <= MFPA_AUG_MAX_IR && ir_offsets[i] >= 0 && ir_offsets[i] + p.ir_len <= ir_bank_len,
+                     "augment: query %d: impulse response [%lld, +%d) is outside the bank of %lld samples (or longer than %d)", i,
+                     (long long)ir_offsets[i], p.ir_len, (long long)ir_bank_len, MFPA_AUG_MAX_IR);
+        q.ir_off = ir_offsets[i];
+      } else {
+        MFPA_REQUIRE(p.ir_len >= 1 && p.ir_len <= ir_stride && p.ir_len <= MFPA_AUG_MAX_IR,
+                     "augment: query %d: ir_len %d not in [1, min(ir_stride %d, %d)]", i, p.ir_len, ir_stride, MFPA_AUG_MAX_IR);
+        q.ir_off = (int64_t)i * ir_stride;
+      }
       q.ir_len = p.ir_len;
       if (p.ir_len > FN / 2) note_long(1, kLongIR, p.ir_len, q, i);
       else up(nbir, blocks_of(true, 0, p.ir_len));
@@ -1192,27 +1224,45 @@ int launch_augment(mfpa_ctx* ctx, const float* x, int B, int T, int64_t x_stride
     return MFPA_OK;
   };
 
+  // one overlap-save block per grid cell; a centred FIR's kernel is the same for low- and high-pass (the
+  // filter carries the difference), blocks per SM by MFPA_OPT_CONV_OCC
+  const int occ = ctx->opt_conv_occ;
+  auto launch_conv = [&](bool causal, dim3 grid, const ConvArgs& a) {
+    const float* tw = (const float*)ctx->aug_tw_dev;
+    if (causal) {
+      if (occ == 2) fftconv_kernel<kModeIR, 2><<<grid, FT, kConvSmem, st>>>(a, tw);
+      else fftconv_kernel<kModeIR, 3><<<grid, FT, kConvSmem, st>>>(a, tw);
+    } else {
+      if (occ == 2) fftconv_kernel<kModeHP, 2><<<grid, FT, kConvSmem, st>>>(a, tw);
+      else fftconv_kernel<kModeHP, 3><<<grid, FT, kConvSmem, st>>>(a, tw);
+    }
+  };
   // stage 1: x -> A
   {
-    ConvArgs a{x, x_stride, bufA, nullptr, 0, dq, ds, T, MFPA_AUG_HPF1, 1, hspec};
+    ConvArgs a{x, x_stride, bufA, nullptr, 0, dq, ds, T, MFPA_AUG_HPF1, 1, hspec, 1};
+    stage_mark(ctx, MFPA_STAGE_HPF1_FILTER, st);
     filter_spectrum_kernel<kModeHP><<<B, FT, kConvSmem, st>>>(a, (const float*)ctx->aug_tw_dev);
-    fftconv_kernel<kModeHP><<<dim3((unsigned)nb1, B), FT, kConvSmem, st>>>(a, (const float*)ctx->aug_tw_dev);
+    stage_mark(ctx, MFPA_STAGE_HPF1_CONV, st);
+    launch_conv(false, dim3((unsigned)nb1, B), a);
     MFPA_CUDA(cudaGetLastError());
     if (int e = run_long(0, kModeHP, a)) return e;
   }
   // stage 2: A -> B
   {
-    ConvArgs a{bufA, T, bufB, ir, ir_stride, dq, ds, T, MFPA_AUG_IR, 0, hspec};
+    ConvArgs a{bufA, T, bufB, ir, ir_stride, dq, ds, T, MFPA_AUG_IR, 0, hspec, 0};
+    stage_mark(ctx, MFPA_STAGE_IR_FILTER, st);
     filter_spectrum_kernel<kModeIR><<<B, FT, kConvSmem, st>>>(a, (const float*)ctx->aug_tw_dev);
-    fftconv_kernel<kModeIR><<<dim3((unsigned)nbir, B), FT, kConvSmem, st>>>(a, (const float*)ctx->aug_tw_dev);
+    stage_mark(ctx, MFPA_STAGE_IR_CONV, st);
+    launch_conv(true, dim3((unsigned)nbir, B), a);
     MFPA_CUDA(cudaGetLastError());
     if (int e = run_long(1, kModeIR, a)) return e;
   }
   // stage 3: B -> A (z)
   {
-    const unsigned gx = (unsigned)((T + 4095) / 4096);
+    const unsigned gx = (unsigned)((T + 8191) / 8192);
     if (ctx->aug_lists.reserve(sizeof(unsigned) * 2 * kSelCap * (size_t)B)) return MFPA_ENOMEM;
     unsigned* lists = (unsigned*)ctx->aug_lists.ptr;
+    stage_mark(ctx, MFPA_STAGE_MIX, st);
     clip_sample_kernel<<<B, kSelThreads, 0, st>>>(bufB, noise, dq, ds, T);
     mix_kernel<<<dim3(gx, B), 256, 0, st>>>(bufB, noise, bufA, dq, ds, T, lists);
     // stage 4: clip thresholds from the listed tails of z
@@ -1220,6 +1270,7 @@ int launch_augment(mfpa_ctx* ctx, const float* x, int B, int T, int64_t x_stride
     MFPA_CUDA(cudaGetLastError());
   }
   // stage 5: A -> B (u)
+  stage_mark(ctx, MFPA_STAGE_CLIP_LPF, st);
   {
     const unsigned gx = (unsigned)((T + 4095) / 4096);
     if (!any_long_lp) {
@@ -1231,18 +1282,20 @@ int launch_augment(mfpa_ctx* ctx, const float* x, int B, int T, int64_t x_stride
       float* bufC = (float*)ctx->aug_c.ptr;
       clip_lpf_kernel<<<dim3(gx, B), 256, 0, st>>>(bufA, bufC, dq, ds, T, 1);
       MFPA_CUDA(cudaGetLastError());
-      ConvArgs a{bufC, T, bufB, nullptr, 0, dq, ds, T, MFPA_AUG_LPF, 2, hspec};
+      ConvArgs a{bufC, T, bufB, nullptr, 0, dq, ds, T, MFPA_AUG_LPF, 2, hspec, 0};
       filter_spectrum_kernel<kModeHP><<<B, FT, kConvSmem, st>>>(a, (const float*)ctx->aug_tw_dev);
-      fftconv_kernel<kModeLP><<<dim3((unsigned)nb2, B), FT, kConvSmem, st>>>(a, (const float*)ctx->aug_tw_dev);
+      launch_conv(false, dim3((unsigned)nb2, B), a);
       MFPA_CUDA(cudaGetLastError());
       if (int e = run_long(2, kModeLP, a)) return e;
     }
   }
   // stage 6: B -> A (v) ; stage 7: A -> out
   {
-    ConvArgs a{bufB, T, bufA, nullptr, 0, dq, ds, T, MFPA_AUG_HPF3, 3, hspec};
+    ConvArgs a{bufB, T, bufA, nullptr, 0, dq, ds, T, MFPA_AUG_HPF3, 3, hspec, 1};
+    stage_mark(ctx, MFPA_STAGE_HPF3_FILTER, st);
     filter_spectrum_kernel<kModeHP><<<B, FT, kConvSmem, st>>>(a, (const float*)ctx->aug_tw_dev);
-    fftconv_kernel<kModeHP><<<dim3((unsigned)nb3, B), FT, kConvSmem, st>>>(a, (const float*)ctx->aug_tw_dev);
+    stage_mark(ctx, MFPA_STAGE_HPF3_CONV, st);
+    launch_conv(false, dim3((unsigned)nb3, B), a);
     MFPA_CUDA(cudaGetLastError());
     if (int e = run_long(3, kModeHP, a)) return e;
     const unsigned gx = (unsigned)((T + 4095) / 4096);

@@ -1,9 +1,11 @@
 // extern "C" surface of libmfpa.so (see include/mfpa.h for the contract).
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
+#include <vector>
 
 #include "common.cuh"
 
@@ -76,9 +78,46 @@ struct DeviceGuard {
 
 }  // namespace mfpa
 
+namespace mfpa {
+
+int stage_begin(mfpa_ctx* ctx) {
+  if (!ctx->opt_stage_times) return MFPA_OK;
+  ctx->stage_slot = ctx->stage_calls % 16;
+  ++ctx->stage_calls;
+  for (int k = 0; k <= MFPA_N_STAGES; ++k) {
+    cudaEvent_t& e = ctx->stage_ev[ctx->stage_slot][k];
+    if (!e) MFPA_CUDA(cudaEventCreate(&e));
+  }
+  return MFPA_OK;
+}
+
+void stage_mark(mfpa_ctx* ctx, int stage, cudaStream_t st) {
+  if (ctx->opt_stage_times && ctx->stage_calls > 0) cudaEventRecord(ctx->stage_ev[ctx->stage_slot][stage], st);
+}
+
+}  // namespace mfpa
+
 using namespace mfpa;
 
 extern "C" {
+
+int mfpa_stage_times(mfpa_ctx* ctx, float* ms_out) {
+  MFPA_REQUIRE(ctx && ms_out, "stage_times: NULL argument");
+  DeviceGuard guard(ctx->device);
+  for (int k = 0; k < MFPA_N_STAGES; ++k) ms_out[k] = 0.f;
+  const int n = ctx->stage_calls < 16 ? ctx->stage_calls : 16;
+  for (int s = 0; s < n; ++s) {
+    cudaEvent_t* e = ctx->stage_ev[s];
+    MFPA_CUDA(cudaEventSynchronize(e[MFPA_N_STAGES]));
+    for (int k = 0; k < MFPA_N_STAGES; ++k) {
+      float ms = 0.f;
+      // a stage that never ran in this call left an event that was never recorded: cudaEventElapsedTime fails, count 0
+      if (cudaEventQuery(e[k]) == cudaSuccess && cudaEventElapsedTime(&ms, e[k], e[k + 1]) == cudaSuccess) ms_out[k] += ms / n;
+      else (void)cudaGetLastError();
+    }
+  }
+  return n;
+}
 
 int mfpa_abi_version(void) { return MFPA_ABI_VERSION; }
 const char* mfpa_last_error(void) { return g_err; }
@@ -111,6 +150,7 @@ int mfpa_create(mfpa_ctx** out, int device) {
   if (!ctx) { set_error("out of host memory"); return MFPA_ENOMEM; }
   ctx->device = device;
   ctx->num_sms = prop.multiProcessorCount;
+  if (const char* e = getenv("MFPA_CONV_OCC")) { if (e[0] == '2') ctx->opt_conv_occ = 2; }
   MFPA_CUDA(cudaMalloc(&ctx->spread_dev, sizeof(double) * kSpreadLen));
   double tab[kSpreadLen];
   for (int k = -kRows; k <= kRows; ++k) { const double u = (double)k / 30.0; tab[k + kRows] = exp(-0.5 * (u * u)); }
@@ -137,11 +177,15 @@ void mfpa_destroy(mfpa_ctx* ctx) {
                     &ctx->aug_small, &ctx->aug_lists, &ctx->aug_long, &ctx->aug_part, &ctx->aug_noise, &ctx->match_a, &ctx->match_b, &ctx->match_c};
   for (Scratch* s : all) s->release();
   for (int b = 0; b < 2; ++b) {
-    ctx->h_x[b].release(); ctx->h_x16[b].release(); ctx->h_rows[b].release(); ctx->h_csr[b].release(); ctx->h_n[b].release(); ctx->h_off[b].release();
+    ctx->h_x[b].release(); ctx->h_x16[b].release(); ctx->h_rows[b].release(); ctx->h_csr[b].release(); ctx->h_n[b].release(); ctx->h_off[b].release(); ctx->h_noise[b].release();
+    if (ctx->pieces_pinned[b]) cudaFreeHost(ctx->pieces_pinned[b]);
     if (ctx->ev_in[b]) cudaEventDestroy(ctx->ev_in[b]);
     if (ctx->ev_run[b]) cudaEventDestroy(ctx->ev_run[b]);
     if (ctx->ev_out[b]) cudaEventDestroy(ctx->ev_out[b]);
   }
+  for (int sl = 0; sl < 16; ++sl)
+    for (int k = 0; k <= MFPA_N_STAGES; ++k)
+      if (ctx->stage_ev[sl][k]) cudaEventDestroy(ctx->stage_ev[sl][k]);
   if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
   if (ctx->s_run) cudaStreamDestroy(ctx->s_run);
   if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
@@ -175,6 +219,14 @@ int mfpa_set_option(mfpa_ctx* ctx, int option, int value) {
     case MFPA_OPT_PART_BUDGET_MB:
       MFPA_REQUIRE(value >= 1, "set_option: MFPA_OPT_PART_BUDGET_MB %d < 1", value);
       ctx->opt_part_budget_mb = value;
+      return MFPA_OK;
+    case MFPA_OPT_CONV_OCC:
+      MFPA_REQUIRE(value == 2 || value == 3, "set_option: MFPA_OPT_CONV_OCC %d not in {2, 3}", value);
+      ctx->opt_conv_occ = value;
+      return MFPA_OK;
+    case MFPA_OPT_STAGE_TIMES:
+      ctx->opt_stage_times = value != 0;
+      ctx->stage_calls = 0;
       return MFPA_OK;
     default: break;
   }
@@ -292,16 +344,27 @@ int mfpa_fingerprint(mfpa_ctx* ctx, const float* x_dev, int B, int T, int64_t x_
   float* mag = (float*)ctx->mag.ptr;
   float* qmax = (float*)ctx->qmax.ptr;
   uint64_t* rec = (uint64_t*)ctx->rec.ptr;
+  if (!ctx->stage_chained) { if (int e = stage_begin(ctx)) return e; }
+  ctx->stage_chained = false;
+  stage_mark(ctx, MFPA_STAGE_STFT, st);
   if (int e = launch_stft_mag(ctx, x_dev, B, T, x_stride, shifts, mag, qmax, st)) return e;
+  stage_mark(ctx, MFPA_STAGE_PEAKS, st);
   if (int e = launch_peaks_f32(ctx, mag, qmax, B, T, shifts, *p, rec, nullptr, st)) return e;
-  if (shifts == 1) return launch_landmark_hashes(rec, items, n_max, *p, 1, hashes_dev, cap, nh_dev, st);
+  stage_mark(ctx, MFPA_STAGE_LANDMARKS, st);
+  if (shifts == 1) {
+    const int e = launch_landmark_hashes(rec, items, n_max, *p, 1, hashes_dev, cap, nh_dev, st);
+    stage_mark(ctx, MFPA_N_STAGES, st);
+    return e;
+  }
   const int cap_in = MFPA_HASHES_PER_FRAME * n_max;
   if (ctx->hashes.reserve(sizeof(int32_t) * 2 * (size_t)items * cap_in)) return MFPA_ENOMEM;
   if (ctx->nh.reserve(sizeof(int32_t) * items)) return MFPA_ENOMEM;
   if (int e = launch_landmark_hashes(rec, items, n_max, *p, 1, (int32_t*)ctx->hashes.ptr, cap_in,
                                      (int32_t*)ctx->nh.ptr, st)) return e;
-  return launch_merge_shifts((int32_t*)ctx->hashes.ptr, (int32_t*)ctx->nh.ptr, B, shifts, cap_in, n_max,
-                             hashes_dev, cap, nh_dev, st);
+  const int e = launch_merge_shifts((int32_t*)ctx->hashes.ptr, (int32_t*)ctx->nh.ptr, B, shifts, cap_in, n_max,
+                                    hashes_dev, cap, nh_dev, st);
+  stage_mark(ctx, MFPA_N_STAGES, st);
+  return e;
 }
 
 int mfpa_compact_rows(mfpa_ctx* ctx, const int32_t* rows_in_dev, const int32_t* n_dev, int items, int cap,
@@ -473,9 +536,143 @@ int mfpa_augment_fingerprint(mfpa_ctx* ctx, const float* x_dev, int B, int T, in
   // PeakNormalization (stage 7) is skipped: the picker divides the magnitudes by their maximum and
   // works on log differences, so a positive scale of the waveform cancels; the fingerprint stages read
   // stage 6's output where launch_augment leaves it (ctx->aug_a) and no copy of the waveform is made.
+  if (int e = stage_begin(ctx)) return e;
   if (int e = launch_augment(ctx, x_dev, B, T, x_stride, sample_rate, params_host, ir_dev, ir_stride, noise_dev, nullptr,
                              false, (cudaStream_t)stream)) return e;
+  ctx->stage_chained = true;   // the analysis continues this call's record
   return mfpa_fingerprint(ctx, (const float*)ctx->aug_a.ptr, B, T, T, shifts, p, hashes_dev, cap, nh_dev, stream);
+}
+
+// Host-buffer form of mfpa_augment_fingerprint: the same chunked pipeline as fingerprint_host_impl, with the
+// degradation chain ahead of the analysis.  Only the queries stream from the host; impulse responses and noise
+// are device-resident (rows, or a bank plus per-query offsets / random_background pieces assembled per chunk).
+int mfpa_augment_fingerprint_host(mfpa_ctx* ctx, const mfpa_chain_inputs* in, int B, int T, int sample_rate,
+                                  const mfpa_aug_params* params_host, int shifts, const mfpa_afp_params* p,
+                                  int32_t* rows_host, int64_t rows_cap, int64_t* offsets_host) {
+  MFPA_REQUIRE(ctx && in && params_host && rows_host && offsets_host, "augment_fingerprint_host: NULL argument");
+  MFPA_REQUIRE((in->x_host != nullptr) != (in->x_pcm16_host != nullptr), "augment_fingerprint_host: give x_host or x_pcm16_host");
+  MFPA_REQUIRE(!(in->noise_dev && in->pieces_host), "augment_fingerprint_host: give noise rows or noise pieces, not both");
+  MFPA_REQUIRE(!in->pieces_host || (in->noise_bank_dev && in->noise_bank_len >= 1 && in->n_pieces >= B),
+               "augment_fingerprint_host: noise pieces need a bank and at least one piece per query");
+  if (int e = check_batch(B, T, shifts)) return e;
+  if (int e = check_afp(p)) return e;
+  MFPA_REQUIRE(T >= 2 && sample_rate > 0 && rows_cap >= 0, "augment_fingerprint_host: n_samples %d, sample_rate %d", T, sample_rate);
+  const bool pcm16 = in->x_pcm16_host != nullptr;
+  DeviceGuard guard(ctx->device);
+  const int n_max = num_frames(T);
+  const int cap = MFPA_HASHES_PER_FRAME * n_max * shifts;
+  int chunk = (int)((int64_t)(256 << 20) / ((int64_t)T * (int64_t)sizeof(float)));  // ~256 MiB of samples
+  if (chunk < 1) chunk = 1;
+  if (chunk > B) chunk = B;
+  // pieces are consumed chunk by chunk: they must come grouped by query, queries ascending
+  std::vector<int> piece_begin;
+  if (in->pieces_host) {
+    piece_begin.assign((size_t)B + 1, 0);
+    int prev = 0;
+    for (int i = 0; i < in->n_pieces; ++i) {
+      const int q = in->pieces_host[i].query;
+      MFPA_REQUIRE(q >= prev && q < B, "augment_fingerprint_host: noise piece %d: query %d out of order or range", i, q);
+      prev = q;
+      piece_begin[(size_t)q + 1] = i + 1;
+    }
+    for (int q = 1; q <= B; ++q) if (piece_begin[q] < piece_begin[q - 1]) piece_begin[q] = piece_begin[q - 1];
+  }
+  for (int b = 0; b < 2; ++b) {
+    if (ctx->h_x[b].reserve(sizeof(float) * (size_t)chunk * T)) return MFPA_ENOMEM;
+    if (pcm16 && ctx->h_x16[b].reserve(sizeof(int16_t) * (size_t)chunk * T + 16)) return MFPA_ENOMEM;
+    if (in->pieces_host && ctx->h_noise[b].reserve(sizeof(float) * (size_t)chunk * T)) return MFPA_ENOMEM;
+    if (ctx->h_rows[b].reserve(sizeof(int32_t) * 2 * (size_t)chunk * cap)) return MFPA_ENOMEM;
+    if (ctx->h_csr[b].reserve(sizeof(int32_t) * 2 * (size_t)chunk * cap)) return MFPA_ENOMEM;
+    if (ctx->h_n[b].reserve(sizeof(int32_t) * chunk)) return MFPA_ENOMEM;
+    if (ctx->h_off[b].reserve(sizeof(int64_t) * ((size_t)chunk + 1))) return MFPA_ENOMEM;
+  }
+  if (ctx->pinned_bytes < 2 * sizeof(int64_t) * ((size_t)chunk + 1)) {
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    ctx->pinned = nullptr;
+    ctx->pinned_bytes = 2 * sizeof(int64_t) * ((size_t)chunk + 1);
+    MFPA_CUDA(cudaMallocHost(&ctx->pinned, ctx->pinned_bytes));
+  }
+  int64_t* off_pinned[2] = {(int64_t*)ctx->pinned, (int64_t*)ctx->pinned + chunk + 1};
+  const int n_chunks = (B + chunk - 1) / chunk;
+  int64_t total = 0;
+  bool overflow = false;
+  offsets_host[0] = 0;
+  auto issue = [&](int ci) -> int {
+    const int b = ci & 1, q0 = ci * chunk, nq = (B - q0 < chunk) ? (B - q0) : chunk;
+    if (ci >= 2) MFPA_CUDA(cudaStreamWaitEvent(ctx->s_in, ctx->ev_run[b], 0));   // chunk ci-2 used these buffers
+    const int64_t n = (int64_t)nq * T;
+    if (pcm16) {
+      MFPA_CUDA(cudaMemcpyAsync(ctx->h_x16[b].ptr, in->x_pcm16_host + (size_t)q0 * T, sizeof(int16_t) * (size_t)n,
+                                cudaMemcpyHostToDevice, ctx->s_in));
+      pcm16_to_f32_kernel<<<(unsigned)((n / 8 + 256) / 256), 256, 0, ctx->s_in>>>((const int16_t*)ctx->h_x16[b].ptr,
+                                                                                 (float*)ctx->h_x[b].ptr, n);
+      MFPA_CUDA(cudaGetLastError());
+    } else {
+      MFPA_CUDA(cudaMemcpyAsync(ctx->h_x[b].ptr, in->x_host + (size_t)q0 * T, sizeof(float) * (size_t)n,
+                                cudaMemcpyHostToDevice, ctx->s_in));
+    }
+    MFPA_CUDA(cudaEventRecord(ctx->ev_in[b], ctx->s_in));
+    MFPA_CUDA(cudaStreamWaitEvent(ctx->s_run, ctx->ev_in[b], 0));
+    if (ci >= 2) MFPA_CUDA(cudaStreamWaitEvent(ctx->s_run, ctx->ev_out[b], 0));
+    const float* noise = in->noise_dev ? in->noise_dev + (size_t)q0 * T : nullptr;
+    if (in->pieces_host) {
+      // this chunk's pieces, rows re-based to the chunk, staged in pinned memory of slot b (free again: the copy
+      // that read it was ordered before ev_run[b] of chunk ci-2, which the caller has waited for)
+      const int p0 = piece_begin[q0], p1 = piece_begin[(size_t)q0 + nq];
+      const size_t bytes = sizeof(mfpa_noise_piece) * (size_t)(p1 - p0);
+      if (ctx->pieces_pinned_bytes[b] < bytes) {
+        if (ctx->pieces_pinned[b]) cudaFreeHost(ctx->pieces_pinned[b]);
+        ctx->pieces_pinned[b] = nullptr;
+        ctx->pieces_pinned_bytes[b] = bytes + bytes / 4 + 64;
+        MFPA_CUDA(cudaMallocHost(&ctx->pieces_pinned[b], ctx->pieces_pinned_bytes[b]));
+      }
+      mfpa_noise_piece* pp = (mfpa_noise_piece*)ctx->pieces_pinned[b];
+      for (int i = p0; i < p1; ++i) { pp[i - p0] = in->pieces_host[i]; pp[i - p0].query -= q0; }
+      if (int e = launch_noise_assemble(ctx, in->noise_bank_dev, in->noise_bank_len, pp, p1 - p0, nq, T,
+                                        (float*)ctx->h_noise[b].ptr, ctx->s_run, true)) return e;
+      noise = (const float*)ctx->h_noise[b].ptr;
+    }
+    const float* ir = in->ir_dev;
+    if (ir && !in->ir_offsets_host) ir += (size_t)q0 * in->ir_stride;
+    if (int e = stage_begin(ctx)) return e;
+    ctx->stage_chained = true;
+    if (int e = launch_augment(ctx, (const float*)ctx->h_x[b].ptr, nq, T, T, sample_rate, params_host + q0, ir, in->ir_stride,
+                               noise, nullptr, false, ctx->s_run, in->ir_offsets_host ? in->ir_offsets_host + q0 : nullptr,
+                               in->ir_bank_len)) return e;
+    if (int e = mfpa_fingerprint(ctx, (const float*)ctx->aug_a.ptr, nq, T, T, shifts, p, (int32_t*)ctx->h_rows[b].ptr, cap,
+                                 (int32_t*)ctx->h_n[b].ptr, ctx->s_run)) return e;
+    if (int e = launch_compact_rows((int32_t*)ctx->h_rows[b].ptr, (int32_t*)ctx->h_n[b].ptr, nq, cap,
+                                    (int64_t*)ctx->h_off[b].ptr, (int32_t*)ctx->h_csr[b].ptr, (int64_t)nq * cap,
+                                    ctx->s_run)) return e;
+    MFPA_CUDA(cudaMemcpyAsync(off_pinned[b], ctx->h_off[b].ptr, sizeof(int64_t) * (nq + 1), cudaMemcpyDeviceToHost,
+                              ctx->s_run));
+    MFPA_CUDA(cudaEventRecord(ctx->ev_run[b], ctx->s_run));
+    return MFPA_OK;
+  };
+  if (int e = issue(0)) return e;
+  for (int ci = 0; ci < n_chunks; ++ci) {
+    const int b = ci & 1, q0 = ci * chunk, nq = (B - q0 < chunk) ? (B - q0) : chunk;
+    if (ci + 1 < n_chunks)
+      if (int e = issue(ci + 1)) return e;
+    MFPA_CUDA(cudaEventSynchronize(ctx->ev_run[b]));
+    const int64_t n_rows = off_pinned[b][nq];
+    for (int i = 1; i <= nq; ++i) offsets_host[q0 + i] = total + off_pinned[b][i];
+    if (total + n_rows > rows_cap) overflow = true;
+    if (!overflow && n_rows > 0) {
+      MFPA_CUDA(cudaStreamWaitEvent(ctx->s_out, ctx->ev_run[b], 0));
+      MFPA_CUDA(cudaMemcpyAsync(rows_host + 2 * total, ctx->h_csr[b].ptr, sizeof(int32_t) * 2 * (size_t)n_rows,
+                                cudaMemcpyDeviceToHost, ctx->s_out));
+    }
+    MFPA_CUDA(cudaEventRecord(ctx->ev_out[b], ctx->s_out));
+    total += n_rows;
+  }
+  MFPA_CUDA(cudaStreamSynchronize(ctx->s_out));
+  MFPA_CUDA(cudaStreamSynchronize(ctx->s_run));
+  if (overflow) {
+    set_error("augment_fingerprint_host: %lld rows produced, capacity %lld", (long long)total, (long long)rows_cap);
+    return MFPA_ECAP;
+  }
+  return MFPA_OK;
 }
 
 void mfpa_match_defaults(mfpa_match_params* p) {

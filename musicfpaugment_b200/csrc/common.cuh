@@ -64,6 +64,12 @@ struct mfpa_ctx {
   int opt_match_packed = 0;         // MFPA_OPT_MATCH_PACKED
   int opt_match_unfused = 0;        // MFPA_OPT_MATCH_UNFUSED
   int opt_part_budget_mb = 2048;    // MFPA_OPT_PART_BUDGET_MB
+  int opt_conv_occ = 3;             // MFPA_OPT_CONV_OCC
+  int opt_stage_times = 0;          // MFPA_OPT_STAGE_TIMES
+  // per-stage CUDA events of the last (up to 16) mfpa_augment_fingerprint / mfpa_fingerprint calls
+  cudaEvent_t stage_ev[16][MFPA_N_STAGES + 1] = {};
+  int stage_calls = 0, stage_slot = 0;
+  bool stage_chained = false;       // the next mfpa_fingerprint continues the record an augment call opened
   double* spread_dev = nullptr;     // [513] Gaussian table
   float2* tw_dev = nullptr;         // FFT twiddles (stft.cu layout)
   float* win_dev = nullptr;         // [512] analysis window
@@ -88,7 +94,9 @@ struct mfpa_ctx {
   // host-path pipeline (capi.cu): copy-in, compute and copy-out streams, double-buffered chunks
   cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_run[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
-  mfpa::Scratch h_x[2], h_x16[2], h_rows[2], h_csr[2], h_n[2], h_off[2];
+  mfpa::Scratch h_x[2], h_x16[2], h_rows[2], h_csr[2], h_n[2], h_off[2], h_noise[2];
+  void* pieces_pinned[2] = {nullptr, nullptr};   // per-slot staging of a chunk's noise pieces (mfpa_augment_fingerprint_host)
+  size_t pieces_pinned_bytes[2] = {0, 0};
 };
 
 // ---- kernel launchers implemented in the stage translation units ----------
@@ -118,9 +126,9 @@ int launch_compact_rows(const int32_t* rows_in, const int32_t* n, int items, int
                         int32_t* rows, int64_t rows_cap, cudaStream_t st);
 int launch_augment(mfpa_ctx* ctx, const float* x, int B, int T, int64_t x_stride, int sample_rate,
                    const mfpa_aug_params* params_host, const float* ir, int ir_stride, const float* noise,
-                   float* out, bool final_norm, cudaStream_t st);
+                   float* out, bool final_norm, cudaStream_t st, const int64_t* ir_offsets = nullptr, int64_t ir_bank_len = 0);
 int launch_noise_assemble(mfpa_ctx* ctx, const float* bank, int64_t bank_len, const mfpa_noise_piece* pieces, int n_pieces,
-                          int B, int T, float* out, cudaStream_t st);
+                          int B, int T, float* out, cudaStream_t st, bool pieces_pinned = false);
 int launch_match_counts(mfpa_ctx* ctx, const int32_t* hashes, const int32_t* nh, int B, int cap, int32_t* counts,
                         cudaStream_t st);
 bool match_fused_ok(const mfpa_ctx* ctx);
@@ -140,5 +148,9 @@ int launch_get_hits(mfpa_ctx* ctx, const int32_t* hashes, int n, int32_t* hits, 
 int launch_dejavu_peaks(const void* arr, int is_f64, int B, int F, int N, int r, double amp_min, uint8_t* mask,
                         int32_t* peaks, int cap, int32_t* npeaks, cudaStream_t st);
 int stft_init_tables(mfpa_ctx* ctx);
+// MFPA_OPT_STAGE_TIMES: stage_begin opens the slot of one chain / fingerprint call, stage_mark(k) stamps the START of
+// stage k (MFPA_STAGE_*) on the stream the kernels run on; a no-op unless the option is set
+int stage_begin(mfpa_ctx* ctx);
+void stage_mark(mfpa_ctx* ctx, int stage, cudaStream_t st);
 
 }  // namespace mfpa

@@ -82,8 +82,9 @@ FC_HD float2 fnma2(float2 a, float2 b, float2 c) {  // c - a * b
 }
 FC_HD float2 bc(float a) { return f2(a, a); }
 FC_HD float2 swp(float2 a) { return f2(a.y, a.x); }
-// (x + y, x - y) of one register pair: FADD2 R, R.HI_LO.NP, R.LO_HI
-FC_HD float2 sumdiff(float2 a) { return add2(f2(a.x, -a.y), f2(a.y, a.x)); }
+// (x + y, x - y) of one register pair.  Two scalar adds: ptxas follows the one-instruction packed form
+// (FADD2 R, R.HI_LO.NP, R.LO_HI) with two register copies whenever its result feeds a vector store.
+FC_HD float2 sumdiff(float2 a) { return f2(a.x + a.y, a.x - a.y); }
 
 // two complex numbers, planar: re = (re of #0, re of #1), im likewise
 struct c2 { float2 re, im; };
@@ -154,7 +155,7 @@ FC_HD void twiddle_powers(c2 w1, c2 (&w)[16]) {
 }
 
 // One radix-16 pass on the double butterfly whose 16 points sit at off0 + t * stride (padded float
-// offsets).  w1 = twiddle pair of the two butterflies (forward) / its conjugate (inverse).
+// offsets).  w1 = twiddle pair of the two butterflies; the inverse multiplies by the conjugate powers.
 template <bool INV> FC_HD void pass16(float* re, float* im, int off0, int stride, c2 w1) {
   c2 v[16], w[16];
 #pragma unroll
@@ -162,7 +163,7 @@ template <bool INV> FC_HD void pass16(float* re, float* im, int off0, int stride
   twiddle_powers(w1, w);
   if (INV) {
 #pragma unroll
-    for (int t = 1; t < 16; ++t) v[t] = cmul(v[t], w[t]);
+    for (int t = 1; t < 16; ++t) v[t] = cmulc(v[t], w[t]);
     dft16<1>(v);
 #pragma unroll
     for (int k = 0; k < 16; ++k) cst(re, im, off0 + k * stride, v[FC_OUT16(k)]);
@@ -196,9 +197,9 @@ FC_HD void pass_last_fwd(float* re, float* im, int m) {
 #pragma unroll
   for (int k = 0; k < 16; ++k) {
     c2 x = v[FC_OUT16(k)];
-    if (k) {   // x.#1 *= (c - i s)
-      const float tr = fmaf(s32[k], x.im.y, c32[k] * x.re.y), ti = fmaf(-s32[k], x.re.y, c32[k] * x.im.y);
-      x.re.y = tr; x.im.y = ti;
+    if (k) {   // (x.#0, x.#1) *= (1, c - i s): constant pairs, no lane shuffling
+      const float2 cc = f2(1.f, c32[k]), ss = f2(0.f, s32[k]);
+      x = mk(fma2(x.im, ss, mul2(x.re, cc)), fnma2(x.re, ss, mul2(x.im, cc)));
     }
     cst(re, im, base + 2 * k, mk(sumdiff(x.re), sumdiff(x.im)));
   }
@@ -212,9 +213,9 @@ FC_HD void pass_last_inv(float* re, float* im, int m) {
   for (int k = 0; k < 16; ++k) {
     const c2 a = cld(re, im, base + 2 * k);
     c2 x = mk(sumdiff(a.re), sumdiff(a.im));
-    if (k) {   // x.#1 *= (c + i s)
-      const float tr = fmaf(-s32[k], x.im.y, c32[k] * x.re.y), ti = fmaf(s32[k], x.re.y, c32[k] * x.im.y);
-      x.re.y = tr; x.im.y = ti;
+    if (k) {   // (x.#0, x.#1) *= (1, c + i s)
+      const float2 cc = f2(1.f, c32[k]), ss = f2(0.f, s32[k]);
+      x = mk(fnma2(x.im, ss, mul2(x.re, cc)), fma2(x.re, ss, mul2(x.im, cc)));
     }
     v[k] = x;
   }
@@ -226,15 +227,13 @@ FC_HD void pass_last_inv(float* re, float* im, int m) {
 // The three passes, thread p of FT (a barrier separates consecutive passes).
 // pass A: sub-transform length 8192, stride 512, butterflies j = 2p, 2p+1
 template <bool INV> FC_HD void pass_a(float* re, float* im, const float* twa_re, const float* twa_im, int p) {
-  c2 w1 = cld(twa_re, twa_im, 2 * p);
-  if (INV) w1.im = f2(-w1.im.x, -w1.im.y);
+  const c2 w1 = cld(twa_re, twa_im, 2 * p);
   pass16<INV>(re, im, padi(2 * p), 544, w1);   // padi(j + 512 t) = padi(j) + 544 t
 }
 // pass B: sub-transform length 512, stride 32, group p >> 4, butterflies j = 2 (p & 15), +1
 template <bool INV> FC_HD void pass_b(float* re, float* im, const float* twb_re, const float* twb_im, int p) {
   const int j = 2 * (p & 15);
-  c2 w1 = cld(twb_re, twb_im, j);
-  if (INV) w1.im = f2(-w1.im.x, -w1.im.y);
+  const c2 w1 = cld(twb_re, twb_im, j);
   pass16<INV>(re, im, padi(512 * (p >> 4) + j), 34, w1);   // padi(base + 32 t) = padi(base) + 34 t
 }
 
@@ -267,18 +266,10 @@ FC_HD void dp_offsets(int m, int mbar, int d2, int& off_a, int& off_b) {
   off_a = 34 * m + 2 * d2;
   off_b = 34 * mbar + 2 * ((m == 0 ? 16 : 15) - d2);
 }
-// cos / sin of pi d2 / 32 (the 256 d2 part of the twiddle)
-#define FC_CD2 {1.f, 0.99518472667219688624f, 0.98078528040323044913f, 0.95694033573220886494f, 0.92387953251128675613f, \
-                0.88192126434835502971f, 0.83146961230254523708f, 0.77301045336273696081f}
-#define FC_SD2 {0.f, 0.09801714032956060199f, 0.19509032201612826785f, 0.29028467725446236764f, 0.38268343236508977173f, \
-                0.47139673682599764856f, 0.55557023301960222474f, 0.63439328416364549822f}
-
-// twiddle pair w' of double pair (m, d2): lane 0 = -i W^{k0} = (-sin, -cos)(pi k0 / FM), lane 1 = -W^{k0}
-FC_HD c2 dp_twiddle(float cw, float sw, int d2) {
-  constexpr float cd[8] = FC_CD2, sd[8] = FC_SD2;
-  const float c = fmaf(-sw, sd[d2], cw * cd[d2]), s = fmaf(cw, sd[d2], sw * cd[d2]);   // angle sum
-  return mk(f2(-s, -c), f2(-c, s));
-}
+// twiddle pair w' of double pair (m, d2): lane 0 = -i W^{k0} = (-sin, -cos)(pi k0 / FM), lane 1 = -W^{k0},
+// k0 = c(m) + 256 d2.  d2 -> d2 + 1 turns both lanes by exp(-i pi / 32): one constant complex multiply.
+FC_HD c2 dp_twiddle0(float cw, float sw) { return mk(f2(-sw, -cw), f2(-cw, sw)); }
+FC_HD c2 dp_twiddle_next(c2 wv) { return cmulk(wv, 0.99518472667219688624f, -0.09801714032956060199f); }
 FC_HD void dp_split(c2 z1, c2 z2raw, c2 wv, c2& ep, c2& f) {
   const float2 z2re = swp(z2raw.re), z2im = swp(z2raw.im);
   ep = mk(add2(z1.re, z2re), sub2(z1.im, z2im));
@@ -383,8 +374,10 @@ FC_HD void filter_pairs_store(const float* re, const float* im, float scale, flo
   float sw, cw;
   block_twiddle(m, cw, sw);
   const float q = 0.25f * scale;
+  c2 wv = dp_twiddle0(cw, sw);
 #pragma unroll
   for (int d2 = 0; d2 < 8; ++d2) {
+    if (d2) wv = dp_twiddle_next(wv);
     if (m == 0 && d2 == 0) {
       const Specials sp = specials_from_filter(re, im, scale);
       hs[0] = f4(sp.a0, sp.a1, sp.bre, sp.bim);
@@ -393,7 +386,6 @@ FC_HD void filter_pairs_store(const float* re, const float* im, float scale, flo
     }
     int oa, ob;
     dp_offsets(m, mbar, d2, oa, ob);
-    const c2 wv = dp_twiddle(cw, sw, d2);
     c2 ep, f;
     dp_split(cld(re, im, oa), cld(re, im, ob), wv, ep, f);
     const int i = dp_index(m, d2);
@@ -407,6 +399,7 @@ FC_HD void filter_pairs_apply(float* re, float* im, const float4* hs, const floa
   const int mbar = partner_block(m);
   float sw, cw;
   block_twiddle(m, cw, sw);
+  c2 wv = dp_twiddle0(cw, sw);
 #pragma unroll
   for (int h4 = 0; h4 < 2; ++h4) {
     float4 vs[4], vr[4];
@@ -419,13 +412,13 @@ FC_HD void filter_pairs_apply(float* re, float* im, const float4* hs, const floa
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int d2 = 4 * h4 + u;
+      if (d2) wv = dp_twiddle_next(wv);
       if (m == 0 && d2 == 0) {
         specials_apply(re, im, specials_unpack(vs[u], vr[u]));
         continue;
       }
       int oa, ob;
       dp_offsets(m, mbar, d2, oa, ob);
-      const c2 wv = dp_twiddle(cw, sw, d2);
       c2 ep, f, za, zb;
       dp_split(cld(re, im, oa), cld(re, im, ob), wv, ep, f);
       const c2 S = c2_unpack(vs[u]), R = c2_unpack(vr[u]);

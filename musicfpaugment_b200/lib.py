@@ -47,6 +47,14 @@ AUG_DTYPE = [("apply", "<u4"), ("fc1_hz", "<f4"), ("fc2_hz", "<f4"), ("fc3_hz", 
 NOISE_PIECE_DTYPE = [("src_a", "<i8"), ("src_b", "<i8"), ("query", "<i4"), ("dst", "<i4"), ("len", "<i4"), ("reserved", "<i4")]
 
 
+class ChainInputs(C.Structure):
+    """mfpa_chain_inputs (include/mfpa.h)."""
+
+    _fields_ = [("x_host", C.c_void_p), ("x_pcm16_host", C.c_void_p), ("ir_dev", C.c_void_p), ("ir_bank_len", C.c_int64),
+                ("ir_offsets_host", C.c_void_p), ("ir_stride", C.c_int32), ("n_pieces", C.c_int32), ("noise_dev", C.c_void_p),
+                ("noise_bank_dev", C.c_void_p), ("noise_bank_len", C.c_int64), ("pieces_host", C.c_void_p)]
+
+
 class MatchParams(C.Structure):
     """mfpa_match_params (include/mfpa.h) = Matcher.__init__ defaults."""
 
@@ -70,6 +78,7 @@ SIGNATURES = {
     "mfpa_afp_defaults": (None, [_P]),
     "mfpa_set_spread_table": (_i, [_vp, _vp]),
     "mfpa_set_option": (_i, [_vp, _i, _i]),
+    "mfpa_stage_times": (_i, [_vp, _vp]),
     "mfpa_num_frames": (_i, [_i]),
     "mfpa_shift_offset": (_i, [_i, _i]),
     "mfpa_stft_mag": (_i, [_vp, _vp, _i, _i, _i64, _i, _vp, _vp, _vp]),
@@ -88,6 +97,7 @@ SIGNATURES = {
     "mfpa_augment": (_i, [_vp, _vp, _i, _i, _i64, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     "mfpa_noise_assemble": (_i, [_vp, _vp, _i64, _vp, _i, _i, _i, _vp, _vp]),
     "mfpa_augment_fingerprint": (_i, [_vp, _vp, _i, _i, _i64, _i, _vp, _vp, _i, _vp, _i, _P, _vp, _i, _vp, _vp]),
+    "mfpa_augment_fingerprint_host": (_i, [_vp, C.POINTER(ChainInputs), _i, _i, _i, _vp, _i, _P, _vp, _i64, _vp]),
     "mfpa_index_load": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i]),
     "mfpa_match_defaults": (None, [C.POINTER(MatchParams)]),
     "mfpa_get_hits": (_i, [_vp, _vp, _i, _vp, _i64, _vp, _vp]),
@@ -125,6 +135,10 @@ OPT_PEAKS_F64 = 1
 OPT_MATCH_PACKED = 2
 OPT_MATCH_UNFUSED = 3
 OPT_PART_BUDGET_MB = 4
+OPT_CONV_OCC = 5
+OPT_STAGE_TIMES = 6
+STAGE_NAMES = ("hpf1_filter", "hpf1_conv", "ir_filter", "ir_conv", "mix", "clip_lpf", "hpf3_filter", "hpf3_conv", "stft",
+               "peaks", "landmarks")
 N_FFT, HOP, BINS, ROWS, MAG_PITCH, MAX_PKS, MAX_SHIFTS, HASHES_PER_FRAME = 512, 256, 257, 256, 264, 5, 8, 15
 
 
@@ -226,6 +240,15 @@ class Context:
         check(_lib.mfpa_set_option(self._h, option, value))
         if option == OPT_MATCH_PACKED:
             self.packed_counts = bool(value)
+
+    def stage_times(self):
+        """Mean milliseconds per stage over the last (up to 16) chain / fingerprint calls made with OPT_STAGE_TIMES set:
+        ({stage name: ms}, number of calls averaged)."""
+        ms = (C.c_float * len(STAGE_NAMES))()
+        n = _lib.mfpa_stage_times(self._h, ms)
+        if n < 0:
+            check(n)
+        return {k: float(v) for k, v in zip(STAGE_NAMES, ms)}, n
 
     # ---- S2 --------------------------------------------------------------
     def stft_mag(self, x, shifts: int = 1):
@@ -382,6 +405,61 @@ class Context:
                                             ir.shape[1] if ir is not None else 0, _ptr(noise), shifts, C.byref(afp),
                                             _ptr(out), cap, _ptr(nh), _stream()))
         return out, nh
+
+    def augment_fingerprint_host(self, x, params, shifts: int, afp: AfpParams, ir=None, ir_offsets=None, noise=None,
+                                 noise_bank=None, pieces=None, sample_rate: int = 8000, rows=None, offsets=None):
+        """AugmentFP chain + wavfile2hashes for a batch of HOST queries (x: [B,T] float32 or int16 PCM, CPU torch tensor
+        or numpy; pinned memory overlaps the copies with the kernels).  Degradation sources are device tensors: `ir`
+        [B,L] rows (or a 1-D bank with `ir_offsets` int64 [B]), `noise` [B,T] rows (or `noise_bank` 1-D + `pieces`,
+        a NOISE_PIECE_DTYPE array grouped by query).  -> (rows int32 [total,2], offsets int64 [B+1]) numpy views."""
+        import numpy as np
+        import torch
+
+        if isinstance(x, np.ndarray):
+            x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.int16 if x.dtype == np.int16 else np.float32))
+        assert not x.is_cuda and x.dtype in (torch.float32, torch.int16) and x.dim() == 2 and x.is_contiguous()
+        B, T = x.shape
+        params = np.ascontiguousarray(params, dtype=AUG_DTYPE)
+        assert params.shape == (B,)
+        inp = ChainInputs()
+        if x.dtype == torch.int16:
+            inp.x_pcm16_host = x.data_ptr()
+        else:
+            inp.x_host = x.data_ptr()
+        keep = [x, params]
+        if ir is not None:
+            assert ir.is_cuda and ir.dtype == torch.float32 and ir.is_contiguous()
+            inp.ir_dev = ir.data_ptr()
+            if ir_offsets is not None:
+                offs = np.ascontiguousarray(ir_offsets, dtype=np.int64)
+                assert offs.shape == (B,) and ir.dim() == 1
+                inp.ir_offsets_host, inp.ir_bank_len, inp.ir_stride = offs.ctypes.data, ir.numel(), 0
+                keep.append(offs)
+            else:
+                assert ir.dim() == 2 and ir.shape[0] == B
+                inp.ir_stride = ir.shape[1]
+        if noise is not None:
+            assert noise.is_cuda and noise.dtype == torch.float32 and noise.is_contiguous() and tuple(noise.shape) == (B, T)
+            inp.noise_dev = noise.data_ptr()
+        if pieces is not None:
+            pieces = np.ascontiguousarray(pieces, dtype=NOISE_PIECE_DTYPE)
+            assert noise_bank is not None and noise_bank.is_cuda and noise_bank.dtype == torch.float32 and noise_bank.dim() == 1
+            inp.noise_bank_dev, inp.noise_bank_len = noise_bank.data_ptr(), noise_bank.numel()
+            inp.pieces_host, inp.n_pieces = pieces.ctypes.data, len(pieces)
+            keep.append(pieces)
+        if rows is None:
+            rows = torch.empty(B * 1024 * shifts, 2, dtype=torch.int32)
+        if offsets is None:
+            offsets = torch.empty(B + 1, dtype=torch.int64)
+        call = lambda r: _lib.mfpa_augment_fingerprint_host(self._h, C.byref(inp), B, T, sample_rate, params.ctypes.data_as(C.c_void_p),
+                                                            shifts, C.byref(afp), _ptr(r), r.shape[0], _ptr(offsets))
+        rc = call(rows)
+        if rc == -4:  # MFPA_ECAP: offsets are valid, retry with the exact size
+            rows = torch.empty(int(offsets[-1]), 2, dtype=torch.int32)
+            rc = call(rows)
+        check(rc)
+        del keep
+        return rows[: int(offsets[-1])].numpy(), offsets.numpy()
 
     # ---- S5 --------------------------------------------------------------
     def index_load(self, table, counts, hashesperid, hash_lo: int = 0, hashbits: int = 20, maxtimebits: int = 14):
