@@ -371,7 +371,21 @@ int mfpa_match_align(mfpa_ctx* ctx, const uint32_t* lists_dev, const int32_t* nl
                      int list_cap, const int32_t* cand_dev, const int32_t* ncand_dev,
                      const mfpa_match_params* p, int32_t* results_dev, int32_t* nrows_dev, int max_rows,
                      void* stream);
-/* Single-shard convenience: steps 1-4 with internal scratch, queries processed in sub-batches. */
+/* Sparse exchange for an index sharded by hash range: instead of summing dense per-track
+ * histograms across the shards, every shard lists the hits of ITS buckets as 32-bit words
+ * (track << 15) | (t_ref - t_q + 16384) - a few thousand per query and shard - and ONE all-to-all keyed by the
+ * query's owner rank moves them; the owner then runs the whole of match_hashes on the words of all shards.
+ *  emit : words_dev [B][words_cap], nwords_dev [B] hits of this shard per query (may exceed words_cap: the owner
+ *         step then reports -1 for the query; -5 = a query time outside [0, 16384))
+ *  owner: words_dev [n_shards][B][words_cap] + nwords_dev [n_shards][B] as the all-to-all leaves them ->
+ *         results / nrows like step 4 above.  Indexes of up to 110000 tracks. */
+int mfpa_match_emit(mfpa_ctx* ctx, const int32_t* hashes_dev, const int32_t* nh_dev, int B, int cap, uint32_t* words_dev,
+                    int words_cap, int32_t* nwords_dev, void* stream);
+int mfpa_match_owner(mfpa_ctx* ctx, const uint32_t* words_dev, const int32_t* nwords_dev, int n_shards, int B, int words_cap,
+                     const mfpa_match_params* p, int32_t* results_dev, int32_t* nrows_dev, int max_rows, void* stream);
+/* Single-shard convenience: steps 1-4 with internal scratch, queries processed in sub-batches.  nrows_dev[q] < 0 flags a
+ * query that could not be matched: -1 / -2 a capacity was exceeded, -5 a query time outside [0, 16384) (the hit
+ * keys hold t_ref - t_q next to the table's 14-bit reference times; the reference has no such limit). */
 int mfpa_match(mfpa_ctx* ctx, const int32_t* hashes_dev, const int32_t* nh_dev, int B, int cap,
                const mfpa_match_params* p, int32_t* results_dev, int32_t* nrows_dev, int max_rows, void* stream);
 

@@ -84,6 +84,7 @@ int stage_begin(mfpa_ctx* ctx) {
   if (!ctx->opt_stage_times) return MFPA_OK;
   ctx->stage_slot = ctx->stage_calls % 16;
   ++ctx->stage_calls;
+  ctx->stage_marked[ctx->stage_slot] = 0;
   for (int k = 0; k <= MFPA_N_STAGES; ++k) {
     cudaEvent_t& e = ctx->stage_ev[ctx->stage_slot][k];
     if (!e) MFPA_CUDA(cudaEventCreate(&e));
@@ -92,7 +93,10 @@ int stage_begin(mfpa_ctx* ctx) {
 }
 
 void stage_mark(mfpa_ctx* ctx, int stage, cudaStream_t st) {
-  if (ctx->opt_stage_times && ctx->stage_calls > 0) cudaEventRecord(ctx->stage_ev[ctx->stage_slot][stage], st);
+  if (ctx->opt_stage_times && ctx->stage_calls > 0) {
+    cudaEventRecord(ctx->stage_ev[ctx->stage_slot][stage], st);
+    ctx->stage_marked[ctx->stage_slot] |= 1u << stage;
+  }
 }
 
 }  // namespace mfpa
@@ -108,12 +112,16 @@ int mfpa_stage_times(mfpa_ctx* ctx, float* ms_out) {
   const int n = ctx->stage_calls < 16 ? ctx->stage_calls : 16;
   for (int s = 0; s < n; ++s) {
     cudaEvent_t* e = ctx->stage_ev[s];
+    const unsigned marked = ctx->stage_marked[s];
+    if (!(marked >> MFPA_N_STAGES & 1u)) continue;   // the call did not reach its end mark
     MFPA_CUDA(cudaEventSynchronize(e[MFPA_N_STAGES]));
     for (int k = 0; k < MFPA_N_STAGES; ++k) {
+      if (!(marked >> k & 1u)) continue;             // stage k did not run in this call
+      int j = k + 1;
+      while (!(marked >> j & 1u)) ++j;               // next stamped stage (the end mark at the latest)
       float ms = 0.f;
-      // a stage that never ran in this call left an event that was never recorded: cudaEventElapsedTime fails, count 0
-      if (cudaEventQuery(e[k]) == cudaSuccess && cudaEventElapsedTime(&ms, e[k], e[k + 1]) == cudaSuccess) ms_out[k] += ms / n;
-      else (void)cudaGetLastError();
+      MFPA_CUDA(cudaEventElapsedTime(&ms, e[k], e[j]));
+      ms_out[k] += ms / n;
     }
   }
   return n;
@@ -597,9 +605,14 @@ int mfpa_augment_fingerprint_host(mfpa_ctx* ctx, const mfpa_chain_inputs* in, in
   int64_t total = 0;
   bool overflow = false;
   offsets_host[0] = 0;
+  // MFPA_DEBUG_PIPE=1: device timeline of the pipeline (copy-in and kernel spans per chunk) on stderr
+  const bool dbg = getenv("MFPA_DEBUG_PIPE") != nullptr;
+  std::vector<cudaEvent_t> dev;
+  if (dbg) { dev.resize(4 * (size_t)n_chunks + 1); for (auto& e : dev) cudaEventCreate(&e); cudaEventRecord(dev[4 * n_chunks], ctx->s_in); }
   auto issue = [&](int ci) -> int {
     const int b = ci & 1, q0 = ci * chunk, nq = (B - q0 < chunk) ? (B - q0) : chunk;
     if (ci >= 2) MFPA_CUDA(cudaStreamWaitEvent(ctx->s_in, ctx->ev_run[b], 0));   // chunk ci-2 used these buffers
+    if (dbg) cudaEventRecord(dev[4 * ci], ctx->s_in);
     const int64_t n = (int64_t)nq * T;
     if (pcm16) {
       MFPA_CUDA(cudaMemcpyAsync(ctx->h_x16[b].ptr, in->x_pcm16_host + (size_t)q0 * T, sizeof(int16_t) * (size_t)n,
@@ -612,8 +625,10 @@ int mfpa_augment_fingerprint_host(mfpa_ctx* ctx, const mfpa_chain_inputs* in, in
                                 cudaMemcpyHostToDevice, ctx->s_in));
     }
     MFPA_CUDA(cudaEventRecord(ctx->ev_in[b], ctx->s_in));
+    if (dbg) cudaEventRecord(dev[4 * ci + 1], ctx->s_in);
     MFPA_CUDA(cudaStreamWaitEvent(ctx->s_run, ctx->ev_in[b], 0));
     if (ci >= 2) MFPA_CUDA(cudaStreamWaitEvent(ctx->s_run, ctx->ev_out[b], 0));
+    if (dbg) cudaEventRecord(dev[4 * ci + 2], ctx->s_run);
     const float* noise = in->noise_dev ? in->noise_dev + (size_t)q0 * T : nullptr;
     if (in->pieces_host) {
       // this chunk's pieces, rows re-based to the chunk, staged in pinned memory of slot b (free again: the copy
@@ -647,6 +662,7 @@ int mfpa_augment_fingerprint_host(mfpa_ctx* ctx, const mfpa_chain_inputs* in, in
     MFPA_CUDA(cudaMemcpyAsync(off_pinned[b], ctx->h_off[b].ptr, sizeof(int64_t) * (nq + 1), cudaMemcpyDeviceToHost,
                               ctx->s_run));
     MFPA_CUDA(cudaEventRecord(ctx->ev_run[b], ctx->s_run));
+    if (dbg) cudaEventRecord(dev[4 * ci + 3], ctx->s_run);
     return MFPA_OK;
   };
   if (int e = issue(0)) return e;
@@ -668,6 +684,14 @@ int mfpa_augment_fingerprint_host(mfpa_ctx* ctx, const mfpa_chain_inputs* in, in
   }
   MFPA_CUDA(cudaStreamSynchronize(ctx->s_out));
   MFPA_CUDA(cudaStreamSynchronize(ctx->s_run));
+  if (dbg) {
+    for (int ci = 0; ci < n_chunks; ++ci) {
+      float t[4];
+      for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&t[k], dev[4 * n_chunks], dev[4 * ci + k]);
+      fprintf(stderr, "pipe chunk %2d: copy %7.2f .. %7.2f ms   kernels %7.2f .. %7.2f ms\n", ci, t[0], t[1], t[2], t[3]);
+    }
+    for (auto& e : dev) cudaEventDestroy(e);
+  }
   if (overflow) {
     set_error("augment_fingerprint_host: %lld rows produced, capacity %lld", (long long)total, (long long)rows_cap);
     return MFPA_ECAP;
@@ -761,6 +785,36 @@ int mfpa_match_align(mfpa_ctx* ctx, const uint32_t* lists_dev, const int32_t* nl
   DeviceGuard guard(ctx->device);
   return launch_match_align(lists_dev, nlists_dev, n_lists, B, list_cap, cand_dev, ncand_dev, p->search_depth, p->window,
                             p->threshcount, p->max_alignments_per_id, results_dev, nrows_dev, max_rows, (cudaStream_t)stream);
+}
+
+int mfpa_match_emit(mfpa_ctx* ctx, const int32_t* hashes_dev, const int32_t* nh_dev, int B, int cap, uint32_t* words_dev,
+                    int words_cap, int32_t* nwords_dev, void* stream) {
+  if (int e = check_match(ctx, nullptr)) return e;
+  MFPA_REQUIRE(hashes_dev && nh_dev && words_dev && nwords_dev && B >= 1 && cap >= 1 && words_cap >= 1, "match_emit: bad argument");
+  MFPA_REQUIRE(match_sparse_ok(ctx), "match_emit: the (track, time skew) hit words hold indexes of up to %d tracks", 110000);
+  DeviceGuard guard(ctx->device);
+  return launch_match_emit(ctx, hashes_dev, nh_dev, B, cap, words_dev, words_cap, nwords_dev, (cudaStream_t)stream);
+}
+
+int mfpa_match_owner(mfpa_ctx* ctx, const uint32_t* words_dev, const int32_t* nwords_dev, int n_shards, int B, int words_cap,
+                     const mfpa_match_params* p, int32_t* results_dev, int32_t* nrows_dev, int max_rows, void* stream) {
+  if (int e = check_match(ctx, p)) return e;
+  MFPA_REQUIRE(p && words_dev && nwords_dev && results_dev && nrows_dev && n_shards >= 1 && B >= 1 && words_cap >= 1 && max_rows >= 1,
+               "match_owner: bad argument");
+  MFPA_REQUIRE(match_sparse_ok(ctx), "match_owner: the (track, time skew) hit words hold indexes of up to %d tracks", 110000);
+  DeviceGuard guard(ctx->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int list_cap = 8192;
+  if (ctx->match_b.reserve(sizeof(int32_t) * (size_t)B * (2 * p->search_depth + 2))) return MFPA_ENOMEM;
+  if (ctx->match_c.reserve(sizeof(uint32_t) * (size_t)B * list_cap)) return MFPA_ENOMEM;
+  int32_t* cand = (int32_t*)ctx->match_b.ptr;
+  int32_t* ncand = cand + (size_t)B * 2 * p->search_depth;
+  int32_t* nlist = ncand + B;
+  uint32_t* list = (uint32_t*)ctx->match_c.ptr;
+  if (int e = launch_match_owner(ctx, words_dev, nwords_dev, n_shards, B, words_cap, p->threshcount, p->search_depth, cand, ncand,
+                                 list, list_cap, nlist, st)) return e;
+  return launch_match_align(list, nlist, 1, B, list_cap, cand, ncand, p->search_depth, p->window, p->threshcount,
+                            p->max_alignments_per_id, results_dev, nrows_dev, max_rows, st);
 }
 
 int mfpa_match(mfpa_ctx* ctx, const int32_t* hashes_dev, const int32_t* nh_dev, int B, int cap,

@@ -69,6 +69,7 @@ struct mfpa_ctx {
   // per-stage CUDA events of the last (up to 16) mfpa_augment_fingerprint / mfpa_fingerprint calls
   cudaEvent_t stage_ev[16][MFPA_N_STAGES + 1] = {};
   int stage_calls = 0, stage_slot = 0;
+  unsigned stage_marked[16] = {};   // bit k: stage k (or the end mark MFPA_N_STAGES) was stamped in this slot
   bool stage_chained = false;       // the next mfpa_fingerprint continues the record an augment call opened
   double* spread_dev = nullptr;     // [513] Gaussian table
   float2* tw_dev = nullptr;         // FFT twiddles (stft.cu layout)
@@ -135,6 +136,12 @@ bool match_fused_ok(const mfpa_ctx* ctx);
 int launch_match_fused(mfpa_ctx* ctx, const int32_t* hashes, const int32_t* nh, int B, int cap, int threshcount,
                        int search_depth, int32_t* cand, int32_t* ncand, uint32_t* list, int list_cap, int32_t* nlist,
                        cudaStream_t st);
+bool match_sparse_ok(const mfpa_ctx* ctx);
+int launch_match_emit(mfpa_ctx* ctx, const int32_t* hashes, const int32_t* nh, int B, int cap, uint32_t* words, int words_cap,
+                      int32_t* nwords, cudaStream_t st);
+int launch_match_owner(mfpa_ctx* ctx, const uint32_t* words, const int32_t* nwords, int n_shards, int B, int words_cap,
+                       int threshcount, int search_depth, int32_t* cand, int32_t* ncand, uint32_t* list, int list_cap,
+                       int32_t* nlist, cudaStream_t st);
 int launch_match_select(mfpa_ctx* ctx, const int32_t* counts, int B, int threshcount, int search_depth, int32_t* cand,
                         int32_t* ncand, cudaStream_t st);
 int launch_match_collect(mfpa_ctx* ctx, const int32_t* hashes, const int32_t* nh, int B, int cap, const int32_t* cand,

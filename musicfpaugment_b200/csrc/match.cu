@@ -200,9 +200,18 @@ constexpr int kFusedRows = 768;
 constexpr int kFusedThreads = 1024;
 struct RowCache { int hb[kFusedRows]; int cnt[kFusedRows]; int t[kFusedRows]; };
 
-template <bool COLLECT>
+enum { kSweepCount = 0, kSweepCollect = 1, kSweepEmit = 2 };
+constexpr int kHitDtBits = 15;          // hit word of the sparse exchange: (track << 15) | (t_ref - t_q + 16384)
+constexpr int kHitMaxTracks = 1 << 17;  // ... which leaves 17 bits for the track
+
+// MODE kSweepCount: raw counts into the packed shared-memory histogram; kSweepCollect: (candidate, delta-t) hits of
+// the tracks marked in it; kSweepEmit: every hit of this shard as a (track, delta-t) word (sparse exchange).
+// A query time outside [0, 2^14) cannot be packed next to the table's 14-bit reference times: *s_bad is raised.
+template <int MODE>
 __device__ __forceinline__ void fused_sweep(const IndexView& ix, const int2* __restrict__ rows, int n, RowCache* rc,
-                                            unsigned* hist, uint32_t* __restrict__ out, int list_cap, int* s_n, int tid) {
+                                            unsigned* hist, uint32_t* __restrict__ out, int list_cap, int* s_n, int tid,
+                                            int* s_bad = nullptr) {
+  constexpr bool COLLECT = MODE == kSweepCollect;
   const int lane = tid & 31, warp = tid >> 5;
   const uint32_t tmask = (1u << ix.maxtimebits) - 1u;
   const unsigned short* mark = reinterpret_cast<const unsigned short*>(hist);
@@ -216,6 +225,7 @@ __device__ __forceinline__ void fused_sweep(const IndexView& ix, const int2* __r
       rc->hb[i] = in ? hb : 0;
       rc->cnt[i] = in ? min(ix.depth, ix.counts[hb]) : 0;
       rc->t[i] = row.x;
+      if (s_bad && (row.x < 0 || row.x >= kDtOff)) *s_bad = 1;
     }
     __syncthreads();
     for (int s0 = 0; s0 < ix.depth; s0 += 128) {   // one trip for depth <= 128 (the reference's is 100)
@@ -238,7 +248,11 @@ __device__ __forceinline__ void fused_sweep(const IndexView& ix, const int2* __r
           for (int i = 0; i < 4; ++i) {
             const unsigned id = (v[a][i] >> ix.maxtimebits) - 1u;   // empty slot -> 0xffffffff
             if (id >= (unsigned)ix.n_tracks) continue;
-            if (!COLLECT) {
+            if (MODE == kSweepEmit) {
+              const int dt = (int)(v[a][i] & tmask) - rc->t[r + a];
+              const int pos = atomicAdd(s_n, 1);
+              if (pos < list_cap) out[pos] = (id << kHitDtBits) | (uint32_t)(dt + kDtOff);
+            } else if (!COLLECT) {
               atomicAdd(&hist[id >> 1], 1u << ((id & 1u) << 4));
             } else {
               const unsigned k = mark[id];
@@ -271,7 +285,7 @@ match_counts_sweep_kernel(const IndexView ix, const int32_t* __restrict__ hashes
   const int2* rows = reinterpret_cast<const int2*>(hashes) + (int64_t)q * cap;
   const int n = min(nh[q], cap);
   for (int i = tid; i < words; i += kFusedThreads) hist[i] = 0;
-  fused_sweep<false>(ix, rows, n, rc, hist, nullptr, 0, nullptr, tid);
+  fused_sweep<kSweepCount>(ix, rows, n, rc, hist, nullptr, 0, nullptr, tid);
   if (packed) {
     unsigned* o = reinterpret_cast<unsigned*>(out) + (int64_t)q * words;
     for (int i = tid; i < words; i += kFusedThreads) o[i] = hist[i];
@@ -306,41 +320,28 @@ match_collect_sweep_kernel(const IndexView ix, const int32_t* __restrict__ hashe
     if (id >= 0 && id < ix.n_tracks) reinterpret_cast<unsigned short*>(hist)[id] = (unsigned short)(k + 1);
   }
   const int2* rows = reinterpret_cast<const int2*>(hashes) + (int64_t)q * cap;
-  fused_sweep<true>(ix, rows, min(nh[q], cap), rc, hist, list + (int64_t)q * list_cap, list_cap, &s_n, tid);
+  fused_sweep<kSweepCollect>(ix, rows, min(nh[q], cap), rc, hist, list + (int64_t)q * list_cap, list_cap, &s_n, tid);
   if (tid == 0) nlist[q] = s_n;
 }
 
-__global__ void __launch_bounds__(kFusedThreads, 1)
-match_fused_kernel(const IndexView ix, const int32_t* __restrict__ hashes, const int32_t* __restrict__ nh, int cap,
-                   int threshcount, int search_depth, int32_t* __restrict__ cand, int32_t* __restrict__ ncand,
-                   uint32_t* __restrict__ list, int list_cap, int32_t* __restrict__ nlist) {
-  extern __shared__ __align__(16) unsigned fused_smem[];
-  const int words = (ix.n_tracks + 1) >> 1;
-  unsigned* hist = fused_smem;
-  RowCache* rc = reinterpret_cast<RowCache*>(fused_smem + ((words + 3) & ~3));
-  constexpr int kFusedWarps = kFusedThreads / 32;
-  __shared__ int s_int[kFusedWarps];
-  __shared__ float s_flt[kFusedWarps];
-  __shared__ Cand s_best[kFusedWarps];
-  __shared__ Cand s_prev;
-  __shared__ int s_n;
-  const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int2* rows = reinterpret_cast<const int2*>(hashes) + (int64_t)q * cap;
-  const int n = min(nh[q], cap);
-  for (int i = tid; i < words; i += kFusedThreads) hist[i] = 0;
-  if (tid == 0) s_n = 0;
-  fused_sweep<false>(ix, rows, n, rc, hist, nullptr, 0, nullptr, tid);
+// select (_best_count_ids, audfprint_match.py:102-129) on the packed shared-memory histogram of one query; all
+// kFusedThreads threads of the block call it.  Returns depth = min(#{raw > threshcount}, search_depth), writes the
+// (id, raw) pairs of the ranked candidates to cand_q and depth to *ncand_q.  `scratch` = kContCap ints.
+// depth tracks are wanted, ranked by raw / hashesperid over ALL tracks.  Every track with raw > threshcount has a
+// quotient >= m = min of theirs, and there are >= depth of them, so the wanted tracks all have quotient >= m: one
+// cheap pass finds the count and m, a second lists the contenders {quotient >= m} (tracks whose raw count is below
+// m * min(hashesperid) are skipped without touching hashesperid), and the exact ranking runs over that short list.
+// float32 quotients carry a relative error < 1e-6; the list is cut at m * (1 - 1e-5) and ranked with exact integer
+// cross products.
+constexpr int kFusedWarps = kFusedThreads / 32;
+constexpr int kContCap = (int)(sizeof(RowCache) / sizeof(int));
+struct SelectSmem { int s_int[kFusedWarps]; float s_flt[kFusedWarps]; Cand s_best[kFusedWarps]; Cand s_prev; int s_n; };
 
+__device__ __forceinline__ int fused_select(const IndexView& ix, const unsigned* hist, int words, int threshcount, int search_depth,
+                                            int* contenders, SelectSmem* sm, int32_t* __restrict__ cand_q,
+                                            int32_t* __restrict__ ncand_q, int tid) {
+  const int lane = tid & 31, warp = tid >> 5;
   auto count_of = [&](int i) -> int { return (int)((hist[i >> 1] >> ((i & 1) * 16)) & 0xffffu); };
-  // select (_best_count_ids, audfprint_match.py:102-129) on the shared-memory histogram.
-  // depth = min(#{raw > threshcount}, search_depth) tracks are wanted, ranked by raw / hashesperid over ALL
-  // tracks.  Every track with raw > threshcount has a quotient >= m = min of theirs, and there are >= depth of
-  // them, so the wanted tracks all have quotient >= m: one cheap pass finds the count and m, a second lists
-  // the contenders {quotient >= m} (tracks whose raw count is below m * min(hashesperid) are skipped without
-  // touching hashesperid), and the exact ranking runs over that short list.  float32 quotients carry a
-  // relative error < 1e-6; the list is cut at m * (1 - 1e-5) and ranked with exact integer cross products.
-  int* contenders = reinterpret_cast<int*>(rc);                       // the row cache is idle here
-  constexpr int kContCap = (int)(sizeof(RowCache) / sizeof(int));
   int gt = 0;
   float fmin = INFINITY;
   // uniform trip count so the (rare) tracks above the count threshold can be handled behind a warp vote:
@@ -360,15 +361,15 @@ match_fused_kernel(const IndexView ix, const int32_t* __restrict__ hashes, const
     gt += __shfl_xor_sync(kFull, gt, o);
     fmin = fminf(fmin, __shfl_xor_sync(kFull, fmin, o));
   }
-  if (lane == 0) { s_int[warp] = gt; s_flt[warp] = fmin; }
-  if (tid == 0) s_n = 0;
+  if (lane == 0) { sm->s_int[warp] = gt; sm->s_flt[warp] = fmin; }
+  if (tid == 0) sm->s_n = 0;
   __syncthreads();
   gt = 0;
-  for (int w = 0; w < kFusedWarps; ++w) { gt += s_int[w]; fmin = fminf(fmin, s_flt[w]); }
+  for (int w = 0; w < kFusedWarps; ++w) { gt += sm->s_int[w]; fmin = fminf(fmin, sm->s_flt[w]); }
   const int depth = min(gt, search_depth);
   const float cut = fmin * 0.99999f;
   const int raw_min = max(1, (int)floorf(cut * (float)ix.hp_min * 0.99999f));   // raw < raw_min => quotient < cut
-  if (tid == 0) ncand[q] = depth;
+  if (tid == 0) *ncand_q = depth;
   bool listed = depth > 0;
   if (listed) {
     for (int w0 = 0; w0 < words; w0 += kFusedThreads) {
@@ -381,26 +382,25 @@ match_fused_kernel(const IndexView ix, const int32_t* __restrict__ hashes, const
           const int raw = e ? r1 : r0, i = 2 * w + e;
           if (raw < raw_min) continue;
           if (__fdividef((float)raw, (float)__ldg(ix.hashesperid + i)) < cut) continue;
-          const int slot = atomicAdd(&s_n, 1);
+          const int slot = atomicAdd(&sm->s_n, 1);
           if (slot < kContCap) contenders[slot] = i;
         }
       }
     }
     __syncthreads();
-    listed = s_n <= kContCap;
+    listed = sm->s_n <= kContCap;
   }
   if (depth > 0 && listed) {
-    const int nc_list = s_n;
-    rank_list<kFusedThreads>(contenders, nc_list, depth, count_of, ix.hashesperid, cand + (int64_t)q * search_depth * 2, s_best, &s_prev, tid);
-    if (tid == 0) s_n = 0;
+    const int nc_list = sm->s_n;
+    rank_list<kFusedThreads>(contenders, nc_list, depth, count_of, ix.hashesperid, cand_q, sm->s_best, &sm->s_prev, tid);
     __syncthreads();
   } else if (depth > 0) {
     // more contenders than the list holds: rank by repeated scans of the whole histogram
     __syncthreads();
-    if (tid == 0) { s_prev = Cand{1, 0, 0x7fffffff}; s_n = 0; }
+    if (tid == 0) sm->s_prev = Cand{1, 0, 0x7fffffff};
     __syncthreads();
     for (int k = 0; k < depth; ++k) {
-      const Cand prev = s_prev;
+      const Cand prev = sm->s_prev;
       Cand best{-1, 1, -1};
       const float f_hi = prev.hp == 0 ? INFINITY : __fdividef((float)prev.raw, (float)prev.hp) * 1.00001f;
       float f_lo = cut;
@@ -425,18 +425,46 @@ match_fused_kernel(const IndexView ix, const int32_t* __restrict__ hashes, const
         y.raw = __shfl_xor_sync(kFull, best.raw, o); y.hp = __shfl_xor_sync(kFull, best.hp, o); y.id = __shfl_xor_sync(kFull, best.id, o);
         if (y.id >= 0 && (best.id < 0 || before(y, best))) best = y;
       }
-      if (lane == 0) s_best[warp] = best;
+      if (lane == 0) sm->s_best[warp] = best;
       __syncthreads();
       if (tid == 0) {
-        Cand b = s_best[0];
-        for (int w = 1; w < kFusedWarps; ++w) if (s_best[w].id >= 0 && (b.id < 0 || before(s_best[w], b))) b = s_best[w];
-        s_prev = b;
-        cand[((int64_t)q * search_depth + k) * 2] = b.id;
-        cand[((int64_t)q * search_depth + k) * 2 + 1] = (int)b.raw;
+        Cand b = sm->s_best[0];
+        for (int w = 1; w < kFusedWarps; ++w) if (sm->s_best[w].id >= 0 && (b.id < 0 || before(sm->s_best[w], b))) b = sm->s_best[w];
+        sm->s_prev = b;
+        cand_q[2 * k] = b.id;
+        cand_q[2 * k + 1] = (int)b.raw;
       }
       __syncthreads();
     }
   }
+  return depth;
+}
+
+constexpr int kBadQueryTime = -5;   // nrows marker: a query time outside [0, 2^14)
+
+__global__ void __launch_bounds__(kFusedThreads, 1)
+match_fused_kernel(const IndexView ix, const int32_t* __restrict__ hashes, const int32_t* __restrict__ nh, int cap,
+                   int threshcount, int search_depth, int32_t* __restrict__ cand, int32_t* __restrict__ ncand,
+                   uint32_t* __restrict__ list, int list_cap, int32_t* __restrict__ nlist) {
+  extern __shared__ __align__(16) unsigned fused_smem[];
+  const int words = (ix.n_tracks + 1) >> 1;
+  unsigned* hist = fused_smem;
+  RowCache* rc = reinterpret_cast<RowCache*>(fused_smem + ((words + 3) & ~3));
+  __shared__ SelectSmem sel;
+  __shared__ int s_n, s_bad;
+  const int q = blockIdx.x, tid = threadIdx.x;
+  const int2* rows = reinterpret_cast<const int2*>(hashes) + (int64_t)q * cap;
+  const int n = min(nh[q], cap);
+  for (int i = tid; i < words; i += kFusedThreads) hist[i] = 0;
+  if (tid == 0) { s_n = 0; s_bad = 0; }
+  fused_sweep<kSweepCount>(ix, rows, n, rc, hist, nullptr, 0, nullptr, tid, &s_bad);
+  if (s_bad) {   // block-uniform after the sweep's closing barrier
+    if (tid == 0) { ncand[q] = 0; nlist[q] = kBadQueryTime; }
+    return;
+  }
+  // the row cache is idle during the select: it holds the contender list
+  const int depth = fused_select(ix, hist, words, threshcount, search_depth, reinterpret_cast<int*>(rc), &sel,
+                                 cand + (int64_t)q * search_depth * 2, ncand + q, tid);
   if (depth == 0) {
     if (tid == 0) nlist[q] = 0;
     return;
@@ -447,7 +475,84 @@ match_fused_kernel(const IndexView ix, const int32_t* __restrict__ hashes, const
   const int nc = min(depth, 128);   // align_kernel handles at most 128 candidates (check_match bounds search_depth)
   for (int k = tid; k < nc; k += kFusedThreads)
     reinterpret_cast<unsigned short*>(hist)[cand[((int64_t)q * search_depth + k) * 2]] = (unsigned short)(k + 1);
-  fused_sweep<true>(ix, rows, n, rc, hist, list + (int64_t)q * list_cap, list_cap, &s_n, tid);
+  fused_sweep<kSweepCollect>(ix, rows, n, rc, hist, list + (int64_t)q * list_cap, list_cap, &s_n, tid);
+  if (tid == 0) nlist[q] = s_n;
+}
+
+// ---- sparse exchange for an index sharded by hash range ("all-to-all the compact hit lists") -------
+// emit: every rank sweeps ITS buckets once per query and lists the hits as (track, delta-t) words - a few thousand
+//       per query and shard, where the dense per-track histogram is 200 KB; one all-to-all keyed by the query's
+//       owner moves them (musicfpaugment_b200/sharded.py);
+// owner: the owner rebuilds the shared-memory histogram from the words of all shards, selects the candidates and
+//       collects their (candidate, delta-t) hits from the same words - no second exchange, no histogram in HBM.
+__global__ void __launch_bounds__(kFusedThreads, 2)
+match_emit_kernel(const IndexView ix, const int32_t* __restrict__ hashes, const int32_t* __restrict__ nh, int cap,
+                  uint32_t* __restrict__ words_out, int words_cap, int32_t* __restrict__ nwords) {
+  __shared__ RowCache rc;
+  __shared__ int s_n, s_bad;
+  const int q = blockIdx.x, tid = threadIdx.x;
+  if (tid == 0) { s_n = 0; s_bad = 0; }
+  const int2* rows = reinterpret_cast<const int2*>(hashes) + (int64_t)q * cap;
+  fused_sweep<kSweepEmit>(ix, rows, min(nh[q], cap), &rc, nullptr, words_out + (int64_t)q * words_cap, words_cap, &s_n, tid, &s_bad);
+  if (tid == 0) nwords[q] = s_bad ? kBadQueryTime : s_n;
+}
+
+// words: [n_shards][B][words_cap], nwords: [n_shards][B] (what the all-to-all leaves on the owner)
+__global__ void __launch_bounds__(kFusedThreads, 1)
+match_owner_kernel(const IndexView ix, const uint32_t* __restrict__ words_in, const int32_t* __restrict__ nwords, int n_shards,
+                   int B, int words_cap, int threshcount, int search_depth, int32_t* __restrict__ cand,
+                   int32_t* __restrict__ ncand, uint32_t* __restrict__ list, int list_cap, int32_t* __restrict__ nlist) {
+  extern __shared__ __align__(16) unsigned fused_smem[];
+  const int words = (ix.n_tracks + 1) >> 1;
+  unsigned* hist = fused_smem;
+  int* contenders = reinterpret_cast<int*>(fused_smem + ((words + 3) & ~3));   // kContCap ints
+  __shared__ SelectSmem sel;
+  __shared__ int s_n, s_err;
+  const int q = blockIdx.x, tid = threadIdx.x;
+  for (int i = tid; i < words; i += kFusedThreads) hist[i] = 0;
+  if (tid == 0) { s_n = 0; s_err = 0; }
+  __syncthreads();
+  for (int l = 0; l < n_shards; ++l) {
+    const int n = nwords[(int64_t)l * B + q];
+    if (n < 0 || n > words_cap) { if (tid == 0) s_err = n < 0 ? n : -1; continue; }
+    const uint32_t* w = words_in + ((int64_t)l * B + q) * words_cap;
+    for (int i = tid; i < n; i += kFusedThreads) {
+      const unsigned id = __ldg(w + i) >> kHitDtBits;
+      atomicAdd(&hist[id >> 1], 1u << ((id & 1u) << 4));
+    }
+  }
+  __syncthreads();
+  if (s_err) {   // a shard's list overflowed (-1) or a query time was out of range: the host wrapper raises
+    if (tid == 0) { ncand[q] = 0; nlist[q] = s_err; }
+    return;
+  }
+  const int depth = fused_select(ix, hist, words, threshcount, search_depth, contenders, &sel,
+                                 cand + (int64_t)q * search_depth * 2, ncand + q, tid);
+  if (depth == 0) {
+    if (tid == 0) nlist[q] = 0;
+    return;
+  }
+  for (int i = tid; i < words; i += kFusedThreads) hist[i] = 0;
+  __syncthreads();
+  const int nc = min(depth, 128);
+  for (int k = tid; k < nc; k += kFusedThreads)
+    reinterpret_cast<unsigned short*>(hist)[cand[((int64_t)q * search_depth + k) * 2]] = (unsigned short)(k + 1);
+  __syncthreads();
+  const unsigned short* mark = reinterpret_cast<const unsigned short*>(hist);
+  uint32_t* out = list + (int64_t)q * list_cap;
+  for (int l = 0; l < n_shards; ++l) {
+    const int n = nwords[(int64_t)l * B + q];
+    const uint32_t* w = words_in + ((int64_t)l * B + q) * words_cap;
+    for (int i = tid; i < n; i += kFusedThreads) {
+      const uint32_t v = __ldg(w + i);
+      const unsigned k = mark[v >> kHitDtBits];
+      if (k) {
+        const int pos = atomicAdd(&s_n, 1);
+        if (pos < list_cap) out[pos] = ((k - 1u) << 16) | (v & ((1u << kHitDtBits) - 1u));
+      }
+    }
+  }
+  __syncthreads();
   if (tid == 0) nlist[q] = s_n;
 }
 
@@ -516,6 +621,10 @@ __global__ void __launch_bounds__(256) match_align_kernel(const uint32_t* __rest
   bool overflow = false;
   for (int l = 0; l < n_lists; ++l) {
     const int n = nlists[(int64_t)l * B + q];
+    if (n < 0) {   // the producer flagged this query (bad query time, overflowed exchange list)
+      if (tid == 0) nrows[q] = n;
+      return;
+    }
     if (n > list_cap) overflow = true;
     const uint32_t* src = lists + ((int64_t)l * B + q) * list_cap;
     __shared__ int s_base;
@@ -707,6 +816,28 @@ int launch_match_fused(mfpa_ctx* ctx, const int32_t* hashes, const int32_t* nh, 
   MFPA_CUDA(cudaFuncSetAttribute(match_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   match_fused_kernel<<<B, kFusedThreads, smem, st>>>(ix, hashes, nh, cap, threshcount, search_depth, cand, ncand, list,
                                                      list_cap, nlist);
+  MFPA_CUDA(cudaGetLastError());
+  return MFPA_OK;
+}
+
+bool match_sparse_ok(const mfpa_ctx* ctx) { return ctx->index_ntracks <= kMaxTracksSmem && ctx->index_ntracks <= kHitMaxTracks; }
+
+int launch_match_emit(mfpa_ctx* ctx, const int32_t* hashes, const int32_t* nh, int B, int cap, uint32_t* words, int words_cap,
+                      int32_t* nwords, cudaStream_t st) {
+  match_emit_kernel<<<B, kFusedThreads, 0, st>>>(view(ctx), hashes, nh, cap, words, words_cap, nwords);
+  MFPA_CUDA(cudaGetLastError());
+  return MFPA_OK;
+}
+
+int launch_match_owner(mfpa_ctx* ctx, const uint32_t* words, const int32_t* nwords, int n_shards, int B, int words_cap,
+                       int threshcount, int search_depth, int32_t* cand, int32_t* ncand, uint32_t* list, int list_cap,
+                       int32_t* nlist, cudaStream_t st) {
+  const IndexView ix = view(ctx);
+  const size_t hw = (size_t)((ix.n_tracks + 1) / 2);
+  const size_t smem = sizeof(unsigned) * ((hw + 3) & ~(size_t)3) + sizeof(int) * kContCap;
+  MFPA_CUDA(cudaFuncSetAttribute(match_owner_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  match_owner_kernel<<<B, kFusedThreads, smem, st>>>(ix, words, nwords, n_shards, B, words_cap, threshcount, search_depth, cand,
+                                                     ncand, list, list_cap, nlist);
   MFPA_CUDA(cudaGetLastError());
   return MFPA_OK;
 }

@@ -105,6 +105,8 @@ SIGNATURES = {
     "mfpa_match_select": (_i, [_vp, _vp, _i, C.POINTER(MatchParams), _vp, _vp, _vp]),
     "mfpa_match_collect": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, C.POINTER(MatchParams), _vp, _i, _vp, _vp]),
     "mfpa_match_align": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, C.POINTER(MatchParams), _vp, _vp, _i, _vp]),
+    "mfpa_match_emit": (_i, [_vp, _vp, _vp, _i, _i, _vp, _i, _vp, _vp]),
+    "mfpa_match_owner": (_i, [_vp, _vp, _vp, _i, _i, _i, C.POINTER(MatchParams), _vp, _vp, _i, _vp]),
     "mfpa_match": (_i, [_vp, _vp, _vp, _i, _i, C.POINTER(MatchParams), _vp, _vp, _i, _vp]),
     "mfpa_dejavu_peaks": (_i, [_vp, _vp, _i, _i, _i, _i, _i, C.c_double, _vp, _vp, _i, _vp, _vp]),
     "mfpa_dejavu_num_frames": (_i, [_i]),
@@ -475,6 +477,7 @@ class Context:
                                    hash_lo, table.shape[0], table.shape[1], hashbits, maxtimebits,
                                    hpid.ctypes.data_as(C.c_void_p), len(hpid)))
         self.n_tracks = len(hpid)
+        self.depth = int(table.shape[1])
 
     def get_hits(self, hashes):
         """hashes: int32 [n,2] cuda -> int32 [nhits,4] cuda (HashTable.get_hits order)."""
@@ -503,6 +506,31 @@ class Context:
         nrows = torch.empty(B, dtype=torch.int32, device=hashes.device)
         check(_lib.mfpa_match(self._h, _ptr(hashes), _ptr(nh), B, cap, C.byref(params), _ptr(res), _ptr(nrows),
                               max_rows, _stream()))
+        return res, nrows
+
+    def match_emit(self, hashes, nh, words_cap: int, words=None, nwords=None):
+        """Hits of this context's index shard as (track << 15 | time skew + 16384) words: (words int32 [B,words_cap],
+        nwords int32 [B])."""
+        import torch
+
+        B, cap, _ = hashes.shape
+        if words is None:
+            words = torch.empty(B, words_cap, dtype=torch.int32, device=hashes.device)
+        if nwords is None:
+            nwords = torch.empty(B, dtype=torch.int32, device=hashes.device)
+        check(_lib.mfpa_match_emit(self._h, _ptr(hashes), _ptr(nh), B, cap, _ptr(words), words_cap, _ptr(nwords), _stream()))
+        return words, nwords
+
+    def match_owner(self, words, nwords, params: MatchParams, max_rows: int = 16):
+        """words int32 [n_shards,B,words_cap], nwords int32 [n_shards,B] (every shard's hits of the queries this rank
+        owns) -> (results int32 [B,max_rows,7], nrows int32 [B])."""
+        import torch
+
+        n_shards, B, words_cap = words.shape
+        res = torch.zeros(B, max_rows, 7, dtype=torch.int32, device=words.device)
+        nrows = torch.empty(B, dtype=torch.int32, device=words.device)
+        check(_lib.mfpa_match_owner(self._h, _ptr(words), _ptr(nwords), n_shards, B, words_cap, C.byref(params), _ptr(res),
+                                    _ptr(nrows), max_rows, _stream()))
         return res, nrows
 
     def match_counts(self, hashes, nh):

@@ -71,7 +71,7 @@ def test_synthetic_saturated_index(mfpa_ctx):
     q, nq, truth = synth.planted_queries(th, 48, n_hashes=400, frac=0.3, seed=6000)
     h, n = torch.from_numpy(q).cuda(), torch.from_numpy(nq).cuda()
     res, nrows = mfpa_ctx.match(h, n)
-    res2, nrows2 = sharded.match_sharded(mfpa_ctx, h, n, sub_batch=20)  # step-wise path, world size 1
+    res2, nrows2 = sharded.match_sharded_dense(mfpa_ctx, h, n, sub_batch=20)  # step-wise path, world size 1
     assert torch.equal(res, res2) and torch.equal(nrows, nrows2)
     res, nrows = res.cpu().numpy(), nrows.cpu().numpy()
     ht = O.HashTable()
@@ -110,6 +110,43 @@ def test_hash_range_shards_sum_to_the_whole(mfpa_ctx):
     mfpa_ctx.index_load(table, counts, hpid)
     res_w, nrows_w = mfpa_ctx.match(h, n)
     assert torch.equal(nrows_s, nrows_w) and torch.equal(res_s, res_w)
+
+
+def test_sparse_exchange_equals_single_shard(mfpa_ctx):
+    """match_emit on three hash-range shards + match_owner on the stacked (track, delta-t) words (what the one
+    all-to-all of sharded.match_sharded delivers) = the single-shard matcher, row for row; an undersized word
+    list and an out-of-range query time are flagged, not mis-matched."""
+    from musicfpaugment_b200 import lib, sharded, synth
+
+    table, counts, hpid, th = synth.hash_index(20000, 1000, seed=5000)
+    q, nq, _ = synth.planted_queries(th, 24, n_hashes=400, frac=0.3, seed=6100)
+    h, n = torch.from_numpy(q).cuda(), torch.from_numpy(nq).cuda()
+    p = lib.match_defaults()
+    mfpa_ctx.index_load(table, counts, hpid)
+    res_w, nrows_w = mfpa_ctx.match(h, n)
+    cap = sharded.default_words_cap(h.shape[1], table.shape[1], 3)
+    words, nwords = [], []
+    for r in range(3):
+        lo, hi = sharded.hash_range(r, 3)
+        mfpa_ctx.index_load(table[lo:hi], counts[lo:hi], hpid, hash_lo=lo)
+        w, nw = mfpa_ctx.match_emit(h, n, cap)
+        words.append(w.clone()); nwords.append(nw.clone())
+    assert int(torch.stack(nwords).max()) <= cap
+    res_s, nrows_s = mfpa_ctx.match_owner(torch.stack(words), torch.stack(nwords), p)
+    assert torch.equal(nrows_s, nrows_w) and torch.equal(res_s, res_w)
+    # a list that does not hold a shard's hits: the owner reports -1 for exactly those queries
+    small = int(torch.stack(nwords).max()) - 1
+    w_s = torch.stack([w[:, :small].contiguous() for w in words])
+    res_o, nrows_o = mfpa_ctx.match_owner(w_s, torch.stack(nwords), p)
+    over = (torch.stack(nwords) > small).any(dim=0)
+    assert bool(over.any()) and torch.equal(nrows_o[over], torch.full_like(nrows_o[over], -1))
+    assert torch.equal(nrows_o[~over], nrows_w[~over])
+    # query times beyond the table's 14-bit time field cannot be packed into a hit key: flagged with -5
+    mfpa_ctx.index_load(table, counts, hpid)
+    h_bad = h.clone()
+    h_bad[0, 0, 0] = 20000
+    _, nrows_b = mfpa_ctx.match(h_bad, n)
+    assert int(nrows_b[0]) == -5 and torch.equal(nrows_b[1:], nrows_w[1:])
 
 
 def test_packed_counts_option(mfpa_ctx):

@@ -2,9 +2,10 @@
 
 The four matching kernels are replaced by a numpy stand-in built from the oracle (test
 infrastructure only), so what is exercised here is the host logic a real run depends on:
-the hash-range partition of the index, the reduce-scatter of per-track raw counts (which
-assigns every query an owner rank), the all-gather of the owners' candidates, the all-to-all
-of the candidates' (track, delta-t) lists and the contiguous query partition.
+the hash-range partition of the index, the one all-to-all of every shard's packed (track, delta-t)
+hit words to the query's owner rank with the next sub-batch's sweep behind it, the owners' result
+rows gathered back into query order, the dense round-1 exchange (reduce-scatter of per-track counts,
+all-gather of candidates, all-to-all of candidate hit lists) and the contiguous query partition.
 The same `match_sharded` drives the CUDA kernels over NCCL on the GPU box.
 """
 import os
@@ -35,6 +36,7 @@ class NumpyShardCtx:
         self.ht.counts[lo:hi] = counts[lo:hi]
         self.ht.hashesperid = hpid
         self.n_tracks = len(hpid)
+        self.depth = table.shape[1]
 
     def _hits(self, hq, n):
         return self.ht.get_hits(hq[:n].numpy())
@@ -106,6 +108,38 @@ class NumpyShardCtx:
         return res, nrows
 
 
+    def match_emit(self, hashes, nh, words_cap):
+        """lib.Context.match_emit: this shard's hits as (track << 15) | (delta-t + 16384) words."""
+        B = hashes.shape[0]
+        words = torch.zeros(B, words_cap, dtype=torch.int32)
+        nwords = torch.zeros(B, dtype=torch.int32)
+        for i in range(B):
+            hits = self._hits(hashes[i], int(nh[i]))
+            w = ((hits[:, 0].astype(np.int64) << 15) | (hits[:, 1].astype(np.int64) + 16384)).astype(np.uint32)
+            nwords[i] = len(w)
+            words[i, : min(len(w), words_cap)] = torch.from_numpy(w[:words_cap].view(np.int32))
+        return words, nwords
+
+    def match_owner(self, words, nwords, p, max_rows):
+        """lib.Context.match_owner: counts, select, collect and align from the hit words of all shards."""
+        n_shards, B, _ = words.shape
+        counts = torch.zeros(B, self.n_tracks, dtype=torch.int32)
+        lists = []
+        for i in range(B):
+            w = np.concatenate([words[s, i, : int(nwords[s, i])].numpy().view(np.uint32) for s in range(n_shards)]).astype(np.int64)
+            lists.append(w)
+            counts[i] = torch.from_numpy(np.bincount(w >> 15, minlength=self.n_tracks).astype(np.int32))
+        cand, ncand = self.match_select(counts, p)
+        list_cap = max(1, max(len(w) for w in lists))
+        lst = torch.zeros(1, B, list_cap, dtype=torch.int32)
+        nlist = torch.zeros(1, B, dtype=torch.int32)
+        for i, w in enumerate(lists):
+            rank = {int(t): k for k, t in enumerate(cand[i, : int(ncand[i]), 0].numpy())}
+            rows = [(rank[int(x >> 15)] << 16) | int(x & 0x7FFF) for x in w if int(x >> 15) in rank]
+            nlist[0, i] = len(rows)
+            lst[0, i, : len(rows)] = torch.tensor(rows, dtype=torch.int32)
+        return self.match_align(lst, nlist, cand, ncand, p, max_rows)
+
     def match(self, hashes, nh, p, max_rows):
         """lib.Context.match (one shard holds the whole index): the four steps back to back."""
         counts = self.match_counts(hashes, nh)
@@ -129,7 +163,11 @@ def _worker(rank, world, port, out_dir):
         lo, hi = sharded.hash_range(rank, world)
         ctx = NumpyShardCtx(table, counts, hpid, lo, hi)
         res, nrows = sharded.match_sharded(ctx, torch.from_numpy(q), torch.from_numpy(nq), params=_P, max_rows=8,
-                                           list_cap=4096, sub_batch=4)
+                                           sub_batch=4)
+        # the round-1 exchange (dense histograms through a reduce-scatter) must give the same rows
+        res_d, nrows_d = sharded.match_sharded_dense(ctx, torch.from_numpy(q), torch.from_numpy(nq), params=_P, max_rows=8,
+                                                     list_cap=4096, sub_batch=4)
+        assert torch.equal(nrows_d, nrows) and torch.equal(res_d, res)
         # every rank must hold identical results
         gathered = [torch.zeros_like(res) for _ in range(world)]
         dist.all_gather(gathered, res)
