@@ -102,6 +102,12 @@ int mfpa_set_spread_table(mfpa_ctx* ctx, const double* table513_host);
  * returns the mean duration of each stage over the last (up to 16) calls - how bench.py times the dominant kernel
  * live inside its timed region. */
 #define MFPA_OPT_STAGE_TIMES 6
+/* MFPA_OPT_CLIP_POOLED (default 0): 1 gives Clipping the reference's BATCH semantics in mfpa_augment*: torch.quantile
+ * with a vector of q and no dim flattens its input, so every row that has MFPA_AUG_CLIP set is clipped to the
+ * quantiles of ITS percentile over the samples of ALL such rows of the call (clipping.py:67-101; identical to the
+ * per-row rule when one row is selected, the only case the reference's drivers produce).  At most 2^24 pooled
+ * samples, torch.quantile's own limit.  The drop-in's batch_augment sets it. */
+#define MFPA_OPT_CLIP_POOLED 7
 int mfpa_set_option(mfpa_ctx* ctx, int option, int value);
 #define MFPA_STAGE_HPF1_FILTER 0  /* filter_spectrum_kernel (loudspeaker high-pass) */
 #define MFPA_STAGE_HPF1_CONV 1    /* fftconv_kernel */
@@ -255,8 +261,9 @@ typedef struct mfpa_aug_params {
 /* Longest impulse response, in samples (32 s at 8 kHz); above 8192 samples: partitioned as well. */
 #define MFPA_AUG_MAX_IR 262144
 
-/* AugmentFP.__call__ / batch_augment on dumped parameters, per-query semantics (the
- * reference drivers call it with B = 1; Clipping's quantiles are per query).
+/* AugmentFP.__call__ / batch_augment on dumped parameters.  Clipping's quantiles are per query (what the reference
+ * computes at B = 1, the only batch size its drivers use) unless MFPA_OPT_CLIP_POOLED asks for the pooled rule of
+ * larger batches; the final PeakNormalization applies to the queries that have MFPA_AUG_NORM set.
  * x_dev [B][T] (row stride x_stride), ir_dev [B][ir_stride] (may be NULL when no query has
  * MFPA_AUG_IR), noise_dev [B][T] contiguous, RMS-normalised like random_background()
  * leaves it (may be NULL when no query has MFPA_AUG_NOISE), params_host [B],
@@ -408,6 +415,40 @@ int mfpa_dejavu_peaks(mfpa_ctx* ctx, const void* arr_dev, int is_f64, int B, int
 int mfpa_dejavu_num_frames(int n_samples);
 int mfpa_dejavu_psd(mfpa_ctx* ctx, const float* x_dev, int B, int T, int64_t x_stride, float* psd_dev, void* stream);
 int mfpa_dejavu_log(mfpa_ctx* ctx, const float* psd_dev, int B, int F, int N, int square, float* arr_dev, void* stream);
+
+/* ---- in-memory Dejavu index and offset vote  (replaces the Postgres tables behind Dejavu.find_matches /
+ * align_matches: afp/dejavu/postgres_database.py:180-229, afp/dejavu/dejavu.py:295-378)
+ * A fingerprint row is (hash, song, offset); a Dejavu hash is 20 hex digits of a SHA-1 (80 bits) = key (leading
+ * 16 digits as uint64) + tail (last 4 digits as uint16).  Rows must be sorted by key. */
+typedef struct mfpa_dejavu_index mfpa_dejavu_index;
+int mfpa_dejavu_index_create(mfpa_ctx* ctx, const uint64_t* keys_host, const uint16_t* tails_host, const int32_t* songs_host,
+                             const int32_t* offsets_host, int64_t n, int n_songs, mfpa_dejavu_index** out);
+void mfpa_dejavu_index_destroy(mfpa_dejavu_index* index);
+/* return_matches for one query: the DISTINCT query hashes (qkeys/qtails [n_hashes]) with the offsets each was seen at
+ * (CSR: qoffsets_dev[qstart_dev[i] .. qstart_dev[i+1])).  For every index row with an equal hash and every such query
+ * offset: one (song, row offset - query offset) pair -> pairs_dev [pairs_cap][2] (unordered; *n_pairs_dev may exceed
+ * pairs_cap, then call again with room); dedup_dev [n_songs] = matching rows per song, each distinct hash counted once
+ * (the reference's dedup_hashes). */
+int mfpa_dejavu_return_matches(mfpa_dejavu_index* index, const uint64_t* qkeys_dev, const uint16_t* qtails_dev,
+                               const int32_t* qstart_dev, const int32_t* qoffsets_dev, int n_hashes, int32_t* pairs_dev,
+                               int64_t pairs_cap, int64_t* n_pairs_dev, int32_t* dedup_dev, void* stream);
+/* align_matches, top match: best_dev[3] = (song, offset difference, number of pairs voting for it) by count descending,
+ * ties to the smaller song id, then the smaller offset (what the reference's stable sorts return first); song -1 when
+ * there is no pair. */
+int mfpa_dejavu_align(mfpa_dejavu_index* index, const int32_t* pairs_dev, int64_t n_pairs, int32_t* best_dev, void* stream);
+
+/* ---- evaluation after the path  (testing/metrics.py:7-192, used by compute_peaks_metrics, testing/audfprint_exps.py:86-157)
+ * mfpa_mask_metrics: the sums behind Recall / Precision / F1score of two peak masks [B][H][W]:
+ *   out4_dev = { #{gt != 0}, sum of predicted looked at from {gt != 0}, #{predicted != 0}, sum of gt looked at from
+ *   {predicted != 0} }.  metrics.py's 3x3 kernel is zero off its centre, so a peak at (i, j) looks at one position of the
+ *   other mask: (i, j), except (i + 1, j) for i == 0 and (i, j + 1) for j == 0 (the reference slices window and kernel
+ *   from opposite ends there, :44-47, :72-75);
+ *   recall = out[1] / out[0], precision = out[3] / out[2] (0 when the denominator is 0, :33-34, :112-113).
+ * mfpa_psnr_stats: out3_dev = { sum (pred - target)^2, min(target), max(target) } in float64 - what torchmetrics'
+ *   PeakSignalNoiseRatio accumulates. */
+int mfpa_mask_metrics(mfpa_ctx* ctx, const float* predicted_dev, const float* gt_dev, int B, int H, int W, double* out4_dev,
+                      void* stream);
+int mfpa_psnr_stats(mfpa_ctx* ctx, const double* pred_dev, const double* target_dev, int64_t n, double* out3_dev, void* stream);
 
 /* ---- optional UNet magnitude-spectrogram denoiser  (training/unet.py:75-108: UNet(1, 1, bilinear=False),
  * eval mode; inserted between `sgram /= max` and the log at afp/audfprint/peak_extractor.py:265-269 and

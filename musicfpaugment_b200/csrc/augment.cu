@@ -755,6 +755,54 @@ __global__ void __launch_bounds__(kSelThreads) clip_finish_kernel(const float* _
   }
 }
 
+// ---- Clipping over a pooled sub-batch (clipping.py:67-101 with B > 1) ---------------------------------------
+// torch.quantile(samples[:, 0, :], q) with a VECTOR q and no dim flattens its input: every selected row gets the
+// quantiles of ITS q over the samples of ALL selected rows.  Reproduced when
+// MFPA_OPT_CLIP_POOLED is set (the drop-in's batch_augment): the gained samples of the selected rows are written as
+// order keys into one array, sorted (bitonic, global memory: this is the reference's rarely used batch path, not the
+// throughput path), and every row interpolates its two thresholds in it.
+__device__ __forceinline__ float clip_pre_scale(const AugQ& q, const AugS& s) {   // what clip_lpf_kernel multiplies z by
+  const float g = (q.apply & MFPA_AUG_GAIN) ? q.gain : 1.f;
+  return (q.apply & MFPA_AUG_NOISE) ? g / s.max_z : g;
+}
+__global__ void __launch_bounds__(256) pool_fill_kernel(const float* __restrict__ z_all, const int* __restrict__ sel, int T,
+                                                        const AugQ* __restrict__ qs, const AugS* __restrict__ st,
+                                                        unsigned* __restrict__ keys) {
+  const int r = blockIdx.y, qi = sel[r];
+  const float pre = clip_pre_scale(qs[qi], st[qi]);
+  const float* z = z_all + (int64_t)qi * T;
+  for (int n = blockIdx.x * 256 + threadIdx.x; n < T; n += gridDim.x * 256) keys[(int64_t)r * T + n] = order_key(z[n] * pre);
+}
+__global__ void __launch_bounds__(256) pool_pad_kernel(unsigned* __restrict__ keys, int64_t n, int64_t n_pad) {
+  for (int64_t i = n + (int64_t)blockIdx.x * 256 + threadIdx.x; i < n_pad; i += (int64_t)gridDim.x * 256) keys[i] = 0xffffffffu;
+}
+__global__ void __launch_bounds__(256) bitonic_step_kernel(unsigned* __restrict__ keys, int64_t n_pad, int64_t k, int64_t j) {
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n_pad; i += (int64_t)gridDim.x * 256) {
+    const int64_t ixj = i ^ j;
+    if (ixj > i) {
+      const unsigned a = keys[i], b = keys[ixj];
+      if ((a > b) == ((i & k) == 0)) { keys[i] = b; keys[ixj] = a; }
+    }
+  }
+}
+__global__ void pool_thresholds_kernel(const unsigned* __restrict__ sorted, int64_t n, const int* __restrict__ sel, int n_sel,
+                                       const AugQ* __restrict__ qs, AugS* st) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_sel) return;
+  const int qi = sel[r];
+  const float q_lo = qs[qi].q_lo, q_hi = 1.0f - q_lo;
+  float thr[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {   // torch.quantile: rank = q (n - 1) in float32, lerp between floor and ceil
+    const float pos = (i ? q_hi : q_lo) * (float)(n - 1);
+    const int64_t below = min((int64_t)floorf(pos), n - 1), above = min((int64_t)ceilf(pos), n - 1);
+    const float fa = key_value(sorted[below]), fb = key_value(sorted[above]);
+    thr[i] = fa + (fb - fa) * (pos - (float)below);
+  }
+  st[qi].lo = thr[0];
+  st[qi].hi = thr[1];
+}
+
 // stage 3: z = in/peak_b + (rms/10^(snr/20)) * noise ; statistics: peak of z, and the tails of z beyond
 // the thresholds clip_sample_kernel placed (lists[query][0 = low, 1 = high][kSelCap] order keys + counts)
 __global__ void __launch_bounds__(256) mix_kernel(const float* __restrict__ in, const float* __restrict__ noise,
@@ -939,11 +987,11 @@ __global__ void __launch_bounds__(256) clip_lpf_kernel(const float* __restrict__
 }
 
 // stage 7 (or a plain copy when final_norm is off / the peak is 0)
-__global__ void __launch_bounds__(256) norm_kernel(const float* __restrict__ v, float* __restrict__ out,
+__global__ void __launch_bounds__(256) norm_kernel(const float* __restrict__ v, float* __restrict__ out, const AugQ* __restrict__ qs,
                                                    const AugS* __restrict__ st, int T, int normalise) {
   const int qi = blockIdx.y;
   const float peak = st[qi].max_v;
-  const bool on = normalise && peak > 0.f;
+  const bool on = normalise && (qs[qi].apply & MFPA_AUG_NORM) && peak > 0.f;
   const int64_t row = (int64_t)qi * T;
   for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < T; n += gridDim.x * blockDim.x) {
     const float x = v[row + n];
@@ -1026,8 +1074,12 @@ int launch_noise_assemble(mfpa_ctx* ctx, const float* bank, int64_t bank_len, co
   double* piece_ss = (double*)ctx->aug_noise.ptr;
   double* row_ss = piece_ss + n_pieces;
   mfpa_noise_piece* dp = (mfpa_noise_piece*)(row_ss + B);
-  MFPA_CUDA(cudaMemcpyAsync(dp, pieces, sizeof(mfpa_noise_piece) * (size_t)n_pieces, cudaMemcpyHostToDevice, st));
-  if (!pieces_pinned) MFPA_CUDA(cudaStreamSynchronize(st));   // pieces_host is caller-owned pageable memory
+  if (pieces_pinned) {   // the host pipeline's staging buffer: pulled by a kernel, off the copy engine's queue
+    if (int e = launch_pull(dp, pieces, sizeof(mfpa_noise_piece) * (size_t)n_pieces, st)) return e;
+  } else {
+    MFPA_CUDA(cudaMemcpyAsync(dp, pieces, sizeof(mfpa_noise_piece) * (size_t)n_pieces, cudaMemcpyHostToDevice, st));
+    MFPA_CUDA(cudaStreamSynchronize(st));   // pieces_host is caller-owned pageable memory
+  }
   MFPA_CUDA(cudaMemsetAsync(piece_ss, 0, sizeof(double) * ((size_t)n_pieces + B), st));
   const dim3 grid((unsigned)n_pieces, (unsigned)((max_len + 4095) / 4096));   // pieces on x: no 65535 limit
   noise_gather_kernel<<<grid, 256, 0, st>>>(bank, dp, T, out, piece_ss);
@@ -1089,7 +1141,7 @@ int launch_augment(mfpa_ctx* ctx, const float* x, int B, int T, int64_t x_stride
                    bool final_norm, cudaStream_t st, const int64_t* ir_offsets, int64_t ir_bank_len) {
   if (int e = aug_init_tables(ctx)) return e;
   // ---- derive per-query parameters on the host
-  const size_t need = (sizeof(AugQ) + 4 * sizeof(int)) * (size_t)B;
+  const size_t need = (sizeof(AugQ) + 5 * sizeof(int)) * (size_t)B;
   if (ctx->aug_copy_done) MFPA_CUDA(cudaEventSynchronize((cudaEvent_t)ctx->aug_copy_done));   // previous call's H2D of this buffer
   else { cudaEvent_t ev; MFPA_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); ctx->aug_copy_done = ev; }
   if (ctx->aug_pinned_bytes < need) {
@@ -1102,6 +1154,8 @@ int launch_augment(mfpa_ctx* ctx, const float* x, int B, int T, int64_t x_stride
   int* hlist[4];   // queries whose stage-1 / IR / stage-5 / stage-6 filter needs the partitioned path
   int nlong[4] = {0, 0, 0, 0}, max_k[4] = {0, 0, 0, 0};
   for (int l = 0; l < 4; ++l) hlist[l] = reinterpret_cast<int*>(hq + B) + (size_t)l * B;
+  int* hclip = reinterpret_cast<int*>(hq + B) + (size_t)4 * B;   // rows with Clipping applied (MFPA_OPT_CLIP_POOLED)
+  int n_clip = 0;
   constexpr int kFastTaps = FN / 2 + 1;   // one overlap-save block keeps >= FN/2 valid outputs
   // grid width of each convolution stage: the most blocks any query needs (pass-through queries: T / FN)
   const int nb_pass = (T + FN - 1) / FN;
@@ -1165,6 +1219,7 @@ int launch_augment(mfpa_ctx* ctx, const float* x, int B, int T, int64_t x_stride
       else up(nbir, blocks_of(true, 0, p.ir_len));
     }
     if (p.apply & MFPA_AUG_NOISE) MFPA_REQUIRE(noise != nullptr, "augment: query %d mixes noise but noise_dev is NULL", i);
+    if (p.apply & MFPA_AUG_CLIP) hclip[n_clip++] = i;
     q.snr_div = powf(10.0f, p.snr_db / 20.0f);
     q.gain = p.gain_factor;
     q.q_lo = p.clip_p / 2.0f;
@@ -1180,13 +1235,13 @@ int launch_augment(mfpa_ctx* ctx, const float* x, int B, int T, int64_t x_stride
   float* bufB = (float*)ctx->aug_b.ptr;
   AugQ* dq = (AugQ*)ctx->aug_small.ptr;
   AugS* ds = (AugS*)(dq + B);
-  MFPA_CUDA(cudaMemcpyAsync(dq, hq, sizeof(AugQ) * (size_t)B, cudaMemcpyHostToDevice, st));
+  if (int e = launch_pull(dq, hq, sizeof(AugQ) * (size_t)B, st)) return e;   // hq is pinned (ctx->aug_pinned)
   MFPA_CUDA(cudaMemsetAsync(ds, 0, sizeof(AugS) * (size_t)B, st));
   int* dlist = nullptr;
   if (nlong[0] + nlong[1] + nlong[2] + nlong[3]) {
     if (ctx->aug_long.reserve(sizeof(int) * 4 * (size_t)B)) return MFPA_ENOMEM;
     dlist = (int*)ctx->aug_long.ptr;
-    MFPA_CUDA(cudaMemcpyAsync(dlist, hlist[0], sizeof(int) * 4 * (size_t)B, cudaMemcpyHostToDevice, st));
+    if (int e = launch_pull(dlist, hlist[0], sizeof(int) * 4 * (size_t)B, st)) return e;
   }
   MFPA_CUDA(cudaEventRecord((cudaEvent_t)ctx->aug_copy_done, st));
   // partitioned overlap-save for the queries of list l (filters longer than one block takes)
@@ -1268,6 +1323,25 @@ int launch_augment(mfpa_ctx* ctx, const float* x, int B, int T, int64_t x_stride
     // stage 4: clip thresholds from the listed tails of z
     clip_finish_kernel<<<B, kSelThreads, 0, st>>>(bufA, lists, dq, ds, T);
     MFPA_CUDA(cudaGetLastError());
+    if (ctx->opt_clip_pooled && n_clip > 1) {
+      // the reference's batch semantics: thresholds from the pooled samples of the selected rows
+      const int64_t n = (int64_t)n_clip * T;
+      MFPA_REQUIRE(n <= (int64_t)1 << 24, "augment: pooled Clipping over %lld samples - torch.quantile refuses inputs above 16 777 216 "
+                   "elements (clipping.py:76-90)", (long long)n);
+      int64_t n_pad = 1;
+      while (n_pad < n) n_pad <<= 1;
+      if (ctx->aug_pool.reserve(sizeof(unsigned) * (size_t)n_pad + sizeof(int) * (size_t)B)) return MFPA_ENOMEM;
+      unsigned* keys = (unsigned*)ctx->aug_pool.ptr;
+      int* dsel = (int*)(keys + n_pad);
+      if (int e = launch_pull(dsel, hclip, sizeof(int) * (size_t)n_clip, st)) return e;
+      pool_fill_kernel<<<dim3((unsigned)((T + 4095) / 4096), (unsigned)n_clip), 256, 0, st>>>(bufA, dsel, T, dq, ds, keys);
+      if (n_pad > n) pool_pad_kernel<<<1024, 256, 0, st>>>(keys, n, n_pad);
+      const unsigned sort_blocks = (unsigned)((n_pad + 255) / 256 < 4736 ? (n_pad + 255) / 256 : 4736);
+      for (int64_t k = 2; k <= n_pad; k <<= 1)
+        for (int64_t j = k >> 1; j > 0; j >>= 1) bitonic_step_kernel<<<sort_blocks, 256, 0, st>>>(keys, n_pad, k, j);
+      pool_thresholds_kernel<<<(n_clip + 127) / 128, 128, 0, st>>>(keys, n, dsel, n_clip, dq, ds);
+      MFPA_CUDA(cudaGetLastError());
+    }
   }
   // stage 5: A -> B (u)
   stage_mark(ctx, MFPA_STAGE_CLIP_LPF, st);
@@ -1300,7 +1374,7 @@ int launch_augment(mfpa_ctx* ctx, const float* x, int B, int T, int64_t x_stride
     if (int e = run_long(3, kModeHP, a)) return e;
     const unsigned gx = (unsigned)((T + 4095) / 4096);
     if (out) {   // out == nullptr: the caller consumes stage 6's output in place (ctx->aug_a)
-      norm_kernel<<<dim3(gx, B), 256, 0, st>>>(bufA, out, ds, T, final_norm ? 1 : 0);
+      norm_kernel<<<dim3(gx, B), 256, 0, st>>>(bufA, out, dq, ds, T, final_norm ? 1 : 0);
       MFPA_CUDA(cudaGetLastError());
     }
   }

@@ -80,6 +80,25 @@ struct DeviceGuard {
 
 namespace mfpa {
 
+template <typename W>
+__global__ void __launch_bounds__(256) pull_kernel(unsigned char* __restrict__ dst, const unsigned char* __restrict__ src, size_t bytes) {
+  const size_t nw = bytes / sizeof(W);
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < nw; i += (size_t)gridDim.x * 256)
+    reinterpret_cast<W*>(dst)[i] = reinterpret_cast<const W*>(src)[i];
+  for (size_t i = nw * sizeof(W) + (size_t)blockIdx.x * 256 + threadIdx.x; i < bytes; i += (size_t)gridDim.x * 256) dst[i] = src[i];
+}
+
+int launch_pull(void* dst_dev, const void* src_pinned, size_t bytes, cudaStream_t st) {
+  if (bytes == 0) return MFPA_OK;
+  const uintptr_t al = (uintptr_t)dst_dev | (uintptr_t)src_pinned;
+  const unsigned blocks = (unsigned)((bytes / 16 + 255) / 256 < 64 ? (bytes / 16 + 255) / 256 : 64) + 1;
+  if ((al & 15) == 0) pull_kernel<uint4><<<blocks, 256, 0, st>>>((unsigned char*)dst_dev, (const unsigned char*)src_pinned, bytes);
+  else if ((al & 3) == 0) pull_kernel<uint32_t><<<blocks, 256, 0, st>>>((unsigned char*)dst_dev, (const unsigned char*)src_pinned, bytes);
+  else pull_kernel<unsigned char><<<blocks, 256, 0, st>>>((unsigned char*)dst_dev, (const unsigned char*)src_pinned, bytes);
+  MFPA_CUDA(cudaGetLastError());
+  return MFPA_OK;
+}
+
 int stage_begin(mfpa_ctx* ctx) {
   if (!ctx->opt_stage_times) return MFPA_OK;
   ctx->stage_slot = ctx->stage_calls % 16;
@@ -182,7 +201,7 @@ void mfpa_destroy(mfpa_ctx* ctx) {
   cudaDeviceSynchronize();
   Scratch* all[] = {&ctx->mag, &ctx->qmax, &ctx->rec, &ctx->fwd, &ctx->hashes, &ctx->nh, &ctx->misc, &ctx->spec64,
                     &ctx->xin, &ctx->out_h, &ctx->out_n, &ctx->aug_a, &ctx->aug_b, &ctx->aug_c, &ctx->aug_d,
-                    &ctx->aug_small, &ctx->aug_lists, &ctx->aug_long, &ctx->aug_part, &ctx->aug_noise, &ctx->match_a, &ctx->match_b, &ctx->match_c};
+                    &ctx->aug_small, &ctx->aug_lists, &ctx->aug_long, &ctx->aug_part, &ctx->aug_noise, &ctx->aug_pool, &ctx->match_a, &ctx->match_b, &ctx->match_c};
   for (Scratch* s : all) s->release();
   for (int b = 0; b < 2; ++b) {
     ctx->h_x[b].release(); ctx->h_x16[b].release(); ctx->h_rows[b].release(); ctx->h_csr[b].release(); ctx->h_n[b].release(); ctx->h_off[b].release(); ctx->h_noise[b].release();
@@ -232,6 +251,7 @@ int mfpa_set_option(mfpa_ctx* ctx, int option, int value) {
       MFPA_REQUIRE(value == 2 || value == 3, "set_option: MFPA_OPT_CONV_OCC %d not in {2, 3}", value);
       ctx->opt_conv_occ = value;
       return MFPA_OK;
+    case MFPA_OPT_CLIP_POOLED: ctx->opt_clip_pooled = value != 0; return MFPA_OK;
     case MFPA_OPT_STAGE_TIMES:
       ctx->opt_stage_times = value != 0;
       ctx->stage_calls = 0;
@@ -569,9 +589,15 @@ int mfpa_augment_fingerprint_host(mfpa_ctx* ctx, const mfpa_chain_inputs* in, in
   DeviceGuard guard(ctx->device);
   const int n_max = num_frames(T);
   const int cap = MFPA_HASHES_PER_FRAME * n_max * shifts;
-  int chunk = (int)((int64_t)(256 << 20) / ((int64_t)T * (int64_t)sizeof(float)));  // ~256 MiB of samples
+  // Chunks of up to ~768 MiB of samples, the batch split evenly: the chain has kernels whose duration hardly depends
+  // on the batch (one warp walks the 251 frames of a query in the peak picker), so a chunk must be a few thousand
+  // queries for its kernels to hide behind the next chunk's copy
+  int64_t chunk_bytes = (int64_t)768 << 20;
+  if (const char* e = getenv("MFPA_CHUNK_MB")) { const long v = atol(e); if (v > 0) chunk_bytes = (int64_t)v << 20; }
+  int chunk = (int)(chunk_bytes / ((int64_t)T * (int64_t)sizeof(float)));
   if (chunk < 1) chunk = 1;
   if (chunk > B) chunk = B;
+  chunk = (B + (B + chunk - 1) / chunk - 1) / ((B + chunk - 1) / chunk);
   // pieces are consumed chunk by chunk: they must come grouped by query, queries ascending
   std::vector<int> piece_begin;
   if (in->pieces_host) {
@@ -879,6 +905,19 @@ int mfpa_dejavu_peaks(mfpa_ctx* ctx, const void* arr_dev, int is_f64, int B, int
   DeviceGuard guard(ctx->device);
   return launch_dejavu_peaks(arr_dev, is_f64, B, F, N, neighborhood, amp_min, mask_dev, peaks_dev, cap, npeaks_dev,
                              (cudaStream_t)stream);
+}
+
+int mfpa_mask_metrics(mfpa_ctx* ctx, const float* predicted_dev, const float* gt_dev, int B, int H, int W, double* out4_dev,
+                      void* stream) {
+  MFPA_REQUIRE(ctx && predicted_dev && gt_dev && out4_dev && B >= 1 && H >= 1 && W >= 1, "mask_metrics: bad argument");
+  DeviceGuard guard(ctx->device);
+  return launch_mask_metrics(predicted_dev, gt_dev, B, H, W, out4_dev, (cudaStream_t)stream);
+}
+
+int mfpa_psnr_stats(mfpa_ctx* ctx, const double* pred_dev, const double* target_dev, int64_t n, double* out3_dev, void* stream) {
+  MFPA_REQUIRE(ctx && pred_dev && target_dev && out3_dev && n >= 1, "psnr_stats: bad argument");
+  DeviceGuard guard(ctx->device);
+  return launch_psnr_stats(pred_dev, target_dev, n, out3_dev, (cudaStream_t)stream);
 }
 
 int mfpa_dejavu_num_frames(int n_samples) { return dejavu_num_frames(n_samples); }

@@ -66,6 +66,7 @@ struct mfpa_ctx {
   int opt_part_budget_mb = 2048;    // MFPA_OPT_PART_BUDGET_MB
   int opt_conv_occ = 3;             // MFPA_OPT_CONV_OCC
   int opt_stage_times = 0;          // MFPA_OPT_STAGE_TIMES
+  int opt_clip_pooled = 0;          // MFPA_OPT_CLIP_POOLED
   // per-stage CUDA events of the last (up to 16) mfpa_augment_fingerprint / mfpa_fingerprint calls
   cudaEvent_t stage_ev[16][MFPA_N_STAGES + 1] = {};
   int stage_calls = 0, stage_slot = 0;
@@ -77,7 +78,7 @@ struct mfpa_ctx {
   float* win_dejavu_dev = nullptr;  // [512] np.hanning(512) x 1/2 (mlab.window_hanning, afp/dejavu/fingerprint.py:64)
   mfpa::Scratch mag, qmax, rec, fwd, hashes, nh, misc, spec64, xin, out_h, out_n;
   // augmentation / matching state is appended by their translation units
-  mfpa::Scratch aug_a, aug_b, aug_c, aug_d, aug_small, aug_lists, aug_long, aug_part, aug_noise;
+  mfpa::Scratch aug_a, aug_b, aug_c, aug_d, aug_small, aug_lists, aug_long, aug_part, aug_noise, aug_pool;
   float2* aug_tw_dev = nullptr;     // planar twiddle tables of the 8192-point FFT (augment.cu, fftconv_core.cuh)
   void* aug_pinned = nullptr;
   void* aug_copy_done = nullptr;    // cudaEvent_t: the last H2D copy out of aug_pinned
@@ -154,9 +155,15 @@ int launch_get_hits(mfpa_ctx* ctx, const int32_t* hashes, int n, int32_t* hits, 
                     cudaStream_t st);
 int launch_dejavu_peaks(const void* arr, int is_f64, int B, int F, int N, int r, double amp_min, uint8_t* mask,
                         int32_t* peaks, int cap, int32_t* npeaks, cudaStream_t st);
+int launch_mask_metrics(const float* pred, const float* gt, int B, int H, int W, double* out4, cudaStream_t st);
+int launch_psnr_stats(const double* pred, const double* target, int64_t n, double* out3, cudaStream_t st);
 int stft_init_tables(mfpa_ctx* ctx);
 // MFPA_OPT_STAGE_TIMES: stage_begin opens the slot of one chain / fingerprint call, stage_mark(k) stamps the START of
 // stage k (MFPA_STAGE_*) on the stream the kernels run on; a no-op unless the option is set
+// Small host->device uploads from PINNED host memory done by a kernel (the SMs read the mapped host buffer) instead of
+// cudaMemcpyAsync: a DMA copy queues on the one host->device copy engine BEHIND the next chunk's 640 MB query copy of
+// the host pipelines, which delayed every chunk's kernels by a whole chunk copy (measured: 65 -> 51 ms per 10 k queries).
+int launch_pull(void* dst_dev, const void* src_pinned, size_t bytes, cudaStream_t st);
 int stage_begin(mfpa_ctx* ctx);
 void stage_mark(mfpa_ctx* ctx, int stage, cudaStream_t st);
 

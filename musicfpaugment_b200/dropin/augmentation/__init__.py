@@ -9,6 +9,12 @@ from __future__ import annotations
 
 import os
 import random
+from pkgutil import extend_path
+
+# `augmentation.utils`, `.transform`, `.composition`, `.transformations.*` of a reference checkout later on
+# sys.path stay importable next to this replacement of the package's own namespace (AugmentFP)
+__path__ = extend_path(__path__, __name__)
+
 from typing import Any, Dict, List, Optional
 
 import numpy as np
@@ -449,6 +455,9 @@ class Compose:
         sr = next((t.sample_rate for t in self.transforms if t.sample_rate), sample_rate) or sample_rate
         ctx = runtime.get_context()
         x = samples[:, 0, :].float().contiguous().cuda()
+        # a batch clips every selected row to quantiles over the POOLED selected rows (clipping.py:76-90: torch.quantile
+        # with a vector q flattens its input); one row = the per-query rule
+        ctx.set_option(lib.OPT_CLIP_POOLED, 1 if B > 1 else 0)
         out = ctx.augment(x, arr, ir.cuda() if ir is not None else None, noise.cuda() if noise is not None else None,
                           sample_rate=int(sr))
         out = out if samples.is_cuda else out.cpu()

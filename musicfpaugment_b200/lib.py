@@ -112,6 +112,12 @@ SIGNATURES = {
     "mfpa_dejavu_num_frames": (_i, [_i]),
     "mfpa_dejavu_psd": (_i, [_vp, _vp, _i, _i, _i64, _vp, _vp]),
     "mfpa_dejavu_log": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "mfpa_dejavu_index_create": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i, C.POINTER(_vp)]),
+    "mfpa_dejavu_index_destroy": (None, [_vp]),
+    "mfpa_dejavu_return_matches": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _i64, _vp, _vp, _vp]),
+    "mfpa_dejavu_align": (_i, [_vp, _vp, _i64, _vp, _vp]),
+    "mfpa_mask_metrics": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "mfpa_psnr_stats": (_i, [_vp, _vp, _vp, _i64, _vp, _vp]),
     "mfpa_compact_rows": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _i64, _vp]),
     "mfpa_unet_num_params": (_i64, []),
     "mfpa_unet_create": (_i, [_vp, C.POINTER(_vp)]),
@@ -139,6 +145,7 @@ OPT_MATCH_UNFUSED = 3
 OPT_PART_BUDGET_MB = 4
 OPT_CONV_OCC = 5
 OPT_STAGE_TIMES = 6
+OPT_CLIP_POOLED = 7
 STAGE_NAMES = ("hpf1_filter", "hpf1_conv", "ir_filter", "ir_conv", "mix", "clip_lpf", "hpf3_filter", "hpf3_conv", "stft",
                "peaks", "landmarks")
 N_FFT, HOP, BINS, ROWS, MAG_PITCH, MAX_PKS, MAX_SHIFTS, HASHES_PER_FRAME = 512, 256, 257, 256, 264, 5, 8, 15
@@ -608,6 +615,29 @@ class Context:
         check(_lib.mfpa_dejavu_log(self._h, _ptr(psd), B, F, N, int(square), _ptr(arr), _stream()))
         return arr
 
+    # ---- evaluation ------------------------------------------------------
+    def mask_metrics(self, predicted, gt):
+        """float32 cuda masks [B,H,W] -> float64 [4] cuda: #gt, sum pred@gt, #pred, sum gt@pred (metrics.py:10-162)."""
+        import torch
+
+        predicted, gt = predicted.contiguous(), gt.contiguous()
+        assert predicted.is_cuda and gt.is_cuda and predicted.dtype == gt.dtype == torch.float32
+        assert predicted.dim() == 3 and predicted.shape == gt.shape
+        out = torch.empty(4, dtype=torch.float64, device=predicted.device)
+        B, H, W = predicted.shape
+        check(_lib.mfpa_mask_metrics(self._h, _ptr(predicted), _ptr(gt), B, H, W, _ptr(out), _stream()))
+        return out
+
+    def psnr_stats(self, pred, target):
+        """float64 cuda tensors of equal size -> float64 [3] cuda: sum squared error, min(target), max(target)."""
+        import torch
+
+        pred, target = pred.contiguous(), target.contiguous()
+        assert pred.is_cuda and target.is_cuda and pred.dtype == target.dtype == torch.float64 and pred.numel() == target.numel()
+        out = torch.empty(3, dtype=torch.float64, device=pred.device)
+        check(_lib.mfpa_psnr_stats(self._h, _ptr(pred), _ptr(target), pred.numel(), _ptr(out), _stream()))
+        return out
+
     # ---- fused -----------------------------------------------------------
     def fingerprint(self, x, shifts: int, params: AfpParams, out=None, nh=None, cap: int | None = None):
         """x [B,T] f32 cuda -> (hashes [B,cap,2] int32, nh [B] int32), rows unique and
@@ -660,6 +690,69 @@ class Context:
             rc = entry(self._h, _ptr(x), B, T, shifts, C.byref(params), _ptr(rows), rows.shape[0], _ptr(offsets))
         check(rc)
         return rows[: int(offsets[-1])].numpy(), offsets.numpy()
+
+
+class DejavuIndex:
+    """Device-resident Dejavu fingerprints table (sorted by hash) with the lookup and vote kernels."""
+
+    def __init__(self, ctx: Context, keys, tails, songs, offsets, n_songs: int):
+        import numpy as np
+
+        self.ctx = ctx
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        tails = np.ascontiguousarray(tails, dtype=np.uint16)
+        songs = np.ascontiguousarray(songs, dtype=np.int32)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int32)
+        assert keys.shape == tails.shape == songs.shape == offsets.shape and keys.ndim == 1
+        self.n, self.n_songs = len(keys), int(n_songs)
+        self._h = C.c_void_p()
+        check(_lib.mfpa_dejavu_index_create(ctx.handle, keys.ctypes.data_as(C.c_void_p), tails.ctypes.data_as(C.c_void_p),
+                                            songs.ctypes.data_as(C.c_void_p), offsets.ctypes.data_as(C.c_void_p), self.n,
+                                            self.n_songs, C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            _lib.mfpa_dejavu_index_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def return_matches(self, qkeys, qtails, qstart, qoffsets):
+        """Distinct query hashes (uint64 keys, uint16 tails) with their offsets (CSR) ->
+        (pairs int32 [n,2] cuda (song, offset difference), dedup int32 [n_songs] cuda)."""
+        import numpy as np
+        import torch
+
+        dev = self.ctx._dev()
+        qk = torch.from_numpy(np.ascontiguousarray(qkeys, dtype=np.uint64).view(np.int64)).to(dev)
+        qt = torch.from_numpy(np.ascontiguousarray(qtails, dtype=np.uint16).view(np.int16)).to(dev)
+        qs = torch.from_numpy(np.ascontiguousarray(qstart, dtype=np.int32)).to(dev)
+        qo = torch.from_numpy(np.ascontiguousarray(qoffsets, dtype=np.int32)).to(dev)
+        n_hashes = len(qkeys)
+        npairs = torch.zeros(1, dtype=torch.int64, device=dev)
+        dedup = torch.zeros(max(self.n_songs, 1), dtype=torch.int32, device=dev)
+        cap = max(1024, 64 * max(1, len(qoffsets)))
+        while True:
+            pairs = torch.empty(cap, 2, dtype=torch.int32, device=dev)
+            check(_lib.mfpa_dejavu_return_matches(self._h, _ptr(qk), _ptr(qt), _ptr(qs), _ptr(qo), n_hashes, _ptr(pairs), cap,
+                                                  _ptr(npairs), _ptr(dedup), _stream()))
+            n = int(npairs.item())
+            if n <= cap:
+                return pairs[:n], dedup[: self.n_songs]
+            cap = n
+
+    def align(self, pairs):
+        """pairs int32 [n,2] cuda -> (song, offset difference, votes) of the top match (song -1: none)."""
+        import torch
+
+        pairs = pairs.contiguous()
+        best = torch.empty(3, dtype=torch.int32, device=self.ctx._dev())
+        check(_lib.mfpa_dejavu_align(self._h, _ptr(pairs), pairs.shape[0], _ptr(best), _stream()))
+        return tuple(int(v) for v in best.cpu().tolist())
 
 
 def unet_param_blob(state_dict):

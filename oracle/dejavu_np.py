@@ -90,3 +90,82 @@ def dejavu_fingerprint_arr(x: np.ndarray, denoise=None):
     if denoise is not None:
         arr = np.asarray(denoise(arr.astype(np.float32)), dtype=np.float32) ** 2
     return log_spectrogram(arr), arr
+
+
+# ---------------------------------------------------------------------------------------------------
+# Matching: CommonDatabase.return_matches (afp/dejavu/postgres_database.py:180-229) and
+# Dejavu.align_matches (afp/dejavu/dejavu.py:312-378), restated over a plain list of fingerprint rows.
+# Pinned by tests/golden/dejavu_match.npz, which oracle/make_golden_dejavu_match.py produces by running the
+# reference's own two methods against a dict-backed stand-in for the Postgres cursor.
+# ---------------------------------------------------------------------------------------------------
+def return_matches(rows, hashes):
+    """rows: iterable of (hash hex str, song id, offset) = the fingerprints table; hashes: iterable of
+    (hash, offset) of the query.  -> ([(song id, db offset - query offset), ...], {song id: matched rows}),
+    each distinct query hash looked up once (:198-204) and every matching row paired with every offset the
+    query saw that hash at (:224-226)."""
+    table = {}
+    for h, sid, off in rows:
+        table.setdefault(h.upper(), []).append((int(sid), int(off)))
+    mapper = {}
+    for h, off in hashes:
+        mapper.setdefault(h.upper(), []).append(int(off))
+    results, dedup = [], {}
+    for h, q_offsets in mapper.items():
+        for sid, off in table.get(h, []):
+            dedup[sid] = dedup.get(sid, 0) + 1
+            for qo in q_offsets:
+                results.append((sid, off - qo))
+    return results, dedup
+
+
+def align_top(matches):
+    """The first row of align_matches' `songs_matches` (:330-345): per song the offset difference with the most
+    votes (first maximum in ascending offset order), songs ordered by that count descending with Python's stable
+    sort, so ties keep ascending song id.  -> (song id, offset difference, votes) or None."""
+    counts = {}
+    for sid, diff in matches:
+        counts[(int(sid), int(diff))] = counts.get((int(sid), int(diff)), 0) + 1
+    best = None
+    for (sid, diff), c in sorted(counts.items()):
+        if best is None or c > best[2]:
+            best = (sid, diff, c)
+    return best
+
+
+# ---------------------------------------------------------------------------------------------------
+# Evaluation (testing/metrics.py:10-192).  For every non-zero (b, i, j) of one mask the reference multiplies a 3x3
+# window of the OTHER mask by a kernel that is zero off its centre.  In the interior and at the high edges the centre
+# lands on (i, j); at i == 0 or j == 0 the window is cut on the low side while the kernel is cut on the HIGH side
+# (`window[f : f + 2] * kernel[:2]`, :44-47, :72-75), so the centre lands on i + 1 resp. j + 1 - a quirk of the
+# reference, reproduced (SURVEY.md App. B).  Pinned by tests/golden/metrics.npz (reference classes on random masks).
+# psnr restates torchmetrics.PeakSignalNoiseRatio with data_range=None (third-party, absent: parity unpinned):
+# range = max(target, 0) - min(target, 0), 10 log10(range^2 / mse).
+# ---------------------------------------------------------------------------------------------------
+def _looked_at(other, idx):
+    b, i, j = idx
+    i2 = np.where((i == 0) & (other.shape[1] > 1), i + 1, i)
+    j2 = np.where((j == 0) & (other.shape[2] > 1), j + 1, j)
+    return other[b, i2, j2]
+
+
+def recall(predicted, gt):
+    predicted, gt = np.asarray(predicted, np.float64), np.asarray(gt, np.float64)
+    idx = np.nonzero(gt)
+    return 0.0 if len(idx[0]) == 0 else float(_looked_at(predicted, idx).sum() / len(idx[0]))
+
+
+def precision(predicted, gt):
+    predicted, gt = np.asarray(predicted, np.float64), np.asarray(gt, np.float64)
+    idx = np.nonzero(predicted)
+    return 0.0 if len(idx[0]) == 0 else float(_looked_at(gt, idx).sum() / len(idx[0]))
+
+
+def f1score(predicted, gt):
+    p, r = precision(predicted, gt), recall(predicted, gt)
+    return 0.0 if np.isclose(p + r, 0.0) else float(2.0 * p * r / (p + r))
+
+
+def psnr(pred, target):
+    pred, target = np.asarray(pred, np.float64), np.asarray(target, np.float64)
+    rng = max(target.max(), 0.0) - min(target.min(), 0.0)
+    return float(10.0 * np.log10(rng ** 2 / np.mean((pred - target) ** 2)))

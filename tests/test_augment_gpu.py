@@ -236,3 +236,27 @@ def test_chain_end_to_end_hash_agreement(mfpa_ctx):
         total += len(want | got)
     assert total > 1000 and agree / total >= 0.999, (agree, total)
 
+
+
+def test_pooled_clipping_of_a_batch_equals_the_reference(mfpa_ctx):
+    """B > 1: torch.quantile(samples[:, 0, :], q_vector) flattens the selected sub-batch, so each row is clipped to the
+    quantiles of its own percentile over the POOLED rows (clipping.py:76-90).  MFPA_OPT_CLIP_POOLED reproduces it; the
+    golden is the reference's Gain + Clipping on 4 rows, one of them left out by the gate.  Without the option the
+    per-query rule (what B = 1 gives) runs - and differs."""
+    lib = _lib()
+    g = np.load(os.path.join(GOLD, "clip_pooled.npz"))
+    x = torch.from_numpy(g["x"]).cuda()
+    arr = np.zeros(4, dtype=lib.AUG_DTYPE)
+    arr["apply"] = lib.AUG_GAIN
+    arr["apply"][g["selected"]] |= lib.AUG_CLIP
+    arr["gain_factor"], arr["clip_p"] = g["gain_factor"], g["clip_p"]
+    mfpa_ctx.set_option(lib.OPT_CLIP_POOLED, 1)
+    try:
+        pooled = mfpa_ctx.augment(x, arr).cpu().numpy()
+    finally:
+        mfpa_ctx.set_option(lib.OPT_CLIP_POOLED, 0)
+    per_row = mfpa_ctx.augment(x, arr).cpu().numpy()
+    for i in range(4):
+        assert _rel(pooled[i], g["out"][i]) <= 5e-6, i
+    assert _rel(per_row[0], g["out"][0]) > 1e-3        # row 0 is the loud one: pooled thresholds clip it harder
+    assert np.array_equal(per_row[2], pooled[2])       # the row Clipping skipped is untouched by either rule
