@@ -258,13 +258,15 @@ __global__ void __launch_bounds__(FT, OCC) fftconv_kernel(const ConvArgs a, cons
       asm volatile("prefetch.global.L2 [%0];" ::"l"(hs + FM / 4 + fc::dp_index(tid, d2)));
     }
     s.load_tables(tw_g, tid);
+    __syncthreads();   // the twiddle tables
     const int s0 = n0 - g.lead;
+    // forward pass A straight from global memory: thread tid's 16 quads are the float4 numbers tid + 256 t of the block
     if (vec_in && s0 >= 0 && s0 + FN <= T) {   // interior block: sixteen 16-byte loads in flight per thread
-      const float4* src = reinterpret_cast<const float4*>(in + s0);
-      fill_planes<16>(s, tid, [&](int i4) { return __ldg(src + i4); });
+      const float4* src = reinterpret_cast<const float4*>(in + s0) + tid;
+      fc::pass_a_fwd_quads(s.re, s.im, s.twa_re, s.twa_im, tid, [&](int t) { return __ldg(src + FT * t); });
     } else {
-      fill_planes<4>(s, tid, [&](int i4) {
-        const int n = s0 + 4 * i4;
+      fc::pass_a_fwd_quads(s.re, s.im, s.twa_re, s.twa_im, tid, [&](int t) {
+        const int n = s0 + 4 * (tid + FT * t);
         if (vec_in && n >= 0 && n + 3 < T) return __ldg(reinterpret_cast<const float4*>(in + n));
         float x[4];
 #pragma unroll
@@ -277,24 +279,25 @@ __global__ void __launch_bounds__(FT, OCC) fftconv_kernel(const ConvArgs a, cons
       });
     }
     __syncthreads();
-    fft_forward(s, tid);
+    fc::pass_b<false>(s.re, s.im, s.twb_re, s.twb_im, tid); __syncthreads();
+    fc::pass_last_fwd(s.re, s.im, tid);                     __syncthreads();
     apply_filter_pairs(s, hs, hs + FM / 4, tid);
     __syncthreads();
-    fft_inverse(s, tid);
-    // y[n0 + 4 g4 + e] sits at packed index e_base + 2 g4 (+1), re / im alternating; a high-pass needs no second
-    // look at x: its filter is delta - lowpass (filter_spectrum_kernel)
+    fc::pass_last_inv(s.re, s.im, tid);                     __syncthreads();
+    fc::pass_b<true>(s.re, s.im, s.twb_re, s.twb_im, tid);  __syncthreads();
+    // the inverse pass A hands over float4s of four consecutive samples c[4 tid + 1024 k ..]: y[n0 + i] = c[off + i], off a
+    // multiple of 4, so they go to global memory as they are.  A high-pass needs no second look at x: its filter is
+    // delta - lowpass (filter_spectrum_kernel)
     const int n_end = min(g.n_total, n0 + g.V);
-    const int e_base = g.off >> 1;
-#pragma unroll 4
-    for (int g4 = tid; n0 + 4 * g4 < n_end; g4 += FT) {
-      const int n = n0 + 4 * g4;
-      const int o = fc::padi(e_base + 2 * g4);
-      const float2 cr = *reinterpret_cast<const float2*>(s.re + o), ci = *reinterpret_cast<const float2*>(s.im + o);
-      const float v[4] = {cr.x, ci.x, cr.y, ci.y};
+    fc::pass_a_inv_quads(s.re, s.im, s.twa_re, s.twa_im, tid, [&](int k, float4 v4) {
+      const int i = 4 * tid + 1024 * k - g.off;
+      const int n = n0 + i;
+      if (i < 0 || n >= n_end) return;
+      const float v[4] = {v4.x, v4.y, v4.z, v4.w};
       if (n + 3 < n_end && n + 3 < T) {
         vmax = fmaxf(fmaxf(vmax, fmaxf(fabsf(v[0]), fabsf(v[1]))), fmaxf(fabsf(v[2]), fabsf(v[3])));
         vss = fmaf(v[0], v[0], fmaf(v[1], v[1], fmaf(v[2], v[2], fmaf(v[3], v[3], vss))));
-        if (vec_out) *reinterpret_cast<float4*>(out + n) = make_float4(v[0], v[1], v[2], v[3]);
+        if (vec_out) *reinterpret_cast<float4*>(out + n) = v4;
         else { out[n] = v[0]; out[n + 1] = v[1]; out[n + 2] = v[2]; out[n + 3] = v[3]; }
       } else {
 #pragma unroll
@@ -304,7 +307,7 @@ __global__ void __launch_bounds__(FT, OCC) fftconv_kernel(const ConvArgs a, cons
             if (n + e < T) { out[n + e] = v[e]; vss += v[e] * v[e]; }
           }
       }
-    }
+    });
   }
   vmax = block_max(vmax, s.red, tid);
   vss = block_sum(vss, s.red, tid);

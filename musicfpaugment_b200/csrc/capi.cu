@@ -589,10 +589,10 @@ int mfpa_augment_fingerprint_host(mfpa_ctx* ctx, const mfpa_chain_inputs* in, in
   DeviceGuard guard(ctx->device);
   const int n_max = num_frames(T);
   const int cap = MFPA_HASHES_PER_FRAME * n_max * shifts;
-  // Chunks of up to ~768 MiB of samples, the batch split evenly: the chain has kernels whose duration hardly depends
-  // on the batch (one warp walks the 251 frames of a query in the peak picker), so a chunk must be a few thousand
-  // queries for its kernels to hide behind the next chunk's copy
-  int64_t chunk_bytes = (int64_t)768 << 20;
+  // Chunks of up to ~256 MiB of samples (MFPA_CHUNK_MB overrides), the batch split evenly: a chunk's kernels (~2 us per
+  // query) hide behind the next chunk's copy (~4.7 us per float32 query over PCIe 5 x16), so only the first copy and the
+  // last chunk's kernels are exposed
+  int64_t chunk_bytes = (int64_t)256 << 20;
   if (const char* e = getenv("MFPA_CHUNK_MB")) { const long v = atol(e); if (v > 0) chunk_bytes = (int64_t)v << 20; }
   int chunk = (int)(chunk_bytes / ((int64_t)T * (int64_t)sizeof(float)));
   if (chunk < 1) chunk = 1;

@@ -237,6 +237,46 @@ template <bool INV> FC_HD void pass_b(float* re, float* im, const float* twb_re,
   pass16<INV>(re, im, padi(512 * (p >> 4) + j), 34, w1);   // padi(base + 32 t) = padi(base) + 34 t
 }
 
+// Pass A fused with the block's global-memory traffic.  The two butterflies of thread p (j = 2p, 2p + 1) take points
+// j + 512 t, which in the packed real block (even sample -> re, odd -> im) are the FOUR consecutive samples
+// 4p + 1024 t .. + 3: one 16-byte load per t, coalesced over p.  So the forward pass A reads its input straight from
+// global memory (no staging pass through shared memory, one barrier less) and the inverse pass A - the last pass of
+// the inverse transform - hands its output to the caller as float4 of four consecutive time samples.
+//   quad(t)     -> float4 = samples 4p + 1024 t .. + 3 of the block (t < 16)
+//   store(k, v) <-  v = samples 4p + 1024 k .. + 3 of the circular convolution (unscaled inverse, k < 16)
+template <typename Q>
+FC_HD void pass_a_fwd_quads(float* re, float* im, const float* twa_re, const float* twa_im, int p, Q quad) {
+  c2 v[16], w[16];
+#pragma unroll
+  for (int t = 0; t < 16; ++t) {
+    const float4 x = quad(t);
+    v[t] = mk(f2(x.x, x.z), f2(x.y, x.w));
+  }
+  twiddle_powers(cld(twa_re, twa_im, 2 * p), w);
+  dft16<-1>(v);
+  const int off0 = padi(2 * p);
+#pragma unroll
+  for (int k = 0; k < 16; ++k) cst(re, im, off0 + k * 544, k ? cmul(v[FC_OUT16(k)], w[k]) : v[FC_OUT16(k)]);
+}
+template <typename S>
+FC_HD void pass_a_inv_quads(const float* re, const float* im, const float* twa_re, const float* twa_im, int p, S store) {
+  c2 v[16], w[16];
+  const int off0 = padi(2 * p);
+#pragma unroll
+  for (int t = 0; t < 16; ++t) v[t] = cld(re, im, off0 + t * 544);
+  twiddle_powers(cld(twa_re, twa_im, 2 * p), w);
+#pragma unroll
+  for (int t = 1; t < 16; ++t) v[t] = cmulc(v[t], w[t]);
+  dft16<1>(v);
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const c2 x = v[FC_OUT16(k)];
+    float4 o;
+    o.x = x.re.x; o.y = x.im.x; o.z = x.re.y; o.w = x.im.y;
+    store(k, o);
+  }
+}
+
 // position of frequency k after the forward transform, and the frequency held at position r
 FC_HD int rev_pos(int k) { return ((k & 15) << 9) | (((k >> 4) & 15) << 5) | (((k >> 8) & 15) << 1) | (k >> 12); }
 FC_HD int pos_freq(int r) { return (r >> 9) | (((r >> 5) & 15) << 4) | (((r >> 1) & 15) << 8) | ((r & 1) << 12); }

@@ -1,123 +1,212 @@
-"""Drop-in for afp/audfprint/hash_table.py.  Same fields and gzip-pickle format
-(hash_table.py:46-68,118-198), so an index the reference built loads here and vice versa;
-`get_hits` and the Matcher run on the GPU against a device copy of the table that is
-refreshed whenever the host table is marked dirty."""
+"""Drop-in for afp/audfprint/hash_table.py.
+
+Same public fields (`hashbits`, `depth`, `maxtimebits`, `table`, `counts`, `names`, `hashesperid`,
+`ht_version`, `dirty`) and the same gzip-pickle file format (hash_table.py:46-68, 118-198), so an index
+the reference built loads here and a file saved here loads in the reference.  `get_hits` and the Matcher
+run on the GPU against a device copy of the table; every mutation bumps a version counter and the copy
+is refreshed when it is behind.
+
+The host-side bookkeeping is vectorised: `store` places all rows that find a free slot at once and only
+the rows that land in a FULL bucket go through Python's `random.randint` - one draw per such row, in row
+order, which is exactly the sequence of draws the reference's per-row loop makes (hash_table.py:91-112), so
+a table built here under the same `random.seed` is identical to the reference's.
+"""
 from __future__ import annotations
 
 import gzip
 import math
 import pickle
 import random
-from typing import Any, List, Union
+from typing import Any, Callable, List, Optional, Union
 
 import numpy as np
 
-HT_VERSION = 20170724
+HT_VERSION = 20170724            # current format: ids stored as id + 1 (hash_table.py:24-30)
 HT_COMPAT_VERSION = 20170724
 HT_OLD_COMPAT_VERSION = 20140920
 
 
 def _bitsfor(maxval: int) -> int:
-    maxvalbits = int(round(math.log(maxval) / math.log(2)))
-    if maxval != (1 << maxvalbits):
+    """log2 of a power of two (hash_table.py:33-43)."""
+    bits = int(round(math.log(maxval) / math.log(2)))
+    if maxval != (1 << bits):
         raise ValueError("maxval must be a power of 2, not %d" % maxval)
-    return maxvalbits
+    return bits
 
 
 class HashTable(object):
-    def __init__(self, filename=None):
+    """Fixed-array landmark index: table[2^hashbits, depth] uint32, entry = ((id + 1) << maxtimebits) + time."""
+
+    def __init__(self, filename: Optional[str] = None, hashbits: int = 20, depth: int = 100, maxtime: int = 16384):
+        self._version = 0
         if filename is not None:
             self.load(filename)
-        else:
-            self.hashbits = 20
-            self.depth = 100
-            self.maxtimebits = _bitsfor(16384)
-            size = 2 ** self.hashbits
-            self.table = np.zeros((size, self.depth), dtype=np.uint32)
-            self.counts = np.zeros(size, dtype=np.int32)
-            self.names: List[Any] = []
-            self.hashesperid = np.zeros(0, np.uint32)
-            self.ht_version = HT_VERSION
-            self.dirty = True
+            return
+        self.hashbits, self.depth, self.maxtimebits = hashbits, depth, _bitsfor(maxtime)
+        self.table = np.zeros((1 << hashbits, depth), dtype=np.uint32)
+        self.counts = np.zeros(1 << hashbits, dtype=np.int32)
+        self.names: List[Any] = []
+        self.hashesperid = np.zeros(0, np.uint32)
+        self.ht_version = HT_VERSION
+        self.dirty = True
 
-    # ---- device residency (not pickled)
+    # ---- device residency (never pickled: the reference's class must be able to load our files) -------------
     def __getstate__(self):
-        return {k: v for k, v in self.__dict__.items() if not k.startswith("_dev")}
+        return {k: v for k, v in self.__dict__.items() if not k.startswith("_")}
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        self._version = 0
+
+    def _touch(self) -> None:
+        self._version = getattr(self, "_version", 0) + 1
+        self.dirty = True
 
     def _device(self):
-        """Upload the table once per modification; returns the libmfpa context holding it."""
+        """The libmfpa context holding a current copy of this table (uploaded when a mutation made it stale, or
+        when another table took the context's index slot)."""
         from musicfpaugment_b200 import runtime
 
         ctx = runtime.get_context()
-        stamp = (id(self.table), int(self.counts.sum()), len(self.hashesperid))
-        if getattr(self, "_dev_stamp", None) != stamp or getattr(ctx, "_index_owner", None) is not self:
+        if getattr(self, "_dev_version", None) != self._version or getattr(ctx, "_index_owner", None) is not self:
             if len(self.hashesperid) == 0:
                 raise ValueError("hash table is empty")
             ctx.index_load(self.table, self.counts, self.hashesperid, 0, self.hashbits, self.maxtimebits)
             ctx._index_owner = self
-            self._dev_stamp = stamp
+            self._dev_version = self._version
         return ctx
 
-    # ---- store (hash_table.py:70-116): host side, index building is not the query hot path
-    def store(self, name, timehashpairs) -> None:
+    # ---- building (hash_table.py:70-116); index building is not the query hot path --------------------------
+    def store(self, name: Union[int, str], timehashpairs) -> None:
         id_ = self.name_to_id(name, add_if_missing=True)
-        hashmask = (1 << self.hashbits) - 1
-        timemask = (1 << self.maxtimebits) - 1
-        idval = (id_ + 1) << self.maxtimebits
-        for time_, hash_ in np.asarray(timehashpairs).reshape(-1, 2):
-            hash_ = int(hash_) & hashmask
-            count = int(self.counts[hash_])
-            val = idval + (int(time_) & timemask)
-            if count < self.depth:
-                self.table[hash_, count] = val
-            else:
-                slot = random.randint(0, count)  # reservoir-style overwrite (:105-110)
+        pairs = np.asarray(timehashpairs, dtype=np.int64).reshape(-1, 2)
+        n = len(pairs)
+        if n:
+            h = pairs[:, 1] & ((1 << self.hashbits) - 1)
+            val = (((id_ + 1) << self.maxtimebits) + (pairs[:, 0] & ((1 << self.maxtimebits) - 1))).astype(np.uint32)
+            # bucket fill level each row sees = level before the call + earlier rows of this call in the same bucket
+            order = np.argsort(h, kind="stable")
+            hs = h[order]
+            first = np.r_[0, np.nonzero(hs[1:] != hs[:-1])[0] + 1]
+            run_len = np.diff(np.r_[first, n])
+            earlier = np.empty(n, np.int64)
+            earlier[order] = np.arange(n) - np.repeat(first, run_len)
+            level = self.counts[h].astype(np.int64) + earlier
+            free = level < self.depth
+            self.table[h[free], level[free]] = val[free]
+            for i in np.nonzero(~free)[0]:                      # full bucket: overwrite a random slot, maybe (:105-110)
+                slot = random.randint(0, int(level[i]))
                 if slot < self.depth:
-                    self.table[hash_, slot] = val
-            self.counts[hash_] = count + 1
-        self.hashesperid[id_] += len(timehashpairs)
-        self.dirty = True
+                    self.table[h[i], slot] = val[i]
+            self.counts[hs[first]] += run_len.astype(np.int32)
+        self.hashesperid[id_] += n
+        self._touch()
 
-    # ---- persistence (hash_table.py:118-198)
-    def save(self, name: str) -> None:
-        with gzip.open(name, "wb") as f:
-            pickle.dump(self, f, pickle.HIGHEST_PROTOCOL)
-        self.dirty = False
+    def name_to_id(self, name: Union[int, str], add_if_missing: bool = False) -> int:
+        """Index of `name` in `names`; a new name takes the first freed slot, else a new one (hash_table.py:254-275)."""
+        if not isinstance(name, str):
+            return name
+        if name in self.names:
+            return self.names.index(name)
+        if not add_if_missing:
+            raise ValueError("name " + name + " not found")
+        if None in self.names:
+            id_ = self.names.index(None)
+            self.names[id_] = name
+            self.hashesperid[id_] = 0
+        else:
+            id_ = len(self.names)
+            self.names.append(name)
+            self.hashesperid = np.append(self.hashesperid, [0]).astype(np.uint32)
+        return id_
 
-    def load(self, name: str) -> None:
-        with gzip.open(name, "rb") as f:
-            temp = pickle.load(f, encoding="latin1")
-        if temp.ht_version < HT_OLD_COMPAT_VERSION:
-            raise ValueError("Version of %s is %s which is not at least %s" % (name, temp.ht_version, HT_OLD_COMPAT_VERSION))
-        self.hashbits = temp.hashbits
-        self.depth = temp.depth
-        self.maxtimebits = temp.maxtimebits if hasattr(temp, "maxtimebits") else _bitsfor(temp.maxtime)
-        if temp.ht_version < HT_COMPAT_VERSION:
-            temp.table += np.array(1 << self.maxtimebits).astype(np.uint32) * (temp.table != 0)
-            temp.ht_version = HT_VERSION
-        self.table = temp.table
-        self.ht_version = temp.ht_version
-        self.counts = temp.counts
-        self.names = temp.names
-        self.hashesperid = np.array(temp.hashesperid).astype(np.uint32)
-        self.dirty = False
+    def remove(self, name: Union[str, int]) -> None:
+        """Drop every entry of one item (hash_table.py:277-297): its buckets are compacted, `counts` forgets the
+        entries those buckets had already dropped, the name slot is freed."""
+        id_ = self.name_to_id(name)
+        mine = (self.table >> self.maxtimebits) == id_ + 1
+        removed = 0
+        for h in np.nonzero(mine.any(axis=1))[0]:
+            stored = min(self.depth, int(self.counts[h]))
+            row = self.table[h, :stored]
+            keep = row[~mine[h, :stored]]
+            self.table[h] = 0
+            self.table[h, : len(keep)] = keep
+            self.counts[h] = len(keep)
+            removed += int(mine[h].sum())
+        self.names[id_] = None
+        self.hashesperid[id_] = 0
+        self._touch()
+        print("Removed", name, "(", removed, "hashes).")
+
+    def retrieve(self, name: Union[str, int]) -> np.ndarray:
+        """(time, hash) rows of one item, buckets ascending, slot order inside a bucket (hash_table.py:299-317)."""
+        id_ = self.name_to_id(name)
+        stored = np.arange(self.depth)[None, :] < np.minimum(self.counts, self.depth)[:, None]
+        h, slot = np.nonzero(((self.table >> self.maxtimebits) == id_ + 1) & stored)
+        times = self.table[h, slot] & ((1 << self.maxtimebits) - 1)
+        return np.stack([times, h], axis=1).astype(np.int32)
+
+    def list(self, print_fn: Optional[Callable[[str], None]] = None) -> None:
+        print_fn = print_fn or print
+        for name, count in zip(self.names, self.hashesperid):
+            if name:
+                print_fn(name + " (" + str(count) + " hashes)")
 
     def reset(self) -> None:
         self.table[:, :] = 0
         self.counts[:] = 0
         self.names = []
         self.hashesperid = np.zeros(0, np.uint32)
-        self.dirty = True
+        self._touch()
 
-    # ---- queries
-    def get_entry(self, hash_: int):
+    # ---- persistence (hash_table.py:118-198) -----------------------------------------------------------------
+    def save(self, name: str, params: Any = None, file_object: Any = None) -> None:
+        self.params = params
+        with (file_object or gzip.open(name, "wb")) as f:
+            pickle.dump(self, f, pickle.HIGHEST_PROTOCOL)
+        self.dirty = False
+        total = int(self.totalhashes())
+        dropped = total - int(np.minimum(self.depth, self.counts).sum())
+        print("Saved fprints for", sum(n is not None for n in self.names), "files (", total, "hashes) to", name,
+              "(%.2f%% dropped)" % (100.0 * dropped / max(1, total)))
+
+    def load(self, name: str) -> None:
+        self.load_pkl(name)
+
+    def load_pkl(self, name: str, file_object: Any = None) -> None:
+        """Read a table the reference (or this class) pickled; tables older than the id + 1 convention are upgraded
+        in memory (hash_table.py:141-198)."""
+        with (file_object or gzip.open(name, "rb")) as f:
+            src = pickle.load(f, encoding="latin1")
+        if src.ht_version < HT_OLD_COMPAT_VERSION:
+            raise ValueError("Version of " + name + " is " + str(src.ht_version) + " which is not at least " + str(HT_OLD_COMPAT_VERSION))
+        self.hashbits, self.depth = src.hashbits, src.depth
+        self.maxtimebits = src.maxtimebits if hasattr(src, "maxtimebits") else _bitsfor(src.maxtime)
+        table = np.asarray(src.table, dtype=np.uint32)
+        if src.ht_version < HT_COMPAT_VERSION:      # ids were stored zero-based: shift every non-empty entry by one id
+            print("Loading database version", src.ht_version, "in compatibility mode.")
+            table = table + np.uint32(1 << self.maxtimebits) * (table != 0)
+        self.table, self.ht_version = table, HT_VERSION
+        self.counts = np.asarray(src.counts, dtype=np.int32)
+        self.names = list(src.names)
+        self.hashesperid = np.array(src.hashesperid).astype(np.uint32)
+        self.params = getattr(src, "params", None)
+        self._touch()
+        self.dirty = False
+        total = int(self.totalhashes())
+        dropped = total - int(np.minimum(self.depth, self.counts).sum())
+        print("Read fprints for", sum(n is not None for n in self.names), "files (", total, "hashes) from", name,
+              "(%.2f%% dropped)" % (100.0 * dropped / max(1, total)))
+
+    # ---- queries ---------------------------------------------------------------------------------------------
+    def get_entry(self, hash_: int) -> np.ndarray:
+        """[id, time] rows of one bucket (hash_table.py:210-218)."""
         vals = self.table[hash_, : min(self.depth, self.counts[hash_])]
-        ids = (vals >> self.maxtimebits) - 1
-        return np.c_[ids, vals & ((1 << self.maxtimebits) - 1)].astype(np.int32)
+        return np.c_[(vals >> self.maxtimebits) - 1, vals & ((1 << self.maxtimebits) - 1)].astype(np.int32)
 
-    def get_hits(self, hashes):
-        """[id, delta_time, hash, time] rows for each (time, hash) query row — GPU gather
-        (hash_table.py:220-246)."""
+    def get_hits(self, hashes) -> np.ndarray:
+        """[id, delta_time, hash, time] rows for each (time, hash) query row - GPU gather (hash_table.py:220-246)."""
         import torch
 
         hashes = np.ascontiguousarray(np.asarray(hashes, dtype=np.int32).reshape(-1, 2))
@@ -127,18 +216,3 @@ class HashTable(object):
 
     def totalhashes(self):
         return np.sum(self.counts)
-
-    def name_to_id(self, name: Union[int, str], add_if_missing: bool = False) -> int:
-        if isinstance(name, str):
-            if name not in self.names:
-                if not add_if_missing:
-                    raise ValueError("name " + name + " not found")
-                try:
-                    id_ = self.names.index(None)
-                    self.names[id_] = name
-                    self.hashesperid[id_] = 0
-                except ValueError:
-                    self.names.append(name)
-                    self.hashesperid = np.append(self.hashesperid, [0]).astype(np.uint32)
-            return self.names.index(name)
-        return name

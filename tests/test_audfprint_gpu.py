@@ -231,7 +231,9 @@ def test_fingerprint_agreement_many_queries(mfpa_ctx):
 
 
 def test_scale_invariance(mfpa_ctx):
-    """The path is scale invariant (sgram /= max) over 24 orders of magnitude of input level."""
+    """The path is scale invariant (sgram /= max) over 24 orders of magnitude of input level: a property test at the
+    ends of float32's range (one query per level; the >= 99.9 % agreement gate is measured by
+    test_fingerprint_agreement_many_queries, here a level may move one or two peaks of the single query)."""
     lib = _lib()
     x = _queries(1, 0)[:, :16000]
     for scale in (1e-12, 1e-4, 1.0, 1e12):

@@ -94,7 +94,84 @@ def test_hash_table_store_and_pickle_format(dropin_modules, tmp_path):
 
     with gzip.open(path, "rb") as f:
         raw = pickle.load(f)
-    assert type(raw).__module__ == "afp.audfprint.hash_table" and not any(k.startswith("_dev") for k in raw.__dict__)
+    assert type(raw).__module__ == "afp.audfprint.hash_table"
+    assert not any(k.startswith("_") for k in ht.__getstate__())     # device state and version counter are not pickled
+
+
+def test_hash_table_remove_retrieve_list_and_version(dropin_modules, capsys):
+    """hash_table.py:277-326: remove() compacts the item's buckets and frees its name slot (re-used by the next new
+    name), retrieve() returns its (time, hash) rows, list() prints the live items; every mutation bumps the version the
+    device copy is keyed on."""
+    ht = dropin_modules["ht"].HashTable()
+    r = np.random.default_rng(9)
+    rows = {n: np.stack([r.integers(0, 500, 40), r.integers(0, 5, 40) * 1000 + 3], axis=1).astype(np.int32) for n in "abc"}
+    versions = [ht._version]
+    for n in "abc":
+        ht.store(n, rows[n])
+        versions.append(ht._version)
+    assert versions == sorted(set(versions))            # strictly increasing
+    for n in "abc":
+        got = ht.retrieve(n)
+        assert sorted(map(tuple, got.tolist())) == sorted(map(tuple, rows[n].tolist()))
+    before = int(ht.totalhashes())
+    ht.remove("b")
+    assert ht._version > versions[-1] and ht.names == ["a", None, "c"] and ht.hashesperid[1] == 0
+    assert int(ht.totalhashes()) == before - 40 and len(ht.retrieve("a")) == 40 and len(ht.retrieve("c")) == 40
+    assert not ((ht.table >> ht.maxtimebits) == 2).any()
+    filled = np.arange(ht.depth)[None, :] < ht.counts[:, None]
+    assert (ht.table[filled] != 0).all() and (ht.table[~filled] == 0).all()     # buckets stay compact
+    ht.store("d", rows["b"])
+    assert ht.names == ["a", "d", "c"] and ht.hashesperid[1] == 40               # freed slot re-used (:262-266)
+    lines = []
+    ht.list(lines.append)
+    assert lines == ["a (40 hashes)", "d (40 hashes)", "c (40 hashes)"]
+    assert "Removed b ( 40 hashes)." in capsys.readouterr().out
+    with pytest.raises(ValueError):
+        ht.name_to_id("nobody")
+
+
+def test_hash_table_files_cross_load_with_the_reference_class(dropin_modules, tmp_path):
+    """f1 (on-disk format): a file the REFERENCE's HashTable.save wrote loads in the drop-in with the same contents,
+    and a file the drop-in wrote loads in the reference's class (hash_table.py:118-198)."""
+    from oracle import ref_loader
+
+    if not ref_loader.available():
+        pytest.skip("reference checkout not mounted")
+    ref_ht_mod = ref_loader.load().hash_table      # imported (and parked) before the drop-ins took the module names
+    r = np.random.default_rng(12)
+    rows = [np.stack([np.sort(r.integers(0, 900, 250)), r.integers(0, 6, 250) * 4099], axis=1).astype(np.int32) for _ in range(5)]
+
+    def fill(ht):
+        for t, rw in enumerate(rows):
+            random.seed(100 + t)
+            ht.store(f"track{t}", rw)
+        return ht
+
+    ref, mine = fill(ref_ht_mod.HashTable()), fill(dropin_modules["ht"].HashTable())
+    assert ref.counts.max() > ref.depth
+    assert np.array_equal(ref.table, mine.table) and np.array_equal(ref.counts, mine.counts) and ref.names == mine.names
+    # the pickles name the class by module path: give each loader the class it expects under afp.audfprint.hash_table
+    p_ref, p_mine = str(tmp_path / "ref.pklz"), str(tmp_path / "mine.pklz")
+    current = sys.modules["afp.audfprint.hash_table"]
+    sys.modules["afp.audfprint.hash_table"] = ref_ht_mod
+    try:
+        ref.save(p_ref)
+        import gc
+
+        gc.collect()     # the reference never closes its gzip stream (hash_table.py:123-125): flushed on collection
+    finally:
+        sys.modules["afp.audfprint.hash_table"] = current
+    mine.save(p_mine)
+    loaded = dropin_modules["ht"].HashTable(p_ref)                   # reference file -> drop-in
+    assert np.array_equal(loaded.table, ref.table) and np.array_equal(loaded.counts, ref.counts)
+    assert loaded.names == ref.names and np.array_equal(loaded.hashesperid, ref.hashesperid)
+    assert (loaded.hashbits, loaded.depth, loaded.maxtimebits) == (ref.hashbits, ref.depth, ref.maxtimebits)
+    sys.modules["afp.audfprint.hash_table"] = ref_ht_mod
+    try:
+        back = ref_ht_mod.HashTable(p_mine)                          # drop-in file -> reference
+    finally:
+        sys.modules["afp.audfprint.hash_table"] = current
+    assert np.array_equal(back.table, mine.table) and np.array_equal(back.counts, mine.counts) and back.names == mine.names
 
 
 def test_matcher_defaults(dropin_modules):

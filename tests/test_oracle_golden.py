@@ -150,3 +150,20 @@ def test_dejavu_specgram_restatement_matches_scipy_definition():
                                               detrend=False, return_onesided=True, scaling="density", mode="psd")
         assert got.shape == want.shape == (257, (T - 256) // 256)
         np.testing.assert_allclose(got, want, rtol=1e-10, atol=1e-18)
+
+
+def test_julius_taps_restatement_against_scipy_firwin():
+    """Independent pin of the restated julius.lowpass_filter taps (oracle/augment_np.lowpass_taps; julius 0.2.7 is a
+    third-party dependency absent from the reference tree and the image): scipy.signal.firwin builds the same
+    Hann-windowed sinc with unit DC gain from its own code (cut-off there is relative to Nyquist: 2 x julius')."""
+    from scipy.signal import firwin
+
+    from oracle import augment_np as A
+
+    for fc_hz in (150.0, 30.0, 3999.0, 3000.0, 4.0, 0.9):
+        cutoff = fc_hz / 8000.0
+        taps = A.lowpass_taps(cutoff)
+        half = int(8.0 / cutoff / 2)
+        assert len(taps) == 2 * half + 1 and abs(float(taps.sum(dtype=np.float64)) - 1.0) < 1e-5
+        ref = firwin(2 * half + 1, 2.0 * cutoff, window="hann")
+        assert np.abs(taps - ref).max() <= 2e-6 * np.abs(ref).max() + 1e-9, fc_hz
