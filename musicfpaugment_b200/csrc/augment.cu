@@ -1078,7 +1078,7 @@ int launch_noise_assemble(mfpa_ctx* ctx, const float* bank, int64_t bank_len, co
   double* row_ss = piece_ss + n_pieces;
   mfpa_noise_piece* dp = (mfpa_noise_piece*)(row_ss + B);
   if (pieces_pinned) {   // the host pipeline's staging buffer: pulled by a kernel, off the copy engine's queue
-    if (int e = launch_pull(dp, pieces, sizeof(mfpa_noise_piece) * (size_t)n_pieces, st)) return e;
+    if (int e = launch_pull(ctx, dp, pieces, sizeof(mfpa_noise_piece) * (size_t)n_pieces, st)) return e;
   } else {
     MFPA_CUDA(cudaMemcpyAsync(dp, pieces, sizeof(mfpa_noise_piece) * (size_t)n_pieces, cudaMemcpyHostToDevice, st));
     MFPA_CUDA(cudaStreamSynchronize(st));   // pieces_host is caller-owned pageable memory
@@ -1238,13 +1238,13 @@ int launch_augment(mfpa_ctx* ctx, const float* x, int B, int T, int64_t x_stride
   float* bufB = (float*)ctx->aug_b.ptr;
   AugQ* dq = (AugQ*)ctx->aug_small.ptr;
   AugS* ds = (AugS*)(dq + B);
-  if (int e = launch_pull(dq, hq, sizeof(AugQ) * (size_t)B, st)) return e;   // hq is pinned (ctx->aug_pinned)
+  if (int e = launch_pull(ctx, dq, hq, sizeof(AugQ) * (size_t)B, st)) return e;   // hq is pinned (ctx->aug_pinned)
   MFPA_CUDA(cudaMemsetAsync(ds, 0, sizeof(AugS) * (size_t)B, st));
   int* dlist = nullptr;
   if (nlong[0] + nlong[1] + nlong[2] + nlong[3]) {
     if (ctx->aug_long.reserve(sizeof(int) * 4 * (size_t)B)) return MFPA_ENOMEM;
     dlist = (int*)ctx->aug_long.ptr;
-    if (int e = launch_pull(dlist, hlist[0], sizeof(int) * 4 * (size_t)B, st)) return e;
+    if (int e = launch_pull(ctx, dlist, hlist[0], sizeof(int) * 4 * (size_t)B, st)) return e;
   }
   MFPA_CUDA(cudaEventRecord((cudaEvent_t)ctx->aug_copy_done, st));
   // partitioned overlap-save for the queries of list l (filters longer than one block takes)
@@ -1336,7 +1336,7 @@ int launch_augment(mfpa_ctx* ctx, const float* x, int B, int T, int64_t x_stride
       if (ctx->aug_pool.reserve(sizeof(unsigned) * (size_t)n_pad + sizeof(int) * (size_t)B)) return MFPA_ENOMEM;
       unsigned* keys = (unsigned*)ctx->aug_pool.ptr;
       int* dsel = (int*)(keys + n_pad);
-      if (int e = launch_pull(dsel, hclip, sizeof(int) * (size_t)n_clip, st)) return e;
+      if (int e = launch_pull(ctx, dsel, hclip, sizeof(int) * (size_t)n_clip, st)) return e;
       pool_fill_kernel<<<dim3((unsigned)((T + 4095) / 4096), (unsigned)n_clip), 256, 0, st>>>(bufA, dsel, T, dq, ds, keys);
       if (n_pad > n) pool_pad_kernel<<<1024, 256, 0, st>>>(keys, n, n_pad);
       const unsigned sort_blocks = (unsigned)((n_pad + 255) / 256 < 4736 ? (n_pad + 255) / 256 : 4736);

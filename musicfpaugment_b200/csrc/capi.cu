@@ -88,8 +88,16 @@ __global__ void __launch_bounds__(256) pull_kernel(unsigned char* __restrict__ d
   for (size_t i = nw * sizeof(W) + (size_t)blockIdx.x * 256 + threadIdx.x; i < bytes; i += (size_t)gridDim.x * 256) dst[i] = src[i];
 }
 
-int launch_pull(void* dst_dev, const void* src_pinned, size_t bytes, cudaStream_t st) {
+int launch_pull(mfpa_ctx* ctx, void* dst_dev, const void* src_pinned, size_t bytes, cudaStream_t st) {
   if (bytes == 0) return MFPA_OK;
+  // Only the chunked host pipelines need it (their big query copies occupy the copy engine); everywhere else the plain
+  // DMA copy is used.  MFPA_NO_PULL forces the DMA copy there too: Nsight Compute hangs on kernels that read mapped
+  // host memory, so profiling runs of the host path set it.
+  static const bool no_pull = getenv("MFPA_NO_PULL") != nullptr;
+  if (no_pull || !ctx->in_host_pipeline) {
+    MFPA_CUDA(cudaMemcpyAsync(dst_dev, src_pinned, bytes, cudaMemcpyHostToDevice, st));
+    return MFPA_OK;
+  }
   const uintptr_t al = (uintptr_t)dst_dev | (uintptr_t)src_pinned;
   const unsigned blocks = (unsigned)((bytes / 16 + 255) / 256 < 64 ? (bytes / 16 + 255) / 256 : 64) + 1;
   if ((al & 15) == 0) pull_kernel<uint4><<<blocks, 256, 0, st>>>((unsigned char*)dst_dev, (const unsigned char*)src_pinned, bytes);
@@ -691,6 +699,11 @@ int mfpa_augment_fingerprint_host(mfpa_ctx* ctx, const mfpa_chain_inputs* in, in
     if (dbg) cudaEventRecord(dev[4 * ci + 3], ctx->s_run);
     return MFPA_OK;
   };
+  struct PipelineFlag {   // small uploads inside the pipeline bypass the copy engine (launch_pull)
+    mfpa_ctx* c;
+    explicit PipelineFlag(mfpa_ctx* ctx) : c(ctx) { c->in_host_pipeline = true; }
+    ~PipelineFlag() { c->in_host_pipeline = false; }
+  } pipeline_flag(ctx);
   if (int e = issue(0)) return e;
   for (int ci = 0; ci < n_chunks; ++ci) {
     const int b = ci & 1, q0 = ci * chunk, nq = (B - q0 < chunk) ? (B - q0) : chunk;

@@ -71,6 +71,7 @@ struct mfpa_ctx {
   cudaEvent_t stage_ev[16][MFPA_N_STAGES + 1] = {};
   int stage_calls = 0, stage_slot = 0;
   unsigned stage_marked[16] = {};   // bit k: stage k (or the end mark MFPA_N_STAGES) was stamped in this slot
+  bool in_host_pipeline = false;    // inside mfpa_augment_fingerprint_host: small uploads go through launch_pull
   bool stage_chained = false;       // the next mfpa_fingerprint continues the record an augment call opened
   double* spread_dev = nullptr;     // [513] Gaussian table
   float2* tw_dev = nullptr;         // FFT twiddles (stft.cu layout)
@@ -163,7 +164,7 @@ int stft_init_tables(mfpa_ctx* ctx);
 // Small host->device uploads from PINNED host memory done by a kernel (the SMs read the mapped host buffer) instead of
 // cudaMemcpyAsync: a DMA copy queues on the one host->device copy engine BEHIND the next chunk's 640 MB query copy of
 // the host pipelines, which delayed every chunk's kernels by a whole chunk copy (measured: 65 -> 51 ms per 10 k queries).
-int launch_pull(void* dst_dev, const void* src_pinned, size_t bytes, cudaStream_t st);
+int launch_pull(mfpa_ctx* ctx, void* dst_dev, const void* src_pinned, size_t bytes, cudaStream_t st);
 int stage_begin(mfpa_ctx* ctx);
 void stage_mark(mfpa_ctx* ctx, int stage, cudaStream_t st);
 

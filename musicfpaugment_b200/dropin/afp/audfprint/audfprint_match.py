@@ -52,6 +52,9 @@ class Matcher(object):
             hb[i, : len(h)], nh[i] = h, len(h)
         res, nrows = ctx.match(torch.from_numpy(hb).cuda(), torch.from_numpy(nh).cuda(), self._params(), max_rows)
         res, nrows = res.cpu().numpy(), nrows.cpu().numpy()
+        if (nrows == -5).any():
+            raise lib.MfpaError("match: a query hash time lies outside [0, 16384) frames - the matching kernels pack "
+                                "t_ref - t_q next to the table's 14-bit reference times (INTEGRATION.md section 5)")
         if (nrows < 0).any():
             raise lib.MfpaError("match: a per-query capacity was exceeded (too many candidate hits / result rows)")
         return [res[i, : nrows[i]].copy() for i in range(len(hashes_list))]
