@@ -89,7 +89,8 @@ int mfpa_set_spread_table(mfpa_ctx* ctx, const double* table513_host);
 #define MFPA_OPT_MATCH_PACKED 2
 /* MFPA_OPT_MATCH_UNFUSED (default 0): mfpa_match normally runs counts + select + collect as one kernel
  * whose histogram never leaves shared memory (indexes of up to 110000 tracks); 1 forces the four-step
- * path (the one the sharded matcher drives with collectives in between) for comparison. */
+ * path (the one the sharded matcher drives with collectives in between) for comparison; 2 forces it with int32
+ * counters in global memory (exact mfpa_match_counts for queries whose packed 16-bit counters overflowed, nrows -6). */
 #define MFPA_OPT_MATCH_UNFUSED 3
 /* MFPA_OPT_PART_BUDGET_MB (default 2048): device scratch, in MiB, that the partitioned long-filter path of
  * mfpa_augment may use for block spectra; queries with long filters are processed in groups that fit. */
@@ -392,7 +393,10 @@ int mfpa_match_owner(mfpa_ctx* ctx, const uint32_t* words_dev, const int32_t* nw
                      const mfpa_match_params* p, int32_t* results_dev, int32_t* nrows_dev, int max_rows, void* stream);
 /* Single-shard convenience: steps 1-4 with internal scratch, queries processed in sub-batches.  nrows_dev[q] < 0 flags a
  * query that could not be matched: -1 / -2 a capacity was exceeded, -5 a query time outside [0, 16384) (the hit
- * keys hold t_ref - t_q next to the table's 14-bit reference times; the reference has no such limit). */
+ * keys hold t_ref - t_q next to the table's 14-bit reference times; the reference has no such limit), -6 one track
+ * collected >= 65536 hits and the packed 16-bit counters of the one-kernel matcher overflowed (detected by a
+ * checksum of the histogram, never silent; such a query is also past the 8192 candidate hits of step 4, and
+ * MFPA_OPT_MATCH_UNFUSED = 2 gives its exact int32 raw counts through mfpa_match_counts). */
 int mfpa_match(mfpa_ctx* ctx, const int32_t* hashes_dev, const int32_t* nh_dev, int B, int cap,
                const mfpa_match_params* p, int32_t* results_dev, int32_t* nrows_dev, int max_rows, void* stream);
 

@@ -250,7 +250,7 @@ int mfpa_set_option(mfpa_ctx* ctx, int option, int value) {
   switch (option) {
     case MFPA_OPT_PEAKS_F64: ctx->opt_peaks_f64 = value != 0; return MFPA_OK;
     case MFPA_OPT_MATCH_PACKED: ctx->opt_match_packed = value != 0; return MFPA_OK;
-    case MFPA_OPT_MATCH_UNFUSED: ctx->opt_match_unfused = value != 0; return MFPA_OK;
+    case MFPA_OPT_MATCH_UNFUSED: ctx->opt_match_unfused = value == 2 ? 2 : (value != 0); return MFPA_OK;
     case MFPA_OPT_PART_BUDGET_MB:
       MFPA_REQUIRE(value >= 1, "set_option: MFPA_OPT_PART_BUDGET_MB %d < 1", value);
       ctx->opt_part_budget_mb = value;

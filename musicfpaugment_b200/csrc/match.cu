@@ -210,7 +210,7 @@ constexpr int kHitMaxTracks = 1 << 17;  // ... which leaves 17 bits for the trac
 template <int MODE>
 __device__ __forceinline__ void fused_sweep(const IndexView& ix, const int2* __restrict__ rows, int n, RowCache* rc,
                                             unsigned* hist, uint32_t* __restrict__ out, int list_cap, int* s_n, int tid,
-                                            int* s_bad = nullptr) {
+                                            int* s_bad = nullptr, unsigned* s_hits = nullptr) {
   constexpr bool COLLECT = MODE == kSweepCollect;
   const int lane = tid & 31, warp = tid >> 5;
   const uint32_t tmask = (1u << ix.maxtimebits) - 1u;
@@ -226,6 +226,7 @@ __device__ __forceinline__ void fused_sweep(const IndexView& ix, const int2* __r
       rc->cnt[i] = in ? min(ix.depth, ix.counts[hb]) : 0;
       rc->t[i] = row.x;
       if (s_bad && (row.x < 0 || row.x >= kDtOff)) *s_bad = 1;
+      if (s_hits && rc->cnt[i]) atomicAdd(s_hits, (unsigned)rc->cnt[i]);
     }
     __syncthreads();
     for (int s0 = 0; s0 < ix.depth; s0 += 128) {   // one trip for depth <= 128 (the reference's is 100)
@@ -441,6 +442,23 @@ __device__ __forceinline__ int fused_select(const IndexView& ix, const unsigned*
 }
 
 constexpr int kBadQueryTime = -5;   // nrows marker: a query time outside [0, 2^14)
+constexpr int kWideCounts = -6;     // nrows marker: a track collected >= 65536 hits, the packed 16-bit counters overflowed
+
+// The packed histogram adds 1 << 16 or 1 to a 32-bit word per hit; a track with >= 65536 hits carries into its
+// neighbour.  Impossible below 65536 hits in total; above, the halves must still add up to the hit count (a carry
+// changes the sum by 65535, a wrap of the upper half by 65536).  All threads call it; returns true when consistent.
+__device__ __forceinline__ bool hist_consistent(const unsigned* hist, int words, unsigned total_hits, unsigned* s_sum, int tid) {
+  if (total_hits < 65536u) return true;   // block-uniform
+  if (tid == 0) *s_sum = 0u;
+  __syncthreads();
+  unsigned acc = 0;
+  for (int w = tid; w < words; w += kFusedThreads) { const unsigned h2 = hist[w]; acc += (h2 & 0xffffu) + (h2 >> 16); }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(kFull, acc, o);
+  if ((tid & 31) == 0) atomicAdd(s_sum, acc);
+  __syncthreads();
+  return *s_sum == total_hits;
+}
 
 __global__ void __launch_bounds__(kFusedThreads, 1)
 match_fused_kernel(const IndexView ix, const int32_t* __restrict__ hashes, const int32_t* __restrict__ nh, int cap,
@@ -452,14 +470,19 @@ match_fused_kernel(const IndexView ix, const int32_t* __restrict__ hashes, const
   RowCache* rc = reinterpret_cast<RowCache*>(fused_smem + ((words + 3) & ~3));
   __shared__ SelectSmem sel;
   __shared__ int s_n, s_bad;
+  __shared__ unsigned s_hits, s_sum;
   const int q = blockIdx.x, tid = threadIdx.x;
   const int2* rows = reinterpret_cast<const int2*>(hashes) + (int64_t)q * cap;
   const int n = min(nh[q], cap);
   for (int i = tid; i < words; i += kFusedThreads) hist[i] = 0;
-  if (tid == 0) { s_n = 0; s_bad = 0; }
-  fused_sweep<kSweepCount>(ix, rows, n, rc, hist, nullptr, 0, nullptr, tid, &s_bad);
+  if (tid == 0) { s_n = 0; s_bad = 0; s_hits = 0u; }
+  fused_sweep<kSweepCount>(ix, rows, n, rc, hist, nullptr, 0, nullptr, tid, &s_bad, &s_hits);
   if (s_bad) {   // block-uniform after the sweep's closing barrier
     if (tid == 0) { ncand[q] = 0; nlist[q] = kBadQueryTime; }
+    return;
+  }
+  if (!hist_consistent(hist, words, s_hits, &s_sum, tid)) {
+    if (tid == 0) { ncand[q] = 0; nlist[q] = kWideCounts; }
     return;
   }
   // the row cache is idle during the select: it holds the contender list
@@ -508,13 +531,16 @@ match_owner_kernel(const IndexView ix, const uint32_t* __restrict__ words_in, co
   int* contenders = reinterpret_cast<int*>(fused_smem + ((words + 3) & ~3));   // kContCap ints
   __shared__ SelectSmem sel;
   __shared__ int s_n, s_err;
+  __shared__ unsigned s_sum;
   const int q = blockIdx.x, tid = threadIdx.x;
   for (int i = tid; i < words; i += kFusedThreads) hist[i] = 0;
   if (tid == 0) { s_n = 0; s_err = 0; }
   __syncthreads();
+  unsigned total_hits = 0;
   for (int l = 0; l < n_shards; ++l) {
     const int n = nwords[(int64_t)l * B + q];
     if (n < 0 || n > words_cap) { if (tid == 0) s_err = n < 0 ? n : -1; continue; }
+    total_hits += (unsigned)n;
     const uint32_t* w = words_in + ((int64_t)l * B + q) * words_cap;
     for (int i = tid; i < n; i += kFusedThreads) {
       const unsigned id = __ldg(w + i) >> kHitDtBits;
@@ -524,6 +550,10 @@ match_owner_kernel(const IndexView ix, const uint32_t* __restrict__ words_in, co
   __syncthreads();
   if (s_err) {   // a shard's list overflowed (-1) or a query time was out of range: the host wrapper raises
     if (tid == 0) { ncand[q] = 0; nlist[q] = s_err; }
+    return;
+  }
+  if (!hist_consistent(hist, words, total_hits, &s_sum, tid)) {
+    if (tid == 0) { ncand[q] = 0; nlist[q] = kWideCounts; }
     return;
   }
   const int depth = fused_select(ix, hist, words, threshcount, search_depth, contenders, &sel,
@@ -791,7 +821,7 @@ IndexView view(const mfpa_ctx* ctx) {
 int launch_match_counts(mfpa_ctx* ctx, const int32_t* hashes, const int32_t* nh, int B, int cap, int32_t* counts,
                         cudaStream_t st) {
   const IndexView ix = view(ctx);
-  if (ix.n_tracks <= kMaxTracksSmem) {
+  if (ix.n_tracks <= kMaxTracksSmem && ctx->opt_match_unfused != 2) {   // 2 = wide: int32 counters in global memory
     const size_t words = (size_t)((ix.n_tracks + 1) / 2);
     const size_t smem = sizeof(unsigned) * ((words + 3) & ~(size_t)3) + sizeof(RowCache);
     MFPA_CUDA(cudaFuncSetAttribute(match_counts_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

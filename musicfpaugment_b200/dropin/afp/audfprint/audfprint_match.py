@@ -50,8 +50,15 @@ class Matcher(object):
         for i, h in enumerate(hashes_list):
             h = np.asarray(h, dtype=np.int32).reshape(-1, 2)
             hb[i, : len(h)], nh[i] = h, len(h)
-        res, nrows = ctx.match(torch.from_numpy(hb).cuda(), torch.from_numpy(nh).cuda(), self._params(), max_rows)
+        hb_d, nh_d = torch.from_numpy(hb).cuda(), torch.from_numpy(nh).cuda()
+        res, nrows = ctx.match(hb_d, nh_d, self._params(), max_rows)
         res, nrows = res.cpu().numpy(), nrows.cpu().numpy()
+        if (nrows == -6).any():
+            # a track collected >= 65536 hits from one query: the packed 16-bit counters of the one-kernel matcher
+            # overflowed. That is detected (never silent); such a query is also far past the 8192 candidate hits the
+            # alignment step sorts, so it cannot be answered - MFPA_OPT_MATCH_UNFUSED = 2 still gives its exact raw
+            # counts through mfpa_match_counts.
+            raise lib.MfpaError("match: a track collected >= 65536 hits from one query (INTEGRATION.md section 5)")
         if (nrows == -5).any():
             raise lib.MfpaError("match: a query hash time lies outside [0, 16384) frames - the matching kernels pack "
                                 "t_ref - t_q next to the table's 14-bit reference times (INTEGRATION.md section 5)")

@@ -270,3 +270,32 @@ def test_match_without_index_raises():
     with pytest.raises(lib.MfpaError):
         ctx.match(torch.zeros(1, 4, 2, dtype=torch.int32, device="cuda"), torch.zeros(1, dtype=torch.int32, device="cuda"))
     ctx.close()
+
+
+def test_packed_counter_overflow_is_detected_not_silent(mfpa_ctx):
+    """One track collecting >= 65536 hits from one query overflows the packed 16-bit counters of the one-kernel matcher:
+    the histogram checksum flags the query (-6); the int32 counters (option value 2) give the exact raw counts."""
+    lib = _lib()
+    depth, n_tracks = 100, 8
+    table = np.zeros((1 << 20, depth), np.uint32)
+    counts = np.zeros(1 << 20, np.int32)
+    n_hashes = 700                                     # 700 buckets x 100 entries of track 3 = 70 000 hits
+    hashes = np.arange(n_hashes, dtype=np.int64) * 1499 + 17
+    table[hashes] = ((3 + 1) << 14) + 50
+    counts[hashes] = depth
+    table[hashes[:40], 0] = ((5 + 1) << 14) + 70       # a second track with a few hits
+    hpid = np.full(n_tracks, 1000, np.uint32)
+    mfpa_ctx.index_load(table, counts, hpid)
+    q = np.stack([np.full(n_hashes, 20, np.int32), hashes.astype(np.int32)], axis=1)[None]
+    h, n = torch.from_numpy(q).cuda(), torch.tensor([n_hashes], dtype=torch.int32).cuda()
+    _, nrows = mfpa_ctx.match(h, n)
+    assert int(nrows[0]) == -6
+    mfpa_ctx.set_option(lib.OPT_MATCH_UNFUSED, 2)    # four-step path, int32 counters in global memory
+    try:
+        raw = mfpa_ctx.match_counts(h, n)
+        _, nrows = mfpa_ctx.match(h, n)
+    finally:
+        mfpa_ctx.set_option(lib.OPT_MATCH_UNFUSED, 0)
+    raw = raw[0].cpu().numpy()
+    assert raw[3] == 70000 - 40 and raw[5] == 40 and raw.sum() == 70000     # exact, no wrap-around
+    assert int(nrows[0]) == -1                         # 70 000 candidate hits: past the alignment capacity, flagged
