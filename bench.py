@@ -560,8 +560,10 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     ctx.close()
 
 
-MATCH_COLLECTIVE = ("one NCCL all-to-all of the shards' packed (track, time skew) hit words to the query owners, then an all-gather of "
-                    "the result rows")
+MATCH_COLLECTIVE = ("none on the data path: the sweep kernel stores each query's packed (track, time skew) hit words straight into "
+                    "its owner rank's memory over NVLink (CUDA IPC peer buffers, mfpa_match_emit_peer), a one-block barrier kernel "
+                    "in peer memory separates it from the owner step; NCCL only all-gathers the result rows "
+                    "(MFPA_MATCH_EXCHANGE=nccl: one all-to-all per sub-batch instead)")
 
 
 # ------------------------------------------------------------------ other BASELINE configs (device-timed)
@@ -613,8 +615,9 @@ def bench_fingerprint_only(ctx, lib, dev, x, B, S, p, steps, warmup, barrier, wo
 
 def bench_match(ctx, lib, dev, rank, world, B, n_tracks, steps, warmup, barrier):
     """BASELINE configs[4]: match B planted 400-hash queries against a synthetic n_tracks-track index
-    sharded by hash range over the ranks; the shards' packed (track, time skew) hit words go to the query owners with
-    one NCCL all-to-all per sub-batch (sharded.match_sharded); at N > 1 the replicated-index mode is timed as well."""
+    sharded by hash range over the ranks; the shards' packed (track, time skew) hit words are stored by the sweep kernel
+    straight into the query owners' memory over NVLink (sharded.match_sharded, exchange "peer"); at N > 1 the
+    replicated-index mode is timed as well."""
     import torch
 
     from musicfpaugment_b200 import sharded, synth
@@ -631,7 +634,9 @@ def bench_match(ctx, lib, dev, rank, world, B, n_tracks, steps, warmup, barrier)
     def step():
         if world == 1:
             return ctx.match(q, nq, mp, max_rows=4)
-        return sharded.match_sharded(ctx, q, nq, mp, max_rows=4, sub_batch=int(os.environ.get("MFPA_MATCH_SUB", "2048")))
+        sub = os.environ.get("MFPA_MATCH_SUB")
+        return sharded.match_sharded(ctx, q, nq, mp, max_rows=4, sub_batch=int(sub) if sub else None,
+                                     exchange=os.environ.get("MFPA_MATCH_EXCHANGE") or None)
 
     for _ in range(warmup):
         res, nrows = step()

@@ -391,6 +391,31 @@ int mfpa_match_emit(mfpa_ctx* ctx, const int32_t* hashes_dev, const int32_t* nh_
                     int words_cap, int32_t* nwords_dev, void* stream);
 int mfpa_match_owner(mfpa_ctx* ctx, const uint32_t* words_dev, const int32_t* nwords_dev, int n_shards, int B, int words_cap,
                      const mfpa_match_params* p, int32_t* results_dev, int32_t* nrows_dev, int max_rows, void* stream);
+/* ---- the exchange fused into the sweep: peer memory over NVLink (one process per GPU, same node)
+ * Replaces the NCCL all-to-all between mfpa_match_emit and mfpa_match_owner: every rank allocates its receive
+ * buffers with mfpa_peer_alloc, passes the 64-byte handle to the other ranks (any side channel - the Python host
+ * uses torch.distributed's object all-gather) and maps theirs with mfpa_peer_open.  mfpa_match_emit_peer then
+ * writes the words of query q of a sub-batch of B queries (B a multiple of world) directly into the memory of its
+ * owner rank q / (B / world), at words[owner] + ((rank * own + q % own) * words_cap) and nwords[owner][rank * own +
+ * q % own] - i.e. the owner's buffer ends up as the [n_shards = world][own][words_cap] array mfpa_match_owner reads.
+ * mfpa_peer_barrier is the cross-rank barrier between the two (a one-block kernel on `stream`: writes `epoch` into
+ * slot `rank` of every rank's flags row - MFPA_MAX_PEERS words, zero-initialised by mfpa_peer_alloc - and waits for
+ * every slot of its own row; epochs must increase by one per barrier on every rank; a rank that never arrives makes
+ * the waiting kernels trap after 20 s).  Pointers of the set are device pointers valid in THIS process. */
+#define MFPA_MAX_PEERS 16
+typedef struct {
+  uint32_t* words[MFPA_MAX_PEERS];
+  int32_t* nwords[MFPA_MAX_PEERS];
+  uint32_t* flags[MFPA_MAX_PEERS];
+  int32_t world, rank;
+} mfpa_peer_set;
+int mfpa_peer_alloc(mfpa_ctx* ctx, uint64_t bytes, void** dev_ptr, void* handle64);   /* cudaMalloc + zero + IPC handle */
+int mfpa_peer_open(mfpa_ctx* ctx, const void* handle64, void** dev_ptr);              /* map another rank's buffer */
+int mfpa_peer_close(mfpa_ctx* ctx, void* dev_ptr);
+int mfpa_peer_free(mfpa_ctx* ctx, void* dev_ptr);
+int mfpa_match_emit_peer(mfpa_ctx* ctx, const int32_t* hashes_dev, const int32_t* nh_dev, int B, int cap,
+                         const mfpa_peer_set* peers, int words_cap, void* stream);
+int mfpa_peer_barrier(mfpa_ctx* ctx, const mfpa_peer_set* peers, uint32_t epoch, void* stream);
 /* Single-shard convenience: steps 1-4 with internal scratch, queries processed in sub-batches.  nrows_dev[q] < 0 flags a
  * query that could not be matched: -1 / -2 a capacity was exceeded, -5 a query time outside [0, 16384) (the hit
  * keys hold t_ref - t_q next to the table's 14-bit reference times; the reference has no such limit), -6 one track

@@ -835,6 +835,71 @@ int mfpa_match_emit(mfpa_ctx* ctx, const int32_t* hashes_dev, const int32_t* nh_
   return launch_match_emit(ctx, hashes_dev, nh_dev, B, cap, words_dev, words_cap, nwords_dev, (cudaStream_t)stream);
 }
 
+int mfpa_peer_alloc(mfpa_ctx* ctx, uint64_t bytes, void** dev_ptr, void* handle64) {
+  MFPA_REQUIRE(ctx && dev_ptr && handle64 && bytes >= 1, "peer_alloc: bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  DeviceGuard guard(ctx->device);
+  void* p = nullptr;
+  MFPA_CUDA(cudaMalloc(&p, (size_t)bytes));
+  cudaIpcMemHandle_t h;
+  if (cudaError_t e = cudaMemset(p, 0, (size_t)bytes); e != cudaSuccess || (e = cudaIpcGetMemHandle(&h, p)) != cudaSuccess) {
+    cudaFree(p);
+    MFPA_REQUIRE(false, "peer_alloc: %s", cudaGetErrorString(e));
+  }
+  MFPA_CUDA(cudaDeviceSynchronize());
+  memcpy(handle64, &h, sizeof(h));
+  *dev_ptr = p;
+  return MFPA_OK;
+}
+
+int mfpa_peer_open(mfpa_ctx* ctx, const void* handle64, void** dev_ptr) {
+  MFPA_REQUIRE(ctx && dev_ptr && handle64, "peer_open: bad argument");
+  DeviceGuard guard(ctx->device);
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof(h));
+  MFPA_CUDA(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return MFPA_OK;
+}
+
+int mfpa_peer_close(mfpa_ctx* ctx, void* dev_ptr) {
+  MFPA_REQUIRE(ctx && dev_ptr, "peer_close: bad argument");
+  DeviceGuard guard(ctx->device);
+  MFPA_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+  return MFPA_OK;
+}
+
+int mfpa_peer_free(mfpa_ctx* ctx, void* dev_ptr) {
+  MFPA_REQUIRE(ctx && dev_ptr, "peer_free: bad argument");
+  DeviceGuard guard(ctx->device);
+  MFPA_CUDA(cudaFree(dev_ptr));
+  return MFPA_OK;
+}
+
+static int check_peers(mfpa_ctx* ctx, const mfpa_peer_set* peers, bool lists) {
+  MFPA_REQUIRE(ctx && peers && peers->world >= 1 && peers->world <= MFPA_MAX_PEERS && peers->rank >= 0 && peers->rank < peers->world,
+               "peer set: world must be in [1, %d] and rank in [0, world)", MFPA_MAX_PEERS);
+  for (int r = 0; r < peers->world; ++r)
+    MFPA_REQUIRE(peers->flags[r] && (!lists || (peers->words[r] && peers->nwords[r])), "peer set: rank %d has a NULL buffer", r);
+  return MFPA_OK;
+}
+
+int mfpa_match_emit_peer(mfpa_ctx* ctx, const int32_t* hashes_dev, const int32_t* nh_dev, int B, int cap,
+                         const mfpa_peer_set* peers, int words_cap, void* stream) {
+  if (int e = check_match(ctx, nullptr)) return e;
+  if (int e = check_peers(ctx, peers, true)) return e;
+  MFPA_REQUIRE(hashes_dev && nh_dev && B >= 1 && cap >= 1 && words_cap >= 1 && B % peers->world == 0,
+               "match_emit_peer: bad argument (the sub-batch must split evenly over the %d ranks)", peers->world);
+  MFPA_REQUIRE(match_sparse_ok(ctx), "match_emit_peer: the (track, time skew) hit words hold indexes of up to %d tracks", 110000);
+  DeviceGuard guard(ctx->device);
+  return launch_match_emit_peer(ctx, hashes_dev, nh_dev, B, cap, peers, words_cap, (cudaStream_t)stream);
+}
+
+int mfpa_peer_barrier(mfpa_ctx* ctx, const mfpa_peer_set* peers, uint32_t epoch, void* stream) {
+  if (int e = check_peers(ctx, peers, false)) return e;
+  DeviceGuard guard(ctx->device);
+  return launch_peer_barrier(peers, epoch, (cudaStream_t)stream);
+}
+
 int mfpa_match_owner(mfpa_ctx* ctx, const uint32_t* words_dev, const int32_t* nwords_dev, int n_shards, int B, int words_cap,
                      const mfpa_match_params* p, int32_t* results_dev, int32_t* nrows_dev, int max_rows, void* stream) {
   if (int e = check_match(ctx, p)) return e;

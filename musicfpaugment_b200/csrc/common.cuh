@@ -139,6 +139,9 @@ int launch_match_fused(mfpa_ctx* ctx, const int32_t* hashes, const int32_t* nh, 
                        int search_depth, int32_t* cand, int32_t* ncand, uint32_t* list, int list_cap, int32_t* nlist,
                        cudaStream_t st);
 bool match_sparse_ok(const mfpa_ctx* ctx);
+int launch_match_emit_peer(mfpa_ctx* ctx, const int32_t* hashes, const int32_t* nh, int B, int cap, const mfpa_peer_set* peers,
+                           int words_cap, cudaStream_t st);
+int launch_peer_barrier(const mfpa_peer_set* peers, uint32_t epoch, cudaStream_t st);
 int launch_match_emit(mfpa_ctx* ctx, const int32_t* hashes, const int32_t* nh, int B, int cap, uint32_t* words, int words_cap,
                       int32_t* nwords, cudaStream_t st);
 int launch_match_owner(mfpa_ctx* ctx, const uint32_t* words, const int32_t* nwords, int n_shards, int B, int words_cap,

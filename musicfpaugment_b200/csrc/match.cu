@@ -248,12 +248,24 @@ __device__ __forceinline__ void fused_sweep(const IndexView& ix, const int2* __r
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const unsigned id = (v[a][i] >> ix.maxtimebits) - 1u;   // empty slot -> 0xffffffff
-            if (id >= (unsigned)ix.n_tracks) continue;
             if (MODE == kSweepEmit) {
-              const int dt = (int)(v[a][i] & tmask) - rc->t[r + a];
-              const int pos = atomicAdd(s_n, 1);
-              if (pos < list_cap) out[pos] = (id << kHitDtBits) | (uint32_t)(dt + kDtOff);
-            } else if (!COLLECT) {
+              // one shared-memory atomic per warp and 32 slots; the warp's words land next to each other, so the
+              // stores (to the local list or straight into the owner rank's memory over NVLink) are coalesced
+              const bool ok = id < (unsigned)ix.n_tracks;
+              const unsigned m = __ballot_sync(kFull, ok);
+              if (m == 0u) continue;   // warp-uniform
+              int base = 0;
+              if (lane == 0) base = atomicAdd(s_n, __popc(m));
+              base = __shfl_sync(kFull, base, 0);
+              const int pos = base + __popc(m & ((1u << lane) - 1u));
+              if (ok && pos < list_cap) {
+                const int dt = (int)(v[a][i] & tmask) - rc->t[r + a];
+                out[pos] = (id << kHitDtBits) | (uint32_t)(dt + kDtOff);
+              }
+              continue;
+            }
+            if (id >= (unsigned)ix.n_tracks) continue;
+            if (!COLLECT) {
               atomicAdd(&hist[id >> 1], 1u << ((id & 1u) << 4));
             } else {
               const unsigned k = mark[id];
@@ -520,7 +532,75 @@ match_emit_kernel(const IndexView ix, const int32_t* __restrict__ hashes, const 
   if (tid == 0) nwords[q] = s_bad ? kBadQueryTime : s_n;
 }
 
-// words: [n_shards][B][words_cap], nwords: [n_shards][B] (what the all-to-all leaves on the owner)
+// The same sweep with the exchange fused in: query q of the sub-batch belongs to rank q / own, and its words go
+// straight into that rank's receive buffer (peer memory mapped through CUDA IPC, NVLink stores) at the slot
+// [this rank][q % own] - the layout match_owner_kernel reads.  No staging list in local HBM, no collective call.
+struct PeerDst { uint32_t* words[MFPA_MAX_PEERS]; int32_t* nwords[MFPA_MAX_PEERS]; int own, rank; };
+__global__ void __launch_bounds__(kFusedThreads, 2)
+match_emit_peer_kernel(const IndexView ix, const int32_t* __restrict__ hashes, const int32_t* __restrict__ nh, int cap,
+                       const PeerDst d, int words_cap) {
+  __shared__ RowCache rc;
+  __shared__ int s_n, s_bad;
+  const int q = blockIdx.x, tid = threadIdx.x;
+  const int owner = q / d.own;
+  const int64_t slot = (int64_t)d.rank * d.own + (q - owner * d.own);
+  if (tid == 0) { s_n = 0; s_bad = 0; }
+  const int2* rows = reinterpret_cast<const int2*>(hashes) + (int64_t)q * cap;
+  fused_sweep<kSweepEmit>(ix, rows, min(nh[q], cap), &rc, nullptr, d.words[owner] + slot * words_cap, words_cap, &s_n, tid, &s_bad);
+  if (tid == 0) d.nwords[owner][slot] = s_bad ? kBadQueryTime : s_n;
+  __threadfence_system();
+}
+
+// Barrier between the ranks' streams, in peer memory: rank r writes the epoch into slot r of every rank's flag
+// row, then waits until every slot of its own row has reached it.  Everything a rank stored to peer memory before
+// the barrier (kernels earlier in its stream) is visible to the peers' kernels after it.  A peer that never
+// arrives traps after 20 s instead of hanging the GPU.
+struct PeerFlags { uint32_t* flags[MFPA_MAX_PEERS]; int world, rank; };
+__global__ void peer_barrier_kernel(const PeerFlags f, uint32_t epoch) {
+  const int r = threadIdx.x;
+  if (r >= f.world) return;
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f.flags[r] + f.rank), "r"(epoch) : "memory");
+  const uint32_t* mine = f.flags[f.rank] + r;
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+    if ((int32_t)(v - epoch) >= 0) break;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > 20000000000ull) __trap();
+    __nanosleep(200);
+  }
+  __threadfence_system();
+}
+
+// Visit the n words of one shard's list with the whole block.  The visits are shared-memory atomics / look-ups that
+// wait on the word, so the loads are batched ahead of them: four 16-byte loads (16 words) per thread in flight
+// when the list is 16-byte aligned (it is for the library's own buffers), one word at a time otherwise.
+template <typename F>
+__device__ __forceinline__ void for_each_word(const uint32_t* __restrict__ w, int n, bool vec, int tid, F f) {
+  if (!vec) {
+    for (int i = tid; i < n; i += kFusedThreads) f(__ldg(w + i));
+    return;
+  }
+  const uint4* w4 = reinterpret_cast<const uint4*>(w);
+  const int n4 = n >> 2;
+  int i = tid;
+  for (; i + 3 * kFusedThreads < n4; i += 4 * kFusedThreads) {
+    const uint4 a = __ldg(w4 + i), b = __ldg(w4 + i + kFusedThreads), c = __ldg(w4 + i + 2 * kFusedThreads),
+                d = __ldg(w4 + i + 3 * kFusedThreads);
+    f(a.x); f(a.y); f(a.z); f(a.w); f(b.x); f(b.y); f(b.z); f(b.w);
+    f(c.x); f(c.y); f(c.z); f(c.w); f(d.x); f(d.y); f(d.z); f(d.w);
+  }
+  for (; i < n4; i += kFusedThreads) {
+    const uint4 a = __ldg(w4 + i);
+    f(a.x); f(a.y); f(a.z); f(a.w);
+  }
+  for (int j = (n4 << 2) + tid; j < n; j += kFusedThreads) f(__ldg(w + j));
+}
+
+// words: [n_shards][B][words_cap], nwords: [n_shards][B] (what the exchange leaves on the owner)
 __global__ void __launch_bounds__(kFusedThreads, 1)
 match_owner_kernel(const IndexView ix, const uint32_t* __restrict__ words_in, const int32_t* __restrict__ nwords, int n_shards,
                    int B, int words_cap, int threshcount, int search_depth, int32_t* __restrict__ cand,
@@ -533,6 +613,7 @@ match_owner_kernel(const IndexView ix, const uint32_t* __restrict__ words_in, co
   __shared__ int s_n, s_err;
   __shared__ unsigned s_sum;
   const int q = blockIdx.x, tid = threadIdx.x;
+  const bool vec = (reinterpret_cast<uintptr_t>(words_in) & 15) == 0 && (words_cap & 3) == 0;
   for (int i = tid; i < words; i += kFusedThreads) hist[i] = 0;
   if (tid == 0) { s_n = 0; s_err = 0; }
   __syncthreads();
@@ -541,11 +622,10 @@ match_owner_kernel(const IndexView ix, const uint32_t* __restrict__ words_in, co
     const int n = nwords[(int64_t)l * B + q];
     if (n < 0 || n > words_cap) { if (tid == 0) s_err = n < 0 ? n : -1; continue; }
     total_hits += (unsigned)n;
-    const uint32_t* w = words_in + ((int64_t)l * B + q) * words_cap;
-    for (int i = tid; i < n; i += kFusedThreads) {
-      const unsigned id = __ldg(w + i) >> kHitDtBits;
+    for_each_word(words_in + ((int64_t)l * B + q) * words_cap, n, vec, tid, [&](uint32_t v) {
+      const unsigned id = v >> kHitDtBits;
       atomicAdd(&hist[id >> 1], 1u << ((id & 1u) << 4));
-    }
+    });
   }
   __syncthreads();
   if (s_err) {   // a shard's list overflowed (-1) or a query time was out of range: the host wrapper raises
@@ -572,15 +652,13 @@ match_owner_kernel(const IndexView ix, const uint32_t* __restrict__ words_in, co
   uint32_t* out = list + (int64_t)q * list_cap;
   for (int l = 0; l < n_shards; ++l) {
     const int n = nwords[(int64_t)l * B + q];
-    const uint32_t* w = words_in + ((int64_t)l * B + q) * words_cap;
-    for (int i = tid; i < n; i += kFusedThreads) {
-      const uint32_t v = __ldg(w + i);
+    for_each_word(words_in + ((int64_t)l * B + q) * words_cap, n, vec, tid, [&](uint32_t v) {
       const unsigned k = mark[v >> kHitDtBits];
       if (k) {
         const int pos = atomicAdd(&s_n, 1);
         if (pos < list_cap) out[pos] = ((k - 1u) << 16) | (v & ((1u << kHitDtBits) - 1u));
       }
-    }
+    });
   }
   __syncthreads();
   if (tid == 0) nlist[q] = s_n;
@@ -855,6 +933,27 @@ bool match_sparse_ok(const mfpa_ctx* ctx) { return ctx->index_ntracks <= kMaxTra
 int launch_match_emit(mfpa_ctx* ctx, const int32_t* hashes, const int32_t* nh, int B, int cap, uint32_t* words, int words_cap,
                       int32_t* nwords, cudaStream_t st) {
   match_emit_kernel<<<B, kFusedThreads, 0, st>>>(view(ctx), hashes, nh, cap, words, words_cap, nwords);
+  MFPA_CUDA(cudaGetLastError());
+  return MFPA_OK;
+}
+
+int launch_match_emit_peer(mfpa_ctx* ctx, const int32_t* hashes, const int32_t* nh, int B, int cap, const mfpa_peer_set* peers,
+                           int words_cap, cudaStream_t st) {
+  PeerDst d;
+  for (int r = 0; r < MFPA_MAX_PEERS; ++r) { d.words[r] = peers->words[r]; d.nwords[r] = peers->nwords[r]; }
+  d.own = B / peers->world;
+  d.rank = peers->rank;
+  match_emit_peer_kernel<<<B, kFusedThreads, 0, st>>>(view(ctx), hashes, nh, cap, d, words_cap);
+  MFPA_CUDA(cudaGetLastError());
+  return MFPA_OK;
+}
+
+int launch_peer_barrier(const mfpa_peer_set* peers, uint32_t epoch, cudaStream_t st) {
+  PeerFlags f;
+  for (int r = 0; r < MFPA_MAX_PEERS; ++r) f.flags[r] = peers->flags[r];
+  f.world = peers->world;
+  f.rank = peers->rank;
+  peer_barrier_kernel<<<1, 32, 0, st>>>(f, epoch);
   MFPA_CUDA(cudaGetLastError());
   return MFPA_OK;
 }

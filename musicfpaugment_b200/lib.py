@@ -62,6 +62,17 @@ class MatchParams(C.Structure):
                 ("max_alignments_per_id", C.c_int32)]
 
 
+MAX_PEERS = 16
+
+
+class PeerSet(C.Structure):
+    """mfpa_peer_set (include/mfpa.h): every rank's receive buffers of the fused sparse exchange, as device pointers
+    valid in this process (the rank's own allocation, the others mapped through CUDA IPC)."""
+
+    _fields_ = [("words", C.c_void_p * MAX_PEERS), ("nwords", C.c_void_p * MAX_PEERS), ("flags", C.c_void_p * MAX_PEERS),
+                ("world", C.c_int32), ("rank", C.c_int32)]
+
+
 class MfpaError(RuntimeError):
     pass
 
@@ -108,6 +119,12 @@ SIGNATURES = {
     "mfpa_match_emit": (_i, [_vp, _vp, _vp, _i, _i, _vp, _i, _vp, _vp]),
     "mfpa_match_owner": (_i, [_vp, _vp, _vp, _i, _i, _i, C.POINTER(MatchParams), _vp, _vp, _i, _vp]),
     "mfpa_match": (_i, [_vp, _vp, _vp, _i, _i, C.POINTER(MatchParams), _vp, _vp, _i, _vp]),
+    "mfpa_peer_alloc": (_i, [_vp, C.c_uint64, C.POINTER(_vp), _vp]),
+    "mfpa_peer_open": (_i, [_vp, _vp, C.POINTER(_vp)]),
+    "mfpa_peer_close": (_i, [_vp, _vp]),
+    "mfpa_peer_free": (_i, [_vp, _vp]),
+    "mfpa_match_emit_peer": (_i, [_vp, _vp, _vp, _i, _i, C.POINTER(PeerSet), _i, _vp]),
+    "mfpa_peer_barrier": (_i, [_vp, C.POINTER(PeerSet), C.c_uint32, _vp]),
     "mfpa_dejavu_peaks": (_i, [_vp, _vp, _i, _i, _i, _i, _i, C.c_double, _vp, _vp, _i, _vp, _vp]),
     "mfpa_dejavu_num_frames": (_i, [_i]),
     "mfpa_dejavu_psd": (_i, [_vp, _vp, _i, _i, _i64, _vp, _vp]),
@@ -186,6 +203,8 @@ def match_defaults() -> MatchParams:
 
 
 def _ptr(t):
+    if isinstance(t, int):   # a raw device address (peer-mapped memory has no tensor around it)
+        return C.c_void_p(t)
     return C.c_void_p(t.data_ptr()) if t is not None else None
 
 
@@ -527,6 +546,44 @@ class Context:
             nwords = torch.empty(B, dtype=torch.int32, device=hashes.device)
         check(_lib.mfpa_match_emit(self._h, _ptr(hashes), _ptr(nh), B, cap, _ptr(words), words_cap, _ptr(nwords), _stream()))
         return words, nwords
+
+    # ---- peer memory (the exchange fused into the sweep)
+    def peer_alloc(self, nbytes: int):
+        """(device address, 64-byte IPC handle) of a zeroed buffer other ranks of this node can map."""
+        p, h = C.c_void_p(), (C.c_char * 64)()
+        check(_lib.mfpa_peer_alloc(self._h, nbytes, C.byref(p), h))
+        return int(p.value), bytes(h.raw)
+
+    def peer_open(self, handle: bytes) -> int:
+        p, h = C.c_void_p(), (C.c_char * 64).from_buffer_copy(handle)
+        check(_lib.mfpa_peer_open(self._h, h, C.byref(p)))
+        return int(p.value)
+
+    def peer_close(self, address: int):
+        check(_lib.mfpa_peer_close(self._h, C.c_void_p(address)))
+
+    def peer_free(self, address: int):
+        check(_lib.mfpa_peer_free(self._h, C.c_void_p(address)))
+
+    def match_emit_peer(self, hashes, nh, peers: PeerSet, words_cap: int):
+        """match_emit with the words stored straight into the owner ranks' buffers of `peers` (NVLink stores)."""
+        B, cap, _ = hashes.shape
+        check(_lib.mfpa_match_emit_peer(self._h, _ptr(hashes), _ptr(nh), B, cap, C.byref(peers), words_cap, _stream()))
+
+    def peer_barrier(self, peers: PeerSet, epoch: int):
+        check(_lib.mfpa_peer_barrier(self._h, C.byref(peers), epoch & 0xFFFFFFFF, _stream()))
+
+    def match_owner_at(self, words_addr: int, nwords_addr: int, n_shards: int, B: int, words_cap: int, params: MatchParams,
+                       max_rows: int = 16):
+        """match_owner on a receive buffer given by address ([n_shards,B,words_cap] words, [n_shards,B] counts)."""
+        import torch
+
+        dev = torch.device("cuda", self.device)
+        res = torch.zeros(B, max_rows, 7, dtype=torch.int32, device=dev)
+        nrows = torch.empty(B, dtype=torch.int32, device=dev)
+        check(_lib.mfpa_match_owner(self._h, _ptr(words_addr), _ptr(nwords_addr), n_shards, B, words_cap, C.byref(params),
+                                    _ptr(res), _ptr(nrows), max_rows, _stream()))
+        return res, nrows
 
     def match_owner(self, words, nwords, params: MatchParams, max_rows: int = 16):
         """words int32 [n_shards,B,words_cap], nwords int32 [n_shards,B] (every shard's hits of the queries this rank

@@ -64,8 +64,72 @@ def default_words_cap(cap_hashes: int, depth: int, world: int) -> int:
     return (int(1.35 * cap_hashes * depth / world) + 512 + 255) // 256 * 256
 
 
-def match_sharded(ctx, hashes, nh, params=None, max_rows: int = 16, words_cap: int | None = None, sub_batch: int = 2048,
-                  group=None, list_cap=None):
+class PeerExchange:
+    """Receive buffers of the fused sparse exchange, one set per (context, world, own, words_cap): two
+    [world, own, words_cap] word buffers (consecutive sub-batches alternate, so a rank may sweep sub-batch i + 1
+    into its peers while they still read sub-batch i), their [world, own] counts and a row of barrier flags, all in
+    ONE allocation made by `mfpa_peer_alloc`; the other ranks' allocations are mapped with `mfpa_peer_open` from the
+    IPC handles all-gathered here.  `turn` counts the sub-batches of every call on this exchange (the same on every
+    rank): buffer = turn % 2, barrier epoch = turn + 1."""
+
+    N_BUF = 2
+
+    def __init__(self, ctx, world: int, rank: int, own: int, words_cap: int, group=None):
+        import torch.distributed as dist
+
+        from . import lib
+
+        if world > lib.MAX_PEERS:
+            raise lib.MfpaError(f"peer exchange: {world} ranks, the peer set holds {lib.MAX_PEERS}")
+        self.ctx, self.world, self.rank, self.own, self.words_cap = ctx, world, rank, own, words_cap
+        rows = world * own
+        self.flag_bytes = 256
+        self.n_bytes = (rows * 4 + 255) // 256 * 256
+        self.w_bytes = (rows * words_cap * 4 + 255) // 256 * 256
+        total = self.flag_bytes + self.N_BUF * (self.n_bytes + self.w_bytes)
+        self.base, handle = ctx.peer_alloc(total)
+        handles = [None] * world
+        dist.all_gather_object(handles, handle, group=group)
+        self.bases = [self.base if r == rank else ctx.peer_open(handles[r]) for r in range(world)]
+        self.sets = []
+        for b in range(self.N_BUF):
+            ps = lib.PeerSet()
+            ps.world, ps.rank = world, rank
+            for r, base in enumerate(self.bases):
+                ps.flags[r] = base
+                ps.nwords[r] = base + self.flag_bytes + b * (self.n_bytes + self.w_bytes)
+                ps.words[r] = ps.nwords[r] + self.n_bytes
+            self.sets.append(ps)
+        self.turn = 0
+        dist.barrier(group=group)     # every rank has mapped every buffer before anyone stores into one
+
+    def buffer(self, b: int):
+        """(words address, counts address) of this rank's receive buffer b."""
+        n = self.base + self.flag_bytes + b * (self.n_bytes + self.w_bytes)
+        return n + self.n_bytes, n
+
+    def close(self):
+        for r, base in enumerate(self.bases):
+            if r != self.rank:
+                self.ctx.peer_close(base)
+        self.ctx.peer_free(self.base)
+        self.bases = []
+
+
+def _peer_exchange(ctx, world, rank, own, words_cap, group):
+    """The context's cached PeerExchange for this geometry (set up once: IPC mapping costs milliseconds)."""
+    cache = ctx.__dict__.setdefault("_peer_exchanges", {})
+    key = (world, rank, own, words_cap, id(group))
+    if key not in cache:
+        cache[key] = PeerExchange(ctx, world, rank, own, words_cap, group)
+    return cache[key]
+
+
+PEER_BUFFER_BYTES = 4 << 30   # both receive buffers of a PeerExchange together (the sub-batch is sized to fit)
+
+
+def match_sharded(ctx, hashes, nh, params=None, max_rows: int = 16, words_cap: int | None = None,
+                  sub_batch: int | None = None, group=None, list_cap=None, exchange: str | None = None):
     """match_hashes for a batch of queries that every rank holds, against an index sharded by
     hash range (each rank's `ctx` holds its shard).  Returns (results [B,max_rows,7], nrows [B])
     identical on every rank.
@@ -76,7 +140,13 @@ def match_sharded(ctx, hashes, nh, params=None, max_rows: int = 16, words_cap: i
     contiguous 1/world slice of the sub-batch) moves them; the owner runs the whole of match_hashes -
     shared-memory histogram, candidate selection, delta-t alignment - on the words of all shards
     (`match_owner`).  The all-to-all of sub-batch i is in flight while the ranks sweep sub-batch i + 1; the
-    owners' result rows are all-gathered once at the end.  `list_cap` is accepted for backward compatibility."""
+    owners' result rows are all-gathered once at the end.  `list_cap` is accepted for backward compatibility.
+
+    exchange = "peer" fuses the exchange into the sweep: the emit kernel stores each query's words straight into
+    its owner rank's memory over NVLink (`match_emit_peer`, buffers of a cached `PeerExchange`), a one-block barrier
+    kernel in peer memory separates it from the owner step - no all-to-all, no staging list, only the words that
+    exist cross the link.  It is the default on GPUs of one node (contexts that have `peer_alloc`); "nccl" keeps
+    the all-to-all (other transports, the gloo tests)."""
     import torch
     import torch.distributed as dist
 
@@ -87,14 +157,33 @@ def match_sharded(ctx, hashes, nh, params=None, max_rows: int = 16, words_cap: i
     B, cap, _ = hashes.shape
     if world == 1:
         return ctx.match(hashes, nh, params, max_rows)
+    dev = hashes.device
+    if words_cap is None:
+        words_cap = default_words_cap(cap, getattr(ctx, "depth", 100), world)
+    if exchange is None:
+        exchange = "peer" if hasattr(ctx, "peer_alloc") and dev.type == "cuda" else "nccl"
+    if sub_batch is None:
+        # peer: nothing overlaps between sub-batches, so take the batch whole if the receive buffers allow;
+        # all-to-all: sub-batches of 2048 pipeline the collective behind the next sweep
+        sub_batch = max(world, PEER_BUFFER_BYTES // (PeerExchange.N_BUF * words_cap * 4)) if exchange == "peer" else 2048
     sub = max(world, min(sub_batch, -(-B // world) * world) // world * world)
     own = sub // world
     n_sub = -(-B // sub)
-    if words_cap is None:
-        words_cap = default_words_cap(cap, getattr(ctx, "depth", 100), world)
-    dev = hashes.device
     res_m = torch.zeros(n_sub * own, max_rows, 7, dtype=torch.int32, device=dev)
     nrows_m = torch.zeros(n_sub * own, dtype=torch.int32, device=dev)
+    if exchange == "peer":
+        rank = dist.get_rank(group)
+        px = _peer_exchange(ctx, world, rank, own, words_cap, group)
+        for i in range(n_sub):
+            hq, nq = _sub_batch(hashes, nh, i, sub)
+            b = px.turn % px.N_BUF
+            ctx.match_emit_peer(hq, nq, px.sets[b], words_cap)
+            px.turn += 1
+            ctx.peer_barrier(px.sets[b], px.turn)
+            w_addr, n_addr = px.buffer(b)
+            r, n = ctx.match_owner_at(w_addr, n_addr, world, own, words_cap, params, max_rows)
+            res_m[i * own:(i + 1) * own], nrows_m[i * own:(i + 1) * own] = r, n
+        return _gather_owned(res_m, nrows_m, world, n_sub, own, sub, B, max_rows, group)
 
     def finish(job):
         i, works, recv_w, recv_n = job
@@ -105,12 +194,8 @@ def match_sharded(ctx, hashes, nh, params=None, max_rows: int = 16, words_cap: i
 
     pending = None
     for i in range(n_sub):
-        hq, nq = hashes[i * sub:(i + 1) * sub], nh[i * sub:(i + 1) * sub]
-        if hq.shape[0] < sub:  # pad the last sub-batch with empty queries so it splits evenly
-            pad = sub - hq.shape[0]
-            hq = torch.cat([hq, torch.zeros(pad, *hq.shape[1:], dtype=hq.dtype, device=dev)])
-            nq = torch.cat([nq, torch.zeros(pad, dtype=nq.dtype, device=dev)])
-        words, nwords = ctx.match_emit(hq.contiguous(), nq.contiguous(), words_cap)
+        hq, nq = _sub_batch(hashes, nh, i, sub)
+        words, nwords = ctx.match_emit(hq, nq, words_cap)
         recv_w, recv_n = torch.empty_like(words), torch.empty_like(nwords)
         works = [dist.all_to_all_single(recv_w, words, group=group, async_op=True),
                  dist.all_to_all_single(recv_n, nwords, group=group, async_op=True)]
@@ -118,8 +203,24 @@ def match_sharded(ctx, hashes, nh, params=None, max_rows: int = 16, words_cap: i
             finish(pending)       # owner step of sub-batch i - 1, behind the sweep of sub-batch i
         pending = (i, works, recv_w, recv_n)
     finish(pending)
+    return _gather_owned(res_m, nrows_m, world, n_sub, own, sub, B, max_rows, group)
+
+
+def _sub_batch(hashes, nh, i, sub):
+    """Sub-batch i, padded with empty queries to `sub` rows so that it splits evenly over the ranks."""
+    import torch
+
+    hq, nq = hashes[i * sub:(i + 1) * sub], nh[i * sub:(i + 1) * sub]
+    if hq.shape[0] < sub:
+        pad = sub - hq.shape[0]
+        hq = torch.cat([hq, torch.zeros(pad, *hq.shape[1:], dtype=hq.dtype, device=hq.device)])
+        nq = torch.cat([nq, torch.zeros(pad, dtype=nq.dtype, device=nq.device)])
+    return hq.contiguous(), nq.contiguous()
+
+
+def _gather_owned(res_m, nrows_m, world, n_sub, own, sub, B, max_rows, group):
+    """All-gather the owners' rows: gathered [owner][sub-batch][own] -> query order [sub-batch][owner][own]."""
     res_all, nrows_all = _all_gather_rows(res_m, world, group), _all_gather_rows(nrows_m, world, group)
-    # gathered [owner][sub-batch][own] -> query order [sub-batch][owner][own]
     res = res_all.view(world, n_sub, own, max_rows, 7).permute(1, 0, 2, 3, 4).reshape(n_sub * sub, max_rows, 7)[:B]
     nrows = nrows_all.view(world, n_sub, own).permute(1, 0, 2).reshape(n_sub * sub)[:B]
     return res.contiguous(), nrows.contiguous()

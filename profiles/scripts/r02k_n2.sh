@@ -1,6 +1,6 @@
 set -u
 OUT=gpurun_out; mkdir -p $OUT
-python __graft_entry__.py --smoke 2>&1 | tail -3
+python -m pytest tests/test_match_gpu.py -m gpu -q -x 2>&1 | tail -3
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 --also match --no-cpu-baseline > $OUT/bench_r02k_n2.json 2> $OUT/bench_r02k_n2.err; echo rc=$?
 tail -5 $OUT/bench_r02k_n2.err
 python - <<PY
