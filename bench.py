@@ -649,6 +649,8 @@ def bench_match(ctx, lib, dev, rank, world, B, n_tracks, steps, warmup, barrier)
     barrier()
     ms = e0.elapsed_time(e1) / steps
     top1 = float(((nrows > 0) & (res[:, 0, 0] == truth)).float().mean().item())
+    if world > 1:
+        sharded.release_peer_exchanges(ctx)
     rep = None
     if world > 1:
         # throughput mode: the whole index on every rank, queries sharded, rows all-gathered

@@ -535,20 +535,24 @@ match_emit_kernel(const IndexView ix, const int32_t* __restrict__ hashes, const 
 // The same sweep with the exchange fused in: query q of the sub-batch belongs to rank q / own, and its words go
 // straight into that rank's receive buffer (peer memory mapped through CUDA IPC, NVLink stores) at the slot
 // [this rank][q % own] - the layout match_owner_kernel reads.  No staging list in local HBM, no collective call.
-struct PeerDst { uint32_t* words[MFPA_MAX_PEERS]; int32_t* nwords[MFPA_MAX_PEERS]; int own, rank; };
+// Consecutive blocks take queries of different owners (block b: owner b % world, its query b / world), so the stores
+// to every peer - and the local ones - are spread over the whole kernel instead of one link at a time.
+struct PeerDst { uint32_t* words[MFPA_MAX_PEERS]; int32_t* nwords[MFPA_MAX_PEERS]; int own, rank, world; };
 __global__ void __launch_bounds__(kFusedThreads, 2)
 match_emit_peer_kernel(const IndexView ix, const int32_t* __restrict__ hashes, const int32_t* __restrict__ nh, int cap,
                        const PeerDst d, int words_cap) {
   __shared__ RowCache rc;
   __shared__ int s_n, s_bad;
-  const int q = blockIdx.x, tid = threadIdx.x;
-  const int owner = q / d.own;
-  const int64_t slot = (int64_t)d.rank * d.own + (q - owner * d.own);
+  const int tid = threadIdx.x;
+  const int owner = (int)(blockIdx.x % (unsigned)d.world), j = (int)(blockIdx.x / (unsigned)d.world);
+  const int q = owner * d.own + j;
+  const int64_t slot = (int64_t)d.rank * d.own + j;
   if (tid == 0) { s_n = 0; s_bad = 0; }
   const int2* rows = reinterpret_cast<const int2*>(hashes) + (int64_t)q * cap;
   fused_sweep<kSweepEmit>(ix, rows, min(nh[q], cap), &rc, nullptr, d.words[owner] + slot * words_cap, words_cap, &s_n, tid, &s_bad);
   if (tid == 0) d.nwords[owner][slot] = s_bad ? kBadQueryTime : s_n;
-  __threadfence_system();
+  // no fence here: the kernel boundary orders these stores before the barrier kernel that follows in the stream,
+  // and that kernel releases them at system scope (a per-thread MEMBAR.SYS cost as much as the sweep itself)
 }
 
 // Barrier between the ranks' streams, in peer memory: rank r writes the epoch into slot r of every rank's flag
@@ -943,6 +947,7 @@ int launch_match_emit_peer(mfpa_ctx* ctx, const int32_t* hashes, const int32_t* 
   for (int r = 0; r < MFPA_MAX_PEERS; ++r) { d.words[r] = peers->words[r]; d.nwords[r] = peers->nwords[r]; }
   d.own = B / peers->world;
   d.rank = peers->rank;
+  d.world = peers->world;
   match_emit_peer_kernel<<<B, kFusedThreads, 0, st>>>(view(ctx), hashes, nh, cap, d, words_cap);
   MFPA_CUDA(cudaGetLastError());
   return MFPA_OK;

@@ -108,12 +108,27 @@ class PeerExchange:
         n = self.base + self.flag_bytes + b * (self.n_bytes + self.w_bytes)
         return n + self.n_bytes, n
 
-    def close(self):
+    def close(self, group=None):
+        """Collective: unmap the peers' buffers, wait until every rank has done so, then free this rank's."""
+        import torch
+        import torch.distributed as dist
+
+        if not self.bases:
+            return
+        torch.cuda.synchronize()
         for r, base in enumerate(self.bases):
             if r != self.rank:
                 self.ctx.peer_close(base)
+        dist.barrier(group=group)
         self.ctx.peer_free(self.base)
         self.bases = []
+
+
+def release_peer_exchanges(ctx, group=None):
+    """Collective: free every cached PeerExchange of `ctx` (call it on all ranks, before the contexts close)."""
+    cache = ctx.__dict__.pop("_peer_exchanges", {})
+    for key in sorted(cache, key=lambda k: k[:4]):
+        cache[key].close(group)
 
 
 def _peer_exchange(ctx, world, rank, own, words_cap, group):
