@@ -32,7 +32,7 @@ def _nvcc() -> str:
     for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if cand and os.path.exists(cand):
             return cand
-    raise RuntimeError("nvcc not found; libmfpa.so cannot be built")
+    raise FileNotFoundError("nvcc not found; libmfpa.so cannot be built")
 
 
 def sources():

@@ -207,6 +207,13 @@ constexpr int kHitMaxTracks = 1 << 17;  // ... which leaves 17 bits for the trac
 // MODE kSweepCount: raw counts into the packed shared-memory histogram; kSweepCollect: (candidate, delta-t) hits of
 // the tracks marked in it; kSweepEmit: every hit of this shard as a (track, delta-t) word (sparse exchange).
 // A query time outside [0, 2^14) cannot be packed next to the table's 14-bit reference times: *s_bad is raised.
+// The packed histogram occupies (words + 3) & ~3 shared-memory words; cleared (padding included, the vector scans of
+// fused_select read it) with 16-byte stores.
+__device__ __forceinline__ void zero_hist(unsigned* hist, int words, int tid) {
+  uint4* h4 = reinterpret_cast<uint4*>(hist);
+  for (int i = tid; i < ((words + 3) >> 2); i += kFusedThreads) h4[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+
 template <int MODE>
 __device__ __forceinline__ void fused_sweep(const IndexView& ix, const int2* __restrict__ rows, int n, RowCache* rc,
                                             unsigned* hist, uint32_t* __restrict__ out, int list_cap, int* s_n, int tid,
@@ -297,7 +304,7 @@ match_counts_sweep_kernel(const IndexView ix, const int32_t* __restrict__ hashes
   const int q = blockIdx.x, tid = threadIdx.x;
   const int2* rows = reinterpret_cast<const int2*>(hashes) + (int64_t)q * cap;
   const int n = min(nh[q], cap);
-  for (int i = tid; i < words; i += kFusedThreads) hist[i] = 0;
+  zero_hist(hist, words, tid);
   fused_sweep<kSweepCount>(ix, rows, n, rc, hist, nullptr, 0, nullptr, tid);
   if (packed) {
     unsigned* o = reinterpret_cast<unsigned*>(out) + (int64_t)q * words;
@@ -325,7 +332,7 @@ match_collect_sweep_kernel(const IndexView ix, const int32_t* __restrict__ hashe
     if (tid == 0) nlist[q] = 0;
     return;
   }
-  for (int i = tid; i < words; i += kFusedThreads) hist[i] = 0;
+  zero_hist(hist, words, tid);
   if (tid == 0) s_n = 0;
   __syncthreads();
   for (int k = tid; k < nc; k += kFusedThreads) {
@@ -357,16 +364,25 @@ __device__ __forceinline__ int fused_select(const IndexView& ix, const unsigned*
   auto count_of = [&](int i) -> int { return (int)((hist[i >> 1] >> ((i & 1) * 16)) & 0xffffu); };
   int gt = 0;
   float fmin = INFINITY;
-  // uniform trip count so the (rare) tracks above the count threshold can be handled behind a warp vote:
-  // the common iteration is one shared-memory load and two compares
-  for (int w0 = 0; w0 < words; w0 += kFusedThreads) {
-    const int w = w0 + tid;
-    const unsigned h2 = w < words ? hist[w] : 0u;
-    const int r0 = (int)(h2 & 0xffffu), r1 = (int)(h2 >> 16);
-    const bool hit = r0 > threshcount || r1 > threshcount;
-    if (__any_sync(kFull, hit)) {
-      if (r0 > threshcount) { ++gt; fmin = fminf(fmin, __fdividef((float)r0, (float)__ldg(ix.hashesperid + 2 * w))); }
-      if (r1 > threshcount) { ++gt; fmin = fminf(fmin, __fdividef((float)r1, (float)__ldg(ix.hashesperid + 2 * w + 1))); }
+  // uniform trip count so the (rare) tracks above the count threshold can be handled behind a warp vote: the
+  // common iteration is one 16-byte shared-memory load (eight counters), three packed maxima and a compare
+  const uint4* hist4 = reinterpret_cast<const uint4*>(hist);
+  const int words4 = (words + 3) >> 2;
+  auto max8 = [](const uint4& h) -> int {
+    const unsigned m = __vmaxu2(__vmaxu2(h.x, h.y), __vmaxu2(h.z, h.w));
+    return (int)max(m & 0xffffu, m >> 16);
+  };
+  for (int w0 = 0; w0 < words4; w0 += kFusedThreads) {
+    const int w4 = w0 + tid;
+    const uint4 h = w4 < words4 ? hist4[w4] : make_uint4(0u, 0u, 0u, 0u);
+    if (__any_sync(kFull, max8(h) > threshcount)) {
+      const unsigned hw[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int r0 = (int)(hw[j] & 0xffffu), r1 = (int)(hw[j] >> 16), w = 4 * w4 + j;
+        if (r0 > threshcount) { ++gt; fmin = fminf(fmin, __fdividef((float)r0, (float)__ldg(ix.hashesperid + 2 * w))); }
+        if (r1 > threshcount) { ++gt; fmin = fminf(fmin, __fdividef((float)r1, (float)__ldg(ix.hashesperid + 2 * w + 1))); }
+      }
     }
   }
 #pragma unroll
@@ -385,18 +401,21 @@ __device__ __forceinline__ int fused_select(const IndexView& ix, const unsigned*
   if (tid == 0) *ncand_q = depth;
   bool listed = depth > 0;
   if (listed) {
-    for (int w0 = 0; w0 < words; w0 += kFusedThreads) {
-      const int w = w0 + tid;
-      const unsigned h2 = w < words ? hist[w] : 0u;
-      const int r0 = (int)(h2 & 0xffffu), r1 = (int)(h2 >> 16);
-      if (__any_sync(kFull, r0 >= raw_min || r1 >= raw_min)) {
+    for (int w0 = 0; w0 < words4; w0 += kFusedThreads) {
+      const int w4 = w0 + tid;
+      const uint4 h = w4 < words4 ? hist4[w4] : make_uint4(0u, 0u, 0u, 0u);
+      if (__any_sync(kFull, max8(h) >= raw_min)) {
+        const unsigned hw[4] = {h.x, h.y, h.z, h.w};
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int raw = e ? r1 : r0, i = 2 * w + e;
-          if (raw < raw_min) continue;
-          if (__fdividef((float)raw, (float)__ldg(ix.hashesperid + i)) < cut) continue;
-          const int slot = atomicAdd(&sm->s_n, 1);
-          if (slot < kContCap) contenders[slot] = i;
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int raw = (int)((hw[j] >> (16 * e)) & 0xffffu), i = 2 * (4 * w4 + j) + e;
+            if (raw < raw_min) continue;
+            if (__fdividef((float)raw, (float)__ldg(ix.hashesperid + i)) < cut) continue;
+            const int slot = atomicAdd(&sm->s_n, 1);
+            if (slot < kContCap) contenders[slot] = i;
+          }
         }
       }
     }
@@ -486,7 +505,7 @@ match_fused_kernel(const IndexView ix, const int32_t* __restrict__ hashes, const
   const int q = blockIdx.x, tid = threadIdx.x;
   const int2* rows = reinterpret_cast<const int2*>(hashes) + (int64_t)q * cap;
   const int n = min(nh[q], cap);
-  for (int i = tid; i < words; i += kFusedThreads) hist[i] = 0;
+  zero_hist(hist, words, tid);
   if (tid == 0) { s_n = 0; s_bad = 0; s_hits = 0u; }
   fused_sweep<kSweepCount>(ix, rows, n, rc, hist, nullptr, 0, nullptr, tid, &s_bad, &s_hits);
   if (s_bad) {   // block-uniform after the sweep's closing barrier
@@ -505,7 +524,7 @@ match_fused_kernel(const IndexView ix, const int32_t* __restrict__ hashes, const
     return;
   }
   // the histogram becomes the candidate map: 16-bit slot of track id = candidate index + 1
-  for (int i = tid; i < words; i += kFusedThreads) hist[i] = 0;
+  zero_hist(hist, words, tid);
   __syncthreads();
   const int nc = min(depth, 128);   // align_kernel handles at most 128 candidates (check_match bounds search_depth)
   for (int k = tid; k < nc; k += kFusedThreads)
@@ -579,29 +598,44 @@ __global__ void peer_barrier_kernel(const PeerFlags f, uint32_t epoch) {
   __threadfence_system();
 }
 
-// Visit the n words of one shard's list with the whole block.  The visits are shared-memory atomics / look-ups that
-// wait on the word, so the loads are batched ahead of them: four 16-byte loads (16 words) per thread in flight
-// when the list is 16-byte aligned (it is for the library's own buffers), one word at a time otherwise.
+// Visit the n words of one shard's list with `gsize` threads (t = this thread's index among them).  The visits are
+// shared-memory atomics / look-ups that wait on the word, so the loads are batched ahead of them: four 16-byte
+// loads (16 words) per thread in flight when the list is 16-byte aligned (it is for the library's own buffers),
+// one word at a time otherwise.
 template <typename F>
-__device__ __forceinline__ void for_each_word(const uint32_t* __restrict__ w, int n, bool vec, int tid, F f) {
+__device__ __forceinline__ void for_each_word(const uint32_t* __restrict__ w, int n, bool vec, int t, int gsize, F f) {
   if (!vec) {
-    for (int i = tid; i < n; i += kFusedThreads) f(__ldg(w + i));
+    for (int i = t; i < n; i += gsize) f(__ldg(w + i));
     return;
   }
   const uint4* w4 = reinterpret_cast<const uint4*>(w);
   const int n4 = n >> 2;
-  int i = tid;
-  for (; i + 3 * kFusedThreads < n4; i += 4 * kFusedThreads) {
-    const uint4 a = __ldg(w4 + i), b = __ldg(w4 + i + kFusedThreads), c = __ldg(w4 + i + 2 * kFusedThreads),
-                d = __ldg(w4 + i + 3 * kFusedThreads);
+  int i = t;
+  for (; i + 3 * gsize < n4; i += 4 * gsize) {
+    const uint4 a = __ldg(w4 + i), b = __ldg(w4 + i + gsize), c = __ldg(w4 + i + 2 * gsize), d = __ldg(w4 + i + 3 * gsize);
     f(a.x); f(a.y); f(a.z); f(a.w); f(b.x); f(b.y); f(b.z); f(b.w);
     f(c.x); f(c.y); f(c.z); f(c.w); f(d.x); f(d.y); f(d.z); f(d.w);
   }
-  for (; i < n4; i += kFusedThreads) {
+  for (; i < n4; i += gsize) {
     const uint4 a = __ldg(w4 + i);
     f(a.x); f(a.y); f(a.z); f(a.w);
   }
-  for (int j = (n4 << 2) + tid; j < n; j += kFusedThreads) f(__ldg(w + j));
+  for (int j = (n4 << 2) + t; j < n; j += gsize) f(__ldg(w + j));
+}
+
+// The shards' lists of one query, visited by the block split into `groups` thread groups (a power of two <= the
+// number of lists): with eight short lists, 128 threads per list keep as many loads in flight as 1024 threads on
+// one long list do.
+template <typename F>
+__device__ __forceinline__ void for_each_list_word(const uint32_t* __restrict__ words_in, const int32_t* __restrict__ nwords,
+                                                   int n_shards, int B, int q, int words_cap, bool vec, int groups, int tid,
+                                                   F f) {
+  const int gsize = kFusedThreads / groups, g = tid / gsize, t = tid - g * gsize;
+  for (int l = g; l < n_shards; l += groups) {
+    const int n = nwords[(int64_t)l * B + q];
+    if (n < 0 || n > words_cap) continue;   // flagged by the caller
+    for_each_word(words_in + ((int64_t)l * B + q) * words_cap, n, vec, t, gsize, f);
+  }
 }
 
 // words: [n_shards][B][words_cap], nwords: [n_shards][B] (what the exchange leaves on the owner)
@@ -618,7 +652,7 @@ match_owner_kernel(const IndexView ix, const uint32_t* __restrict__ words_in, co
   __shared__ unsigned s_sum;
   const int q = blockIdx.x, tid = threadIdx.x;
   const bool vec = (reinterpret_cast<uintptr_t>(words_in) & 15) == 0 && (words_cap & 3) == 0;
-  for (int i = tid; i < words; i += kFusedThreads) hist[i] = 0;
+  zero_hist(hist, words, tid);
   if (tid == 0) { s_n = 0; s_err = 0; }
   __syncthreads();
   unsigned total_hits = 0;
@@ -626,11 +660,13 @@ match_owner_kernel(const IndexView ix, const uint32_t* __restrict__ words_in, co
     const int n = nwords[(int64_t)l * B + q];
     if (n < 0 || n > words_cap) { if (tid == 0) s_err = n < 0 ? n : -1; continue; }
     total_hits += (unsigned)n;
-    for_each_word(words_in + ((int64_t)l * B + q) * words_cap, n, vec, tid, [&](uint32_t v) {
-      const unsigned id = v >> kHitDtBits;
-      atomicAdd(&hist[id >> 1], 1u << ((id & 1u) << 4));
-    });
   }
+  int groups = 1;
+  while (groups * 2 <= n_shards && groups < 32) groups *= 2;
+  for_each_list_word(words_in, nwords, n_shards, B, q, words_cap, vec, groups, tid, [&](uint32_t v) {
+    const unsigned id = v >> kHitDtBits;
+    atomicAdd(&hist[id >> 1], 1u << ((id & 1u) << 4));
+  });
   __syncthreads();
   if (s_err) {   // a shard's list overflowed (-1) or a query time was out of range: the host wrapper raises
     if (tid == 0) { ncand[q] = 0; nlist[q] = s_err; }
@@ -646,7 +682,7 @@ match_owner_kernel(const IndexView ix, const uint32_t* __restrict__ words_in, co
     if (tid == 0) nlist[q] = 0;
     return;
   }
-  for (int i = tid; i < words; i += kFusedThreads) hist[i] = 0;
+  zero_hist(hist, words, tid);
   __syncthreads();
   const int nc = min(depth, 128);
   for (int k = tid; k < nc; k += kFusedThreads)
@@ -654,16 +690,13 @@ match_owner_kernel(const IndexView ix, const uint32_t* __restrict__ words_in, co
   __syncthreads();
   const unsigned short* mark = reinterpret_cast<const unsigned short*>(hist);
   uint32_t* out = list + (int64_t)q * list_cap;
-  for (int l = 0; l < n_shards; ++l) {
-    const int n = nwords[(int64_t)l * B + q];
-    for_each_word(words_in + ((int64_t)l * B + q) * words_cap, n, vec, tid, [&](uint32_t v) {
-      const unsigned k = mark[v >> kHitDtBits];
-      if (k) {
-        const int pos = atomicAdd(&s_n, 1);
-        if (pos < list_cap) out[pos] = ((k - 1u) << 16) | (v & ((1u << kHitDtBits) - 1u));
-      }
-    });
-  }
+  for_each_list_word(words_in, nwords, n_shards, B, q, words_cap, vec, groups, tid, [&](uint32_t v) {
+    const unsigned k = mark[v >> kHitDtBits];
+    if (k) {
+      const int pos = atomicAdd(&s_n, 1);
+      if (pos < list_cap) out[pos] = ((k - 1u) << 16) | (v & ((1u << kHitDtBits) - 1u));
+    }
+  });
   __syncthreads();
   if (tid == 0) nlist[q] = s_n;
 }

@@ -93,6 +93,35 @@ def test_wavfile2hashes_and_match_file(mods, tmp_path):
     assert res.shape == ref.shape and np.array_equal(res[:, :4], ref[:, :4])
 
 
+def test_matcher_exact_count_time_range_hashesfor(mods):
+    """Matcher(exact_count / find_time_range) and hashesfor on the golden index: rows and matching hashes equal the
+    reference Matcher's own output (tests/golden/match_exact.npz, oracle/make_golden_match_exact.py)."""
+    gold = os.path.join(ROOT, "tests", "golden")
+    g, e = np.load(os.path.join(gold, "match.npz")), np.load(os.path.join(gold, "match_exact.npz"))
+    ht = mods["ht"].HashTable()
+    idx = g["counts_nonzero_idx"]
+    ht.table[idx], ht.counts[idx] = g["table_rows"], g["counts_nonzero"]
+    ht.hashesperid = g["hashesperid"].copy()
+    ht.names = [f"track{t:04d}" for t in range(int(g["n_tracks"]))]
+    rows = lambda a: sorted(map(tuple, np.asarray(a).tolist()))
+    checked = 0
+    for i in range(int(g["n_queries"])):
+        if f"exact{i}" not in e.files:
+            continue
+        q, want = g[f"q{i}"], e[f"exact{i}"]
+        m = mods["match"].Matcher()
+        m.exact_count, m.find_time_range = True, True
+        got, hf = m.match_hashes(ht, q, hashesfor=0 if len(want) else None)
+        assert got.dtype == np.int32 and got.shape == want.shape and rows(got) == rows(want), i
+        if len(want):
+            assert np.array_equal(hf, e[f"hashesfor{i}"]), i
+            checked += 1
+        m2 = mods["match"].Matcher()
+        m2.find_time_range = True
+        assert rows(m2.match_hashes(ht, q)[0]) == rows(e[f"approx_tr{i}"]), i
+    assert checked >= 20
+
+
 def test_get_2d_peaks(mods):
     from oracle import dejavu_np as D
 

@@ -68,6 +68,27 @@ def test_match_hashes_golden():
         assert sorted(map(tuple, got.tolist())) == sorted(map(tuple, want.tolist()))
 
 
+def test_match_exact_count_time_range_hashesfor_golden():
+    """exact_count / find_time_range / hashesfor restated (audfprint_match.py:130-233, 296-304) vs the reference
+    Matcher's own output on the golden index (oracle/make_golden_match_exact.py)."""
+    g = np.load(os.path.join(GOLD, "match.npz"))
+    e = np.load(os.path.join(GOLD, "match_exact.npz"))
+    ht = _golden_table(g)
+    n = 0
+    for i in range(int(g["n_queries"])):
+        if f"exact{i}" not in e.files:
+            continue
+        q, want = g[f"q{i}"], e[f"exact{i}"]
+        got, hf = O.match_hashes_exact(ht, q, find_time_range=True, hashesfor=0 if len(want) else None)
+        assert got.shape == want.shape and sorted(map(tuple, got.tolist())) == sorted(map(tuple, want.tolist())), i
+        if len(want):
+            assert np.array_equal(hf, e[f"hashesfor{i}"]), i
+            n += 1
+        tr = O.approx_time_ranges(ht, q, O.match_hashes(ht, q))
+        assert sorted(map(tuple, tr.tolist())) == sorted(map(tuple, e[f"approx_tr{i}"].tolist())), i
+    assert n >= 20
+
+
 def test_hash_table_store_matches_layout():
     """store(): bucket fill order, saturation counting, id/time packing (hash_table.py:70-116)."""
     ht = O.HashTable()
