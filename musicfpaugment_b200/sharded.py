@@ -115,7 +115,8 @@ class PeerExchange:
 
         if not self.bases:
             return
-        torch.cuda.synchronize()
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
         for r, base in enumerate(self.bases):
             if r != self.rank:
                 self.ctx.peer_close(base)

@@ -43,7 +43,8 @@ def main():
         return float(t.item())
 
     out = {}
-    for sub in (1024, 2048, 5000, 10000):
+    for sub in [int(v) for v in os.environ.get("MFPA_PHASE_SUBS", "1024,2048,5000,10000").split(",")]:
+        sub = sub // world * world
         own = sub // world
         wc = sharded.default_words_cap(cap, ctx.depth, world)
         n_sub = -(-B // sub)

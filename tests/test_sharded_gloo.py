@@ -5,7 +5,9 @@ infrastructure only), so what is exercised here is the host logic a real run dep
 the hash-range partition of the index, the one all-to-all of every shard's packed (track, delta-t)
 hit words to the query's owner rank with the next sub-batch's sweep behind it, the owners' result
 rows gathered back into query order, the dense round-1 exchange (reduce-scatter of per-track counts,
-all-gather of candidates, all-to-all of candidate hit lists) and the contiguous query partition.
+all-gather of candidates, all-to-all of candidate hit lists), the peer-memory exchange (`PeerExchange`: buffer layout,
+alternating receive buffers and barrier epochs, over POSIX shared memory instead of CUDA IPC) and the contiguous
+query partition.
 The same `match_sharded` drives the CUDA kernels over NCCL on the GPU box.
 """
 import os
@@ -148,6 +150,64 @@ class NumpyShardCtx:
         return self.match_align(lst[None], nlist[None], cand, ncand, p, max_rows)
 
 
+class PeerShardCtx(NumpyShardCtx):
+    """NumpyShardCtx + the peer-memory entry points of lib.Context (peer_alloc / peer_open / match_emit_peer /
+    peer_barrier / match_owner_at) over POSIX shared memory: what `sharded.PeerExchange` and the "peer" exchange of
+    `match_sharded` drive on GPUs through CUDA IPC.  Addresses are (segment number << 40) + byte offset."""
+
+    def __init__(self, *a):
+        super().__init__(*a)
+        self._segs = {}
+
+    def _attach(self, shm):
+        k = len(self._segs) + 1
+        self._segs[k] = shm
+        return k << 40
+
+    def _view(self, addr, n, dtype=np.int32):
+        shm = self._segs[addr >> 40]
+        return np.ndarray((n,), dtype=dtype, buffer=shm.buf, offset=addr & ((1 << 40) - 1))
+
+    def peer_alloc(self, nbytes):
+        from multiprocessing import shared_memory
+
+        shm = shared_memory.SharedMemory(create=True, size=nbytes)
+        shm.buf[:nbytes] = bytes(nbytes)
+        return self._attach(shm), shm.name.encode().ljust(64, b"\0")
+
+    def peer_open(self, handle):
+        from multiprocessing import shared_memory
+
+        return self._attach(shared_memory.SharedMemory(name=handle.rstrip(b"\0").decode()))
+
+    def peer_close(self, addr):
+        self._segs.pop(addr >> 40).close()
+
+    def peer_free(self, addr):
+        shm = self._segs.pop(addr >> 40)
+        shm.close()
+        shm.unlink()
+
+    def match_emit_peer(self, hashes, nh, peers, words_cap):
+        B = hashes.shape[0]
+        own = B // peers.world
+        words, nwords = self.match_emit(hashes, nh, words_cap)
+        for q in range(B):
+            owner, j = divmod(q, own)
+            slot = peers.rank * own + j
+            self._view(peers.words[owner] + slot * words_cap * 4, words_cap)[:] = words[q].numpy()
+            self._view(peers.nwords[owner] + slot * 4, 1)[0] = int(nwords[q])
+
+    def peer_barrier(self, peers, epoch):
+        self._view(peers.flags[peers.rank] + 4 * peers.rank, 1)[0] = epoch   # the kernel's flag word, for the record
+        dist.barrier()
+
+    def match_owner_at(self, w_addr, n_addr, n_shards, B, words_cap, p, max_rows):
+        words = torch.from_numpy(self._view(w_addr, n_shards * B * words_cap).copy()).view(n_shards, B, words_cap)
+        nwords = torch.from_numpy(self._view(n_addr, n_shards * B).copy()).view(n_shards, B)
+        return self.match_owner(words, nwords, p, max_rows)
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -168,6 +228,15 @@ def _worker(rank, world, port, out_dir):
         res_d, nrows_d = sharded.match_sharded_dense(ctx, torch.from_numpy(q), torch.from_numpy(nq), params=_P, max_rows=8,
                                                      list_cap=4096, sub_batch=4)
         assert torch.equal(nrows_d, nrows) and torch.equal(res_d, res)
+        # the exchange fused into the sweep: words written straight into the owners' (shared-memory) buffers; three
+        # calls so that the two receive buffers and the barrier epochs carry over from call to call
+        pctx = PeerShardCtx(table, counts, hpid, lo, hi)
+        for sub in (4, 4, 1000):
+            res_p, nrows_p = sharded.match_sharded(pctx, torch.from_numpy(q), torch.from_numpy(nq), params=_P, max_rows=8,
+                                                   sub_batch=sub, exchange="peer")
+            assert torch.equal(nrows_p, nrows) and torch.equal(res_p, res)
+        sharded.release_peer_exchanges(pctx)
+        assert not pctx._segs
         # every rank must hold identical results
         gathered = [torch.zeros_like(res) for _ in range(world)]
         dist.all_gather(gathered, res)
