@@ -556,7 +556,7 @@ match_emit_kernel(const IndexView ix, const int32_t* __restrict__ hashes, const 
 // [this rank][q % own] - the layout match_owner_kernel reads.  No staging list in local HBM, no collective call.
 // Consecutive blocks take queries of different owners (block b: owner b % world, its query b / world), so the stores
 // to every peer - and the local ones - are spread over the whole kernel instead of one link at a time.
-struct PeerDst { uint32_t* words[MFPA_MAX_PEERS]; int32_t* nwords[MFPA_MAX_PEERS]; int own, rank, world; };
+struct PeerDst { uint32_t* words[MFPA_MAX_PEERS]; int32_t* nwords[MFPA_MAX_PEERS]; int own, rank, world, fence; };
 __global__ void __launch_bounds__(kFusedThreads, 2)
 match_emit_peer_kernel(const IndexView ix, const int32_t* __restrict__ hashes, const int32_t* __restrict__ nh, int cap,
                        const PeerDst d, int words_cap) {
@@ -569,9 +569,13 @@ match_emit_peer_kernel(const IndexView ix, const int32_t* __restrict__ hashes, c
   if (tid == 0) { s_n = 0; s_bad = 0; }
   const int2* rows = reinterpret_cast<const int2*>(hashes) + (int64_t)q * cap;
   fused_sweep<kSweepEmit>(ix, rows, min(nh[q], cap), &rc, nullptr, d.words[owner] + slot * words_cap, words_cap, &s_n, tid, &s_bad);
-  if (tid == 0) d.nwords[owner][slot] = s_bad ? kBadQueryTime : s_n;
-  // no fence here: the kernel boundary orders these stores before the barrier kernel that follows in the stream,
-  // and that kernel releases them at system scope (a per-thread MEMBAR.SYS cost as much as the sweep itself)
+  // One system-scope fence per block, by the thread that publishes the count, after the block barrier that ends
+  // the sweep: it is cumulative over the words the other threads stored before that barrier.  (A fence in every
+  // thread cost as much as the sweep itself; none at all leaves the ordering to the kernel boundary alone.)
+  if (tid == 0) {
+    d.nwords[owner][slot] = s_bad ? kBadQueryTime : s_n;
+    if (d.fence) __threadfence_system();
+  }
 }
 
 // Barrier between the ranks' streams, in peer memory: rank r writes the epoch into slot r of every rank's flag
@@ -981,6 +985,8 @@ int launch_match_emit_peer(mfpa_ctx* ctx, const int32_t* hashes, const int32_t* 
   d.own = B / peers->world;
   d.rank = peers->rank;
   d.world = peers->world;
+  static const bool no_fence = getenv("MFPA_PEER_NO_FENCE") != nullptr;   // measurement knob
+  d.fence = no_fence ? 0 : 1;
   match_emit_peer_kernel<<<B, kFusedThreads, 0, st>>>(view(ctx), hashes, nh, cap, d, words_cap);
   MFPA_CUDA(cudaGetLastError());
   return MFPA_OK;

@@ -58,10 +58,20 @@ def _to_owners(x, world, group):
     return out.view(world, x.shape[0] // world, *x.shape[1:])
 
 
-def default_words_cap(cap_hashes: int, depth: int, world: int) -> int:
-    """Capacity of one query's hit-word list on one shard: the expected share of the query's
-    cap_hashes * depth table entries, 35 % head-room for uneven hash ranges, rounded up to 256."""
-    return (int(1.35 * cap_hashes * depth / world) + 512 + 255) // 256 * 256
+def default_words_cap(cap_hashes: int, depth: int, world: int, bound: bool = False) -> int:
+    """Capacity of one query's hit-word list on one shard, rounded up to 256 words.
+
+    bound=True: cap_hashes * depth, what a query whose hashes ALL fall into one shard produces - it cannot overflow.
+    The peer exchange uses it: capacity there is only address space in the receive buffer, the words that exist
+    are all that crosses the link.  bound=False (the all-to-all, which moves the capacity): the expected share
+    cap_hashes / world of the query's buckets plus six standard deviations of that binomial count, every bucket
+    taken as full - an overflow (flagged per query, never silent) is then a < 1e-8 event per query and shard."""
+    if bound or world == 1:
+        rows = cap_hashes
+    else:
+        mean = cap_hashes / world
+        rows = min(cap_hashes, mean + 6.0 * (mean * (1.0 - 1.0 / world)) ** 0.5 + 1.0)
+    return (int(rows * depth) + 255) // 256 * 256
 
 
 class PeerExchange:
@@ -174,10 +184,10 @@ def match_sharded(ctx, hashes, nh, params=None, max_rows: int = 16, words_cap: i
     if world == 1:
         return ctx.match(hashes, nh, params, max_rows)
     dev = hashes.device
-    if words_cap is None:
-        words_cap = default_words_cap(cap, getattr(ctx, "depth", 100), world)
     if exchange is None:
         exchange = "peer" if hasattr(ctx, "peer_alloc") and dev.type == "cuda" else "nccl"
+    if words_cap is None:
+        words_cap = default_words_cap(cap, getattr(ctx, "depth", 100), world, bound=exchange == "peer")
     if sub_batch is None:
         # peer: nothing overlaps between sub-batches, so take the batch whole if the receive buffers allow;
         # all-to-all: sub-batches of 2048 pipeline the collective behind the next sweep
