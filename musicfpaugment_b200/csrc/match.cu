@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(512) match_select_kernel(const int32_t* __rest
 // the per-row (bucket, count, query time) triples are staged through a small shared-memory cache first.
 constexpr int kFusedRows = 768;
 constexpr int kFusedThreads = 1024;
-struct RowCache { int hb[kFusedRows]; int cnt[kFusedRows]; int t[kFusedRows]; };
+struct RowCache { int hb[kFusedRows]; int cnt[kFusedRows]; int t[kFusedRows]; int n; };   // n: rows kept (non-empty buckets of this shard)
 
 enum { kSweepCount = 0, kSweepCollect = 1, kSweepEmit = 2 };
 constexpr int kHitDtBits = 15;          // hit word of the sparse exchange: (track << 15) | (t_ref - t_q + 16384)
@@ -223,25 +223,32 @@ __device__ __forceinline__ void fused_sweep(const IndexView& ix, const int2* __r
   const uint32_t tmask = (1u << ix.maxtimebits) - 1u;
   const unsigned short* mark = reinterpret_cast<const unsigned short*>(hist);
   for (int c0 = 0; c0 < n; c0 += kFusedRows) {
-    const int nc = min(kFusedRows, n - c0);
+    const int n_in = min(kFusedRows, n - c0);
+    if (tid == 0) rc->n = 0;
     __syncthreads();
-    for (int i = tid; i < nc; i += kFusedThreads) {
+    // keep the rows whose bucket lies in this shard and is not empty (1 in `world` on a hash-range shard): the
+    // warps then sweep only those, spread evenly (warp w takes kept rows w, w + 32, w + 64, w + 96 of a round)
+    for (int i = tid; i < n_in; i += kFusedThreads) {
       const int2 row = rows[c0 + i];
       const int hb = (row.y & ix.hashmask) - ix.hash_lo;
-      const bool in = hb >= 0 && hb < ix.n_buckets;
-      rc->hb[i] = in ? hb : 0;
-      rc->cnt[i] = in ? min(ix.depth, ix.counts[hb]) : 0;
-      rc->t[i] = row.x;
+      const int cnt = (hb >= 0 && hb < ix.n_buckets) ? min(ix.depth, ix.counts[hb]) : 0;
       if (s_bad && (row.x < 0 || row.x >= kDtOff)) *s_bad = 1;
-      if (s_hits && rc->cnt[i]) atomicAdd(s_hits, (unsigned)rc->cnt[i]);
+      if (cnt > 0) {
+        const int slot = atomicAdd(&rc->n, 1);
+        rc->hb[slot] = hb;
+        rc->cnt[slot] = cnt;
+        rc->t[slot] = row.x;
+        if (s_hits) atomicAdd(s_hits, (unsigned)cnt);
+      }
     }
     __syncthreads();
+    const int nc = rc->n;
     for (int s0 = 0; s0 < ix.depth; s0 += 128) {   // one trip for depth <= 128 (the reference's is 100)
-      for (int r = warp * 4; r < nc; r += (kFusedThreads / 32) * 4) {
+      for (int r = warp; r < nc; r += 128) {   // rounds of 4 x 32 rows
         uint32_t v[4][4];
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
-          const int rr = r + a;
+          const int rr = r + 32 * a;
           const int cnt = rr < nc ? rc->cnt[rr] : 0;
           const uint32_t* bucket = ix.table + (int64_t)(rr < nc ? rc->hb[rr] : 0) * ix.depth;
 #pragma unroll
@@ -266,7 +273,7 @@ __device__ __forceinline__ void fused_sweep(const IndexView& ix, const int2* __r
               base = __shfl_sync(kFull, base, 0);
               const int pos = base + __popc(m & ((1u << lane) - 1u));
               if (ok && pos < list_cap) {
-                const int dt = (int)(v[a][i] & tmask) - rc->t[r + a];
+                const int dt = (int)(v[a][i] & tmask) - rc->t[r + 32 * a];
                 out[pos] = (id << kHitDtBits) | (uint32_t)(dt + kDtOff);
               }
               continue;
@@ -277,7 +284,7 @@ __device__ __forceinline__ void fused_sweep(const IndexView& ix, const int2* __r
             } else {
               const unsigned k = mark[id];
               if (k) {
-                const int dt = (int)(v[a][i] & tmask) - rc->t[r + a];
+                const int dt = (int)(v[a][i] & tmask) - rc->t[r + 32 * a];
                 const int pos = atomicAdd(s_n, 1);
                 if (pos < list_cap) out[pos] = ((k - 1u) << 16) | (uint32_t)(dt + kDtOff);
               }
