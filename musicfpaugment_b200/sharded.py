@@ -151,6 +151,45 @@ def _peer_exchange(ctx, world, rank, own, words_cap, group):
     return cache[key]
 
 
+def peer_supported(ctx, group=None) -> bool:
+    """Collective, cached on the context: can every rank map every other rank's memory (CUDA IPC + peer access; all
+    ranks on one node)?  Probed once with a 4 KiB buffer.  When some rank cannot, `match_sharded` keeps the NCCL
+    all-to-all - another transport for the same words, not another implementation."""
+    import sys
+
+    import torch
+    import torch.distributed as dist
+
+    if "_peer_ok" in ctx.__dict__:
+        return ctx._peer_ok
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    ok, base, opened = 1, None, []
+    try:
+        base, handle = ctx.peer_alloc(4096)
+    except Exception as e:  # noqa: BLE001 - any failure means "not here"
+        ok, handle = 0, b""
+        print(f"rank {rank}: peer memory unavailable ({e})", file=sys.stderr)
+    handles = [None] * world
+    dist.all_gather_object(handles, handle, group=group)
+    if ok and all(len(h) == 64 for h in handles):
+        try:
+            opened = [ctx.peer_open(handles[r]) for r in range(world) if r != rank]
+        except Exception as e:  # noqa: BLE001
+            ok = 0
+            print(f"rank {rank}: cannot map a peer's memory ({e}); sharded matching uses the NCCL all-to-all", file=sys.stderr)
+    else:
+        ok = 0
+    flag = torch.tensor([ok], dtype=torch.int32, device=torch.device("cuda", ctx.device))
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    for a in opened:
+        ctx.peer_close(a)
+    dist.barrier(group=group)
+    if base is not None:
+        ctx.peer_free(base)
+    ctx._peer_ok = bool(flag.item())
+    return ctx._peer_ok
+
+
 PEER_BUFFER_BYTES = 4 << 30   # both receive buffers of a PeerExchange together (the sub-batch is sized to fit)
 
 
@@ -185,7 +224,7 @@ def match_sharded(ctx, hashes, nh, params=None, max_rows: int = 16, words_cap: i
         return ctx.match(hashes, nh, params, max_rows)
     dev = hashes.device
     if exchange is None:
-        exchange = "peer" if hasattr(ctx, "peer_alloc") and dev.type == "cuda" else "nccl"
+        exchange = "peer" if hasattr(ctx, "peer_alloc") and dev.type == "cuda" and peer_supported(ctx, group) else "nccl"
     if words_cap is None:
         words_cap = default_words_cap(cap, getattr(ctx, "depth", 100), world, bound=exchange == "peer")
     if sub_batch is None:
