@@ -122,6 +122,28 @@ def test_matcher_exact_count_time_range_hashesfor(mods):
     assert checked >= 20
 
 
+def test_add_colored_noise_drop_in(mods):
+    """augmentation.transformations.colored_noise.AddColoredNoise: same seeded draws as the reference (gate, SNRs,
+    decays, noise periods) and the mix on the GPU within 2e-6 of the reference's output
+    (tests/golden/colored_noise.npz, oracle/make_golden_colored_noise.py)."""
+    from augmentation.transformations.colored_noise import AddColoredNoise
+
+    g = np.load(os.path.join(ROOT, "tests", "golden", "colored_noise.npz"))
+    t = AddColoredNoise(min_snr_in_db=3.0, max_snr_in_db=30.0, min_f_decay=-2.0, max_f_decay=2.0, p=0.7,
+                        sample_rate=int(g["sample_rate"]))
+    torch.manual_seed(int(g["seed"]))
+    out = t(samples=torch.from_numpy(g["x"].copy()), sample_rate=int(g["sample_rate"]))
+    tp = t.transform_parameters
+    assert np.array_equal(tp["should_apply"].numpy(), g["should_apply"])
+    assert np.array_equal(tp["snr_in_db"].numpy(), g["snr_in_db"]) and np.array_equal(tp["f_decay"].numpy(), g["f_decay"])
+    got = out.samples.numpy()
+    assert got.shape == g["out"].shape and out.sample_rate == int(g["sample_rate"])
+    assert np.array_equal(got[~g["should_apply"]], g["x"][~g["should_apply"]])     # untouched examples pass through
+    assert float(np.abs(got - g["out"]).max()) <= 2e-6                                # outputs are peak-normalised: |y| <= 1
+    with pytest.raises(RuntimeError):
+        t(samples=torch.zeros(4, 8000), sample_rate=8000)
+
+
 def test_get_2d_peaks(mods):
     from oracle import dejavu_np as D
 
