@@ -274,6 +274,16 @@ int mfpa_augment(mfpa_ctx* ctx, const float* x_dev, int B, int T, int64_t x_stri
                  const mfpa_aug_params* params_host, const float* ir_dev, int ir_stride,
                  const float* noise_dev, float* out_dev, void* stream);
 
+/* One filter of a julius.LowPassFilters bank per row (julius 0.2.7 lowpass.py; the reference's BandPassFilter /
+ * BandStopFilter call julius.bandpass_filter = bank([low, high]) and subtract, band_filters.py:126-156,195):
+ * taps = hann(2 half + 1) * 2c * sinc(2c pi t) normalised to sum 1 with c = cutoff_host[row] and
+ * half = int(8 / width_host[row] / 2) - the bank gives all its filters the window of its lowest cut-off, so a band
+ * filter passes the low cut-off as `width` of both rows; replicate padding; any length up to MFPA_AUG_MAX_TAPS.
+ * Both arrays are fractions of the sample rate in (0, 0.5] (else MFPA_EINVAL, where julius raises ValueError).
+ * x_dev [B][T] (row stride x_stride), out_dev [B][T] contiguous.  Runs the low-pass stage of mfpa_augment. */
+int mfpa_lowpass_filters(mfpa_ctx* ctx, const float* x_dev, int B, int T, int64_t x_stride, const double* cutoff_host,
+                         const double* width_host, float* out_dev, void* stream);
+
 /* ---- noise preparation ahead of the chain
  * AddBackgroundNoise.random_background (augmentation/transformations/background_noise.py:64-141):
  * a query's noise row is the concatenation of pieces cut from randomly chosen background files

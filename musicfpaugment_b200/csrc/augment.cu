@@ -1141,7 +1141,7 @@ static int fir_half(float fc_hz, int sample_rate, const char* name, int qi, doub
 
 int launch_augment(mfpa_ctx* ctx, const float* x, int B, int T, int64_t x_stride, int sample_rate,
                    const mfpa_aug_params* pp, const float* ir, int ir_stride, const float* noise, float* out,
-                   bool final_norm, cudaStream_t st, const int64_t* ir_offsets, int64_t ir_bank_len) {
+                   bool final_norm, cudaStream_t st, const int64_t* ir_offsets, int64_t ir_bank_len, const LpfShape* lpf) {
   if (int e = aug_init_tables(ctx)) return e;
   // ---- derive per-query parameters on the host
   const size_t need = (sizeof(AugQ) + 5 * sizeof(int)) * (size_t)B;
@@ -1187,7 +1187,16 @@ int launch_augment(mfpa_ctx* ctx, const float* x, int B, int T, int64_t x_stride
       else up(nb1, blocks_of(false, q.half1, 0));
     }
     if (p.apply & MFPA_AUG_LPF) {
-      q.half2 = fir_half(p.fc2_hz, sample_rate, "low-pass", i, &c);
+      if (lpf) {   // cut-off and window width given separately, as fractions of the sample rate
+        c = lpf->cutoff[i];
+        const double w = lpf->width[i];
+        MFPA_REQUIRE(c > 0.0 && c <= 0.5 && w > 0.0 && w <= 0.5, "lowpass_filters: row %d: cut-off %g / window cut-off %g outside "
+                     "(0, 0.5] of the sample rate (julius raises ValueError)", i, c, w);
+        const double h = 8.0 / w / 2.0;
+        q.half2 = h > 1e9 ? 1 << 30 : (int)h;
+      } else {
+        q.half2 = fir_half(p.fc2_hz, sample_rate, "low-pass", i, &c);
+      }
       if (q.half2 < 0) return MFPA_EINVAL;
       MFPA_REQUIRE(2 * (int64_t)q.half2 + 1 <= MFPA_AUG_MAX_TAPS, "augment: query %d: low-pass cut-off %g Hz needs %lld taps "
                    "(limit %d)", i, (double)p.fc2_hz, 2ll * q.half2 + 1, MFPA_AUG_MAX_TAPS);

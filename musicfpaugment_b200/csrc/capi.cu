@@ -555,6 +555,23 @@ int mfpa_augment(mfpa_ctx* ctx, const float* x_dev, int B, int T, int64_t x_stri
                         true, (cudaStream_t)stream);
 }
 
+int mfpa_lowpass_filters(mfpa_ctx* ctx, const float* x_dev, int B, int T, int64_t x_stride, const double* cutoff_host,
+                         const double* width_host, float* out_dev, void* stream) {
+  MFPA_REQUIRE(ctx && x_dev && cutoff_host && width_host && out_dev && B >= 1 && T >= 1 && x_stride >= T,
+               "lowpass_filters: bad argument");
+  DeviceGuard guard(ctx->device);
+  std::vector<mfpa_aug_params> pp((size_t)B);
+  for (int i = 0; i < B; ++i) {
+    pp[i] = mfpa_aug_params{};
+    pp[i].apply = MFPA_AUG_LPF;
+    pp[i].fc2_hz = (float)cutoff_host[i];   // for messages only: the shape below is what the stage uses
+    pp[i].gain_factor = 1.0f;
+  }
+  const LpfShape shape{cutoff_host, width_host};
+  return launch_augment(ctx, x_dev, B, T, x_stride, 1, pp.data(), nullptr, 0, nullptr, out_dev, false, (cudaStream_t)stream,
+                        nullptr, 0, &shape);
+}
+
 int mfpa_noise_assemble(mfpa_ctx* ctx, const float* bank_dev, int64_t bank_len, const mfpa_noise_piece* pieces_host,
                         int n_pieces, int B, int T, float* out_dev, void* stream) {
   MFPA_REQUIRE(ctx && bank_dev && pieces_host && out_dev, "noise_assemble: NULL argument");

@@ -129,7 +129,11 @@ int launch_compact_rows(const int32_t* rows_in, const int32_t* n, int items, int
                         int32_t* rows, int64_t rows_cap, cudaStream_t st);
 int launch_augment(mfpa_ctx* ctx, const float* x, int B, int T, int64_t x_stride, int sample_rate,
                    const mfpa_aug_params* params_host, const float* ir, int ir_stride, const float* noise,
-                   float* out, bool final_norm, cudaStream_t st, const int64_t* ir_offsets = nullptr, int64_t ir_bank_len = 0);
+                   float* out, bool final_norm, cudaStream_t st, const int64_t* ir_offsets = nullptr, int64_t ir_bank_len = 0,
+                   const struct LpfShape* lpf = nullptr);
+// Overrides the low-pass stage's filter per query (mfpa_lowpass_filters): cut-off and window width as fractions of the
+// sample rate - julius.LowPassFilters gives every filter of a bank the window of the LOWEST cut-off.
+struct LpfShape { const double* cutoff; const double* width; };
 int launch_noise_assemble(mfpa_ctx* ctx, const float* bank, int64_t bank_len, const mfpa_noise_piece* pieces, int n_pieces,
                           int B, int T, float* out, cudaStream_t st, bool pieces_pinned = false);
 int launch_match_counts(mfpa_ctx* ctx, const int32_t* hashes, const int32_t* nh, int B, int cap, int32_t* counts,

@@ -109,6 +109,7 @@ SIGNATURES = {
     "mfpa_noise_assemble": (_i, [_vp, _vp, _i64, _vp, _i, _i, _i, _vp, _vp]),
     "mfpa_augment_fingerprint": (_i, [_vp, _vp, _i, _i, _i64, _i, _vp, _vp, _i, _vp, _i, _P, _vp, _i, _vp, _vp]),
     "mfpa_augment_fingerprint_host": (_i, [_vp, C.POINTER(ChainInputs), _i, _i, _i, _vp, _i, _P, _vp, _i64, _vp]),
+    "mfpa_lowpass_filters": (_i, [_vp, _vp, _i, _i, _i64, _vp, _vp, _vp, _vp]),
     "mfpa_index_load": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i]),
     "mfpa_match_defaults": (None, [C.POINTER(MatchParams)]),
     "mfpa_get_hits": (_i, [_vp, _vp, _i, _vp, _i64, _vp, _vp]),
@@ -404,6 +405,21 @@ class Context:
         out = torch.empty(B, T, dtype=torch.float32, device=x.device)
         check(_lib.mfpa_augment(self._h, _ptr(x), B, T, _row_stride(x), sample_rate, params.ctypes.data_as(C.c_void_p),
                                 _ptr(ir), ir.shape[1] if ir is not None else 0, _ptr(noise), _ptr(out), _stream()))
+        return out
+
+    def lowpass_filters(self, x, cutoff, width=None):
+        """One julius.LowPassFilters filter per row: x [B,T] f32 cuda, cutoff / width float64 [B] fractions of the sample
+        rate (width = the cut-off whose window the bank uses; default the filter's own) -> [B,T] f32 cuda."""
+        import numpy as np
+        import torch
+
+        assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
+        B, T = x.shape
+        cutoff = np.ascontiguousarray(cutoff, dtype=np.float64).reshape(B)
+        width = cutoff if width is None else np.ascontiguousarray(width, dtype=np.float64).reshape(B)
+        out = torch.empty(B, T, dtype=torch.float32, device=x.device)
+        check(_lib.mfpa_lowpass_filters(self._h, _ptr(x), B, T, _row_stride(x), cutoff.ctypes.data_as(C.c_void_p),
+                                        width.ctypes.data_as(C.c_void_p), _ptr(out), _stream()))
         return out
 
     def noise_assemble(self, bank, pieces, B: int, T: int):

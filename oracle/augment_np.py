@@ -14,6 +14,9 @@ Parity status
     published algorithm (windowed-sinc, zeros = 8, Hann window, replicate padding,
     conv1d) — **parity unpinned** for that one function.  The golden vectors use the
     same restatement (oracle/ref_loader.py::_julius_lowpass_filter, torch float32).
+    The taps are pinned independently against scipy.signal.firwin (tests/test_oracle_golden.py);
+  * `julius.bandpass_filter` (`bandpass`, `bandstop` below; same package, same situation): restated,
+    **parity unpinned**; the parameter draws of the band filters ARE pinned (tests/golden/band_params.npz).
 
 Stage boundaries are float32 like the reference's tensors; inside a stage the
 oracle accumulates in float64 (differences to torch's float32 kernels are ~1e-6,
@@ -27,17 +30,18 @@ F32 = np.float32
 
 
 # ------------------------------------------------------------------ FIR (julius restated)
-def lowpass_taps(cutoff: float, zeros: float = 8.0) -> np.ndarray:
+def lowpass_taps(cutoff: float, zeros: float = 8.0, width: float | None = None) -> np.ndarray:
     """julius.lowpass.LowPassFilters.__init__ for one cutoff (fraction of the sample rate):
     half = int(zeros / cutoff / 2); hann(2*half+1, periodic=False) * 2c * sinc(2c*pi*t), sum -> 1.
-    float32 like torch (window, argument and sinc are float32 tensors there)."""
+    float32 like torch (window, argument and sinc are float32 tensors there).  `width`: the cut-off that sets the
+    window (a bank of several cut-offs takes half from the lowest positive one)."""
     if cutoff < 0:
         raise ValueError("Minimum cutoff must be larger than zero.")
     if cutoff > 0.5:
         raise ValueError("A cutoff above 0.5 does not make sense.")
     if cutoff == 0:
         raise ValueError("min() arg is an empty sequence")
-    half = int(zeros / cutoff / 2)
+    half = int(zeros / (cutoff if width is None else width) / 2)
     n = 2 * half + 1
     k = np.arange(n, dtype=np.float64)
     win = (0.5 - 0.5 * np.cos(2.0 * np.pi * k / (n - 1))).astype(F32) if n > 1 else np.ones(1, F32)
@@ -49,10 +53,10 @@ def lowpass_taps(cutoff: float, zeros: float = 8.0) -> np.ndarray:
     return (h / h.sum(dtype=F32)).astype(F32)
 
 
-def lowpass(x: np.ndarray, cutoff: float) -> np.ndarray:
+def lowpass(x: np.ndarray, cutoff: float, width: float | None = None) -> np.ndarray:
     """julius.lowpass_filter(x, cutoff, fft=False): replicate-pad `half` each side, conv1d.
     Call site: augmentation/transformations/pass_filters.py:100-102."""
-    h = lowpass_taps(cutoff).astype(np.float64)
+    h = lowpass_taps(cutoff, width=width).astype(np.float64)
     half = (len(h) - 1) // 2
     xp = np.pad(np.asarray(x, np.float64), half, mode="edge")
     if len(h) > 256:  # long filters: FFT convolution (same numbers to ~1e-12)
@@ -69,6 +73,27 @@ def highpass(x: np.ndarray, cutoff: float) -> np.ndarray:
     """HighPassFilter.apply_transform: x - lowpass(x).  pass_filters.py:144-155."""
     x = np.asarray(x, F32)
     return (x - lowpass(x, cutoff)).astype(F32)
+
+
+def bandpass(x: np.ndarray, cutoff_low: float, cutoff_high: float) -> np.ndarray:
+    """julius.bandpass_filter(x, cutoff_low, cutoff_high, fft=False) - julius 0.2.7 bands.py / lowpass.py, restated
+    (julius is not in this image: PARITY UNPINNED for this function): LowPassFilters([low, high]) builds both filters
+    on the window of the lowest positive cut-off, the band is high-passed-low = lows[1] - lows[0]; a low cut-off of 0
+    makes lows[0] zero, a high cut-off of 0.5 makes lows[1] the identity.
+    Call site: augmentation/transformations/band_filters.py:126-135."""
+    if cutoff_low > cutoff_high:
+        raise ValueError("Lower cutoff must be smaller than higher cutoff.")
+    x = np.asarray(x, F32)
+    width = min(c for c in (cutoff_low, cutoff_high) if c > 0)
+    low = lowpass(x, cutoff_low, width) if cutoff_low > 0 else np.zeros_like(x)
+    high = lowpass(x, cutoff_high, width)
+    return (high - low).astype(F32)
+
+
+def bandstop(x: np.ndarray, cutoff_low: float, cutoff_high: float) -> np.ndarray:
+    """BandStopFilter.apply_transform (band_filters.py:187-199): x - bandpass(x)."""
+    x = np.asarray(x, F32)
+    return (x - bandpass(x, cutoff_low, cutoff_high)).astype(F32)
 
 
 def cutoff_fraction(cutoff_hz, sample_rate: int) -> float:

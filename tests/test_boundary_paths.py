@@ -26,7 +26,7 @@ def test_dropins_alone_import():
     r = _run("import afp.audfprint.peak_extractor, afp.audfprint.hash_table, afp.audfprint.audfprint_match, afp.audfprint.stft\n"
              "import afp.dejavu.fingerprint, afp.dejavu.variables, afp.dejavu.dejavu, afp.dejavu.file_recognizer\n"
              "import dejavu.dejavu, dejavu.postgres_database, dejavu.variables, afp.dejavu.postgres_database\n"
-             "import augmentation, testing.metrics, augmentation.transformations.colored_noise\n"
+             "import augmentation, testing.metrics, augmentation.transformations.colored_noise, augmentation.transformations.band_filters\n"
              "assert dejavu.dejavu is afp.dejavu.dejavu and dejavu.postgres_database is afp.dejavu.postgres_database\n"
              "assert dejavu.variables.SONG_ID == 'song_id' and dejavu.variables.TOPN == 1\n"
              "print('ok')", with_ref=False)
@@ -52,6 +52,8 @@ def test_reference_drivers_import_through_the_dropins():
         "spec = importlib.util.find_spec('augmentation.transformations.colored_noise')\n"
         "assert spec is not None and spec.origin.startswith(D), 'AddColoredNoise did not come from the drop-ins'\n"
         "spec = importlib.util.find_spec('augmentation.transformations.band_filters')\n"
+        "assert spec is not None and spec.origin.startswith(D), 'the band filters did not come from the drop-ins'\n"
+        "spec = importlib.util.find_spec('augmentation.transformations.gain')\n"
         "assert spec is not None and spec.origin.startswith(R), 'the unreplaced transforms must stay with the reference'\n"
         "print('ok')")
     r = _run(code, with_ref=True)

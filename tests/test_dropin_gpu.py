@@ -144,6 +144,39 @@ def test_add_colored_noise_drop_in(mods):
         t(samples=torch.zeros(4, 8000), sample_rate=8000)
 
 
+def test_band_filters_drop_in(mods):
+    """BandPassFilter / BandStopFilter: the seeded draws equal the reference's (tests/golden/band_params.npz, made by the
+    reference's own class), the filtering equals the restated julius.bandpass_filter (oracle/augment_np.bandpass -
+    julius is absent, that part is unpinned) within 1e-5 of the signal's peak; one example needs an 11 909-tap window
+    (a 5.4 Hz low cut-off: the partitioned FFT path), the others 100-600 taps."""
+    from augmentation.transformations.band_filters import BandPassFilter, BandStopFilter
+    from oracle import augment_np as A
+
+    g = np.load(os.path.join(ROOT, "tests", "golden", "band_params.npz"))
+    B, sr, T = int(g["batch"]), int(g["sample_rate"]), 24000
+    x = np.random.default_rng(5).standard_normal((B, 1, T)).astype(np.float32) * 0.3
+    for cls in (BandPassFilter, BandStopFilter):
+        t = cls(min_center_frequency=200, max_center_frequency=1900, min_bandwidth_fraction=0.5, max_bandwidth_fraction=1.99,
+                p=0.8, sample_rate=sr)
+        torch.manual_seed(int(g["seed"]))
+        out = t(samples=torch.from_numpy(x.copy()), sample_rate=sr).samples.numpy()
+        tp = t.transform_parameters
+        gate = g["should_apply"]
+        assert np.array_equal(tp["should_apply"].numpy(), gate)
+        assert np.array_equal(tp["center_freq"].numpy(), g["center_freq"]) and np.array_equal(tp["bandwidth"].numpy(), g["bandwidth"])
+        assert np.array_equal(out[~gate], x[~gate])
+        worst = 0.0
+        for k, i in enumerate(np.nonzero(gate)[0]):
+            band = A.bandpass(x[i, 0], float(g["low"][k]), float(g["high"][k]))
+            want = band if cls is BandPassFilter else x[i, 0] - band
+            worst = max(worst, float(np.abs(out[i, 0] - want).max()))
+        assert worst <= 1e-5 * float(np.abs(x).max()) * 4, worst
+    with pytest.raises(ValueError):      # a band reaching past sr / 2: julius raises, so does the drop-in
+        t = BandPassFilter(min_center_frequency=3900, max_center_frequency=4000, min_bandwidth_fraction=1.0,
+                           max_bandwidth_fraction=1.5, p=1.0, sample_rate=sr)
+        t(samples=torch.from_numpy(x[:2].copy()), sample_rate=sr)
+
+
 def test_get_2d_peaks(mods):
     from oracle import dejavu_np as D
 

@@ -292,3 +292,34 @@ def test_parameter_draws_match_reference_rng_order(dropin_modules):
         ref.randomize_parameters(x[ref.transform_parameters["should_apply"]])
         assert torch.equal(mine.transform_parameters["should_apply"], ref.transform_parameters["should_apply"])
         assert torch.equal(mine.transform_parameters[key], ref.transform_parameters[key]), key
+
+
+def test_band_filter_and_colored_noise_draws_match_the_reference(dropin_modules):
+    """BandPassFilter / AddColoredNoise host side: gate and parameter draws in the reference's RNG order
+    (tests/golden/band_params.npz and colored_noise.npz were made by the reference's own classes)."""
+    from augmentation.transformations.band_filters import BandPassFilter
+    from augmentation.transformations.colored_noise import AddColoredNoise
+
+    gold = os.path.join(ROOT, "tests", "golden")
+    g = np.load(os.path.join(gold, "band_params.npz"))
+    t = BandPassFilter(min_center_frequency=200, max_center_frequency=1900, min_bandwidth_fraction=0.5, max_bandwidth_fraction=1.99,
+                       p=0.8, sample_rate=int(g["sample_rate"]))
+    torch.manual_seed(int(g["seed"]))
+    gate = torch.distributions.Bernoulli(torch.tensor(0.8)).sample(sample_shape=(int(g["batch"]),)).to(torch.bool)
+    assert np.array_equal(gate.numpy(), g["should_apply"])
+    t.randomize_parameters(torch.zeros(int(gate.sum()), 1, 16))
+    assert np.array_equal(t.transform_parameters["center_freq"].numpy(), g["center_freq"])
+    assert np.array_equal(t.transform_parameters["bandwidth"].numpy(), g["bandwidth"])
+    for bad in (dict(max_center_frequency=100), dict(min_bandwidth_fraction=0.0), dict(max_bandwidth_fraction=2.0)):
+        with pytest.raises(ValueError):
+            BandPassFilter(**bad)
+    c = np.load(os.path.join(gold, "colored_noise.npz"))
+    n = AddColoredNoise(p=0.7, sample_rate=int(c["sample_rate"]))
+    torch.manual_seed(int(c["seed"]))
+    gate = torch.distributions.Bernoulli(torch.tensor(0.7)).sample(sample_shape=(len(c["x"]),)).to(torch.bool)
+    assert np.array_equal(gate.numpy(), c["should_apply"])
+    n.randomize_parameters(torch.zeros(int(gate.sum()), 1, 16))
+    assert np.array_equal(n.transform_parameters["snr_in_db"].numpy(), c["snr_in_db"])
+    assert np.array_equal(n.transform_parameters["f_decay"].numpy(), c["f_decay"])
+    with pytest.raises(ValueError):
+        AddColoredNoise(min_snr_in_db=10.0, max_snr_in_db=5.0)
