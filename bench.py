@@ -67,12 +67,15 @@ STAGE_BYTES = {
     "mix": 768_000, "clip_lpf": 512_000, "hpf3_filter": 65_536, "hpf3_conv": 512_000, "stft": BYTES_STFT,
     "peaks": BYTES_PEAKS, "landmarks": 8_000,
 }
-# dram__bytes_read.sum + dram__bytes_write.sum per launch at 10 000 queries from the `ncu --set full` captures
-# summarised under profiles/ (r02b_aug_summary.txt for the chain, r01k_summary.txt for the analysis kernels)
-NCU_TRAFFIC_10K = {"hpf1_conv": 3.217e9 + 2.525e9, "ir_conv": 3.218e9 + 2.526e9, "hpf3_conv": 3.217e9 + 2.525e9,
-                   "mix": 5.122e9 + 2.663e9, "clip_lpf": 2.561e9 + 2.518e9,
-                   "stft": 2.692782e9 + 2.607007e9, "peaks": 2.963450e9 + 0.020312e9, "landmarks": 0.020157e9 + 0.000076e9}
-NCU_TRAFFIC_SOURCE = "profiles/r02b_aug_summary.txt, profiles/r01k_summary.txt (ncu --set full, dram read+write)"
+# dram__bytes_read.sum + dram__bytes_write.sum per launch at 10 000 queries from the `ncu --set full` capture of one step
+# of the chain (profiles/r02z_chain_summary.txt)
+NCU_TRAFFIC_10K = {"hpf1_filter": 0.000768e9 + 0.596881e9, "hpf1_conv": 3.216819e9 + 2.534520e9,
+                   "ir_filter": 0.320955e9 + 0.600439e9, "ir_conv": 3.217038e9 + 2.526299e9,
+                   "mix": (1.312196e9 + 0.004278e9) + (5.122590e9 + 2.662157e9) + (0.133051e9 + 0.003880e9),   # sample + mix + finish
+                   "clip_lpf": 2.561486e9 + 2.518094e9, "hpf3_filter": 0.000876e9 + 0.596374e9,
+                   "hpf3_conv": 3.216898e9 + 2.531945e9, "stft": 2.693002e9 + 2.607849e9,
+                   "peaks": 2.890073e9 + 0.020177e9, "landmarks": 0.020131e9 + 0.000042e9}
+NCU_TRAFFIC_SOURCE = "profiles/r02z_chain_summary.txt (ncu --set full of one step of the chain, dram read + write)"
 
 
 def _measured(keys, default):
