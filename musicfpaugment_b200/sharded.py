@@ -143,12 +143,18 @@ def release_peer_exchanges(ctx, group=None):
 
 
 def _peer_exchange(ctx, world, rank, own, words_cap, group):
-    """The context's cached PeerExchange for this geometry (set up once: IPC mapping costs milliseconds)."""
+    """The context's cached PeerExchange for this list capacity (set up once: IPC mapping costs milliseconds).  One
+    that was built for at least `own` queries per rank serves smaller sub-batches too (a sub-batch's lists fill a
+    prefix of the buffer); a larger request replaces it - collectively, every rank takes the same path."""
     cache = ctx.__dict__.setdefault("_peer_exchanges", {})
-    key = (world, rank, own, words_cap, id(group))
-    if key not in cache:
-        cache[key] = PeerExchange(ctx, world, rank, own, words_cap, group)
-    return cache[key]
+    key = (world, rank, 0, words_cap, id(group))
+    px = cache.get(key)
+    if px is not None and px.own < own:
+        px.close(group)
+        px = None
+    if px is None:
+        px = cache[key] = PeerExchange(ctx, world, rank, own, words_cap, group)
+    return px
 
 
 def peer_supported(ctx, group=None) -> bool:
