@@ -233,6 +233,9 @@ __global__ void __launch_bounds__(FT, OCC) fftconv_kernel(const ConvArgs a, cons
   float* __restrict__ out = a.out + (int64_t)qi * a.T;
   const int T = a.T;
   float vmax = 0.f, vss = 0.f;
+  // statistics the later stages read: peak and energy of the response stage's output (noise mix), peak of the last
+  // stage's (final normalisation); the first stage's output needs neither
+  const bool want_max = MODE == kModeIR || a.which == 3, want_ss = MODE == kModeIR;
   if ((q.apply & a.bit) && (q.long_mask & long_bit<MODE>(a.which))) return;   // part_conv_kernel's query
   // 16-byte accesses need aligned rows (the in-block offsets are multiples of 4 samples by construction)
   const bool vec_in = ((reinterpret_cast<uintptr_t>(in) & 15) == 0), vec_out = ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
@@ -295,8 +298,8 @@ __global__ void __launch_bounds__(FT, OCC) fftconv_kernel(const ConvArgs a, cons
       if (i < 0 || n >= n_end) return;
       const float v[4] = {v4.x, v4.y, v4.z, v4.w};
       if (n + 3 < n_end && n + 3 < T) {
-        vmax = fmaxf(fmaxf(vmax, fmaxf(fabsf(v[0]), fabsf(v[1]))), fmaxf(fabsf(v[2]), fabsf(v[3])));
-        vss = fmaf(v[0], v[0], fmaf(v[1], v[1], fmaf(v[2], v[2], fmaf(v[3], v[3], vss))));
+        if (want_max) vmax = fmaxf(fmaxf(vmax, fmaxf(fabsf(v[0]), fabsf(v[1]))), fmaxf(fabsf(v[2]), fabsf(v[3])));
+        if (want_ss) vss = fmaf(v[0], v[0], fmaf(v[1], v[1], fmaf(v[2], v[2], fmaf(v[3], v[3], vss))));
         if (vec_out) *reinterpret_cast<float4*>(out + n) = v4;
         else { out[n] = v[0]; out[n + 1] = v[1]; out[n + 2] = v[2]; out[n + 3] = v[3]; }
       } else {
@@ -309,13 +312,13 @@ __global__ void __launch_bounds__(FT, OCC) fftconv_kernel(const ConvArgs a, cons
       }
     });
   }
+  if (!want_max) return;   // block-uniform
   vmax = block_max(vmax, s.red, tid);
-  vss = block_sum(vss, s.red, tid);
+  if (want_ss) vss = block_sum(vss, s.red, tid);
   if (tid == 0) {
     AugS* st = a.st + qi;
-    if (MODE != kModeIR && a.which == 1) { atomic_max_pos(&st->max_a, vmax); atomicAdd(&st->ss_a, (double)vss); }
-    else if (MODE == kModeIR) { atomic_max_pos(&st->max_b, vmax); atomicAdd(&st->ss_b, (double)vss); }
-    else if (MODE != kModeIR && a.which == 3) atomic_max_pos(&st->max_v, vmax);
+    if (MODE == kModeIR) { atomic_max_pos(&st->max_b, vmax); atomicAdd(&st->ss_b, (double)vss); }
+    else atomic_max_pos(&st->max_v, vmax);
   }
 }
 
