@@ -180,7 +180,7 @@ template <int BATCH, typename F> __device__ __forceinline__ void fill_planes(con
 // One block per query: double pairs of the query's filter (zero-padded to FN real samples), scaled by
 // 1/FM (the unscaled inverse transform) and, for the FIRs, by 1/sum(taps) (julius normalises to DC gain 1).
 template <int MODE>
-__global__ void __launch_bounds__(FT, 2) filter_spectrum_kernel(const ConvArgs a, const float* __restrict__ tw_g) {
+__global__ void __launch_bounds__(FT, 3) filter_spectrum_kernel(const ConvArgs a, const float* __restrict__ tw_g) {
   extern __shared__ __align__(16) float smem_f[];
   const ConvSmem s(smem_f);
   const int tid = threadIdx.x, qi = blockIdx.x;

@@ -1,9 +1,9 @@
 set -u
 OUT=gpurun_out; mkdir -p $OUT
-python -m pytest tests/test_augment_gpu.py tests/test_dropin_gpu.py tests/test_drivers_gpu.py -m gpu -q -x 2>&1 | tail -2
-python bench.py --steps 10 --warmup 3 --also none > $OUT/bench_r02y.json 2> $OUT/bench_r02y.err
+python -m pytest tests/test_augment_gpu.py -m gpu -q -x 2>&1 | tail -2
+python bench.py --steps 10 --warmup 3 --also none --no-cpu-baseline > $OUT/bench_r02y2.json 2> $OUT/bench_r02y.err
 python - <<PY
 import json
-d=json.loads(open("$OUT/bench_r02y.json").read())
-print(round(d["ms_per_step"],3), {k: round(v,3) for k,v in d["stage_ms"].items()}, d["parity"]["hash_agreement"])
+d=json.loads(open("$OUT/bench_r02y2.json").read())
+print(round(d["ms_per_step"],3), {k: round(v,3) for k,v in d["stage_ms"].items()})
 PY
