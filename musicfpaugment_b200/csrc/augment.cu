@@ -331,7 +331,7 @@ __device__ __forceinline__ float key_value(unsigned k) {
   return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
-constexpr int kSelThreads = 512;
+constexpr int kSelThreads = 256;
 constexpr int kSelSample = 512;    // strided sample that places the tail thresholds (each sample costs a DRAM sector)
 constexpr int kSelCap = 4096;      // capacity of each tail list
 constexpr int kMixStage = 256;     // per-block staging of the tails in mix_kernel
@@ -599,7 +599,7 @@ __device__ void smem_select(const unsigned* a, int n, int r, unsigned* hist, uns
     const int shift = 24 - 8 * pass;
     const unsigned himask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
     __syncthreads();
-    if (tid < 256) hist[tid] = 0;
+    for (int i = tid; i < 256; i += kSelThreads) hist[i] = 0;
     __syncthreads();
     for (int i = tid; i < n; i += kSelThreads) {
       const unsigned k = a[i];

@@ -1,6 +1,6 @@
 set -u
 OUT=gpurun_out; mkdir -p $OUT
-python -m pytest tests/test_augment_gpu.py -m gpu -q -x 2>&1 | tail -2
+python -m pytest tests/test_augment_gpu.py -m gpu -q -x 2>&1 | tail -1
 python bench.py --steps 10 --warmup 3 --also none --no-cpu-baseline > $OUT/bench_r02y2.json 2> $OUT/bench_r02y.err
 python - <<PY
 import json
