@@ -58,3 +58,27 @@ def test_reference_drivers_import_through_the_dropins():
         "print('ok')")
     r = _run(code, with_ref=True)
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-3000:]
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "testing")), reason="reference checkout not mounted")
+def test_dropin_constants_equal_the_reference():
+    """The drop-ins' copies of the configuration constants (augmentation/constants.py, afp/dejavu/variables.py) are
+    written in their own form; every name of the reference modules must carry the same value and type."""
+    import importlib.util
+
+    def load(path, name):
+        spec = importlib.util.spec_from_file_location(name, path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod
+
+    for rel in ("augmentation/constants.py", "afp/dejavu/variables.py"):
+        ours, ref = load(os.path.join(DROPIN, rel), "ours_" + rel[-6:-3]), load(os.path.join(REF, rel), "ref_" + rel[-6:-3])
+        names = [n for n in dir(ref) if n.isupper()]
+        assert len(names) >= 3
+        for n in names:
+            a, b = getattr(ours, n), getattr(ref, n)
+            assert a == b and type(a) is type(b), (rel, n)
+            if isinstance(b, dict):
+                assert list(a) == list(b) or set(a) == set(b)
+                assert all(type(a[k]) is type(b[k]) for k in b), (rel, n)
