@@ -30,8 +30,9 @@ constexpr size_t kStftSmem =
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// complex add / subtract of interleaved (re, im) pairs: one packed f32x2 instruction each (same roundings)
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
 
 // forward 4-point DFT in place: (a, b, c, d) = inputs n = 0..3 -> outputs k = 0..3
 __device__ __forceinline__ void dft4(float2& a, float2& b, float2& c, float2& d) {
